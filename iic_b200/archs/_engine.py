@@ -1,0 +1,318 @@
+"""Execution engine shared by the iic_b200 networks.
+
+The nn.Module classes in this package hold parameters under the SAME state_dict
+keys / shapes as the reference (so its checkpoints load), but never call a
+torch op to compute: ``forward`` hands raw device pointers to the sm_100a
+kernels of libiic_b200.so, and one ``torch.autograd.Function`` per trunk /
+head group runs the hand-written backward.
+
+Precision modes (``net.precision``):
+  "bf16" (default): NHWC bf16 activations, tcgen05 bf16 MMA with fp32 TMEM accumulation;
+                    BN statistics, parameters, heads and losses stay fp32.
+  "fp32":           NHWC fp32 activations, fp32 SIMT convolutions (reference precision).
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import kernels as K
+from .._lib import BF16, F32
+
+_PRECISIONS = {"bf16": BF16, "fp32": F32}
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter containers (state_dict-compatible with nn.Conv2d / nn.BatchNorm2d / nn.Linear)
+# ---------------------------------------------------------------------------------------------
+class ConvParams(nn.Module):
+  """Holds ``weight`` [cout, cin, kh, kw] like nn.Conv2d(bias=False); no forward."""
+
+  def __init__(self, cin, cout, ksize, stride=1, padding=0, dilation=1):
+    super().__init__()
+    self.cin, self.cout, self.ksize, self.stride, self.padding, self.dilation = cin, cout, ksize, stride, padding, dilation
+    self.weight = nn.Parameter(torch.empty(cout, cin, ksize, ksize))
+
+  def geom(self, n, h, w):
+    return K.conv_geom(n, h, w, self.cin, self.cout, self.ksize, self.ksize, self.stride, self.padding, self.dilation)
+
+  def extra_repr(self):
+    return "%d, %d, kernel_size=%d, stride=%d, padding=%d, dilation=%d" % (
+      self.cin, self.cout, self.ksize, self.stride, self.padding, self.dilation)
+
+
+class BNParams(nn.Module):
+  """Holds weight/bias (+ running stats when tracking) like nn.BatchNorm2d; no forward."""
+
+  def __init__(self, c, track_running_stats=True, eps=1e-5, momentum=0.1):
+    super().__init__()
+    self.num_features, self.eps, self.momentum = c, eps, momentum
+    self.track_running_stats = track_running_stats
+    self.weight = nn.Parameter(torch.ones(c))
+    self.bias = nn.Parameter(torch.zeros(c))
+    if track_running_stats:
+      self.register_buffer("running_mean", torch.zeros(c))
+      self.register_buffer("running_var", torch.ones(c))
+      self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+    else:
+      self.register_buffer("running_mean", None)
+      self.register_buffer("running_var", None)
+      self.register_buffer("num_batches_tracked", None)
+
+
+class LinearParams(nn.Module):
+  def __init__(self, fin, fout):
+    super().__init__()
+    self.in_features, self.out_features = fin, fout
+    self.weight = nn.Parameter(torch.empty(fout, fin))
+    self.bias = nn.Parameter(torch.empty(fout))
+
+
+class Identity(nn.Module):
+  """Placeholder keeping Sequential indices identical to the reference (e.g. the Softmax at
+  heads.{i}.1, the ReLU / MaxPool entries of the VGG ``features`` list)."""
+
+
+def init_conv_kaiming(w, mode):
+  # nn.init.kaiming_normal_(w, mode=mode, nonlinearity='relu') -- residual.py:77-78, vgg.py:45
+  cout, cin, kh, kw = w.shape
+  fan = (cout if mode == "fan_out" else cin) * kh * kw
+  with torch.no_grad():
+    w.normal_(0, math.sqrt(2.0 / fan))
+
+
+def initialize_weights(net, mode):
+  """residual.py:75-85 (mode fan_out) / vgg.py:42-54 (mode fan_in)."""
+  for m in net.modules():
+    if isinstance(m, ConvParams):
+      init_conv_kaiming(m.weight, mode)
+    elif isinstance(m, BNParams):
+      assert m.track_running_stats == net.batchnorm_track
+      m.weight.data.fill_(1)
+      m.bias.data.zero_()
+    elif isinstance(m, LinearParams):
+      m.weight.data.normal_(0, 0.01)
+      m.bias.data.zero_()
+
+
+# ---------------------------------------------------------------------------------------------
+# forward / backward building blocks (all activations NHWC)
+# ---------------------------------------------------------------------------------------------
+class _Ctx(object):
+  """Per-forward record of what backward needs."""
+
+  def __init__(self, dt, training, need_grad):
+    self.dt, self.training, self.need_grad = dt, training, need_grad
+    self.saved = []
+    self.wcache = {}
+
+  def packed(self, conv, kind):
+    key = (id(conv), kind)
+    if key not in self.wcache:
+      self.wcache[key] = K.pack_weight(conv.weight.detach(), self.dt, kind)
+    return self.wcache[key]
+
+
+def _bn_stats(ctx, bn, y):
+  use_running = (not ctx.training) and bn.track_running_stats
+  rm = bn.running_mean if bn.track_running_stats else None
+  rv = bn.running_var if bn.track_running_stats else None
+  if ctx.training and bn.track_running_stats:
+    bn.num_batches_tracked += 1
+  update = ctx.training and bn.track_running_stats
+  return K.bn_stats(y, bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum, rm if (update or use_running) else None,
+                    rv if (update or use_running) else None, use_running)
+
+
+class GradSink(object):
+  """Collects parameter gradients produced by a trunk backward, keyed by parameter object."""
+
+  def __init__(self):
+    self.g = {}
+
+  def buf(self, p):
+    if id(p) not in self.g:
+      self.g[id(p)] = torch.empty_like(p, dtype=torch.float32)
+      return self.g[id(p)], False
+    return self.g[id(p)], True
+
+  def get(self, p):
+    return self.g.get(id(p))
+
+
+def _bn_backward(ctx, sink, bn, g_in, act, y, mi, want_g_out):
+  dg, acc1 = sink.buf(bn.weight)
+  db, acc2 = sink.buf(bn.bias)
+  assert acc1 == acc2
+  return K.bn_bwd(g_in, act, y, mi, bn.weight.detach(), dg, db, acc1, want_g_out)
+
+
+def _conv_wgrad(ctx, sink, conv, x, dy, g):
+  gw, acc = sink.buf(conv.weight)
+  K.conv_wgrad(x, dy, g, ctx.dt, gw, acc)
+
+
+# ---- stem: conv(NCHW input) + BN + ReLU [+ MaxPool(2,2,pad)] -----------------------------------
+def stem_forward(ctx, conv, bn, x_nchw, pool_pad):
+  n, c, h, w = x_nchw.shape
+  g = conv.geom(n, h, w)
+  y = K.stem_fprop(x_nchw, conv.weight.detach(), g, ctx.dt)
+  ss, mi = _bn_stats(ctx, bn, y)
+  out = K.bn_relu_maxpool(y, ss, pool_pad) if pool_pad is not None else K.bn_apply(y, ss, relu=True)
+  if ctx.need_grad:
+    ctx.saved.append(("stem", conv, bn, x_nchw, g, y, ss, mi, out if pool_pad is None else None, pool_pad))
+  return out
+
+
+def stem_backward(ctx, sink, rec, d_out):
+  _, conv, bn, x_nchw, g, y, ss, mi, act, pool_pad = rec
+  if pool_pad is not None:
+    gmask = K.bn_relu_maxpool_bwd(y, ss, d_out, pool_pad)
+    dy, _ = _bn_backward(ctx, sink, bn, gmask, None, y, mi, False)
+  else:
+    dy, _ = _bn_backward(ctx, sink, bn, d_out, act, y, mi, False)
+  gw, acc = sink.buf(conv.weight)
+  K.stem_wgrad(x_nchw, dy, g, ctx.dt, gw, acc)
+  return None
+
+
+# ---- VGG unit: conv + BN + ReLU [+ MaxPool(2,2)] (vgg.py:8-35) -----------------------------------
+def convbn_forward(ctx, conv, bn, x, pool_pad):
+  n, h, w, _ = x.shape
+  g = conv.geom(n, h, w)
+  y = K.conv_fprop(x, ctx.packed(conv, 0), g, ctx.dt)
+  ss, mi = _bn_stats(ctx, bn, y)
+  out = K.bn_relu_maxpool(y, ss, pool_pad) if pool_pad is not None else K.bn_apply(y, ss, relu=True)
+  if ctx.need_grad:
+    ctx.saved.append(("convbn", conv, bn, x, g, y, ss, mi, out if pool_pad is None else None, pool_pad))
+  return out
+
+
+def convbn_backward(ctx, sink, rec, d_out):
+  _, conv, bn, x, g, y, ss, mi, act, pool_pad = rec
+  if pool_pad is not None:
+    gmask = K.bn_relu_maxpool_bwd(y, ss, d_out, pool_pad)
+    dy, _ = _bn_backward(ctx, sink, bn, gmask, None, y, mi, False)
+  else:
+    dy, _ = _bn_backward(ctx, sink, bn, d_out, act, y, mi, False)
+  _conv_wgrad(ctx, sink, conv, x, dy, g)
+  return K.conv_dgrad(dy, ctx.packed(conv, 1), g, ctx.dt)
+
+
+# ---- residual BasicBlock (residual.py:10-43) -----------------------------------------------------
+def block_forward(ctx, blk, x):
+  n, h, w, _ = x.shape
+  g1 = blk.conv1.geom(n, h, w)
+  y1 = K.conv_fprop(x, ctx.packed(blk.conv1, 0), g1, ctx.dt)
+  ss1, mi1 = _bn_stats(ctx, blk.bn1, y1)
+  a1 = K.bn_apply(y1, ss1, relu=True)
+  g2 = blk.conv2.geom(n, g1.oh, g1.ow)
+  y2 = K.conv_fprop(a1, ctx.packed(blk.conv2, 0), g2, ctx.dt)
+  ss2, mi2 = _bn_stats(ctx, blk.bn2, y2)
+  if blk.downsample is not None:
+    dconv, dbn = blk.downsample[0], blk.downsample[1]
+    gd = dconv.geom(n, h, w)
+    yd = K.conv_fprop(x, ctx.packed(dconv, 0), gd, ctx.dt)
+    ssd, mid = _bn_stats(ctx, dbn, yd)
+    out = K.bn_apply(y2, ss2, relu=True, res=yd, rss=ssd)
+  else:
+    gd = yd = mid = None
+    out = K.bn_apply(y2, ss2, relu=True, res=x)
+  if ctx.need_grad:
+    ctx.saved.append(("block", blk, x, g1, y1, mi1, a1, g2, y2, mi2, gd, yd, mid, out))
+  return out
+
+
+def block_backward(ctx, sink, rec, d_out):
+  _, blk, x, g1, y1, mi1, a1, g2, y2, mi2, gd, yd, mid, out = rec
+  # out = relu(bn2(y2) + r): g = d_out * (out > 0) goes both into bn2 and the residual branch
+  dy2, gres = _bn_backward(ctx, sink, blk.bn2, d_out, out, y2, mi2, True)
+  _conv_wgrad(ctx, sink, blk.conv2, a1, dy2, g2)
+  da1 = K.conv_dgrad(dy2, ctx.packed(blk.conv2, 1), g2, ctx.dt)
+  dy1, _ = _bn_backward(ctx, sink, blk.bn1, da1, a1, y1, mi1, False)
+  _conv_wgrad(ctx, sink, blk.conv1, x, dy1, g1)
+  if blk.downsample is not None:
+    dconv, dbn = blk.downsample[0], blk.downsample[1]
+    dyd, _ = _bn_backward(ctx, sink, dbn, gres, None, yd, mid, False)
+    _conv_wgrad(ctx, sink, dconv, x, dyd, gd)
+    dxd = K.conv_dgrad(dyd, ctx.packed(dconv, 1), gd, ctx.dt)
+    return K.conv_dgrad(dy1, ctx.packed(blk.conv1, 1), g1, ctx.dt, addend=dxd)
+  return K.conv_dgrad(dy1, ctx.packed(blk.conv1, 1), g1, ctx.dt, addend=gres)
+
+
+_BACKWARD = {"stem": stem_backward, "convbn": convbn_backward, "block": block_backward}
+
+
+class TrunkFunction(torch.autograd.Function):
+  """x (NCHW fp32, no grad) -> trunk feature (fp32).  ``run(ctx_, x)`` executes the forward plan
+  and returns (feature, finisher) where finisher maps d_feature -> gradient w.r.t. the last
+  NHWC activation."""
+
+  @staticmethod
+  def forward(ctx, trunk, run, x, *params):
+    need_grad = any(ctx.needs_input_grad[3:])  # inputs are (trunk, run, x, *params)
+    ectx = _Ctx(_PRECISIONS[trunk.precision], trunk.training, need_grad)
+    feat, finisher = run(ectx, x)
+    ctx.ectx, ctx.finisher, ctx.params = ectx, finisher, params
+    return feat
+
+  @staticmethod
+  def backward(ctx, dfeat):
+    ectx = ctx.ectx
+    sink = GradSink()
+    d = ctx.finisher(dfeat.contiguous().float())
+    for rec in reversed(ectx.saved):
+      d = _BACKWARD[rec[0]](ectx, sink, rec, d)
+    ectx.saved = []
+    ectx.wcache = {}
+    grads = tuple(sink.get(p) for p in ctx.params)
+    return (None, None, None) + grads
+
+
+def run_trunk(trunk, run, x):
+  if not x.is_cuda:
+    raise RuntimeError("iic_b200 networks run on CUDA tensors only (no CPU fallback; the CPU restatement in "
+                       "oracle/ is a test checker)")
+  assert trunk.precision in _PRECISIONS, "precision must be 'bf16' or 'fp32'"
+  params = [p for p in trunk.parameters()]
+  return TrunkFunction.apply(trunk, run, x.detach().float().contiguous(), *params)
+
+
+# ---------------------------------------------------------------------------------------------
+# sub-heads: S x (Linear + Softmax)   (net5g_two_head.py:11-39)
+# ---------------------------------------------------------------------------------------------
+class HeadsFunction(torch.autograd.Function):
+  @staticmethod
+  def forward(ctx, feat, w, b, S, k):
+    feat = feat.contiguous()
+    z = K.heads_fwd(feat, w.contiguous(), b.contiguous(), S, k)
+    ctx.save_for_backward(feat, w, z)
+    ctx.S, ctx.k = S, k
+    return z
+
+  @staticmethod
+  def backward(ctx, dz):
+    feat, w, z = ctx.saved_tensors
+    dw, db, dfeat = K.heads_bwd(feat, w.contiguous(), z, dz.contiguous(), ctx.S, ctx.k, ctx.needs_input_grad[0])
+    return dfeat, dw, db, None, None
+
+
+class SubHeads(nn.Module):
+  """num_sub_heads x (Linear(F -> k) + Softmax(dim=1)); parameters live at
+  ``heads.{i}.0.{weight,bias}`` exactly like the reference's nn.Sequential(Linear, Softmax)."""
+
+  def __init__(self, nfeat, output_k, num_sub_heads):
+    super().__init__()
+    self.num_sub_heads, self.output_k, self.nfeat = num_sub_heads, output_k, nfeat
+    self.heads = nn.ModuleList([nn.Sequential(LinearParams(nfeat, output_k), Identity())
+                                for _ in range(num_sub_heads)])
+
+  def forward_stacked(self, x):
+    w = torch.cat([h[0].weight for h in self.heads], dim=0)
+    b = torch.cat([h[0].bias for h in self.heads], dim=0)
+    return HeadsFunction.apply(x, w, b, self.num_sub_heads, self.output_k)  # [S, bn, k]
+
+  def forward(self, x, kmeans_use_features=False):
+    if kmeans_use_features:
+      return [x for _ in range(self.num_sub_heads)]  # duplicates (net5g_two_head.py:31-34)
+    return list(self.forward_stacked(x).unbind(0))

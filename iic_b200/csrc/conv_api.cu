@@ -1,0 +1,78 @@
+// Dispatch of the conv entry points onto the two kernels: IIC_F32 -> fp32 SIMT implicit GEMM
+// (conv_simt.cu), IIC_BF16 -> tcgen05 implicit GEMM (conv_tc.cu).  This is a precision mode of
+// one sm_100a code base, not a backend switch: there is no CPU or library fallback.
+#include "common.cuh"
+
+namespace iic {
+int simt_conv_fprop(const float* x, const float* w, float* y, const iic_conv_geom* g, cudaStream_t st);
+int simt_conv_dgrad(const float* dy, const float* wt, const float* addend, float* dx, const iic_conv_geom* g, cudaStream_t st);
+long long simt_conv_wgrad_workspace(const iic_conv_geom* g);
+int simt_conv_wgrad(const float* x, const float* dy, float* dw, float* ws, const iic_conv_geom* g, cudaStream_t st);
+int tc_conv_gather_gemm(const __nv_bfloat16* src, int srcH, int srcW, int srcC, int rowH, int rowW, int nimg,
+                        const iic_conv_geom* g, int transposed, const __nv_bfloat16* wpacked, int N,
+                        const __nv_bfloat16* addend, __nv_bfloat16* out, cudaStream_t st);
+long long tc_conv_wgrad_workspace(const iic_conv_geom* g);
+int tc_conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* ws, const iic_conv_geom* g, cudaStream_t st);
+}  // namespace iic
+
+using namespace iic;
+
+static int geom_check(const iic_conv_geom* g, const char* who) {
+  IIC_REQUIRE(g != nullptr, IIC_ERR_BAD_ARG, "%s: null geometry", who);
+  IIC_REQUIRE(g->n > 0 && g->h > 0 && g->w > 0 && g->cin > 0 && g->cout > 0 && g->kh > 0 && g->kw > 0 &&
+                  g->stride > 0 && g->pad >= 0 && g->dil > 0,
+              IIC_ERR_BAD_ARG, "%s: bad geometry", who);
+  IIC_REQUIRE(g->oh == (g->h + 2 * g->pad - g->dil * (g->kh - 1) - 1) / g->stride + 1 &&
+                  g->ow == (g->w + 2 * g->pad - g->dil * (g->kw - 1) - 1) / g->stride + 1,
+              IIC_ERR_BAD_ARG, "%s: output size %dx%d inconsistent with the geometry", who, g->oh, g->ow);
+  IIC_REQUIRE((long long)g->n * g->h * g->w < (1ll << 31) && (long long)g->n * g->oh * g->ow < (1ll << 31),
+              IIC_ERR_UNSUPPORTED, "%s: more than 2^31 pixels", who);
+  return IIC_OK;
+}
+
+extern "C" int iic_conv_fprop(const void* x, const void* w_packed, void* y, const iic_conv_geom* g, int dtype, void* stream) {
+  int rc = geom_check(g, "iic_conv_fprop");
+  if (rc != IIC_OK) return rc;
+  IIC_REQUIRE(x && w_packed && y, IIC_ERR_BAD_ARG, "iic_conv_fprop: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == IIC_F32) return simt_conv_fprop((const float*)x, (const float*)w_packed, (float*)y, g, st);
+  if (dtype == IIC_BF16)
+    return tc_conv_gather_gemm((const __nv_bfloat16*)x, g->h, g->w, g->cin, g->oh, g->ow, g->n, g, 0,
+                               (const __nv_bfloat16*)w_packed, g->cout, nullptr, (__nv_bfloat16*)y, st);
+  set_error("iic_conv_fprop: bad dtype %d", dtype);
+  return IIC_ERR_BAD_ARG;
+}
+
+extern "C" int iic_conv_dgrad(const void* dy, const void* w_packed_t, const void* addend, void* dx, const iic_conv_geom* g,
+                              int dtype, void* stream) {
+  int rc = geom_check(g, "iic_conv_dgrad");
+  if (rc != IIC_OK) return rc;
+  IIC_REQUIRE(dy && w_packed_t && dx, IIC_ERR_BAD_ARG, "iic_conv_dgrad: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == IIC_F32)
+    return simt_conv_dgrad((const float*)dy, (const float*)w_packed_t, (const float*)addend, (float*)dx, g, st);
+  if (dtype == IIC_BF16)
+    return tc_conv_gather_gemm((const __nv_bfloat16*)dy, g->oh, g->ow, g->cout, g->h, g->w, g->n, g, 1,
+                               (const __nv_bfloat16*)w_packed_t, g->cin, (const __nv_bfloat16*)addend,
+                               (__nv_bfloat16*)dx, st);
+  set_error("iic_conv_dgrad: bad dtype %d", dtype);
+  return IIC_ERR_BAD_ARG;
+}
+
+extern "C" long long iic_conv_wgrad_workspace(const iic_conv_geom* g, int dtype) {
+  if (g == nullptr) return -1;
+  return dtype == IIC_BF16 ? tc_conv_wgrad_workspace(g) : simt_conv_wgrad_workspace(g);
+}
+
+extern "C" int iic_conv_wgrad(const void* x, const void* dy, float* dw_packed, void* workspace, const iic_conv_geom* g,
+                              int dtype, void* stream) {
+  int rc = geom_check(g, "iic_conv_wgrad");
+  if (rc != IIC_OK) return rc;
+  IIC_REQUIRE(x && dy && dw_packed && workspace, IIC_ERR_BAD_ARG, "iic_conv_wgrad: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == IIC_F32) return simt_conv_wgrad((const float*)x, (const float*)dy, dw_packed, (float*)workspace, g, st);
+  if (dtype == IIC_BF16)
+    return tc_conv_wgrad((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw_packed, (float*)workspace, g, st);
+  set_error("iic_conv_wgrad: bad dtype %d", dtype);
+  return IIC_ERR_BAD_ARG;
+}

@@ -1,0 +1,609 @@
+// HBM-bound passes of the IIC trunk (NHWC activations, 8-channel / 16-32 B vector accesses):
+// layout plumbing, sobel, BatchNorm statistics / apply / backward, ReLU, residual add, max / avg
+// pooling, weight repacking.  Each kernel cites the reference op it replaces.
+#include "common.cuh"
+
+namespace iic {
+
+static inline int ew_grid(long long work_items, int threads) {
+  long long blocks = (work_items + threads - 1) / threads;
+  long long cap = (long long)device_sm_count() * 16;  // multiple of the SM count, enough waves
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout / dtype plumbing
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int n, int c, int h, int w) {
+  const long long total = (long long)n * c * h * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int ci = (int)(i % c);
+    long long p = i / c;  // n*h*w index
+    int hw = (int)(p % ((long long)h * w));
+    int ni = (int)(p / ((long long)h * w));
+    dst[i] = from_f<T>(src[((long long)ni * c + ci) * h * w + hw]);
+  }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int n, int c, int h, int w) {
+  const long long total = (long long)n * c * h * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int hw = (int)(i % ((long long)h * w));
+    long long q = i / ((long long)h * w);
+    int ci = (int)(q % c);
+    int ni = (int)(q / c);
+    dst[i] = to_f(src[((long long)ni * h * w + hw) * c + ci]);
+  }
+}
+template <typename S, typename D>
+__global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, long long count) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = from_f<D>(to_f(src[i]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// sobel_process -- code/utils/cluster/transforms.py:47-96
+// ---------------------------------------------------------------------------------------------
+__global__ void sobel_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int cin, int cout, int h,
+                             int w, int grey_ch, int n_rgb, int ir_ch /* -1: none */) {
+  const long long total = (long long)n * h * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(i % w);
+    int y = (int)((i / w) % h);
+    int ni = (int)(i / ((long long)w * h));
+    const float* g = in + ((long long)ni * cin + grey_ch) * h * w;
+    float v[3][3];
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        int yy = y + dy, xx = x + dx;
+        v[dy + 1][dx + 1] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? g[(long long)yy * w + xx] : 0.f;
+      }
+    // cross-correlation with [[1,0,-1],[2,0,-2],[1,0,-1]] (:69) and [[1,2,1],[0,0,0],[-1,-2,-1]] (:75);
+    // summed in the same row-major tap order a 3x3 conv uses
+    float sx = v[0][0] - v[0][2] + 2.f * v[1][0] - 2.f * v[1][2] + v[2][0] - v[2][2];
+    float sy = v[0][0] + 2.f * v[0][1] + v[0][2] - v[2][0] - 2.f * v[2][1] - v[2][2];
+    float* o = out + (long long)ni * cout * h * w + (long long)y * w + x;
+    const float* src = in + (long long)ni * cin * h * w + (long long)y * w + x;
+    for (int c = 0; c < n_rgb; ++c) o[(long long)c * h * w] = src[(long long)c * h * w];
+    o[(long long)n_rgb * h * w] = sx;
+    o[(long long)(n_rgb + 1) * h * w] = sy;
+    if (ir_ch >= 0) o[(long long)(n_rgb + 2) * h * w] = src[(long long)ir_ch * h * w];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm2d (train mode) -- net5g.py:24, residual.py:20,23,56, vgg.py:28
+// ---------------------------------------------------------------------------------------------
+// Per-channel sum / sum of squares over M rows of y[M][C].  Threads are laid out so that a warp
+// reads whole 128 B+ row segments; each thread owns 8 channels and walks rows with a grid stride.
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ y, const T* __restrict__ gin,
+                                                        const T* __restrict__ act,
+                                                        const float* __restrict__ mean_invstd, long long M, int C,
+                                                        double* __restrict__ sums) {
+  // BWD=false: sums[c] += y, sums[C+c] += y*y
+  // BWD=true : g = gin * (act > 0 if act) ; yhat = (y-mean)*invstd ; sums[c] += g ; sums[C+c] += g*yhat
+  __shared__ float sh[256 * 17];
+  const int cg = C >> 3;                     // channel groups per row
+  const int tpr = cg < 256 ? cg : 256;       // threads per row (C <= 2048)
+  const int rows_per_it = 256 / tpr;
+  const int my_cg = threadIdx.x % tpr, my_r = threadIdx.x / tpr;
+  float a0[8], a1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
+  if (my_r < rows_per_it) {
+    for (int c8 = my_cg; c8 < cg; c8 += tpr) {  // (only loops when C > 2048)
+      float mean[8], istd[8];
+      if (BWD) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          mean[j] = mean_invstd[c8 * 8 + j];
+          istd[j] = mean_invstd[C + c8 * 8 + j];
+        }
+      }
+      for (long long r = (long long)blockIdx.x * rows_per_it + my_r; r < M; r += (long long)gridDim.x * rows_per_it) {
+        float v[8];
+        load8(y + r * C + c8 * 8, v);
+        if (!BWD) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            a0[j] += v[j];
+            a1[j] = fmaf(v[j], v[j], a1[j]);
+          }
+        } else {
+          float g[8];
+          load8(gin + r * C + c8 * 8, g);
+          if (act != nullptr) {
+            float a[8];
+            load8(act + r * C + c8 * 8, a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            a0[j] += g[j];
+            a1[j] = fmaf(g[j], (v[j] - mean[j]) * istd[j], a1[j]);
+          }
+        }
+      }
+    }
+  }
+  // block reduce over the row-lanes that share a channel group (only valid when cg <= 256)
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sh[threadIdx.x * 17 + j] = a0[j];
+    sh[threadIdx.x * 17 + 8 + j] = a1[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < tpr * 16; i += 256) {
+    const int g = i / 16, j = i % 16;
+    double t = 0.0;
+    for (int r = 0; r < rows_per_it; ++r) t += (double)sh[(r * tpr + g) * 17 + j];
+    // channel index: g*8 + (j&7); second half of `sums` for j >= 8
+    atomicAdd(&sums[(j >> 3) * C + g * 8 + (j & 7)], t);
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, long long M, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* running_mean,
+                                   float* running_var, int use_running, float* __restrict__ scale_shift,
+                                   float* __restrict__ mean_invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, invstd;
+  if (use_running) {
+    mean = running_mean[c];
+    invstd = 1.f / sqrtf(running_var[c] + eps);
+  } else {
+    const double m = sums[c] / (double)M;
+    double var = sums[C + c] / (double)M - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    invstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean != nullptr) {
+      const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  }
+  const float sc = gamma[c] * invstd;
+  scale_shift[c] = sc;
+  scale_shift[C + c] = beta[c] - mean * sc;
+  mean_invstd[c] = mean;
+  mean_invstd[C + c] = invstd;
+}
+
+// out = relu?( y*scale+shift [+ res | + res*rscale + rshift] )   (residual.py:27-43)
+template <typename T>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ ss,
+                                                       const T* __restrict__ res, const float* __restrict__ rss,
+                                                       T* __restrict__ out, long long M, int C, int relu) {
+  const int cg = C >> 3;
+  const long long total = M * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cg);
+    float v[8];
+    load8(y + i * 8, v);
+    float sc[8], sh[8];
+    load8(ss + c8 * 8, sc);
+    load8(ss + C + c8 * 8, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+    if (res != nullptr) {
+      float r[8];
+      load8(res + i * 8, r);
+      if (rss != nullptr) {
+        load8(rss + c8 * 8, sc);
+        load8(rss + C + c8 * 8, sh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = fmaf(r[j], sc[j], sh[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    store8(out + i * 8, v);
+  }
+}
+
+// BN + ReLU + MaxPool2d(2, 2, pad) in one pass (net5g.py:24-26).  One thread per (window, 8 ch).
+template <typename T>
+__global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const T* __restrict__ y, const float* __restrict__ ss,
+                                                              T* __restrict__ out, int n, int h, int w, int C, int pad,
+                                                              int oh, int ow) {
+  const int cg = C >> 3;
+  const long long total = (long long)n * oh * ow * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cg);
+    long long p = i / cg;
+    const int ox = (int)(p % ow);
+    p /= ow;
+    const int oy = (int)(p % oh);
+    const int ni = (int)(p / oh);
+    float sc[8], sh[8], m[8];
+    load8(ss + c8 * 8, sc);
+    load8(ss + C + c8 * 8, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int iy = oy * 2 - pad + dy, ix = ox * 2 - pad + dx;
+        if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
+          float v[8];
+          load8(y + (((long long)ni * h + iy) * w + ix) * C + c8 * 8, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f));
+        }
+      }
+    store8(out + i * 8, m);
+  }
+}
+
+// Backward of the fused BN+ReLU+MaxPool: routes dP to the first arg-max of each window (torch's
+// max_pool2d tie rule: strict '>' in row-major window order), masked by the ReLU.
+template <typename T>
+__global__ void __launch_bounds__(256) bn_relu_maxpool_bwd_kernel(const T* __restrict__ y, const float* __restrict__ ss,
+                                                                  const T* __restrict__ dpool, T* __restrict__ g, int n,
+                                                                  int h, int w, int C, int pad, int oh, int ow) {
+  const int cg = C >> 3;
+  const long long total = (long long)n * oh * ow * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cg);
+    long long p = i / cg;
+    const int ox = (int)(p % ow);
+    p /= ow;
+    const int oy = (int)(p % oh);
+    const int ni = (int)(p / oh);
+    float sc[8], sh[8], m[8], dp[8];
+    int arg[8];
+    load8(ss + c8 * 8, sc);
+    load8(ss + C + c8 * 8, sh);
+    load8(dpool + i * 8, dp);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      m[j] = -INFINITY;
+      arg[j] = -1;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int iy = oy * 2 - pad + (q >> 1), ix = ox * 2 - pad + (q & 1);
+      if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
+        float v[8];
+        load8(y + (((long long)ni * h + iy) * w + ix) * C + c8 * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float a = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+          if (a > m[j]) {
+            m[j] = a;
+            arg[j] = q;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int iy = oy * 2 - pad + (q >> 1), ix = ox * 2 - pad + (q & 1);
+      if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (arg[j] == q && m[j] > 0.f) ? dp[j] : 0.f;
+        store8(g + (((long long)ni * h + iy) * w + ix) * C + c8 * 8, o);
+      }
+    }
+  }
+}
+
+// dy = scale * (g - mean(g) - yhat * mean(g*yhat));  optional g_out (masked gradient for the residual branch)
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ gin, const T* __restrict__ act,
+                                                           const T* __restrict__ y,
+                                                           const float* __restrict__ mean_invstd,
+                                                           const float* __restrict__ gamma,
+                                                           const double* __restrict__ sums, T* __restrict__ dy,
+                                                           T* __restrict__ g_out, float* dgamma, float* dbeta,
+                                                           int accumulate, long long M, int C) {
+  const int cg = C >> 3;
+  const long long total = M * cg;
+  const double invM = 1.0 / (double)M;
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float db = (float)sums[c], dg = (float)sums[C + c];
+      if (dgamma) dgamma[c] = accumulate ? dgamma[c] + dg : dg;
+      if (dbeta) dbeta[c] = accumulate ? dbeta[c] + db : db;
+    }
+  }
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cg);
+    float g[8], v[8];
+    load8(gin + i * 8, g);
+    load8(y + i * 8, v);
+    if (act != nullptr) {
+      float a[8];
+      load8(act + i * 8, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
+    }
+    if (g_out != nullptr) store8(g_out + i * 8, g);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c8 * 8 + j;
+      const float mean = mean_invstd[c], istd = mean_invstd[C + c];
+      const float yhat = (v[j] - mean) * istd;
+      const float m1 = (float)(sums[c] * invM), m2 = (float)(sums[C + c] * invM);
+      o[j] = gamma[c] * istd * (g[j] - m1 - yhat * m2);
+    }
+    store8(dy + i * 8, o);
+  }
+}
+
+// AvgPool2d(full extent) + flatten (net5g.py:31-39,:56)
+template <typename T>
+__global__ void avgpool_kernel(const T* __restrict__ x, float* __restrict__ feat, int n, int hw, int C) {
+  const long long total = (long long)n * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int ni = (int)(i / C);
+    float s = 0.f;
+    for (int p = 0; p < hw; ++p) s += to_f(x[((long long)ni * hw + p) * C + c]);
+    feat[i] = s / (float)hw;
+  }
+}
+template <typename T>
+__global__ void avgpool_bwd_kernel(const float* __restrict__ dfeat, T* __restrict__ dx, int n, int hw, int C) {
+  const long long total = (long long)n * hw * C;
+  const float inv = 1.f / (float)hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int ni = (int)(i / ((long long)hw * C));
+    dx[i] = from_f<T>(dfeat[(long long)ni * C + c] * inv);
+  }
+}
+
+// weight repacking: torch [cout][cin][kh][kw] -> kind0 [cout][kh][kw][cin] / kind1 [cin][kh][kw][cout]
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ dst, int kind, int cout, int cin,
+                                   int kh, int kw) {
+  const long long total = (long long)cout * cin * kh * kw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    int inner, a, b, outer;
+    if (kind == 0) {  // i = ((co*kh + a)*kw + b)*cin + ci
+      inner = (int)(t % cin); t /= cin;
+      b = (int)(t % kw); t /= kw;
+      a = (int)(t % kh); outer = (int)(t / kh);
+      dst[i] = from_f<T>(w[(((long long)outer * cin + inner) * kh + a) * kw + b]);
+    } else {  // i = ((ci*kh + a)*kw + b)*cout + co
+      inner = (int)(t % cout); t /= cout;
+      b = (int)(t % kw); t /= kw;
+      a = (int)(t % kh); outer = (int)(t / kh);
+      dst[i] = from_f<T>(w[(((long long)inner * cin + outer) * kh + a) * kw + b]);
+    }
+  }
+}
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ grad, int accumulate, int cout,
+                                    int cin, int kh, int kw) {
+  const long long total = (long long)cout * cin * kh * kw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // i indexes torch layout [co][ci][a][b]
+    long long t = i;
+    const int b = (int)(t % kw); t /= kw;
+    const int a = (int)(t % kh); t /= kh;
+    const int ci = (int)(t % cin);
+    const int co = (int)(t / cin);
+    const float v = dwp[(((long long)co * kh + a) * kw + b) * cin + ci];
+    grad[i] = accumulate ? grad[i] + v : v;
+  }
+}
+
+}  // namespace iic
+
+using namespace iic;
+
+#define DISPATCH_T(dtype, ...)                                  \
+  if ((dtype) == IIC_F32) { using T = float; __VA_ARGS__ }       \
+  else if ((dtype) == IIC_BF16) { using T = __nv_bfloat16; __VA_ARGS__ } \
+  else { set_error("unknown dtype %d", (int)(dtype)); return IIC_ERR_BAD_ARG; }
+
+extern "C" int iic_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int n, int c, int h, int w, void* stream) {
+  IIC_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0, IIC_ERR_BAD_ARG, "iic_nchw_to_nhwc: bad arguments");
+  const long long total = (long long)n * c * h * w;
+  DISPATCH_T(dst_dtype, nchw_to_nhwc_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(src, (T*)dst, n, c, h, w);)
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+extern "C" int iic_nhwc_to_nchw(const void* src, int src_dtype, float* dst, int n, int c, int h, int w, void* stream) {
+  IIC_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0, IIC_ERR_BAD_ARG, "iic_nhwc_to_nchw: bad arguments");
+  const long long total = (long long)n * c * h * w;
+  DISPATCH_T(src_dtype, nhwc_to_nchw_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)src, dst, n, c, h, w);)
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+extern "C" int iic_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long count, void* stream) {
+  IIC_REQUIRE(src && dst && count > 0, IIC_ERR_BAD_ARG, "iic_cast: bad arguments");
+  const int g = ew_grid(count, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (src_dtype == IIC_F32 && dst_dtype == IIC_BF16)
+    cast_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, count);
+  else if (src_dtype == IIC_BF16 && dst_dtype == IIC_F32)
+    cast_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, count);
+  else if (src_dtype == IIC_F32 && dst_dtype == IIC_F32)
+    cast_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, count);
+  else if (src_dtype == IIC_BF16 && dst_dtype == IIC_BF16)
+    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, count);
+  else {
+    set_error("iic_cast: bad dtypes");
+    return IIC_ERR_BAD_ARG;
+  }
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
+extern "C" int iic_sobel(const float* imgs, float* out, int n, int c_in, int h, int w, int include_rgb, int using_ir,
+                         void* stream) {
+  IIC_REQUIRE(imgs && out && n > 0 && h > 0 && w > 0, IIC_ERR_BAD_ARG, "iic_sobel: bad arguments");
+  int grey, nrgb, ir, expect;
+  if (!using_ir) {
+    if (!include_rgb) { expect = 1; grey = 0; nrgb = 0; ir = -1; }
+    else { expect = 4; grey = 3; nrgb = 3; ir = -1; }
+  } else {
+    if (!include_rgb) { expect = 2; grey = 0; nrgb = 0; ir = 1; }
+    else { expect = 5; grey = 3; nrgb = 3; ir = 4; }
+  }
+  // the reference asserts the channel count (transforms.py:52,56,60,64)
+  IIC_REQUIRE(c_in == expect, IIC_ERR_BAD_ARG, "iic_sobel: expected %d input channels, got %d", expect, c_in);
+  const int cout = nrgb + 2 + (ir >= 0 ? 1 : 0);
+  sobel_kernel<<<ew_grid((long long)n * h * w, 256), 256, 0, (cudaStream_t)stream>>>(imgs, out, n, c_in, cout, h, w,
+                                                                                     grey, nrgb, ir);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
+extern "C" int iic_bn_stats(const void* y, int dtype, long long M, int C, const float* gamma, const float* beta,
+                            float eps, float momentum, float* running_mean, float* running_var, int use_running,
+                            double* stats_ws, float* scale_shift, float* mean_invstd, void* stream) {
+  IIC_REQUIRE(y && gamma && beta && stats_ws && scale_shift && mean_invstd && M > 0, IIC_ERR_BAD_ARG,
+              "iic_bn_stats: bad arguments");
+  IIC_REQUIRE(C % 8 == 0 && C <= 2048, IIC_ERR_UNSUPPORTED, "iic_bn_stats: C=%d must be a multiple of 8, <= 2048", C);
+  IIC_REQUIRE(!use_running || (running_mean && running_var), IIC_ERR_BAD_ARG,
+              "iic_bn_stats: eval mode needs running statistics");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!use_running) {
+    IIC_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * C, st));
+    const int tpr = C / 8 < 256 ? C / 8 : 256;
+    const int rpi = 256 / tpr;
+    long long blocks = (M + rpi - 1) / rpi;
+    const long long cap = (long long)device_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    DISPATCH_T(dtype, bn_reduce_kernel<T, false><<<(int)blocks, 256, 0, st>>>((const T*)y, nullptr, nullptr, nullptr, M, C, stats_ws);)
+    IIC_LAUNCH_CHECK();
+    count_launch();
+  }
+  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(stats_ws, M, C, gamma, beta, eps, momentum, running_mean,
+                                                    running_var, use_running, scale_shift, mean_invstd);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
+extern "C" int iic_bn_apply(const void* y, const float* scale_shift, const void* res, const float* res_scale_shift,
+                            void* out, int dtype, long long M, int C, int relu, void* stream) {
+  IIC_REQUIRE(y && scale_shift && out && M > 0 && C % 8 == 0, IIC_ERR_BAD_ARG, "iic_bn_apply: bad arguments");
+  const long long total = M * (C / 8);
+  DISPATCH_T(dtype, bn_apply_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const T*)y, scale_shift, (const T*)res, res_scale_shift, (T*)out, M, C, relu);)
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
+extern "C" int iic_bn_relu_maxpool(const void* y, const float* scale_shift, void* out, int dtype, int n, int h, int w,
+                                   int C, int pad, int oh, int ow, void* stream) {
+  IIC_REQUIRE(y && scale_shift && out && C % 8 == 0, IIC_ERR_BAD_ARG, "iic_bn_relu_maxpool: bad arguments");
+  IIC_REQUIRE(oh == (h + 2 * pad - 2) / 2 + 1 && ow == (w + 2 * pad - 2) / 2 + 1 && pad >= 0 && pad <= 1,
+              IIC_ERR_BAD_ARG, "iic_bn_relu_maxpool: inconsistent geometry");
+  const long long total = (long long)n * oh * ow * (C / 8);
+  DISPATCH_T(dtype, bn_relu_maxpool_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const T*)y, scale_shift, (T*)out, n, h, w, C, pad, oh, ow);)
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
+extern "C" int iic_bn_relu_maxpool_bwd(const void* y, const float* scale_shift, const void* dpool, void* g, int dtype,
+                                       int n, int h, int w, int C, int pad, int oh, int ow, void* stream) {
+  IIC_REQUIRE(y && scale_shift && dpool && g && C % 8 == 0, IIC_ERR_BAD_ARG, "iic_bn_relu_maxpool_bwd: bad arguments");
+  IIC_REQUIRE(oh == (h + 2 * pad - 2) / 2 + 1 && ow == (w + 2 * pad - 2) / 2 + 1 && pad >= 0 && pad <= 1,
+              IIC_ERR_BAD_ARG, "iic_bn_relu_maxpool_bwd: inconsistent geometry");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool covered = (2 * oh - pad >= h) && (2 * ow - pad >= w);
+  const size_t esz = dtype == IIC_F32 ? 4 : 2;
+  if (!covered) IIC_CUDA(cudaMemsetAsync(g, 0, (size_t)n * h * w * C * esz, st));
+  const long long total = (long long)n * oh * ow * (C / 8);
+  DISPATCH_T(dtype, bn_relu_maxpool_bwd_kernel<T><<<ew_grid(total, 256), 256, 0, st>>>(
+      (const T*)y, scale_shift, (const T*)dpool, (T*)g, n, h, w, C, pad, oh, ow);)
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
+extern "C" int iic_bn_bwd_reduce(const void* g_in, const void* act, const void* y, const float* mean_invstd, int dtype,
+                                 long long M, int C, double* sums, void* stream) {
+  IIC_REQUIRE(g_in && y && mean_invstd && sums && M > 0, IIC_ERR_BAD_ARG, "iic_bn_bwd_reduce: bad arguments");
+  IIC_REQUIRE(C % 8 == 0 && C <= 2048, IIC_ERR_UNSUPPORTED, "iic_bn_bwd_reduce: C=%d unsupported", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  IIC_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+  const int tpr = C / 8 < 256 ? C / 8 : 256;
+  const int rpi = 256 / tpr;
+  long long blocks = (M + rpi - 1) / rpi;
+  const long long cap = (long long)device_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  DISPATCH_T(dtype, bn_reduce_kernel<T, true><<<(int)blocks, 256, 0, st>>>((const T*)y, (const T*)g_in, (const T*)act, mean_invstd, M, C, sums);)
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
+extern "C" int iic_bn_bwd_apply(const void* g_in, const void* act, const void* y, const float* mean_invstd,
+                                const float* gamma, const double* sums, void* dy, void* g_out, float* dgamma,
+                                float* dbeta, int accumulate, int dtype, long long M, int C, void* stream) {
+  IIC_REQUIRE(g_in && y && mean_invstd && gamma && sums && dy && M > 0 && C % 8 == 0, IIC_ERR_BAD_ARG,
+              "iic_bn_bwd_apply: bad arguments");
+  const long long total = M * (C / 8);
+  DISPATCH_T(dtype, bn_bwd_apply_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const T*)g_in, (const T*)act, (const T*)y, mean_invstd, gamma, sums, (T*)dy, (T*)g_out, dgamma, dbeta,
+      accumulate, M, C);)
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
+extern "C" int iic_avgpool(const void* x, int dtype, float* feat, int n, int hw, int C, void* stream) {
+  IIC_REQUIRE(x && feat && n > 0 && hw > 0 && C > 0, IIC_ERR_BAD_ARG, "iic_avgpool: bad arguments");
+  DISPATCH_T(dtype, avgpool_kernel<T><<<ew_grid((long long)n * C, 128), 128, 0, (cudaStream_t)stream>>>((const T*)x, feat, n, hw, C);)
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+extern "C" int iic_avgpool_bwd(const float* dfeat, void* dx, int dtype, int n, int hw, int C, void* stream) {
+  IIC_REQUIRE(dfeat && dx && n > 0 && hw > 0 && C > 0, IIC_ERR_BAD_ARG, "iic_avgpool_bwd: bad arguments");
+  DISPATCH_T(dtype, avgpool_bwd_kernel<T><<<ew_grid((long long)n * hw * C, 256), 256, 0, (cudaStream_t)stream>>>(dfeat, (T*)dx, n, hw, C);)
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
+extern "C" int iic_pack_weight(const float* w_oihw, void* dst, int dst_dtype, int kind, int cout, int cin, int kh,
+                               int kw, void* stream) {
+  IIC_REQUIRE(w_oihw && dst && (kind == 0 || kind == 1) && cout > 0 && cin > 0 && kh > 0 && kw > 0, IIC_ERR_BAD_ARG,
+              "iic_pack_weight: bad arguments");
+  const long long total = (long long)cout * cin * kh * kw;
+  DISPATCH_T(dst_dtype, pack_weight_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, (T*)dst, kind, cout, cin, kh, kw);)
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+extern "C" int iic_unpack_wgrad(const float* dw_packed, float* grad_oihw, int accumulate, int cout, int cin, int kh,
+                                int kw, void* stream) {
+  IIC_REQUIRE(dw_packed && grad_oihw && cout > 0 && cin > 0, IIC_ERR_BAD_ARG, "iic_unpack_wgrad: bad arguments");
+  const long long total = (long long)cout * cin * kh * kw;
+  unpack_wgrad_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(dw_packed, grad_oihw, accumulate, cout,
+                                                                              cin, kh, kw);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}

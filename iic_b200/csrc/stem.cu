@@ -1,0 +1,220 @@
+// Stem convolution (first conv of every IIC net: net5g.py:21-23 cin=2 (sobel dx,dy) 3x3;
+// vgg.py/net6c cin=1 5x5; net10a cin=5 3x3).  K = cin*kh*kw is 18..45: far too small for a
+// tensor-core tile to matter and the op is bound by writing the 64-channel output, so it is a
+// direct SIMT convolution that reads the reference's NCHW fp32 input and writes NHWC
+// activations (fp32 or bf16) with 16/32 B vector stores.  No dgrad (the input needs no gradient).
+// wgrad is a tall-skinny Gram product  dW[co][k] = sum_p dy[p][co] * patch[p][k]  done with 4x4
+// register tiles out of shared memory, per-block partials and a deterministic reduction.
+#include "common.cuh"
+
+namespace iic {
+
+constexpr int STEM_MAXK = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(256) stem_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         T* __restrict__ y, iic_conv_geom g) {
+  extern __shared__ __align__(16) float ws[];  // [K][cout]
+  const int K = g.cin * g.kh * g.kw, cout = g.cout;
+  for (int i = threadIdx.x; i < K * cout; i += blockDim.x) {
+    const int co = i % cout, k = i / cout;
+    ws[i] = w[(long long)co * K + k];
+  }
+  __syncthreads();
+  const int groups = cout >> 3, ppb = 256 / groups;
+  const int cgi = threadIdx.x % groups, pl = threadIdx.x / groups;
+  const long long P = (long long)g.n * g.oh * g.ow;
+  if (pl >= ppb) return;
+  for (long long p = (long long)blockIdx.x * ppb + pl; p < P; p += (long long)gridDim.x * ppb) {
+    const int ox = (int)(p % g.ow);
+    const int oy = (int)((p / g.ow) % g.oh);
+    const int n = (int)(p / ((long long)g.ow * g.oh));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    int k = 0;
+    for (int ci = 0; ci < g.cin; ++ci) {
+      const float* xc = x + ((long long)n * g.cin + ci) * g.h * g.w;
+      for (int a = 0; a < g.kh; ++a) {
+        const int iy = oy * g.stride - g.pad + a * g.dil;
+        for (int b = 0; b < g.kw; ++b, ++k) {
+          const int ix = ox * g.stride - g.pad + b * g.dil;
+          const float v = (iy >= 0 && iy < g.h && ix >= 0 && ix < g.w) ? __ldg(xc + (long long)iy * g.w + ix) : 0.f;
+          const float4 w0 = *reinterpret_cast<const float4*>(ws + k * cout + cgi * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(ws + k * cout + cgi * 8 + 4);
+          acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
+          acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+          acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
+          acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+        }
+      }
+    }
+    store8(y + p * cout + cgi * 8, acc);
+  }
+}
+
+constexpr int SW_PC = 32;  // pixels per chunk
+
+template <typename T>
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy,
+                                                         float* __restrict__ partial, iic_conv_geom g, int Kp, int tkk,
+                                                         int T_tiles, int G) {
+  extern __shared__ __align__(16) float sm[];
+  const int K = g.cin * g.kh * g.kw, cout = g.cout;
+  float* dys = sm;                   // [SW_PC][cout]
+  float* pat = dys + SW_PC * cout;   // [SW_PC][Kp]
+  float* red = pat + SW_PC * Kp;     // [G][cout*Kp] (reused at the end)
+  const long long P = (long long)g.n * g.oh * g.ow;
+  const int tid = threadIdx.x;
+  const int my_g = tid / T_tiles, my_t = tid % T_tiles;
+  const bool active = my_g < G;
+  const int tc = my_t / tkk, tk = my_t % tkk;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const long long nchunks = (P + SW_PC - 1) / SW_PC;
+  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const long long p0 = ch * SW_PC;
+    __syncthreads();
+    for (int i = tid; i < SW_PC * cout; i += 256) {
+      const long long p = p0 + i / cout;
+      dys[i] = p < P ? to_f(dy[p * cout + (i % cout)]) : 0.f;
+    }
+    for (int i = tid; i < SW_PC * Kp; i += 256) {
+      const int r = i % SW_PC, k = i / SW_PC;  // consecutive threads -> consecutive pixels (coalesced in NCHW)
+      const long long p = p0 + r;
+      float v = 0.f;
+      if (p < P && k < K) {
+        const int ox = (int)(p % g.ow);
+        const int oy = (int)((p / g.ow) % g.oh);
+        const int n = (int)(p / ((long long)g.ow * g.oh));
+        const int b = k % g.kw, a = (k / g.kw) % g.kh, ci = k / (g.kw * g.kh);
+        const int iy = oy * g.stride - g.pad + a * g.dil, ix = ox * g.stride - g.pad + b * g.dil;
+        if (iy >= 0 && iy < g.h && ix >= 0 && ix < g.w) v = __ldg(x + (((long long)n * g.cin + ci) * g.h + iy) * g.w + ix);
+      }
+      pat[r * Kp + k] = v;
+    }
+    __syncthreads();
+    if (active) {
+      for (int r = my_g; r < SW_PC; r += G) {
+        const float4 a = *reinterpret_cast<const float4*>(dys + r * cout + 4 * tc);
+        const float4 b = *reinterpret_cast<const float4*>(pat + r * Kp + 4 * tk);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+    }
+  }
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[(long long)my_g * cout * Kp + (4 * tc + i) * Kp + 4 * tk + j] = acc[i][j];
+  }
+  __syncthreads();
+  for (int e = tid; e < cout * K; e += 256) {
+    const int co = e / K, k = e % K;
+    float t = 0.f;
+    for (int gg = 0; gg < G; ++gg) t += red[(long long)gg * cout * Kp + co * Kp + k];
+    partial[(long long)blockIdx.x * cout * K + e] = t;
+  }
+}
+
+__global__ void stem_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad, int count,
+                                         int nblk, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float t = 0.f;
+  for (int b = 0; b < nblk; ++b) t += partial[(long long)b * count + i];
+  grad[i] = accumulate ? grad[i] + t : t;
+}
+
+}  // namespace iic
+
+using namespace iic;
+
+static int stem_check(const iic_conv_geom* g, const char* who) {
+  IIC_REQUIRE(g != nullptr, IIC_ERR_BAD_ARG, "%s: null geometry", who);
+  const int K = g->cin * g->kh * g->kw;
+  IIC_REQUIRE(K > 0 && K <= STEM_MAXK, IIC_ERR_UNSUPPORTED, "%s: cin*kh*kw=%d exceeds %d", who, K, STEM_MAXK);
+  IIC_REQUIRE(g->cout % 8 == 0 && 256 % (g->cout / 8) == 0 && g->cout <= 256, IIC_ERR_UNSUPPORTED,
+              "%s: cout=%d unsupported", who, g->cout);
+  IIC_REQUIRE(g->oh == (g->h + 2 * g->pad - g->dil * (g->kh - 1) - 1) / g->stride + 1 &&
+                  g->ow == (g->w + 2 * g->pad - g->dil * (g->kw - 1) - 1) / g->stride + 1,
+              IIC_ERR_BAD_ARG, "%s: inconsistent output size", who);
+  return IIC_OK;
+}
+
+extern "C" int iic_stem_fprop(const float* x_nchw, const float* w_oihw, void* y, const iic_conv_geom* g, int dtype,
+                              void* stream) {
+  int rc = stem_check(g, "iic_stem_fprop");
+  if (rc != IIC_OK) return rc;
+  IIC_REQUIRE(x_nchw && w_oihw && y, IIC_ERR_BAD_ARG, "iic_stem_fprop: null pointer");
+  const int K = g->cin * g->kh * g->kw;
+  const size_t smem = (size_t)K * g->cout * sizeof(float);
+  const int ppb = 256 / (g->cout / 8);
+  const long long P = (long long)g->n * g->oh * g->ow;
+  long long blocks = (P + ppb - 1) / ppb;
+  const long long cap = (long long)device_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == IIC_F32) {
+    IIC_CUDA(cudaFuncSetAttribute(stem_fprop_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stem_fprop_kernel<float><<<(int)blocks, 256, smem, st>>>(x_nchw, w_oihw, (float*)y, *g);
+  } else if (dtype == IIC_BF16) {
+    IIC_CUDA(cudaFuncSetAttribute(stem_fprop_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stem_fprop_kernel<__nv_bfloat16><<<(int)blocks, 256, smem, st>>>(x_nchw, w_oihw, (__nv_bfloat16*)y, *g);
+  } else {
+    set_error("iic_stem_fprop: bad dtype");
+    return IIC_ERR_BAD_ARG;
+  }
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
+extern "C" int iic_stem_wgrad(const float* x_nchw, const void* dy, float* grad_oihw, int accumulate, void* workspace,
+                              long long workspace_bytes, const iic_conv_geom* g, int dtype, void* stream) {
+  int rc = stem_check(g, "iic_stem_wgrad");
+  if (rc != IIC_OK) return rc;
+  IIC_REQUIRE(x_nchw && dy && grad_oihw && workspace, IIC_ERR_BAD_ARG, "iic_stem_wgrad: null pointer");
+  IIC_REQUIRE(g->cout % 4 == 0, IIC_ERR_UNSUPPORTED, "iic_stem_wgrad: cout must be a multiple of 4");
+  const int K = g->cin * g->kh * g->kw, Kp = (K + 3) & ~3, tkk = Kp / 4;
+  const int T_tiles = (g->cout / 4) * tkk;
+  IIC_REQUIRE(T_tiles <= 256, IIC_ERR_UNSUPPORTED, "iic_stem_wgrad: cout*K too large (%d tiles)", T_tiles);
+  int G = 256 / T_tiles;
+  if (G > SW_PC) G = SW_PC;
+  const long long per_block = (long long)g->cout * K * sizeof(float);
+  long long nblk = (long long)device_sm_count() * 4;
+  const long long P = (long long)g->n * g->oh * g->ow;
+  const long long nchunks = (P + SW_PC - 1) / SW_PC;
+  if (nblk > nchunks) nblk = nchunks;
+  if (nblk > workspace_bytes / per_block) nblk = workspace_bytes / per_block;
+  IIC_REQUIRE(nblk >= 1, IIC_ERR_BAD_ARG, "iic_stem_wgrad: workspace too small (%lld B, need >= %lld)", workspace_bytes,
+              per_block);
+  const size_t smem = (size_t)(SW_PC * g->cout + SW_PC * Kp + (size_t)G * g->cout * Kp) * sizeof(float);
+  IIC_REQUIRE(smem <= 200 * 1024, IIC_ERR_UNSUPPORTED, "iic_stem_wgrad: needs %zu B smem", smem);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == IIC_F32) {
+    IIC_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stem_wgrad_kernel<float><<<(int)nblk, 256, smem, st>>>(x_nchw, (const float*)dy, (float*)workspace, *g, Kp, tkk, T_tiles, G);
+  } else if (dtype == IIC_BF16) {
+    IIC_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stem_wgrad_kernel<__nv_bfloat16><<<(int)nblk, 256, smem, st>>>(x_nchw, (const __nv_bfloat16*)dy, (float*)workspace, *g, Kp, tkk, T_tiles, G);
+  } else {
+    set_error("iic_stem_wgrad: bad dtype");
+    return IIC_ERR_BAD_ARG;
+  }
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  const int count = g->cout * K;
+  stem_wgrad_reduce_kernel<<<cdiv(count, 256), 256, 0, st>>>((const float*)workspace, grad_oihw, count, (int)nblk, accumulate);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}

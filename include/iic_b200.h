@@ -1,0 +1,174 @@
+/* iic_b200 -- C-ABI of the B200-native (sm_100a) IIC training hot path.
+ *
+ * This is the drop-in boundary for the hot path of xu-ji/IIC.  The
+ * reference has no FFI -- its "API" is a set of plain Python call signatures -- so
+ * each entry point below cites the reference function (file:line under the
+ * reference tree) whose device work it replaces.  The Python host side
+ * (iic_b200/) mirrors those signatures and calls these symbols through ctypes.
+ *
+ * Conventions
+ *   - plain pointers / ints / floats only; no torch types; all pointers are DEVICE
+ *     pointers unless a name ends in _host.  The library never allocates
+ *     caller-visible memory: outputs and workspaces are caller-allocated.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all
+ *     work is enqueued asynchronously on it; no entry point synchronises the host.
+ *   - return value: 0 on success, negative IIC_ERR_* otherwise; iic_last_error()
+ *     returns a thread-local human-readable message.  Nothing throws.
+ *   - activation tensors inside the network are NHWC ("pixel rows x channels",
+ *     row-major [M = n*h*w][C]) in one of two storage dtypes:
+ *       IIC_F32  (fp32 storage, fp32 SIMT convolutions  -- reference-precision mode)
+ *       IIC_BF16 (bf16 storage, tcgen05 bf16 MMA with fp32 TMEM accumulation)
+ *     Parameters, BN statistics, the heads and every loss are fp32 in both modes.
+ *   - entry points are re-entrant; the only global state is a per-device cache of
+ *     device properties.
+ */
+#ifndef IIC_B200_H_
+#define IIC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IIC_OK 0
+#define IIC_ERR_BAD_ARG (-1)
+#define IIC_ERR_UNSUPPORTED (-2)
+#define IIC_ERR_CUDA (-3)
+
+#define IIC_F32 0
+#define IIC_BF16 1
+
+/* phases of the joint/MI kernels (multi-GPU splits at the all-reduce of the joint) */
+#define IIC_PHASE_FUSED 0    /* partial joint -> reduce -> MI -> gradients, one launch      */
+#define IIC_PHASE_PARTIAL 1  /* write this rank's un-normalised joint to joint_ws and stop  */
+#define IIC_PHASE_FINISH 2   /* joint_ws holds the (all-reduced) joint: MI + local gradients */
+
+int iic_abi_version(void);
+const char* iic_last_error(void);
+/* number of kernels launched by this library on the calling thread since the last reset */
+long long iic_launch_count(int reset);
+
+/* ---- a7/a8: clustering objective -- code/utils/cluster/IID_losses.py:6-33 (IID_loss) and
+ *      :36-47 (compute_joint).
+ * z, zt: [S][n][k] fp32 softmax outputs of the two views (S sub-heads, contiguous).
+ * loss:  [S][2]  (loss, loss_no_lamb)                     (written unless phase==PARTIAL)
+ * dz,dzt:[S][n][k] d loss / d z, d loss / d zt  (either may be NULL: no-grad callers,
+ *        cluster_eval.py:281-288)
+ * joint_ws: [S][k][k] fp32.  PARTIAL: out (raw sum_n z z'^T of this rank).  FINISH: in.
+ *        FUSED: may be NULL.
+ * joint_out: optional [S][k][k]; receives the symmetrised, normalised P (compute_joint).
+ * eps: the reference passes sys.float_info.epsilon (a double); it is applied in fp32
+ *      exactly as torch does when comparing / assigning into an fp32 tensor.            */
+int iic_iid_loss(const float* z, const float* zt, int S, int n, int k, float lamb, double eps,
+                 float* loss, float* dz, float* dzt, float* joint_ws, float* joint_out, int phase,
+                 void* stream);
+
+/* ---- a1: sobel_process -- code/utils/cluster/transforms.py:47-96.
+ * imgs NCHW fp32 (n, c_in, h, w) -> out NCHW fp32 (n, c_out, h, w); channel rules of
+ * :50-66,:84-94 selected by include_rgb / using_ir. */
+int iic_sobel(const float* imgs, float* out, int n, int c_in, int h, int w, int include_rgb,
+              int using_ir, void* stream);
+
+/* ---- layout / dtype plumbing between the reference's NCHW fp32 tensors and the internal
+ *      NHWC activations (no reference counterpart: torch does this implicitly). */
+int iic_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int n, int c, int h, int w, void* stream);
+int iic_nhwc_to_nchw(const void* src, int src_dtype, float* dst, int n, int c, int h, int w, void* stream);
+int iic_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long count, void* stream);
+
+/* ---- convolution geometry shared by the conv entry points (nn.Conv2d, bias=False:
+ *      residual.py:4-7,:53-55, net5g.py:21-23, vgg.py:25-27, net10a.py:46-47). */
+typedef struct {
+  int n, h, w, cin;      /* input  NHWC */
+  int oh, ow, cout;      /* output NHWC */
+  int kh, kw, stride, pad, dil;
+} iic_conv_geom;
+
+/* weights are repacked from torch's [cout][cin][kh][kw] fp32:
+ *   kind 0 (fprop/wgrad layout): [cout][kh][kw][cin]
+ *   kind 1 (dgrad layout):       [cin][kh][kw][cout]                                   */
+int iic_pack_weight(const float* w_oihw, void* dst, int dst_dtype, int kind, int cout, int cin, int kh,
+                    int kw, void* stream);
+/* dw_packed fp32 [cout][kh][kw][cin] -> (accumulate ? += : =) torch-layout grad [cout][cin][kh][kw] */
+int iic_unpack_wgrad(const float* dw_packed, float* grad_oihw, int accumulate, int cout, int cin, int kh,
+                     int kw, void* stream);
+
+/* fprop: y[M][cout] = conv(x, w).  dtype IIC_F32 -> SIMT fp32 kernel; IIC_BF16 -> tcgen05.
+ * w is the kind-0 packed weight in the same dtype.  y has dtype `dtype`. */
+int iic_conv_fprop(const void* x, const void* w_packed, void* y, const iic_conv_geom* g, int dtype,
+                   void* stream);
+/* dgrad: dx[n,h,w,cin] = conv_transpose(dy, w) (+ addend, same shape/dtype as dx, may be NULL).
+ * w is the kind-1 packed weight. */
+int iic_conv_dgrad(const void* dy, const void* w_packed_t, const void* addend, void* dx,
+                   const iic_conv_geom* g, int dtype, void* stream);
+/* wgrad: dw_packed fp32 [cout][kh][kw][cin] = sum over pixels.  workspace: fp32, at least
+ * iic_conv_wgrad_workspace(g, dtype) bytes (split-K partials; deterministic reduction). */
+long long iic_conv_wgrad_workspace(const iic_conv_geom* g, int dtype);
+int iic_conv_wgrad(const void* x, const void* dy, float* dw_packed, void* workspace, const iic_conv_geom* g,
+                   int dtype, void* stream);
+
+/* ---- stem: first conv of ClusterNet5g (net5g.py:21-23) / 6c (vgg.py) / 10a: tiny cin
+ *      (1..5), read straight from the reference's NCHW fp32 input. Direct SIMT conv.
+ *      w: torch layout [cout][cin][kh][kw] fp32.  y: NHWC `dtype`. */
+int iic_stem_fprop(const float* x_nchw, const float* w_oihw, void* y, const iic_conv_geom* g, int dtype,
+                   void* stream);
+int iic_stem_wgrad(const float* x_nchw, const void* dy, float* grad_oihw, int accumulate, void* workspace,
+                   long long workspace_bytes, const iic_conv_geom* g, int dtype, void* stream);
+
+/* ---- BatchNorm2d, train mode (net5g.py:24, residual.py:20,23,56, vgg.py:28-29): statistics
+ *      are per forward call over all M = n*h*w rows.
+ * stats ws: double[2*C] (sum, sumsq), zeroed by the call.
+ * scale_shift: float[2*C]  (gamma*invstd, beta - mean*gamma*invstd)
+ * mean_invstd: float[2*C]  saved for backward
+ * running_mean/var: updated in place with `momentum` (unbiased var) when non-NULL.
+ * When `use_running` != 0 (eval mode) no statistics are computed: scale/shift come from the
+ * running buffers. */
+int iic_bn_stats(const void* y, int dtype, long long M, int C, const float* gamma, const float* beta,
+                 float eps, float momentum, float* running_mean, float* running_var, int use_running,
+                 double* stats_ws, float* scale_shift, float* mean_invstd, void* stream);
+/* out = relu?( y*scale+shift  [+ res  | + res*rscale+rshift] ) */
+int iic_bn_apply(const void* y, const float* scale_shift, const void* res, const float* res_scale_shift,
+                 void* out, int dtype, long long M, int C, int relu, void* stream);
+/* fused BN + ReLU + MaxPool2d(k=2, s=2, pad) (net5g.py:24-26; vgg.py 'M'): y (n,h,w,C) -> out (n,oh,ow,C) */
+int iic_bn_relu_maxpool(const void* y, const float* scale_shift, void* out, int dtype, int n, int h, int w,
+                        int C, int pad, int oh, int ow, void* stream);
+/* backward of the above: g (n,h,w,C) = dP routed to the arg-max, masked by ReLU, i.e. the
+ * gradient w.r.t. the BN output. */
+int iic_bn_relu_maxpool_bwd(const void* y, const float* scale_shift, const void* dpool, void* g, int dtype,
+                            int n, int h, int w, int C, int pad, int oh, int ow, void* stream);
+/* BN backward.  g_in = dL/d(out of the BN [+res] [relu]) ; if `act` != NULL the ReLU mask
+ * (act > 0) is applied first.  Pass 1 (reduce): sums[2*C] double (sum g, sum g*yhat),
+ * zeroed by the call.  Pass 2 (apply): dy = scale*(g - mean(g) - yhat*mean(g*yhat)); also
+ * writes dgamma/dbeta (accumulate ? += : =) and, if g_out != NULL, the masked g
+ * (gradient for the residual branch). */
+int iic_bn_bwd_reduce(const void* g_in, const void* act, const void* y, const float* mean_invstd, int dtype,
+                      long long M, int C, double* sums, void* stream);
+int iic_bn_bwd_apply(const void* g_in, const void* act, const void* y, const float* mean_invstd,
+                     const float* gamma, const double* sums, void* dy, void* g_out, float* dgamma,
+                     float* dbeta, int accumulate, int dtype, long long M, int C, void* stream);
+
+/* AvgPool2d(full extent) + flatten (net5g.py:31-39,:56): x (n,hw,C) -> feat fp32 (n,C) */
+int iic_avgpool(const void* x, int dtype, float* feat, int n, int hw, int C, void* stream);
+int iic_avgpool_bwd(const float* dfeat, void* dx, int dtype, int n, int hw, int C, void* stream);
+
+/* ---- a3: sub-heads -- net5g_two_head.py:22-36 / net6c_two_head.py:31-49:
+ *      S x (Linear(F -> k) + Softmax(dim=1)) on the same feature.
+ * feat [n][F] fp32; w [S*k][F] fp32 (the S Linear weights stacked); b [S*k];
+ * logits_ws [n][S*k] fp32 workspace; z out [S][n][k]. */
+int iic_heads_fwd(const float* feat, const float* w, const float* b, float* logits_ws, float* z, int n,
+                  int F, int S, int k, void* stream);
+/* dz [S][n][k] -> dlogits_ws [n][S*k]; dw [S*k][F], db [S*k] (overwritten), dfeat [n][F]
+ * (overwritten; may be NULL). */
+int iic_heads_bwd(const float* feat, const float* w, const float* z, const float* dz, float* dlogits_ws,
+                  float* dw, float* db, float* dfeat, int n, int F, int S, int k, void* stream);
+
+/* ---- a12: torch.optim.Adam step (utils/cluster/general.py:8-9; defaults of
+ *      cluster_sobel_twohead.py:184): one launch over a list of tensors.
+ *  ptrs_host: 4*T device pointers [param, grad, exp_avg, exp_avg_sq] per tensor, sizes_host: T counts. */
+int iic_adam_step(const void* const* ptrs_host, const long long* sizes_host, int T, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IIC_B200_H_ */

@@ -1,0 +1,302 @@
+"""GPU unit tests of the individual sm_100a kernels against plain PyTorch fp32 ops.
+
+(Parity with the reference proper is in test_gpu_parity_*.py, against the oracle and the
+golden vectors; these tests localise a failure to one kernel.)"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import transforms as otf  # noqa: E402
+from oracle import weights  # noqa: E402
+
+
+def _K():
+  from iic_b200 import kernels
+  return kernels
+
+
+def _dev():
+  return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+  torch.backends.cudnn.allow_tf32 = False
+  torch.backends.cuda.matmul.allow_tf32 = False
+  yield
+
+
+def to_nhwc(x, dt):
+  return x.permute(0, 2, 3, 1).contiguous().to(dt)
+
+
+def from_nhwc(x):
+  return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+CONV_CASES = [
+  # n, h, cin, cout, k, stride, pad, dil
+  (3, 13, 64, 64, 3, 1, 1, 1),
+  (2, 49, 64, 64, 3, 1, 1, 1),
+  (3, 25, 64, 128, 3, 2, 1, 1),
+  (3, 25, 64, 128, 1, 2, 0, 1),
+  (5, 13, 128, 256, 3, 2, 1, 1),
+  (4, 7, 256, 512, 3, 1, 1, 1),
+  (9, 7, 512, 512, 3, 1, 1, 1),
+  (2, 12, 64, 128, 5, 1, 2, 1),
+  (2, 16, 256, 512, 3, 1, 1, 2),
+  (1, 5, 128, 128, 3, 1, 1, 1),
+]
+
+
+def _conv_inputs(case, seed=0):
+  n, h, cin, cout, k, s, p, d = case
+  g = torch.Generator().manual_seed(seed)
+  x = torch.randn(n, cin, h, h, generator=g)
+  w = torch.randn(cout, cin, k, k, generator=g) * math.sqrt(2.0 / (cin * k * k))
+  oh = (h + 2 * p - d * (k - 1) - 1) // s + 1
+  dy = torch.randn(n, cout, oh, oh, generator=g)
+  add = torch.randn(n, cin, h, h, generator=g)
+  return x.cuda(), w.cuda(), dy.cuda(), add.cuda()
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_conv_fprop_dgrad_wgrad(case, mode):
+  K = _K()
+  from iic_b200._lib import BF16, F32
+  n, h, cin, cout, k, s, p, d = case
+  dt, tdt = (F32, torch.float32) if mode == "fp32" else (BF16, torch.bfloat16)
+  x, w, dy, add = _conv_inputs(case)
+  if mode == "bf16":  # compare against the same rounded operands
+    x, w, dy, add = [t.bfloat16().float() for t in (x, w, dy, add)]
+  g = K.conv_geom(n, h, h, cin, cout, k, k, s, p, d)
+  xr = x.clone().requires_grad_(True)
+  wr = w.clone().requires_grad_(True)
+  yr = F.conv2d(xr, wr, None, s, p, d)
+  yr.backward(dy)
+  tol = dict(rtol=2e-4, atol=2e-4) if mode == "fp32" else dict(rtol=2e-2, atol=2e-2)
+
+  xh = to_nhwc(x, tdt)
+  y = K.conv_fprop(xh, K.pack_weight(w, dt, 0), g, dt)
+  torch.cuda.synchronize()
+  err = (from_nhwc(y) - yr.detach()).abs().max().item()
+  assert torch.allclose(from_nhwc(y), yr.detach(), **tol), "fprop max err %g" % err
+
+  dyh = to_nhwc(dy, tdt)
+  dx = K.conv_dgrad(dyh, K.pack_weight(w, dt, 1), g, dt)
+  torch.cuda.synchronize()
+  err = (from_nhwc(dx) - xr.grad).abs().max().item()
+  assert torch.allclose(from_nhwc(dx), xr.grad, **tol), "dgrad max err %g" % err
+  dx2 = K.conv_dgrad(dyh, K.pack_weight(w, dt, 1), g, dt, addend=to_nhwc(add, tdt))
+  assert torch.allclose(from_nhwc(dx2), xr.grad + add, **tol), "dgrad+addend"
+
+  gw = torch.zeros_like(w)
+  K.conv_wgrad(xh, dyh, g, dt, gw, False)
+  torch.cuda.synchronize()
+  scale = wr.grad.abs().max().item()
+  err = (gw - wr.grad).abs().max().item()
+  wtol = 2e-4 if mode == "fp32" else 1e-2
+  assert err <= wtol * scale + 1e-4, "wgrad max err %g (scale %g)" % (err, scale)
+  K.conv_wgrad(xh, dyh, g, dt, gw, True)  # accumulate
+  assert (gw - 2 * wr.grad).abs().max().item() <= 2 * wtol * scale + 2e-4
+
+
+def test_tc_conv_exact_small_integers():
+  """bf16 tensor-core path must be EXACT on small-integer operands (fp32 accumulation of
+  exactly representable products): catches any swizzle / descriptor / gather indexing slip."""
+  K = _K()
+  from iic_b200._lib import BF16
+  n, h, cin, cout, k = 2, 9, 128, 128, 3
+  g = torch.Generator().manual_seed(3)
+  x = torch.randint(-3, 4, (n, cin, h, h), generator=g).float().cuda()
+  w = torch.randint(-2, 3, (cout, cin, k, k), generator=g).float().cuda()
+  geo = K.conv_geom(n, h, h, cin, cout, k, k, 1, 1, 1)
+  y = K.conv_fprop(to_nhwc(x, torch.bfloat16), K.pack_weight(w, BF16, 0), geo, BF16)
+  ref = F.conv2d(x, w, None, 1, 1)
+  # outputs are integers < 2^8 * ... may exceed bf16's 8-bit mantissa after the final rounding -> compare rounded
+  assert torch.equal(from_nhwc(y), ref.bfloat16().float())
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(5, 13, 13, 64), (2, 25, 25, 128), (3, 7, 7, 512), (64, 3, 3, 256)])
+def test_bn_forward_backward(mode, shape):
+  K = _K()
+  tdt = torch.float32 if mode == "fp32" else torch.bfloat16
+  n, h, w, C = shape
+  g = torch.Generator().manual_seed(1)
+  y = (torch.randn(n, C, h, w, generator=g) * 2 + 0.5).cuda()
+  res = torch.randn(n, C, h, w, generator=g).cuda()
+  gamma = (torch.rand(C, generator=g) + 0.5).cuda()
+  beta = (torch.randn(C, generator=g) * 0.1).cuda()
+  dout = torch.randn(n, C, h, w, generator=g).cuda()
+  if mode == "bf16":
+    y, res, dout = [t.bfloat16().float() for t in (y, res, dout)]
+  rm, rv = torch.zeros(C).cuda(), torch.ones(C).cuda()
+  yh = to_nhwc(y, tdt)
+  ss, mi = K.bn_stats(yh, gamma, beta, 1e-5, 0.1, rm, rv, False)
+  # reference
+  yr = y.clone().requires_grad_(True)
+  gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+  rr = res.clone().requires_grad_(True)
+  rm_r, rv_r = torch.zeros(C).cuda(), torch.ones(C).cuda()
+  o = F.relu(F.batch_norm(yr, rm_r, rv_r, gr, br, True, 0.1, 1e-5) + rr)
+  o.backward(dout)
+  assert torch.allclose(rm, rm_r, atol=1e-5) and torch.allclose(rv, rv_r, rtol=1e-4, atol=1e-5)
+  out = K.bn_apply(yh, ss, relu=True, res=to_nhwc(res, tdt))
+  tol = dict(rtol=1e-4, atol=1e-4) if mode == "fp32" else dict(rtol=2e-2, atol=2e-2)
+  assert torch.allclose(from_nhwc(out), o.detach(), **tol)
+  dg, db = torch.empty(C).cuda(), torch.empty(C).cuda()
+  dy, gres = K.bn_bwd(to_nhwc(dout, tdt), out, yh, mi, gamma, dg, db, False, True)
+  if mode == "fp32":
+    assert torch.allclose(from_nhwc(gres), rr.grad, **tol)
+    assert torch.allclose(from_nhwc(dy), yr.grad, rtol=1e-3, atol=1e-4)
+    assert torch.allclose(dg, gr.grad, rtol=1e-3, atol=1e-3) and torch.allclose(db, br.grad, rtol=1e-3, atol=1e-3)
+  else:
+    # the ReLU mask is taken from the bf16-rounded output: compare away from the kink
+    far = (o.detach().abs() > 0.05) | (o.detach() == 0)
+    assert ((from_nhwc(dy) - yr.grad).abs()[far] < 0.05 * yr.grad.abs().max()).float().mean() > 0.995
+    assert torch.allclose(dg, gr.grad, rtol=5e-2, atol=0.5) and torch.allclose(db, br.grad, rtol=5e-2, atol=0.5)
+  # eval mode uses the running statistics
+  ss_e, _ = K.bn_stats(yh, gamma, beta, 1e-5, 0.1, rm, rv, True)
+  oe = F.batch_norm(y, rm_r, rv_r, gamma, beta, False, 0.1, 1e-5)
+  assert torch.allclose(from_nhwc(K.bn_apply(yh, ss_e, relu=False)), oe, **tol)
+  # downsample-style residual: out = relu(bn(y) + bn_r(res))
+  ss_r, _ = K.bn_stats(to_nhwc(res, tdt), gamma, beta, 1e-5, 0.1, None, None, False)
+  o2 = F.relu(F.batch_norm(y, None, None, gamma, beta, True, 0.1, 1e-5) +
+              F.batch_norm(res, None, None, gamma, beta, True, 0.1, 1e-5))
+  out2 = K.bn_apply(yh, ss, relu=True, res=to_nhwc(res, tdt), rss=ss_r)
+  assert torch.allclose(from_nhwc(out2), o2, **tol)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("hw,pad", [(96, 1), (24, 0), (13, 0), (32, 1)])
+def test_bn_relu_maxpool(mode, hw, pad):
+  K = _K()
+  tdt = torch.float32 if mode == "fp32" else torch.bfloat16
+  n, C = 2, 64
+  g = torch.Generator().manual_seed(2)
+  y = torch.randn(n, C, hw, hw, generator=g).cuda()
+  if mode == "bf16":
+    y = y.bfloat16().float()
+  gamma = (torch.rand(C, generator=g) + 0.5).cuda()
+  beta = (torch.randn(C, generator=g) * 0.1).cuda()
+  yh = to_nhwc(y, tdt)
+  ss, mi = K.bn_stats(yh, gamma, beta, 1e-5, 0.1, None, None, False)
+  yr = y.clone().requires_grad_(True)
+  a = F.relu(F.batch_norm(yr, None, None, gamma, beta, True, 0.1, 1e-5))
+  a.retain_grad()
+  pr = F.max_pool2d(a, 2, 2, pad)
+  out = K.bn_relu_maxpool(yh, ss, pad)
+  tol = dict(rtol=1e-4, atol=1e-4) if mode == "fp32" else dict(rtol=2e-2, atol=2e-2)
+  assert out.shape[1] == pr.shape[2]
+  assert torch.allclose(from_nhwc(out), pr.detach(), **tol)
+  dp = torch.randn(pr.shape, generator=torch.Generator().manual_seed(5)).cuda()
+  if mode == "bf16":
+    dp = dp.bfloat16().float()
+  pr.backward(dp)
+  gmask = K.bn_relu_maxpool_bwd(yh, ss, to_nhwc(dp, tdt), pad)
+  if mode == "fp32":
+    assert torch.allclose(from_nhwc(gmask), a.grad, rtol=1e-5, atol=1e-6)
+  else:
+    agree = (from_nhwc(gmask) - a.grad).abs() < 1e-2
+    assert agree.float().mean() > 0.995  # bf16 rounding can flip an arg-max between near-equal values
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_avgpool_and_layout(mode):
+  K = _K()
+  from iic_b200._lib import BF16, F32
+  dt, tdt = (F32, torch.float32) if mode == "fp32" else (BF16, torch.bfloat16)
+  x = torch.randn(5, 512, 7, 7, generator=torch.Generator().manual_seed(0)).cuda()
+  xh = K.nchw_to_nhwc(x, dt)
+  assert torch.equal(xh, to_nhwc(x, tdt))
+  assert torch.equal(K.nhwc_to_nchw(xh), xh.float().permute(0, 3, 1, 2))
+  f = K.avgpool(xh)
+  assert torch.allclose(f, xh.float().mean(dim=(1, 2)), rtol=1e-5, atol=1e-6)
+  df = torch.randn(5, 512).cuda()
+  dx = K.avgpool_bwd(df, tuple(xh.shape), dt)
+  assert torch.allclose(dx.float(), (df / 49.)[:, None, None, :].expand(5, 7, 7, 512), rtol=1e-2, atol=1e-6)
+  assert torch.equal(K.cast(x, dt), x.to(tdt))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("cin,k,pad,hw", [(2, 3, 1, 32), (1, 5, 2, 24), (5, 3, 1, 20)])
+def test_stem(mode, cin, k, pad, hw):
+  K = _K()
+  from iic_b200._lib import BF16, F32
+  dt, tdt = (F32, torch.float32) if mode == "fp32" else (BF16, torch.bfloat16)
+  n, cout = 3, 64
+  g = torch.Generator().manual_seed(4)
+  x = torch.randn(n, cin, hw, hw, generator=g).cuda()
+  w = (torch.randn(cout, cin, k, k, generator=g) * 0.3).cuda()
+  dy = torch.randn(n, cout, hw, hw, generator=g).cuda()
+  if mode == "bf16":
+    dy = dy.bfloat16().float()
+  geo = K.conv_geom(n, hw, hw, cin, cout, k, k, 1, pad, 1)
+  y = K.stem_fprop(x, w, geo, dt)
+  wr = w.clone().requires_grad_(True)
+  yr = F.conv2d(x, wr, None, 1, pad)
+  tol = dict(rtol=1e-4, atol=1e-4) if mode == "fp32" else dict(rtol=2e-2, atol=2e-2)
+  assert torch.allclose(from_nhwc(y), yr.detach(), **tol)
+  yr.backward(dy)
+  gw = torch.zeros_like(w)
+  K.stem_wgrad(x, to_nhwc(dy, tdt), geo, dt, gw, False)
+  assert torch.allclose(gw, wr.grad, rtol=1e-3, atol=1e-3 * wr.grad.abs().max().item())
+  K.stem_wgrad(x, to_nhwc(dy, tdt), geo, dt, gw, True)
+  assert torch.allclose(gw, 2 * wr.grad, rtol=1e-3, atol=2e-3 * wr.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("n,F_,S,k", [(37, 512, 5, 10), (64, 512, 5, 70), (33, 4608, 5, 50), (5, 512, 1, 3)])
+def test_heads(n, F_, S, k):
+  K = _K()
+  g = torch.Generator().manual_seed(6)
+  feat = torch.randn(n, F_, generator=g).cuda()
+  w = (torch.randn(S * k, F_, generator=g) * 0.05).cuda()
+  b = (torch.randn(S * k, generator=g) * 0.1).cuda()
+  dz = torch.randn(S, n, k, generator=g).cuda()
+  z = K.heads_fwd(feat, w, b, S, k)
+  fr, wr, br = [t.clone().requires_grad_(True) for t in (feat, w, b)]
+  zr = torch.softmax((fr @ wr.t() + br).view(n, S, k), dim=2).permute(1, 0, 2)
+  assert torch.allclose(z, zr.detach(), rtol=1e-4, atol=1e-6)
+  zr.backward(dz)
+  dw, db, dfeat = K.heads_bwd(feat, w, z, dz, S, k, True)
+  assert torch.allclose(dw, wr.grad, rtol=1e-3, atol=1e-5)
+  assert torch.allclose(db, br.grad, rtol=1e-3, atol=1e-5)
+  assert torch.allclose(dfeat, fr.grad, rtol=1e-3, atol=1e-5)
+
+
+def test_sobel_matches_oracle():
+  from iic_b200.utils.cluster.transforms import sobel_process
+  for (c, rgb, ir) in [(1, False, False), (4, True, False), (2, False, True), (5, True, True)]:
+    x = weights.uniform("sobel.gpu.%d" % c, (3, c, 33, 47))
+    o = sobel_process(x.cuda(), rgb, ir)
+    r = otf.sobel_process(x, rgb, ir)
+    assert o.shape == r.shape
+    assert torch.allclose(o.cpu(), r, rtol=0, atol=2e-6)
+  with pytest.raises(AssertionError):
+    sobel_process(torch.zeros(1, 3, 8, 8).cuda(), False)
+
+
+def test_adam_matches_torch():
+  K = _K()
+  g = torch.Generator().manual_seed(7)
+  shapes = [(64, 2, 3, 3), (64,), (512, 512, 3, 3), (10, 512), (3,)] * 13  # > 48 tensors: several launches
+  ps = [torch.randn(s, generator=g).cuda() for s in shapes]
+  ref = [p.clone().requires_grad_(True) for p in ps]
+  opt = torch.optim.Adam(ref, lr=1e-3)
+  ms = [torch.zeros_like(p) for p in ps]
+  vs = [torch.zeros_like(p) for p in ps]
+  for step in range(1, 4):
+    gs = [torch.randn(s, generator=g).cuda() for s in shapes]
+    for r, gg in zip(ref, gs):
+      r.grad = gg.clone()
+    opt.step()
+    K.adam_step(ps, gs, ms, vs, 1e-3, 0.9, 0.999, 1e-8, 0.0, step)
+  for p, r in zip(ps, ref):
+    assert torch.allclose(p, r.detach(), rtol=1e-5, atol=1e-6)

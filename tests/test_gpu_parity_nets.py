@@ -1,0 +1,173 @@
+"""GPU parity of the full networks (trunk + sub-heads + IID loss + backward) against the
+golden vectors produced by the reference modules, and against the CPU oracle.
+
+Stated tolerances:
+  precision="fp32" (fp32 SIMT convolutions): softmax outputs within 2e-4 abs, loss within 2e-5 abs,
+      parameter-gradient norms within 2e-3 relative, selected full gradients within 1e-2 of max|g|.
+  precision="bf16" (tcgen05 bf16 MMA, fp32 accumulate, bf16 activations): outputs within 4e-2 abs,
+      gradient norms within 15 % (bf16 has 8 mantissa bits and the trunk is 34 layers deep)."""
+import os
+import sys
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+import make_golden  # noqa: E402
+from oracle import iid_losses as oracle_iid  # noqa: E402
+from oracle import nets as oracle_nets  # noqa: E402
+from oracle import weights  # noqa: E402
+
+
+def _build(name, precision):
+  import iic_b200.archs as archs
+  ctor, cfg, batch, head, lamb = make_golden.NET_SPECS[name]
+  net = archs.__dict__[ctor](Namespace(precision=precision, **cfg))
+  weights.fill_state_dict(net)
+  net.cuda().train()
+  x, xt = make_golden.net_input("net." + name, cfg, batch)
+  return net, x.cuda(), xt.cuda(), head, lamb
+
+
+def _step(net, x, xt, head, lamb):
+  from iic_b200.utils.cluster.IID_losses import IID_loss
+  kw = {} if head is None else {"head": head}
+  o, ot = net(x, **kw), net(xt, **kw)
+  loss = sum(IID_loss(a, b, lamb=lamb)[0] for a, b in zip(o, ot)) / len(o)
+  loss.backward()
+  return o, ot, loss
+
+
+NAMES = ["5g2h_32_A", "5g2h_32_B", "5g2h_96_B", "5g_64", "6c2h_24_A", "6c_24"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_fp32_mode_matches_reference_goldens(name, golden_nets):
+  c = golden_nets.sub("net/" + name)
+  net, x, xt, head, lamb = _build(name, "fp32")
+  o, ot, loss = _step(net, x, xt, head, lamb)
+  got = torch.stack(o).detach().cpu().numpy()
+  np.testing.assert_allclose(got, c["ref_out"], rtol=0, atol=2e-4)
+  np.testing.assert_allclose(torch.stack(ot).detach().cpu().numpy(), c["ref_out_tf"], rtol=0, atol=2e-4)
+  assert abs(loss.item() - float(c["loss"])) < 2e-5
+  params = dict(net.named_parameters())
+  assert list(params) == [str(s) for s in c["grad_names"]]
+  for pn, norm in zip(c["grad_names"], c["grad_norms"]):
+    g = params[str(pn)].grad
+    mine = 0.0 if g is None else float(g.double().norm())
+    assert abs(mine - norm) <= 2e-3 * norm + 1e-7, (str(pn), mine, norm)
+  for key in c.sub("grad"):
+    want = c["grad/" + key]
+    err = np.abs(params[key].grad.cpu().numpy() - want).max()
+    assert err <= 1e-2 * np.abs(want).max() + 1e-8, (key, err)
+  sd = net.state_dict()
+  for key in c.sub("buf"):
+    np.testing.assert_allclose(sd[key].cpu().numpy(), c["buf/" + key], rtol=1e-4, atol=1e-5)
+  # eval-mode forward (running statistics) of the trunk feature
+  net.eval()
+  with torch.no_grad():
+    kw = {} if head is None else {"head": head}
+    f = net(x, trunk_features=True, **kw)
+  want = c["ref_trunk_eval"]
+  np.testing.assert_allclose(f.cpu().numpy()[:, :want.shape[1]], want, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("name", ["5g2h_32_A", "5g2h_96_B", "6c2h_24_A"])
+def test_bf16_mode_matches_reference_goldens(name, golden_nets):
+  c = golden_nets.sub("net/" + name)
+  net, x, xt, head, lamb = _build(name, "bf16")
+  o, ot, loss = _step(net, x, xt, head, lamb)
+  got = torch.stack(o).detach().cpu().numpy()
+  assert np.abs(got - c["ref_out"]).max() < 4e-2, np.abs(got - c["ref_out"]).max()
+  params = dict(net.named_parameters())
+  bad = []
+  for pn, norm in zip(c["grad_names"], c["grad_norms"]):
+    g = params[str(pn)].grad
+    mine = 0.0 if g is None else float(g.double().norm())
+    if abs(mine - norm) > 0.15 * norm + 1e-6:
+      bad.append((str(pn), mine, norm))
+  assert len(bad) <= len(params) // 20, bad[:10]
+  # direction of the full gradient: cosine similarity with the fp32 reference gradient
+  for key in c.sub("grad"):
+    want = c["grad/" + key].ravel().astype(np.float64)
+    gotg = params[key].grad.cpu().numpy().ravel().astype(np.float64)
+    cos = float(want @ gotg / (np.linalg.norm(want) * np.linalg.norm(gotg) + 1e-30))
+    assert cos > 0.98, (key, cos)
+
+
+def test_oracle_live_batch_and_kwargs():
+  """Against the CPU oracle run live (not only fixtures): other batch size, eval mode, the
+  forward kwargs of SURVEY.md S3.4."""
+  import iic_b200.archs as archs
+  cfg = dict(in_channels=2, input_sz=32, num_sub_heads=3, output_k_A=20, output_k_B=5, batchnorm_track=True)
+  net = archs.ClusterNet5gTwoHead(Namespace(precision="fp32", **cfg))
+  weights.fill_state_dict(net, salt=3)
+  ora = oracle_nets.ClusterNet5gTwoHead(Namespace(**cfg))
+  ora.load_state_dict(net.state_dict())
+  net.cuda().train()
+  ora.train()
+  x = weights.normal("live.x", (9, 2, 32, 32))
+  for head in ("A", "B"):
+    a = net(x.cuda(), head=head)
+    b = ora(x, head=head)
+    assert isinstance(a, list) and len(a) == 3
+    for u, v in zip(a, b):
+      assert torch.allclose(u.cpu(), v, rtol=0, atol=2e-4)
+  f = net(x.cuda(), trunk_features=True)
+  assert f.shape == (9, 512) and torch.allclose(f.cpu(), ora(x, trunk_features=True), rtol=1e-3, atol=1e-3)
+  dup = net(x.cuda(), kmeans_use_features=True)
+  assert len(dup) == 3 and dup[0].shape == (9, 512)
+  net.eval(), ora.eval()
+  with torch.no_grad():
+    pen = net(x.cuda(), trunk_features=True, penultimate_features=True)
+    assert torch.allclose(pen.cpu(), ora(x, trunk_features=True, penultimate_features=True), rtol=1e-3, atol=1e-3)
+  with pytest.raises(AssertionError):
+    net(x.cuda(), head="C")
+  with pytest.raises(RuntimeError):
+    net(x)  # CPU tensors: no fallback
+
+
+def test_shard_equivalence_per_rank_batchnorm():
+  """W-GPU result == single-device oracle with BN statistics per contiguous chunk.
+  Emulated on one GPU: two chunked forwards + summed partial joints (what the NCCL path does)."""
+  import iic_b200.archs as archs
+  from iic_b200 import _lib, kernels
+  cfg = dict(in_channels=2, input_sz=32, num_sub_heads=2, output_k_A=12, output_k_B=4, batchnorm_track=False)
+  net = archs.ClusterNet5gTwoHead(Namespace(precision="fp32", **cfg))
+  weights.fill_state_dict(net, salt=5)
+  ora = oracle_nets.ClusterNet5gTwoHead(Namespace(**cfg))
+  ora.load_state_dict(net.state_dict())
+  net.cuda().train(), ora.train()
+  x = weights.normal("shard.x", (8, 2, 32, 32))
+  xt = x + 0.3 * weights.normal("shard.xt", (8, 2, 32, 32))
+  # oracle: chunked forward (per-chunk BN), loss on the concatenated batch
+  oz = [torch.cat([ora(x[i:i + 4], head="A")[s] for i in (0, 4)]) for s in range(2)]
+  ozt = [torch.cat([ora(xt[i:i + 4], head="A")[s] for i in (0, 4)]) for s in range(2)]
+  oloss = sum(oracle_iid.IID_loss(a, b)[0] for a, b in zip(oz, ozt)) / 2
+  oloss.backward()
+  # ours: per-shard forward, PARTIAL joints summed, FINISH per shard
+  zs, zts = [], []
+  for i in (0, 4):
+    zs.append(net.forward_stacked(x[i:i + 4].cuda(), head="A"))
+    zts.append(net.forward_stacked(xt[i:i + 4].cuda(), head="A"))
+  joint = torch.zeros(2, 12, 12, device="cuda")
+  for z, zt in zip(zs, zts):
+    j = torch.empty_like(joint)
+    kernels.iid_loss(z.detach().contiguous(), zt.detach().contiguous(), 1.0, sys.float_info.epsilon, False,
+                     phase=_lib.PHASE_PARTIAL, joint_ws=j)
+    joint += j
+  for z, zt in zip(zs, zts):
+    loss, dz, dzt, _ = kernels.iid_loss(z.detach().contiguous(), zt.detach().contiguous(), 1.0,
+                                        sys.float_info.epsilon, True, phase=_lib.PHASE_FINISH, joint_ws=joint)
+    assert abs(loss[:, 0].mean().item() - oloss.item()) < 2e-5
+    torch.autograd.backward([z, zt], [dz / 2, dzt / 2])
+  op = dict(ora.named_parameters())
+  for pn, p in net.named_parameters():
+    if p.grad is None:
+      continue
+    want = op[pn].grad
+    assert (p.grad.cpu() - want).abs().max() <= 2e-2 * want.abs().max() + 1e-7, pn
