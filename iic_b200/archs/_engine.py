@@ -249,8 +249,7 @@ class TrunkFunction(torch.autograd.Function):
   NHWC activation."""
 
   @staticmethod
-  def forward(ctx, trunk, run, x, *params):
-    need_grad = any(ctx.needs_input_grad[3:])  # inputs are (trunk, run, x, *params)
+  def forward(ctx, trunk, run, need_grad, x, *params):
     ectx = _Ctx(_PRECISIONS[trunk.precision], trunk.training, need_grad)
     feat, finisher = run(ectx, x)
     ctx.ectx, ctx.finisher, ctx.params = ectx, finisher, params
@@ -266,7 +265,7 @@ class TrunkFunction(torch.autograd.Function):
     ectx.saved = []
     ectx.wcache = {}
     grads = tuple(sink.get(p) for p in ctx.params)
-    return (None, None, None) + grads
+    return (None, None, None, None) + grads
 
 
 def run_trunk(trunk, run, x):
@@ -275,7 +274,9 @@ def run_trunk(trunk, run, x):
                        "oracle/ is a test checker)")
   assert trunk.precision in _PRECISIONS, "precision must be 'bf16' or 'fp32'"
   params = [p for p in trunk.parameters()]
-  return TrunkFunction.apply(trunk, run, x.detach().float().contiguous(), *params)
+  # (inside Function.forward grad mode is off and needs_input_grad ignores torch.no_grad())
+  need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+  return TrunkFunction.apply(trunk, run, need_grad, x.detach().float().contiguous(), *params)
 
 
 # ---------------------------------------------------------------------------------------------

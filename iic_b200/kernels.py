@@ -44,6 +44,43 @@ def conv_geom(n, h, w, cin, cout, kh, kw, stride, pad, dil):
   return ConvGeom(n, h, w, cin, oh, ow, cout, kh, kw, stride, pad, dil)
 
 
+# ---- optional per-launch timing of the convolution kernels (bench.py roofline leg) ---------------
+_conv_timing = {"on": False, "records": []}
+
+
+def conv_timing(enable):
+  _conv_timing["on"] = bool(enable)
+  _conv_timing["records"] = []
+
+
+def conv_timing_summary():
+  """-> dict kind -> (launches, algorithmic FLOPs, device ms); call after torch.cuda.synchronize()."""
+  out = {}
+  for kind, flops, e0, e1 in _conv_timing["records"]:
+    n, f, ms = out.get(kind, (0, 0.0, 0.0))
+    out[kind] = (n + 1, f + flops, ms + e0.elapsed_time(e1))
+  return out
+
+
+class _timed(object):
+  def __init__(self, kind, g):
+    self.kind, self.g = kind, g
+
+  def __enter__(self):
+    if _conv_timing["on"]:
+      self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      self.e0.record()
+    return self
+
+  def __exit__(self, *exc):
+    if _conv_timing["on"]:
+      self.e1.record()
+      g = self.g
+      flops = 2.0 * g.n * g.oh * g.ow * g.cout * g.kh * g.kw * g.cin  # 2*MAC, identical for fprop/dgrad/wgrad
+      _conv_timing["records"].append((self.kind, flops, self.e0, self.e1))
+    return False
+
+
 def launch_count(reset=False):
   return int(_lib.lib().iic_launch_count(1 if reset else 0))
 
@@ -103,14 +140,16 @@ def pack_weight(w, dt, kind):
 
 def conv_fprop(x, wp, g, dt):
   y = torch.empty((g.n, g.oh, g.ow, g.cout), device=x.device, dtype=_TORCH_DT[dt])
-  check(_lib.lib().iic_conv_fprop(_p(x), _p(wp), _p(y), ctypes.byref(g), dt, _stream()), "iic_conv_fprop")
+  with _timed("fprop", g):
+    check(_lib.lib().iic_conv_fprop(_p(x), _p(wp), _p(y), ctypes.byref(g), dt, _stream()), "iic_conv_fprop")
   return y
 
 
 def conv_dgrad(dy, wpt, g, dt, addend=None):
   dx = torch.empty((g.n, g.h, g.w, g.cin), device=dy.device, dtype=_TORCH_DT[dt])
-  check(_lib.lib().iic_conv_dgrad(_p(dy), _p(wpt), _p(addend), _p(dx), ctypes.byref(g), dt, _stream()),
-        "iic_conv_dgrad")
+  with _timed("dgrad", g):
+    check(_lib.lib().iic_conv_dgrad(_p(dy), _p(wpt), _p(addend), _p(dx), ctypes.byref(g), dt, _stream()),
+          "iic_conv_dgrad")
   return dx
 
 
@@ -119,7 +158,8 @@ def conv_wgrad(x, dy, g, dt, grad_out, accumulate):
   nbytes = int(_lib.lib().iic_conv_wgrad_workspace(ctypes.byref(g), dt))
   ws = torch.empty((max(nbytes, 4) + 3) // 4, device=x.device, dtype=torch.float32)
   dwp = torch.empty((g.cout, g.kh, g.kw, g.cin), device=x.device, dtype=torch.float32)
-  check(_lib.lib().iic_conv_wgrad(_p(x), _p(dy), _p(dwp), _p(ws), ctypes.byref(g), dt, _stream()), "iic_conv_wgrad")
+  with _timed("wgrad", g):
+    check(_lib.lib().iic_conv_wgrad(_p(x), _p(dy), _p(dwp), _p(ws), ctypes.byref(g), dt, _stream()), "iic_conv_wgrad")
   check(_lib.lib().iic_unpack_wgrad(_p(dwp), _p(grad_out), int(bool(accumulate)), g.cout, g.cin, g.kh, g.kw, _stream()),
         "iic_unpack_wgrad")
   return grad_out

@@ -21,9 +21,8 @@ from ... import _lib, distributed, kernels
 
 class _IIDLoss(torch.autograd.Function):
   @staticmethod
-  def forward(ctx, z, zt, lamb, eps):
+  def forward(ctx, z, zt, lamb, eps, want_grad):
     # z, zt: [S, n, k] fp32 contiguous
-    want_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
     if distributed.active():
       S, n, k = z.shape
       joint = torch.empty((S, k, k), device=z.device, dtype=torch.float32)
@@ -56,7 +55,12 @@ class _IIDLoss(torch.autograd.Function):
       s1 = g_nolamb.reshape(-1, 1, 1)
       gz = dz1 * s1 if gz is None else gz + dz1 * s1
       gzt = dzt1 * s1 if gzt is None else gzt + dzt1 * s1
-    return gz, gzt, None, None
+    return gz, gzt, None, None, None
+
+
+def _want_grad(a, b):
+  # the gradient sweep is skipped for no-grad callers (cluster_eval.py:281-288)
+  return torch.is_grad_enabled() and (a.requires_grad or b.requires_grad)
 
 
 def _prep(x):
@@ -71,7 +75,8 @@ def IID_loss(x_out, x_tf_out, lamb=1.0, EPS=sys.float_info.epsilon):
   # has had softmax applied
   bn, k = x_out.size()
   assert (x_tf_out.size(0) == bn and x_tf_out.size(1) == k)
-  loss, loss_no_lamb = _IIDLoss.apply(_prep(x_out), _prep(x_tf_out), float(lamb), float(EPS))
+  loss, loss_no_lamb = _IIDLoss.apply(_prep(x_out), _prep(x_tf_out), float(lamb), float(EPS),
+                                      _want_grad(x_out, x_tf_out))
   return loss[0], loss_no_lamb[0]
 
 
@@ -85,7 +90,8 @@ def IID_loss_subheads(x_outs, x_tf_outs, lamb=1.0, EPS=sys.float_info.epsilon):
   if isinstance(x_tf_outs, (list, tuple)):
     x_tf_outs = torch.stack(list(x_tf_outs))
   assert x_outs.dim() == 3 and x_outs.shape == x_tf_outs.shape
-  return _IIDLoss.apply(x_outs.float().contiguous(), x_tf_outs.float().contiguous(), float(lamb), float(EPS))
+  return _IIDLoss.apply(x_outs.float().contiguous(), x_tf_outs.float().contiguous(), float(lamb), float(EPS),
+                        _want_grad(x_outs, x_tf_outs))
 
 
 def compute_joint(x_out, x_tf_out):

@@ -13,9 +13,54 @@ reference_net.state_dict())`` works; tests/golden/make_golden.py uses exactly
 that (with named deterministic weights, oracle/weights.py) to pin these
 restatements against the real reference modules' outputs and gradients.
 """
+import contextlib
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+# ---- optional emulation of the product's bf16 storage points ---------------------------------
+# The sm_100a path in bf16 mode (iic_b200, precision="bf16") keeps every NHWC activation and
+# every activation-gradient in bf16 and feeds bf16 operands to the tensor cores (fp32 accumulate).
+# `bf16_rounding()` makes this oracle round at exactly those points (forward value AND the
+# gradient flowing back through the same point), so the bf16 path can be checked against "the
+# reference algorithm with bf16 storage" instead of only loosely against the fp32 reference.
+_ROUND = {"on": False}
+
+
+class _RoundBF16(torch.autograd.Function):
+  @staticmethod
+  def forward(ctx, x):
+    return x.bfloat16().to(x.dtype)
+
+  @staticmethod
+  def backward(ctx, g):
+    return g.bfloat16().to(g.dtype)
+
+
+def q(x):
+  """storage point of an activation (and of its gradient)"""
+  return _RoundBF16.apply(x) if _ROUND["on"] else x
+
+
+def qw(w):
+  """tensor-core weight operand (value only; the gradient stays fp32)"""
+  return (w + (w.detach().bfloat16().to(w.dtype) - w.detach())) if _ROUND["on"] else w
+
+
+@contextlib.contextmanager
+def bf16_rounding(on=True):
+  old = _ROUND["on"]
+  _ROUND["on"] = on
+  try:
+    yield
+  finally:
+    _ROUND["on"] = old
+
+
+def _conv(m, x, stem=False):
+  w = m.weight if stem else qw(m.weight)
+  return q(F.conv2d(x, w, None, m.stride, m.padding, m.dilation))
 
 
 def _bn(c, track):
@@ -37,10 +82,10 @@ class _Block(nn.Module):
                                       _bn(cout, track))
 
   def forward(self, x):
-    y = F.relu(self.bn1(self.conv1(x)))
-    y = self.bn2(self.conv2(y))
-    r = x if self.downsample is None else self.downsample(x)
-    return F.relu(y + r)
+    y = q(F.relu(self.bn1(_conv(self.conv1, x))))
+    y = self.bn2(_conv(self.conv2, y))
+    r = x if self.downsample is None else self.downsample[1](_conv(self.downsample[0], x))
+    return q(F.relu(y + r))
 
 
 def _init_resnet(net):
@@ -84,7 +129,7 @@ class Trunk5g(nn.Module):
     self.avgpool = nn.AvgPool2d({96: 7, 64: 5, 32: 3}[config.input_sz], stride=1)
 
   def forward(self, x, penultimate_features=False):
-    x = self.maxpool(F.relu(self.bn1(self.conv1(x))))
+    x = q(self.maxpool(F.relu(self.bn1(_conv(self.conv1, x, stem=True)))))
     x = self.layer3(self.layer2(self.layer1(x)))
     if not penultimate_features:
       x = self.avgpool(self.layer4(x))
@@ -146,6 +191,22 @@ def _vgg_features(cfg, cin, ksz, pad, track):
   return nn.Sequential(*layers)
 
 
+def _run_vgg(features, x):
+  """features = [conv, bn, relu, (pool)]*: the product stores conv outputs and the
+  (pooled) activations, so those are the rounding points."""
+  first, pending = True, False
+  for m in features:
+    if isinstance(m, nn.Conv2d):
+      if pending:
+        x = q(x)
+      x = _conv(m, x, stem=first)
+      first, pending = False, False
+    else:
+      x = m(x)
+      pending = True
+  return q(x) if pending else x
+
+
 CFG_6C = [(64, 1), ("M", None), (128, 1), ("M", None), (256, 1), ("M", None), (512, 1)]
 CFG_10A = [(64, 1), (128, 1), ("M", None), (256, 1), (256, 1), (512, 2), (512, 2)]
 
@@ -156,7 +217,7 @@ class Trunk6c(nn.Module):
     self.features = _vgg_features(CFG_6C, config.in_channels, 5, 2, config.batchnorm_track)
 
   def forward(self, x):
-    x = self.features(x)
+    x = _run_vgg(self.features, x)
     return x.reshape(x.size(0), -1)
 
 
@@ -202,7 +263,7 @@ class Trunk10a(nn.Module):
     self.features = _vgg_features(CFG_10A, cin, 3, 1, config.batchnorm_track)
 
   def forward(self, x):
-    return self.features(x)
+    return _run_vgg(self.features, x)
 
 
 class _SegHeads(nn.Module):

@@ -76,35 +76,38 @@ def test_conv_fprop_dgrad_wgrad(case, mode):
   if mode == "bf16":  # compare against the same rounded operands
     x, w, dy, add = [t.bfloat16().float() for t in (x, w, dy, add)]
   g = K.conv_geom(n, h, h, cin, cout, k, k, s, p, d)
-  xr = x.clone().requires_grad_(True)
-  wr = w.clone().requires_grad_(True)
+  # exact reference: CPU fp64 (cuDNN may pick FFT / Winograd algorithms with ~1e-2 error)
+  xr = x.double().cpu().requires_grad_(True)
+  wr = w.double().cpu().requires_grad_(True)
   yr = F.conv2d(xr, wr, None, s, p, d)
-  yr.backward(dy)
+  yr.backward(dy.double().cpu())
+  yr = yr.detach().float().cuda()
+  xr_grad, wr_grad = xr.grad.float().cuda(), wr.grad.float().cuda()
   tol = dict(rtol=2e-4, atol=2e-4) if mode == "fp32" else dict(rtol=2e-2, atol=2e-2)
 
   xh = to_nhwc(x, tdt)
   y = K.conv_fprop(xh, K.pack_weight(w, dt, 0), g, dt)
   torch.cuda.synchronize()
-  err = (from_nhwc(y) - yr.detach()).abs().max().item()
-  assert torch.allclose(from_nhwc(y), yr.detach(), **tol), "fprop max err %g" % err
+  err = (from_nhwc(y) - yr).abs().max().item()
+  assert torch.allclose(from_nhwc(y), yr, **tol), "fprop max err %g" % err
 
   dyh = to_nhwc(dy, tdt)
   dx = K.conv_dgrad(dyh, K.pack_weight(w, dt, 1), g, dt)
   torch.cuda.synchronize()
-  err = (from_nhwc(dx) - xr.grad).abs().max().item()
-  assert torch.allclose(from_nhwc(dx), xr.grad, **tol), "dgrad max err %g" % err
+  err = (from_nhwc(dx) - xr_grad).abs().max().item()
+  assert torch.allclose(from_nhwc(dx), xr_grad, **tol), "dgrad max err %g" % err
   dx2 = K.conv_dgrad(dyh, K.pack_weight(w, dt, 1), g, dt, addend=to_nhwc(add, tdt))
-  assert torch.allclose(from_nhwc(dx2), xr.grad + add, **tol), "dgrad+addend"
+  assert torch.allclose(from_nhwc(dx2), xr_grad + add, **tol), "dgrad+addend"
 
   gw = torch.zeros_like(w)
   K.conv_wgrad(xh, dyh, g, dt, gw, False)
   torch.cuda.synchronize()
-  scale = wr.grad.abs().max().item()
-  err = (gw - wr.grad).abs().max().item()
+  scale = wr_grad.abs().max().item()
+  err = (gw - wr_grad).abs().max().item()
   wtol = 2e-4 if mode == "fp32" else 1e-2
   assert err <= wtol * scale + 1e-4, "wgrad max err %g (scale %g)" % (err, scale)
   K.conv_wgrad(xh, dyh, g, dt, gw, True)  # accumulate
-  assert (gw - 2 * wr.grad).abs().max().item() <= 2 * wtol * scale + 2e-4
+  assert (gw - 2 * wr_grad).abs().max().item() <= 2 * wtol * scale + 2e-4
 
 
 def test_tc_conv_exact_small_integers():
@@ -114,13 +117,22 @@ def test_tc_conv_exact_small_integers():
   from iic_b200._lib import BF16
   n, h, cin, cout, k = 2, 9, 128, 128, 3
   g = torch.Generator().manual_seed(3)
-  x = torch.randint(-3, 4, (n, cin, h, h), generator=g).float().cuda()
-  w = torch.randint(-2, 3, (cout, cin, k, k), generator=g).float().cuda()
+  x = torch.randint(-1, 2, (n, cin, h, h), generator=g).float()
+  w = torch.randint(-1, 2, (cout, cin, k, k), generator=g).float()
+  dy = torch.randint(-1, 2, (n, cout, h, h), generator=g).float()
   geo = K.conv_geom(n, h, h, cin, cout, k, k, 1, 1, 1)
-  y = K.conv_fprop(to_nhwc(x, torch.bfloat16), K.pack_weight(w, BF16, 0), geo, BF16)
-  ref = F.conv2d(x, w, None, 1, 1)
-  # outputs are integers < 2^8 * ... may exceed bf16's 8-bit mantissa after the final rounding -> compare rounded
-  assert torch.equal(from_nhwc(y), ref.bfloat16().float())
+  xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+  ref = F.conv2d(xr, wr, None, 1, 1)  # CPU fp64: exact integers
+  ref.backward(dy.double())
+  assert ref.abs().max() <= 256 and xr.grad.abs().max() <= 256  # exactly representable in bf16
+  xh, dyh = to_nhwc(x.cuda(), torch.bfloat16), to_nhwc(dy.cuda(), torch.bfloat16)
+  y = K.conv_fprop(xh, K.pack_weight(w.cuda(), BF16, 0), geo, BF16)
+  assert torch.equal(from_nhwc(y).cpu(), ref.detach().float())
+  dx = K.conv_dgrad(dyh, K.pack_weight(w.cuda(), BF16, 1), geo, BF16)
+  assert torch.equal(from_nhwc(dx).cpu(), xr.grad.float())
+  gw = torch.zeros_like(w).cuda()
+  K.conv_wgrad(xh, dyh, geo, BF16, gw, False)
+  assert torch.equal(gw.cpu(), wr.grad.float())  # fp32 output of exact integer sums
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
@@ -189,8 +201,9 @@ def test_bn_relu_maxpool(mode, hw, pad):
   yh = to_nhwc(y, tdt)
   ss, mi = K.bn_stats(yh, gamma, beta, 1e-5, 0.1, None, None, False)
   yr = y.clone().requires_grad_(True)
-  a = F.relu(F.batch_norm(yr, None, None, gamma, beta, True, 0.1, 1e-5))
-  a.retain_grad()
+  bno = F.batch_norm(yr, None, None, gamma, beta, True, 0.1, 1e-5)
+  bno.retain_grad()  # the kernel returns the gradient w.r.t. the BN output (pool routing x ReLU mask)
+  a = F.relu(bno)
   pr = F.max_pool2d(a, 2, 2, pad)
   out = K.bn_relu_maxpool(yh, ss, pad)
   tol = dict(rtol=1e-4, atol=1e-4) if mode == "fp32" else dict(rtol=2e-2, atol=2e-2)
@@ -202,9 +215,9 @@ def test_bn_relu_maxpool(mode, hw, pad):
   pr.backward(dp)
   gmask = K.bn_relu_maxpool_bwd(yh, ss, to_nhwc(dp, tdt), pad)
   if mode == "fp32":
-    assert torch.allclose(from_nhwc(gmask), a.grad, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(from_nhwc(gmask), bno.grad, rtol=1e-5, atol=1e-6)
   else:
-    agree = (from_nhwc(gmask) - a.grad).abs() < 1e-2
+    agree = (from_nhwc(gmask) - bno.grad).abs() < 1e-2
     assert agree.float().mean() > 0.995  # bf16 rounding can flip an arg-max between near-equal values
 
 
