@@ -132,6 +132,7 @@ def test_oracle_live_batch_and_kwargs():
   f = net(x.cuda(), trunk_features=True)
   assert f.shape == (9, 512) and torch.allclose(f.cpu(), ora(x, trunk_features=True), rtol=1e-3, atol=1e-3)
   dup = net(x.cuda(), kmeans_use_features=True)
+  ora(x, kmeans_use_features=True)  # keep the two nets' running statistics in step
   assert len(dup) == 3 and dup[0].shape == (9, 512)
   net.eval(), ora.eval()
   with torch.no_grad():
