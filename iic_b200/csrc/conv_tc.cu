@@ -206,9 +206,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(TcParams P) {
     const long long planeHW = (long long)P.srcH * P.srcW;
 
     if (MODE == MODE_FPROP) {
-      // per-thread gather rows: r = it*16 + rsub, it = 0..7
+      // Per-thread gather rows r = it*16 + rsub (it = 0..7).  Everything that does not depend on
+      // the filter tap is hoisted: a base pointer per row plus the tap-free input coordinate; per
+      // k-block only 2 adds, 2 unsigned compares and one 64-bit add remain per row.
+      const __nv_bfloat16* rp[8];
       int gy[8], gx[8];
-      long long gimg[8];
+      const int smask = P.s - 1, sshift = P.s >> 1;  // stride is 1 or 2 on the tensor-core path
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const long long m = m0 + it * 16 + rsub;
@@ -216,14 +219,15 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(TcParams P) {
           const int ox = (int)(m % P.rowW);
           const long long q = m / P.rowW;
           const int oy = (int)(q % P.rowH);
-          gimg[it] = (q / P.rowH) * planeHW;
+          rp[it] = P.src + ((q / P.rowH) * planeHW * P.srcC + chunk * 8);
           gy[it] = P.transposed ? oy + P.p : oy * P.s - P.p;
           gx[it] = P.transposed ? ox + P.p : ox * P.s - P.p;
         } else {
-          gimg[it] = -1;
-          gy[it] = gx[it] = 0;
+          rp[it] = P.src;
+          gy[it] = gx[it] = -(1 << 28);  // fails every range check below -> zero fill
         }
       }
+      const bool transposed = P.transposed != 0;
       for (int i = 0; i < nk; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
@@ -232,31 +236,31 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(TcParams P) {
         const int j = (kb_begin + i) * 64;
         const int tap = j / P.srcC, c0 = j - tap * P.srcC;
         const int ta = tap / P.KW, tb = tap - ta * P.KW;
+        const int dyy = ta * P.d, dxx = tb * P.d;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int r = it * 16 + rsub;
-          bool ok = gimg[it] >= 0;
           int iy, ix;
-          if (!P.transposed) {
-            iy = gy[it] + ta * P.d;
-            ix = gx[it] + tb * P.d;
+          bool ok = true;
+          if (!transposed) {
+            iy = gy[it] + dyy;
+            ix = gx[it] + dxx;
           } else {
-            const int ty = gy[it] - ta * P.d, tx = gx[it] - tb * P.d;
-            ok = ok && ty >= 0 && tx >= 0 && (ty % P.s) == 0 && (tx % P.s) == 0;
-            iy = ty / P.s;
-            ix = tx / P.s;
+            const int ty = gy[it] - dyy, tx = gx[it] - dxx;
+            ok = ((ty | tx) & smask) == 0;
+            iy = ty >> sshift;
+            ix = tx >> sshift;
           }
-          ok = ok && iy >= 0 && iy < P.srcH && ix >= 0 && ix < P.srcW;
-          const __nv_bfloat16* src =
-              ok ? P.src + ((gimg[it] + (long long)iy * P.srcW + ix) * P.srcC + c0 + chunk * 8) : P.src;
+          ok = ok && (unsigned)iy < (unsigned)P.srcH && (unsigned)ix < (unsigned)P.srcW;
+          const __nv_bfloat16* src = ok ? rp[it] + ((iy * P.srcW + ix) * P.srcC + c0) : P.src;
           cp_async16_ca(sa + r * 128 + ((chunk ^ (r & 7)) << 4), src, ok ? 16u : 0u);
         }
         // weights: BN rows (cout) x 128 B
+        const __nv_bfloat16* wsrc = P.dense + ((long long)(n0 + rsub) * P.Ktot + j + chunk * 8);
 #pragma unroll
         for (int it = 0; it < BN / 16; ++it) {
           const int r = it * 16 + rsub;
-          const __nv_bfloat16* src = P.dense + ((long long)(n0 + r) * P.Ktot + j + chunk * 8);
-          cp_async16_cg(sb + r * 128 + ((chunk ^ (r & 7)) << 4), src, 16u);
+          cp_async16_cg(sb + r * 128 + ((chunk ^ (r & 7)) << 4), wsrc + (long long)it * 16 * P.Ktot, 16u);
         }
         cp_async_commit();
         if (i >= TC_LAG) {
@@ -266,51 +270,61 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(TcParams P) {
         }
       }
     } else {
-      // wgrad: k-rows are pixels of the dy grid; A atoms (64 (tap,cin) columns) x2, B atoms BN/64
-      int atap_a[2], atap_b[2], ac0[2];
+      // wgrad: k-rows are pixels of the dy grid; A atoms (64 (tap,cin) columns) x2, B atoms BN/64.
+      // Each thread owns 4 pixel rows per stage; their (ox, oy, image) coordinates advance by 64
+      // pixels per k-block incrementally (no divisions in the loop).
+      int aoff_y[2], aoff_x[2], ac0[2];
       bool aval[2];
 #pragma unroll
       for (int a = 0; a < 2; ++a) {
         const long long j = m0 + a * 64;
         aval[a] = j < P.Ktot;
         const int tap = (int)(j / P.srcC);
-        ac0[a] = (int)(j - (long long)tap * P.srcC);
-        atap_a[a] = tap / P.KW;
-        atap_b[a] = tap - atap_a[a] * P.KW;
+        ac0[a] = (int)(j - (long long)tap * P.srcC) + chunk * 8;
+        const int ta = tap / P.KW;
+        aoff_y[a] = ta * P.d - P.p;
+        aoff_x[a] = (tap - ta * P.KW) * P.d - P.p;
       }
+      int pox[4], poy[4];
+      long long pimg[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const long long pix = (long long)kb_begin * 64 + it * 16 + rsub;
+        pox[it] = (int)(pix % P.rowW);
+        const long long q = pix / P.rowW;
+        poy[it] = (int)(q % P.rowH);
+        pimg[it] = q / P.rowH;
+      }
+      const int step_x = 64 % P.rowW, step_y = 64 / P.rowW;
+      const long long nimg_rows = P.rows / ((long long)P.rowH * P.rowW);
       for (int i = 0; i < nk; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t sa = base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
-        const long long p0 = (long long)(kb_begin + i) * 64;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int r = it * 16 + rsub;
-          const long long pix = p0 + r;
-          const bool pv = pix < P.rows;
-          int oy = 0, ox = 0;
-          long long img = 0;
-          if (pv) {
-            ox = (int)(pix % P.rowW);
-            const long long q = pix / P.rowW;
-            oy = (int)(q % P.rowH);
-            img = (q / P.rowH) * planeHW;
-          }
+          const bool pv = pimg[it] < nimg_rows;
+          const int oy = poy[it], ox = pox[it];
           const uint32_t roff = r * 128 + ((chunk ^ (r & 7)) << 4);
+          const __nv_bfloat16* ibase = P.src + pimg[it] * planeHW * P.srcC;
 #pragma unroll
           for (int a = 0; a < 2; ++a) {
-            const int iy = oy * P.s - P.p + atap_a[a] * P.d, ix = ox * P.s - P.p + atap_b[a] * P.d;
-            const bool ok = pv && aval[a] && iy >= 0 && iy < P.srcH && ix >= 0 && ix < P.srcW;
-            const __nv_bfloat16* src =
-                ok ? P.src + ((img + (long long)iy * P.srcW + ix) * P.srcC + ac0[a] + chunk * 8) : P.src;
+            const int iy = oy * P.s + aoff_y[a], ix = ox * P.s + aoff_x[a];
+            const bool ok = pv && aval[a] && (unsigned)iy < (unsigned)P.srcH && (unsigned)ix < (unsigned)P.srcW;
+            const __nv_bfloat16* src = ok ? ibase + ((iy * P.srcW + ix) * P.srcC + ac0[a]) : P.src;
             cp_async16_ca(sa + a * 8192 + roff, src, ok ? 16u : 0u);
           }
+          const __nv_bfloat16* dsrc =
+              pv ? P.dense + (((pimg[it] * P.rowH + oy) * P.rowW + ox) * P.N + n0 + chunk * 8) : P.dense;
 #pragma unroll
-          for (int b = 0; b < BN / 64; ++b) {
-            const __nv_bfloat16* src = pv ? P.dense + (pix * P.N + n0 + b * 64 + chunk * 8) : P.dense;
-            cp_async16_cg(sb + b * 8192 + roff, src, pv ? 16u : 0u);
-          }
+          for (int b = 0; b < BN / 64; ++b) cp_async16_cg(sb + b * 8192 + roff, pv ? dsrc + b * 64 : P.dense, pv ? 16u : 0u);
+          // advance this row by 64 pixels
+          pox[it] += step_x;
+          poy[it] += step_y;
+          if (pox[it] >= P.rowW) { pox[it] -= P.rowW; poy[it] += 1; }
+          while (poy[it] >= P.rowH) { poy[it] -= P.rowH; pimg[it] += 1; }
         }
         cp_async_commit();
         if (i >= TC_LAG) {
@@ -442,6 +456,7 @@ int tc_conv_gather_gemm(const __nv_bfloat16* src, int srcH, int srcW, int srcC, 
                         const iic_conv_geom* g, int transposed, const __nv_bfloat16* wpacked, int N,
                         const __nv_bfloat16* addend, __nv_bfloat16* out, cudaStream_t st) {
   IIC_REQUIRE(srcC % 64 == 0, IIC_ERR_UNSUPPORTED, "tcgen05 conv: gathered channels (%d) must be a multiple of 64", srcC);
+  IIC_REQUIRE(g->stride == 1 || g->stride == 2, IIC_ERR_UNSUPPORTED, "tcgen05 conv: stride %d (only 1 or 2)", g->stride);
   const int bn = pick_bn(N);
   IIC_REQUIRE(bn != 0, IIC_ERR_UNSUPPORTED, "tcgen05 conv: N=%d must be a multiple of 64", N);
   TcParams P = {};
