@@ -1,0 +1,448 @@
+// tcgen05 implicit-GEMM convolution, TMA-fed persistent version (sm_100a).
+//
+// Same math and tile shapes as conv_tc.cu, but the operands are staged by the Tensor Memory
+// Accelerator instead of 16-byte cp.async gathers (which saturate the LSU at ~1/3-2/3 of the
+// tensor rate, profiles/r01_conv_sweep_v1.md):
+//   * activation operand: ONE `cp.async.bulk.tensor.4d...im2col` per 128x64 tile -- the TMA unit
+//     walks the output pixels of the tile (n, oh, ow order), applies the conv stride, the filter-tap
+//     offset and zero-fills the padding, writing 128-byte rows with the SWIZZLE_128B pattern the
+//     UMMA descriptor expects (im2col is never materialised);
+//   * dense operand (packed weights, or dy for wgrad): one tiled 2-D / 3-D TMA box per stage.
+// Warp roles (192 threads, one persistent CTA per SM, static tile schedule):
+//   warp 5 lane 0: TMA producer (mbarrier expect_tx)      warp 4 lane 0: tcgen05.mma issuer
+//   warps 0-3    : epilogue; TMEM accumulators are double-buffered (2 x BN columns) so the
+//                  epilogue of tile i overlaps the main loop of tile i+1.
+// Used for fprop (stride 1/2), dgrad of stride-1 convs (im2col of dy with reversed taps) and wgrad
+// (both operands MN-major).  Stride-2 dgrad keeps the cp.async kernel (fractional stride is not an
+// im2col access pattern).
+#include <cuda.h>
+
+#include "tc_ptx.cuh"
+
+namespace iic {
+
+enum { M2_FPROP = 0, M2_WGRAD = 1 };
+constexpr int TC2_THREADS = 192;
+
+struct Tc2Params {
+  long long rows;   // pixels enumerated by the gather (n * rowH * rowW)
+  int rowH, rowW;
+  int KH, KW, s, d;
+  int lower;        // input-space coordinate offset of filter tap 0 (same for h and w)
+  int flip;         // dgrad: tap t reads offset (K-1-t)*d
+  int srcC, Ktot, N;
+  int mtiles, ntiles, splits, kb_per_split, total_kb;
+  __nv_bfloat16* out;
+  const __nv_bfloat16* addend;
+  float* partial;
+};
+
+template <int BN> struct Tc2Cfg {
+  static constexpr int A_BYTES = TC_BM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+template <int MODE, int BN>
+__global__ void __launch_bounds__(TC2_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Tc2Params P) {
+  using Cfg = Tc2Cfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t bars = base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + STAGES * Cfg::STAGE_BYTES + (2 * STAGES + 4) * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = P.mtiles * P.ntiles;
+  const int total_work = tiles_mn * P.splits;
+
+  // work item -> (split z, m tile, n tile, k-block range)
+  auto decode = [&](int w, int& z, long long& m0, int& n0, int& kb0, int& nk) {
+    z = w / tiles_mn;
+    const int r = w - z * tiles_mn;
+    n0 = (r % P.ntiles) * BN;
+    m0 = (long long)(r / P.ntiles) * TC_BM;
+    if (MODE == M2_FPROP) {
+      kb0 = 0;
+      nk = P.total_kb;
+    } else {
+      kb0 = z * P.kb_per_split;
+      nk = min(P.total_kb, kb0 + P.kb_per_split) - kb0;
+      if (nk < 0) nk = 0;
+    }
+  };
+
+  if (warp == 5) {
+    // =============================== TMA producer ============================================
+    if (lane == 0) {
+      uint32_t it = 0;  // global k-block counter -> stage / phase
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        int z, n0, kb0, nk;
+        long long m0;
+        decode(w, z, m0, n0, kb0, nk);
+        if (MODE == M2_FPROP) {
+          const int ox = (int)(m0 % P.rowW);
+          const long long q = m0 / P.rowW;
+          const int oy = (int)(q % P.rowH);
+          const int img = (int)(q / P.rowH);
+          const int cw = ox * P.s + P.lower, ch = oy * P.s + P.lower;
+          for (int i = 0; i < nk; ++i, ++it) {
+            const int s = it % STAGES;
+            mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u);
+            const uint32_t sa = base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+            const int j = i * 64;
+            const int tap = j / P.srcC, c0 = j - tap * P.srcC;
+            int ta = tap / P.KW, tb = tap - ta * P.KW;
+            if (P.flip) {
+              ta = P.KH - 1 - ta;
+              tb = P.KW - 1 - tb;
+            }
+            mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+            tma_load_im2col(sa, &tmA, full_bar(s), c0, cw, ch, img, (uint16_t)(tb * P.d), (uint16_t)(ta * P.d));
+            tma_load_2d(sb, &tmB, full_bar(s), j, n0);
+          }
+        } else {
+          int a_tap_a[2], a_tap_b[2], a_c0[2];
+          bool a_ok[2];
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const long long j = m0 + a * 64;
+            a_ok[a] = j < P.Ktot;
+            const int tap = (int)(j / P.srcC);
+            a_c0[a] = (int)(j - (long long)tap * P.srcC);
+            a_tap_a[a] = tap / P.KW;
+            a_tap_b[a] = tap - a_tap_a[a] * P.KW;
+          }
+          const uint32_t bytes = (uint32_t)((a_ok[0] ? 8192 : 0) + (a_ok[1] ? 8192 : 0) + Cfg::B_BYTES);
+          for (int i = 0; i < nk; ++i, ++it) {
+            const int s = it % STAGES;
+            mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u);
+            const uint32_t sa = base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+            const long long p0 = (long long)(kb0 + i) * 64;
+            const int ox = (int)(p0 % P.rowW);
+            const long long q = p0 / P.rowW;
+            const int oy = (int)(q % P.rowH);
+            const int img = (int)(q / P.rowH);
+            mbar_expect_tx(full_bar(s), bytes);
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+              if (a_ok[a])
+                tma_load_im2col(sa + a * 8192, &tmA, full_bar(s), a_c0[a], ox * P.s + P.lower, oy * P.s + P.lower, img,
+                                (uint16_t)(a_tap_b[a] * P.d), (uint16_t)(a_tap_a[a] * P.d));
+            tma_load_3d(sb, &tmB, full_bar(s), 0, (int)p0, n0 / 64);
+          }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // =============================== MMA issuer ==============================================
+    constexpr uint32_t idesc = (MODE == M2_FPROP) ? make_idesc(BN, 0, 0) : make_idesc(BN, 1, 1);
+    uint32_t it = 0, tile_it = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tile_it) {
+      int z, n0, kb0, nk;
+      long long m0;
+      decode(w, z, m0, n0, kb0, nk);
+      const uint32_t as = tile_it & 1u;
+      mbar_wait(tempty_bar(as), ((tile_it >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + as * BN;
+      for (int i = 0; i < nk; ++i, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(full_bar(s), (it / STAGES) & 1u);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            uint64_t ad, bd;
+            if (MODE == M2_FPROP) {
+              ad = make_desc(sa + kk * 32, 16, 1024);
+              bd = make_desc(sb + kk * 32, 16, 1024);
+            } else {
+              ad = make_desc(sa + kk * 2048, 8192, 1024);
+              bd = make_desc(sb + kk * 2048, 8192, 1024);
+            }
+            umma_bf16(tmem_acc, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));
+        }
+        __syncwarp();
+      }
+      if (lane == 0) umma_commit(tfull_bar(as));  // (also correct for nk == 0: arrives immediately)
+      __syncwarp();
+    }
+  } else {
+    // =============================== epilogue (warps 0-3) ======================================
+    uint32_t tile_it = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tile_it) {
+      int z, n0, kb0, nk;
+      long long m0;
+      decode(w, z, m0, n0, kb0, nk);
+      const uint32_t as = tile_it & 1u;
+      mbar_wait(tfull_bar(as), (tile_it >> 1) & 1u);
+      tc_fence_after();
+      const long long m = m0 + warp * 32 + lane;  // TMEM lane == tile row
+      const uint32_t tmem_acc = tmem_base + as * BN + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        if (nk > 0) {
+          tmem_ld32(tmem_acc + (uint32_t)c0, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int qq = 0; qq < 32; ++qq) v[qq] = 0u;
+        }
+        if (MODE == M2_FPROP) {
+          if (m < P.rows) {
+            __nv_bfloat16* o = P.out + m * P.N + n0 + c0;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[qq * 8 + e]);
+              if (P.addend != nullptr) {
+                float ad[8];
+                load8(P.addend + m * P.N + n0 + c0 + qq * 8, ad);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += ad[e];
+              }
+              store8(o + qq * 8, f);
+            }
+          }
+        } else {
+          if (m < P.Ktot) {
+            float* o = P.partial + ((long long)z * P.Ktot + m) * P.N + n0 + c0;
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq)
+              *reinterpret_cast<float4*>(o + qq * 4) =
+                  make_float4(__uint_as_float(v[qq * 4]), __uint_as_float(v[qq * 4 + 1]), __uint_as_float(v[qq * 4 + 2]),
+                              __uint_as_float(v[qq * 4 + 3]));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(as));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ---- host side: tensor-map construction through the driver entry points ----------------------
+typedef CUresult (*PFN_tmEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_tmEncodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmEncodeTiled g_encodeTiled = nullptr;
+static PFN_tmEncodeIm2col g_encodeIm2col = nullptr;
+static int g_driver_version = 0;
+
+static int tma_init() {
+  if (g_encodeTiled && g_encodeIm2col) return IIC_OK;
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  IIC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  IIC_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, IIC_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  g_encodeTiled = (PFN_tmEncodeTiled)fn;
+  fn = nullptr;
+  IIC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres));
+  IIC_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, IIC_ERR_CUDA, "cuTensorMapEncodeIm2col unavailable");
+  g_encodeIm2col = (PFN_tmEncodeIm2col)fn;
+  cudaDriverGetVersion(&g_driver_version);
+  return IIC_OK;
+}
+
+// NHWC bf16 activation [nimg][H][W][C] as the rank-4 (C, W, H, N) im2col tensor map
+static int make_im2col_map(CUtensorMap* tm, const void* ptr, int nimg, int H, int W, int C, int lower, int upper, int stride,
+                           int pixels) {
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  int lo[2] = {lower, lower}, up[2] = {upper, upper};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = g_encodeIm2col(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, lo, up, 64,
+                              (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IIC_REQUIRE(r == CUDA_SUCCESS, IIC_ERR_CUDA, "cuTensorMapEncodeIm2col failed (%d) H=%d W=%d C=%d lower=%d upper=%d stride=%d",
+              (int)r, H, W, C, lower, upper, stride);
+  // driver workaround also applied by CUTLASS (copy_traits_sm90_im2col.hpp): small tensors, drivers <= 13.1
+  if (g_driver_version <= 13010 && (long long)nimg * H * W * C * 2 < 131072)
+    reinterpret_cast<uint64_t*>(tm)[1] &= ~(1llu << 21);
+  return IIC_OK;
+}
+
+template <int MODE, int BN>
+static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc2Params& P, int splits, cudaStream_t st) {
+  using Cfg = Tc2Cfg<BN>;
+  IIC_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  long long work = (long long)P.mtiles * P.ntiles * splits;
+  int grid = (int)(work < device_sm_count() ? work : device_sm_count());
+  conv_tc2_kernel<MODE, BN><<<grid, TC2_THREADS, Cfg::SMEM, st>>>(tmA, tmB, P);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
+static int pick_bn2(int N) {
+  if (N % 256 == 0) return 256;
+  if (N % 128 == 0) return 128;
+  if (N % 64 == 0) return 64;
+  return 0;
+}
+
+// fprop (transposed == 0) or dgrad of a stride-1 conv (transposed == 1; src = dy, N = cin)
+int tc2_conv_gather_gemm(const __nv_bfloat16* src, int srcH, int srcW, int srcC, int rowH, int rowW, int nimg,
+                         const iic_conv_geom* g, int transposed, const __nv_bfloat16* wpacked, int N,
+                         const __nv_bfloat16* addend, __nv_bfloat16* out, cudaStream_t st) {
+  int rc = tma_init();
+  if (rc != IIC_OK) return rc;
+  const int bn = pick_bn2(N);
+  IIC_REQUIRE(bn != 0 && srcC % 64 == 0, IIC_ERR_UNSUPPORTED, "tcgen05/TMA conv: channels must be multiples of 64");
+  IIC_REQUIRE(g->kh == g->kw, IIC_ERR_UNSUPPORTED, "tcgen05/TMA conv: square filters only");
+  IIC_REQUIRE(!transposed || g->stride == 1, IIC_ERR_UNSUPPORTED, "tcgen05/TMA dgrad: stride-1 only");
+  Tc2Params P = {};
+  P.rows = (long long)nimg * rowH * rowW;
+  P.rowH = rowH; P.rowW = rowW; P.KH = g->kh; P.KW = g->kw; P.d = g->dil;
+  const int span = (g->kh - 1) * g->dil;
+  int upper;
+  if (!transposed) {
+    P.s = g->stride; P.lower = -g->pad; P.flip = 0;
+    upper = g->pad - span;
+  } else {
+    P.s = 1; P.lower = g->pad - span; P.flip = 1;
+    upper = P.lower + (rowH - srcH);  // number of base positions == rows of dx
+  }
+  IIC_REQUIRE(P.lower >= -128 && P.lower <= 127 && upper >= -128 && upper <= 127, IIC_ERR_UNSUPPORTED, "im2col corner range");
+  P.srcC = srcC; P.Ktot = g->kh * g->kw * srcC; P.N = N;
+  P.mtiles = (int)((P.rows + TC_BM - 1) / TC_BM); P.ntiles = N / bn; P.splits = 1; P.total_kb = P.Ktot / 64;
+  P.out = out; P.addend = addend;
+  alignas(64) CUtensorMap tmA, tmB;
+  rc = make_im2col_map(&tmA, src, nimg, srcH, srcW, srcC, P.lower, upper, P.s, TC_BM);
+  if (rc != IIC_OK) return rc;
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)P.Ktot, (cuuint64_t)N};
+    cuuint64_t gstr[1] = {(cuuint64_t)P.Ktot * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)bn};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encodeTiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(wpacked), gdim, gstr, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IIC_REQUIRE(r == CUDA_SUCCESS, IIC_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed (%d)", (int)r);
+  }
+  switch (bn) {
+    case 256: return launch_tc2<M2_FPROP, 256>(tmA, tmB, P, 1, st);
+    case 128: return launch_tc2<M2_FPROP, 128>(tmA, tmB, P, 1, st);
+    default: return launch_tc2<M2_FPROP, 64>(tmA, tmB, P, 1, st);
+  }
+}
+
+static int tc2_wgrad_splits(const iic_conv_geom* g) {
+  const long long rows = (long long)g->n * g->oh * g->ow;
+  const int total_kb = (int)((rows + 63) / 64);
+  const int Ktot = g->kh * g->kw * g->cin;
+  const int bn = pick_bn2(g->cout);
+  const long long tiles = (long long)((Ktot + TC_BM - 1) / TC_BM) * (g->cout / (bn ? bn : 64));
+  long long want = ((long long)device_sm_count() * 2 + tiles - 1) / tiles;
+  if (want > total_kb / 8) want = total_kb / 8;  // at least 8 k-blocks per work item
+  if (want < 1) want = 1;
+  if (want > 512) want = 512;
+  return (int)want;
+}
+
+long long tc2_conv_wgrad_workspace(const iic_conv_geom* g) {
+  return (long long)tc2_wgrad_splits(g) * g->kh * g->kw * g->cin * g->cout * (long long)sizeof(float);
+}
+
+__global__ void wgrad2_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Ktot, int N, int splits) {
+  const long long total = (long long)Ktot * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % N);
+    const int j = (int)(i / N);
+    float t = 0.f;
+    for (int z = 0; z < splits; ++z) t += partial[(long long)z * total + i];
+    dw[(long long)co * Ktot + j] = t;
+  }
+}
+
+int tc2_conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* ws, const iic_conv_geom* g, cudaStream_t st) {
+  int rc = tma_init();
+  if (rc != IIC_OK) return rc;
+  const int bn = pick_bn2(g->cout);
+  IIC_REQUIRE(bn != 0 && g->cin % 64 == 0, IIC_ERR_UNSUPPORTED, "tcgen05/TMA wgrad: channels must be multiples of 64");
+  IIC_REQUIRE(g->kh == g->kw, IIC_ERR_UNSUPPORTED, "tcgen05/TMA wgrad: square filters only");
+  Tc2Params P = {};
+  P.rows = (long long)g->n * g->oh * g->ow;
+  P.rowH = g->oh; P.rowW = g->ow; P.KH = g->kh; P.KW = g->kw; P.s = g->stride; P.d = g->dil; P.lower = -g->pad; P.flip = 0;
+  const int upper = g->pad - (g->kh - 1) * g->dil;
+  P.srcC = g->cin; P.Ktot = g->kh * g->kw * g->cin; P.N = g->cout;
+  P.mtiles = (P.Ktot + TC_BM - 1) / TC_BM; P.ntiles = g->cout / bn;
+  P.splits = tc2_wgrad_splits(g);
+  P.total_kb = (int)((P.rows + 63) / 64);
+  P.kb_per_split = (P.total_kb + P.splits - 1) / P.splits;
+  P.partial = ws;
+  alignas(64) CUtensorMap tmA, tmB;
+  rc = make_im2col_map(&tmA, x, g->n, g->h, g->w, g->cin, P.lower, upper, P.s, 64);
+  if (rc != IIC_OK) return rc;
+  {
+    // dy [rows][cout] viewed as (64 ch, rows, cout/64): box = 64 ch x 64 pixels x (bn/64) column blocks,
+    // landing in shared memory as [block][pixel][128 B] = the MN-major SWIZZLE_128B atoms.
+    cuuint64_t gdim[3] = {64, (cuuint64_t)P.rows, (cuuint64_t)(g->cout / 64)};
+    cuuint64_t gstr[2] = {(cuuint64_t)g->cout * 2, 128};
+    cuuint32_t box[3] = {64, 64, (cuuint32_t)(bn / 64)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encodeTiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(dy), gdim, gstr, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IIC_REQUIRE(r == CUDA_SUCCESS, IIC_ERR_CUDA, "cuTensorMapEncodeTiled(dy) failed (%d)", (int)r);
+  }
+  switch (bn) {
+    case 256: rc = launch_tc2<M2_WGRAD, 256>(tmA, tmB, P, P.splits, st); break;
+    case 128: rc = launch_tc2<M2_WGRAD, 128>(tmA, tmB, P, P.splits, st); break;
+    default: rc = launch_tc2<M2_WGRAD, 64>(tmA, tmB, P, P.splits, st); break;
+  }
+  if (rc != IIC_OK) return rc;
+  const long long total = (long long)P.Ktot * g->cout;
+  int blocks = cdiv(total, 256);
+  if (blocks > device_sm_count() * 8) blocks = device_sm_count() * 8;
+  wgrad2_reduce_kernel<<<blocks, 256, 0, st>>>(ws, dw, P.Ktot, g->cout, P.splits);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
+}  // namespace iic
