@@ -1,6 +1,8 @@
 // Dispatch of the conv entry points onto the two kernels: IIC_F32 -> fp32 SIMT implicit GEMM
 // (conv_simt.cu), IIC_BF16 -> tcgen05 implicit GEMM (conv_tc.cu).  This is a precision mode of
 // one sm_100a code base, not a backend switch: there is no CPU or library fallback.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace iic {
@@ -13,9 +15,25 @@ int tc_conv_gather_gemm(const __nv_bfloat16* src, int srcH, int srcW, int srcC, 
                         const __nv_bfloat16* addend, __nv_bfloat16* out, cudaStream_t st);
 long long tc_conv_wgrad_workspace(const iic_conv_geom* g);
 int tc_conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* ws, const iic_conv_geom* g, cudaStream_t st);
+int tc2_conv_gather_gemm(const __nv_bfloat16* src, int srcH, int srcW, int srcC, int rowH, int rowW, int nimg,
+                         const iic_conv_geom* g, int transposed, const __nv_bfloat16* wpacked, int N,
+                         const __nv_bfloat16* addend, __nv_bfloat16* out, cudaStream_t st);
+long long tc2_conv_wgrad_workspace(const iic_conv_geom* g);
+int tc2_conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* ws, const iic_conv_geom* g, cudaStream_t st);
 }  // namespace iic
 
 using namespace iic;
+
+// The TMA-fed persistent kernel (conv_tc2.cu) is the default tensor-core path; IIC_TC_CPASYNC=1 selects the
+// cp.async-fed kernel (conv_tc.cu) everywhere (kept for stride-2 dgrad and for A/B measurements).
+static bool use_tma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IIC_TC_CPASYNC");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 static int geom_check(const iic_conv_geom* g, const char* who) {
   IIC_REQUIRE(g != nullptr, IIC_ERR_BAD_ARG, "%s: null geometry", who);
@@ -37,8 +55,9 @@ extern "C" int iic_conv_fprop(const void* x, const void* w_packed, void* y, cons
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == IIC_F32) return simt_conv_fprop((const float*)x, (const float*)w_packed, (float*)y, g, st);
   if (dtype == IIC_BF16)
-    return tc_conv_gather_gemm((const __nv_bfloat16*)x, g->h, g->w, g->cin, g->oh, g->ow, g->n, g, 0,
-                               (const __nv_bfloat16*)w_packed, g->cout, nullptr, (__nv_bfloat16*)y, st);
+    return (use_tma() ? tc2_conv_gather_gemm : tc_conv_gather_gemm)(
+        (const __nv_bfloat16*)x, g->h, g->w, g->cin, g->oh, g->ow, g->n, g, 0, (const __nv_bfloat16*)w_packed, g->cout,
+        nullptr, (__nv_bfloat16*)y, st);
   set_error("iic_conv_fprop: bad dtype %d", dtype);
   return IIC_ERR_BAD_ARG;
 }
@@ -52,16 +71,17 @@ extern "C" int iic_conv_dgrad(const void* dy, const void* w_packed_t, const void
   if (dtype == IIC_F32)
     return simt_conv_dgrad((const float*)dy, (const float*)w_packed_t, (const float*)addend, (float*)dx, g, st);
   if (dtype == IIC_BF16)
-    return tc_conv_gather_gemm((const __nv_bfloat16*)dy, g->oh, g->ow, g->cout, g->h, g->w, g->n, g, 1,
-                               (const __nv_bfloat16*)w_packed_t, g->cin, (const __nv_bfloat16*)addend,
-                               (__nv_bfloat16*)dx, st);
+    return ((use_tma() && g->stride == 1) ? tc2_conv_gather_gemm : tc_conv_gather_gemm)(
+        (const __nv_bfloat16*)dy, g->oh, g->ow, g->cout, g->h, g->w, g->n, g, 1, (const __nv_bfloat16*)w_packed_t, g->cin,
+        (const __nv_bfloat16*)addend, (__nv_bfloat16*)dx, st);
   set_error("iic_conv_dgrad: bad dtype %d", dtype);
   return IIC_ERR_BAD_ARG;
 }
 
 extern "C" long long iic_conv_wgrad_workspace(const iic_conv_geom* g, int dtype) {
   if (g == nullptr) return -1;
-  return dtype == IIC_BF16 ? tc_conv_wgrad_workspace(g) : simt_conv_wgrad_workspace(g);
+  if (dtype == IIC_BF16) return use_tma() ? tc2_conv_wgrad_workspace(g) : tc_conv_wgrad_workspace(g);
+  return simt_conv_wgrad_workspace(g);
 }
 
 extern "C" int iic_conv_wgrad(const void* x, const void* dy, float* dw_packed, void* workspace, const iic_conv_geom* g,
@@ -72,7 +92,8 @@ extern "C" int iic_conv_wgrad(const void* x, const void* dy, float* dw_packed, v
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == IIC_F32) return simt_conv_wgrad((const float*)x, (const float*)dy, dw_packed, (float*)workspace, g, st);
   if (dtype == IIC_BF16)
-    return tc_conv_wgrad((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw_packed, (float*)workspace, g, st);
+    return (use_tma() ? tc2_conv_wgrad : tc_conv_wgrad)((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw_packed,
+                                                        (float*)workspace, g, st);
   set_error("iic_conv_wgrad: bad dtype %d", dtype);
   return IIC_ERR_BAD_ARG;
 }

@@ -7,7 +7,7 @@
 //     walks the output pixels of the tile (n, oh, ow order), applies the conv stride, the filter-tap
 //     offset and zero-fills the padding, writing 128-byte rows with the SWIZZLE_128B pattern the
 //     UMMA descriptor expects (im2col is never materialised);
-//   * dense operand (packed weights, or dy for wgrad): one tiled 2-D / 3-D TMA box per stage.
+//   * dense operand (packed weights, or dy for wgrad): tiled 2-D TMA boxes (1 per stage; BN/64 for wgrad).
 // Warp roles (192 threads, one persistent CTA per SM, static tile schedule):
 //   warp 5 lane 0: TMA producer (mbarrier expect_tx)      warp 4 lane 0: tcgen05.mma issuer
 //   warps 0-3    : epilogue; TMEM accumulators are double-buffered (2 x BN columns) so the
@@ -160,7 +160,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               if (a_ok[a])
                 tma_load_im2col(sa + a * 8192, &tmA, full_bar(s), a_c0[a], ox * P.s + P.lower, oy * P.s + P.lower, img,
                                 (uint16_t)(a_tap_b[a] * P.d), (uint16_t)(a_tap_a[a] * P.d));
-            tma_load_3d(sb, &tmB, full_bar(s), 0, (int)p0, n0 / 64);
+#pragma unroll
+            for (int b = 0; b < BN / 64; ++b) tma_load_2d(sb + b * 8192, &tmB, full_bar(s), n0 + b * 64, (int)p0);
           }
         }
       }
@@ -419,13 +420,13 @@ int tc2_conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, f
   rc = make_im2col_map(&tmA, x, g->n, g->h, g->w, g->cin, P.lower, upper, P.s, 64);
   if (rc != IIC_OK) return rc;
   {
-    // dy [rows][cout] viewed as (64 ch, rows, cout/64): box = 64 ch x 64 pixels x (bn/64) column blocks,
-    // landing in shared memory as [block][pixel][128 B] = the MN-major SWIZZLE_128B atoms.
-    cuuint64_t gdim[3] = {64, (cuuint64_t)P.rows, (cuuint64_t)(g->cout / 64)};
-    cuuint64_t gstr[2] = {(cuuint64_t)g->cout * 2, 128};
-    cuuint32_t box[3] = {64, 64, (cuuint32_t)(bn / 64)};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encodeTiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(dy), gdim, gstr, box, estr,
+    // dy [rows][cout]: one 64-channel x 64-pixel box per column block; each lands in shared memory as
+    // [pixel][128 B] = one MN-major SWIZZLE_128B atom column (bn/64 loads per stage).
+    cuuint64_t gdim[2] = {(cuuint64_t)g->cout, (cuuint64_t)P.rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)g->cout * 2};
+    cuuint32_t box[2] = {64, 64};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encodeTiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(dy), gdim, gstr, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     IIC_REQUIRE(r == CUDA_SUCCESS, IIC_ERR_CUDA, "cuTensorMapEncodeTiled(dy) failed (%d)", (int)r);
