@@ -378,8 +378,16 @@ static int tc2_wgrad_splits(const iic_conv_geom* g) {
   const int Ktot = g->kh * g->kw * g->cin;
   const int bn = pick_bn2(g->cout);
   const long long tiles = (long long)((Ktot + TC_BM - 1) / TC_BM) * (g->cout / (bn ? bn : 64));
-  long long want = ((long long)device_sm_count() * 2 + tiles - 1) / tiles;
-  if (want > total_kb / 8) want = total_kb / 8;  // at least 8 k-blocks per work item
+  // persistent CTAs take work items round-robin: make (tiles x splits) fill a whole number of rounds of
+  // one item per SM (never 2.1 rounds), with at least 8 k-blocks per item
+  const long long sms = device_sm_count();
+  long long want = 1;
+  if (tiles < sms) {
+    want = sms / tiles;
+    const long long two = (2 * sms) / tiles;  // two full rounds if the items stay long enough
+    if (two > want && total_kb / two >= 32) want = two;
+  }
+  if (want > total_kb / 8) want = total_kb / 8;
   if (want < 1) want = 1;
   if (want > 512) want = 512;
   return (int)want;

@@ -80,60 +80,74 @@ __global__ void sobel_kernel(const float* __restrict__ in, float* __restrict__ o
 // BatchNorm2d (train mode) -- net5g.py:24, residual.py:20,23,56, vgg.py:28
 // ---------------------------------------------------------------------------------------------
 // Per-channel sum / sum of squares over M rows of y[M][C].  Threads are laid out so that a warp
-// reads whole 128 B+ row segments; each thread owns 8 channels and walks rows with a grid stride.
+// reads whole 128 B+ row segments; each thread owns 8 channels and walks rows with a grid stride,
+// two independent rows in flight.  Each block writes ONE partial row (no atomics: 1184 blocks
+// hammering 128 addresses cost more than the streaming pass itself); bn_sum_partials_kernel folds them.
 template <typename T, bool BWD>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ y, const T* __restrict__ gin,
                                                         const T* __restrict__ act,
                                                         const float* __restrict__ mean_invstd, long long M, int C,
-                                                        double* __restrict__ sums) {
-  // BWD=false: sums[c] += y, sums[C+c] += y*y
-  // BWD=true : g = gin * (act > 0 if act) ; yhat = (y-mean)*invstd ; sums[c] += g ; sums[C+c] += g*yhat
+                                                        float* __restrict__ partial /* [gridDim.x][2C] */) {
+  // BWD=false: sum y, sum y*y
+  // BWD=true : g = gin * (act > 0 if act) ; yhat = (y-mean)*invstd ; sum g ; sum g*yhat
   __shared__ float sh[256 * 17];
-  const int cg = C >> 3;                     // channel groups per row
-  const int tpr = cg < 256 ? cg : 256;       // threads per row (C <= 2048)
+  const int cg = C >> 3;                // channel groups per row (C <= 2048)
+  const int tpr = cg;                   // threads per row
   const int rows_per_it = 256 / tpr;
   const int my_cg = threadIdx.x % tpr, my_r = threadIdx.x / tpr;
   float a0[8], a1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
   if (my_r < rows_per_it) {
-    for (int c8 = my_cg; c8 < cg; c8 += tpr) {  // (only loops when C > 2048)
-      float mean[8], istd[8];
-      if (BWD) {
+    const int c8 = my_cg;
+    float mean[8], istd[8];
+    if (BWD) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          mean[j] = mean_invstd[c8 * 8 + j];
-          istd[j] = mean_invstd[C + c8 * 8 + j];
+      for (int j = 0; j < 8; ++j) {
+        mean[j] = mean_invstd[c8 * 8 + j];
+        istd[j] = mean_invstd[C + c8 * 8 + j];
+      }
+    }
+    const long long stride = (long long)gridDim.x * rows_per_it;
+    for (long long r = (long long)blockIdx.x * rows_per_it + my_r; r < M; r += 2 * stride) {
+      const long long r2 = r + stride;
+      const bool two = r2 < M;
+      float v[8], v2[8], g[8], g2[8], a[8], a2[8];
+      load8(y + r * C + c8 * 8, v);
+      if (two) load8(y + r2 * C + c8 * 8, v2);
+      if (BWD) {
+        load8(gin + r * C + c8 * 8, g);
+        if (two) load8(gin + r2 * C + c8 * 8, g2);
+        if (act != nullptr) {
+          load8(act + r * C + c8 * 8, a);
+          if (two) load8(act + r2 * C + c8 * 8, a2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            g[j] = a[j] > 0.f ? g[j] : 0.f;
+            if (two) g2[j] = a2[j] > 0.f ? g2[j] : 0.f;
+          }
         }
       }
-      for (long long r = (long long)blockIdx.x * rows_per_it + my_r; r < M; r += (long long)gridDim.x * rows_per_it) {
-        float v[8];
-        load8(y + r * C + c8 * 8, v);
-        if (!BWD) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            a0[j] += v[j];
-            a1[j] = fmaf(v[j], v[j], a1[j]);
+      for (int j = 0; j < 8; ++j) {
+        if (!BWD) {
+          a0[j] += v[j];
+          a1[j] = fmaf(v[j], v[j], a1[j]);
+          if (two) {
+            a0[j] += v2[j];
+            a1[j] = fmaf(v2[j], v2[j], a1[j]);
           }
         } else {
-          float g[8];
-          load8(gin + r * C + c8 * 8, g);
-          if (act != nullptr) {
-            float a[8];
-            load8(act + r * C + c8 * 8, a);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            a0[j] += g[j];
-            a1[j] = fmaf(g[j], (v[j] - mean[j]) * istd[j], a1[j]);
+          a0[j] += g[j];
+          a1[j] = fmaf(g[j], (v[j] - mean[j]) * istd[j], a1[j]);
+          if (two) {
+            a0[j] += g2[j];
+            a1[j] = fmaf(g2[j], (v2[j] - mean[j]) * istd[j], a1[j]);
           }
         }
       }
     }
   }
-  // block reduce over the row-lanes that share a channel group (only valid when cg <= 256)
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     sh[threadIdx.x * 17 + j] = a0[j];
@@ -142,11 +156,20 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ y,
   __syncthreads();
   for (int i = threadIdx.x; i < tpr * 16; i += 256) {
     const int g = i / 16, j = i % 16;
-    double t = 0.0;
-    for (int r = 0; r < rows_per_it; ++r) t += (double)sh[(r * tpr + g) * 17 + j];
-    // channel index: g*8 + (j&7); second half of `sums` for j >= 8
-    atomicAdd(&sums[(j >> 3) * C + g * 8 + (j & 7)], t);
+    float t = 0.f;
+    for (int r = 0; r < rows_per_it; ++r) t += sh[(r * tpr + g) * 17 + j];
+    partial[(long long)blockIdx.x * 2 * C + (j >> 3) * C + g * 8 + (j & 7)] = t;
   }
+}
+
+// sums[i] = sum_b partial[b][i]  (double, fixed order => deterministic); one warp per entry
+__global__ void bn_sum_partials_kernel(const float* __restrict__ partial, int nblk, int n2c, double* __restrict__ sums) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n2c) return;
+  double t = 0.0;
+  for (int b = lane; b < nblk; b += 32) t += (double)partial[(long long)b * n2c + warp];
+  t = warp_sum(t);
+  if (lane == 0) sums[warp] = t;
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, long long M, int C, const float* __restrict__ gamma,
@@ -303,7 +326,9 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_bwd_kernel(const T* __res
   }
 }
 
-// dy = scale * (g - mean(g) - yhat * mean(g*yhat));  optional g_out (masked gradient for the residual branch)
+// dy = gamma*istd * (g - mean(g) - yhat * mean(g*yhat)) = A*g + B*y + Cc with per-channel coefficients
+// (computed once per block into shared memory; no fp64 in the streaming loop).  Optional g_out =
+// masked gradient for the residual branch.
 template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ gin, const T* __restrict__ act,
                                                            const T* __restrict__ y,
@@ -312,16 +337,24 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
                                                            const double* __restrict__ sums, T* __restrict__ dy,
                                                            T* __restrict__ g_out, float* dgamma, float* dbeta,
                                                            int accumulate, long long M, int C) {
+  extern __shared__ __align__(16) float coef[];  // [3][C]
   const int cg = C >> 3;
   const long long total = M * cg;
   const double invM = 1.0 / (double)M;
-  if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float mean = mean_invstd[c], istd = mean_invstd[C + c];
+    const float m1 = (float)(sums[c] * invM), m2 = (float)(sums[C + c] * invM);
+    const float A = gamma[c] * istd;
+    coef[c] = A;
+    coef[C + c] = -A * m2 * istd;
+    coef[2 * C + c] = -A * m1 + A * m2 * istd * mean;
+    if (blockIdx.x == 0) {
       const float db = (float)sums[c], dg = (float)sums[C + c];
       if (dgamma) dgamma[c] = accumulate ? dgamma[c] + dg : dg;
       if (dbeta) dbeta[c] = accumulate ? dbeta[c] + db : db;
     }
   }
+  __syncthreads();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c8 = (int)(i % cg);
     float g[8], v[8];
@@ -334,15 +367,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
       for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
     }
     if (g_out != nullptr) store8(g_out + i * 8, g);
-    float o[8];
+    float cA[8], cB[8], cC[8], o[8];
+    load8(coef + c8 * 8, cA);
+    load8(coef + C + c8 * 8, cB);
+    load8(coef + 2 * C + c8 * 8, cC);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = c8 * 8 + j;
-      const float mean = mean_invstd[c], istd = mean_invstd[C + c];
-      const float yhat = (v[j] - mean) * istd;
-      const float m1 = (float)(sums[c] * invM), m2 = (float)(sums[C + c] * invM);
-      o[j] = gamma[c] * istd * (g[j] - m1 - yhat * m2);
-    }
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(cA[j], g[j], fmaf(cB[j], v[j], cC[j]));
     store8(dy + i * 8, o);
   }
 }
@@ -473,23 +503,50 @@ extern "C" int iic_sobel(const float* imgs, float* out, int n, int c_in, int h, 
   return IIC_OK;
 }
 
+static int bn_reduce_blocks(long long M, int C) {
+  const int rpi = 256 / (C / 8);
+  long long blocks = (M + 2 * rpi - 1) / (2 * rpi);
+  const long long cap = (long long)device_sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// scratch for the per-block partial sums: [blocks][2C] floats, kept per device (grown on demand;
+// stream-ordered use only, like every workspace of this library)
+static float* bn_partial_scratch(size_t bytes) {
+  static float* buf[64] = {nullptr};
+  static size_t cap[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (cap[dev] < bytes) {
+    if (buf[dev]) cudaFree(buf[dev]);
+    buf[dev] = nullptr;
+    cap[dev] = 0;
+    if (cudaMalloc(&buf[dev], bytes) != cudaSuccess) return nullptr;
+    cap[dev] = bytes;
+  }
+  return buf[dev];
+}
+
 extern "C" int iic_bn_stats(const void* y, int dtype, long long M, int C, const float* gamma, const float* beta,
                             float eps, float momentum, float* running_mean, float* running_var, int use_running,
                             double* stats_ws, float* scale_shift, float* mean_invstd, void* stream) {
   IIC_REQUIRE(y && gamma && beta && stats_ws && scale_shift && mean_invstd && M > 0, IIC_ERR_BAD_ARG,
               "iic_bn_stats: bad arguments");
-  IIC_REQUIRE(C % 8 == 0 && C <= 2048, IIC_ERR_UNSUPPORTED, "iic_bn_stats: C=%d must be a multiple of 8, <= 2048", C);
+  IIC_REQUIRE(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, IIC_ERR_UNSUPPORTED,
+              "iic_bn_stats: C=%d must be 8 * (a divisor of 256)", C);
   IIC_REQUIRE(!use_running || (running_mean && running_var), IIC_ERR_BAD_ARG,
               "iic_bn_stats: eval mode needs running statistics");
   cudaStream_t st = (cudaStream_t)stream;
   if (!use_running) {
-    IIC_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * C, st));
-    const int tpr = C / 8 < 256 ? C / 8 : 256;
-    const int rpi = 256 / tpr;
-    long long blocks = (M + rpi - 1) / rpi;
-    const long long cap = (long long)device_sm_count() * 8;
-    if (blocks > cap) blocks = cap;
-    DISPATCH_T(dtype, bn_reduce_kernel<T, false><<<(int)blocks, 256, 0, st>>>((const T*)y, nullptr, nullptr, nullptr, M, C, stats_ws);)
+    const int blocks = bn_reduce_blocks(M, C);
+    float* partial = bn_partial_scratch((size_t)device_sm_count() * 4 * 2 * 2048 * sizeof(float));
+    IIC_REQUIRE(partial != nullptr, IIC_ERR_CUDA, "iic_bn_stats: scratch allocation failed");
+    DISPATCH_T(dtype, bn_reduce_kernel<T, false><<<blocks, 256, 0, st>>>((const T*)y, nullptr, nullptr, nullptr, M, C, partial);)
+    IIC_LAUNCH_CHECK();
+    count_launch();
+    bn_sum_partials_kernel<<<cdiv(2 * C * 32, 256), 256, 0, st>>>(partial, blocks, 2 * C, stats_ws);
     IIC_LAUNCH_CHECK();
     count_launch();
   }
@@ -544,15 +601,15 @@ extern "C" int iic_bn_relu_maxpool_bwd(const void* y, const float* scale_shift, 
 extern "C" int iic_bn_bwd_reduce(const void* g_in, const void* act, const void* y, const float* mean_invstd, int dtype,
                                  long long M, int C, double* sums, void* stream) {
   IIC_REQUIRE(g_in && y && mean_invstd && sums && M > 0, IIC_ERR_BAD_ARG, "iic_bn_bwd_reduce: bad arguments");
-  IIC_REQUIRE(C % 8 == 0 && C <= 2048, IIC_ERR_UNSUPPORTED, "iic_bn_bwd_reduce: C=%d unsupported", C);
+  IIC_REQUIRE(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, IIC_ERR_UNSUPPORTED, "iic_bn_bwd_reduce: C=%d unsupported", C);
   cudaStream_t st = (cudaStream_t)stream;
-  IIC_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
-  const int tpr = C / 8 < 256 ? C / 8 : 256;
-  const int rpi = 256 / tpr;
-  long long blocks = (M + rpi - 1) / rpi;
-  const long long cap = (long long)device_sm_count() * 8;
-  if (blocks > cap) blocks = cap;
-  DISPATCH_T(dtype, bn_reduce_kernel<T, true><<<(int)blocks, 256, 0, st>>>((const T*)y, (const T*)g_in, (const T*)act, mean_invstd, M, C, sums);)
+  const int blocks = bn_reduce_blocks(M, C);
+  float* partial = bn_partial_scratch((size_t)device_sm_count() * 4 * 2 * 2048 * sizeof(float));
+  IIC_REQUIRE(partial != nullptr, IIC_ERR_CUDA, "iic_bn_bwd_reduce: scratch allocation failed");
+  DISPATCH_T(dtype, bn_reduce_kernel<T, true><<<blocks, 256, 0, st>>>((const T*)y, (const T*)g_in, (const T*)act, mean_invstd, M, C, partial);)
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  bn_sum_partials_kernel<<<cdiv(2 * C * 32, 256), 256, 0, st>>>(partial, blocks, 2 * C, sums);
   IIC_LAUNCH_CHECK();
   count_launch();
   return IIC_OK;
@@ -564,7 +621,8 @@ extern "C" int iic_bn_bwd_apply(const void* g_in, const void* act, const void* y
   IIC_REQUIRE(g_in && y && mean_invstd && gamma && sums && dy && M > 0 && C % 8 == 0, IIC_ERR_BAD_ARG,
               "iic_bn_bwd_apply: bad arguments");
   const long long total = M * (C / 8);
-  DISPATCH_T(dtype, bn_bwd_apply_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  const size_t smem = (size_t)3 * C * sizeof(float);
+  DISPATCH_T(dtype, bn_bwd_apply_kernel<T><<<ew_grid(total, 256), 256, smem, (cudaStream_t)stream>>>(
       (const T*)g_in, (const T*)act, (const T*)y, mean_invstd, gamma, sums, (T*)dy, (T*)g_out, dgamma, dbeta,
       accumulate, M, C);)
   IIC_LAUNCH_CHECK();
