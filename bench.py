@@ -286,6 +286,9 @@ def run_ours(args):
 
 
 def main():
+  # keep stdout to the single JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+  if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
   args = parse()
   if args.impl == "reference":
     run_reference(args)

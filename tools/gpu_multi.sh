@@ -9,7 +9,7 @@ for n in $N; do
   echo "bench n=$n rc=$?"; tail -2 gpurun_out/bench_n$n.err | cut -c1-300
   python - <<PY
 import json
-d = json.load(open("gpurun_out/bench_n$n.json"))
+d = json.loads(open("gpurun_out/bench_n$n.json").read().strip().splitlines()[-1])
 print("N=%d pairs/s %.0f ms/step %.1f e2e %.0f conv frac %.3f" % (d["n_gpus"], d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["frac"]))
 PY
 done
