@@ -25,6 +25,14 @@ _SIGS = {
   "iic_last_error": (c_char_p, []),
   "iic_launch_count": (c_longlong, [c_int]),
   "iic_iid_loss": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_double, _P, _P, _P, _P, _P, c_int, _P]),
+  "iic_joint_mi": (c_int, [_P, c_int, c_int, c_float, c_double, c_int, _P, _P, _P]),
+  "iic_seg_kp": (c_int, [c_int]),
+  "iic_seg_prepare": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+  "iic_seg_unprepare": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+  "iic_seg_joint_workspace": (c_longlong, [c_int, c_int, c_int]),
+  "iic_seg_joint": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+  "iic_seg_corr_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
+  "iic_box_filter": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
   "iic_sobel": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
   "iic_nchw_to_nhwc": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
   "iic_nhwc_to_nchw": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P]),
@@ -47,6 +55,10 @@ _SIGS = {
   "iic_avgpool_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
   "iic_heads_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
   "iic_heads_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+  "iic_seg_head_workspace": (c_longlong, [c_int, c_int, c_int, c_int, c_int]),
+  "iic_seg_head_fwd": (c_int, [_P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+  "iic_seg_head_bwd": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
+                               c_int, c_int, _P]),
   "iic_adam_step": (c_int, [POINTER(c_void_p), POINTER(c_longlong), c_int, c_float, c_float, c_float, c_float,
                             c_float, c_int, _P]),
 }

@@ -259,7 +259,7 @@ class TrunkFunction(torch.autograd.Function):
   def backward(ctx, dfeat):
     ectx = ctx.ectx
     sink = GradSink()
-    d = ctx.finisher(dfeat.contiguous().float())
+    d = ctx.finisher(dfeat)
     for rec in reversed(ectx.saved):
       d = _BACKWARD[rec[0]](ectx, sink, rec, d)
     ectx.saved = []

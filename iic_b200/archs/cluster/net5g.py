@@ -44,7 +44,7 @@ class ClusterNet5gTrunk(ResNetTrunk):
       n, h, w, c = a.shape
       assert h == self.avg_pool_sz and w == self.avg_pool_sz, "input_sz does not match the input"
       shape, dt = tuple(a.shape), ctx.dt
-      return K.avgpool(a), (lambda dfeat: K.avgpool_bwd(dfeat, shape, dt))
+      return K.avgpool(a), (lambda dfeat: K.avgpool_bwd(dfeat.contiguous().float(), shape, dt))
 
     return E.run_trunk(self, run, x)
 

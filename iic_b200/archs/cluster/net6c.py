@@ -42,7 +42,7 @@ class ClusterNet6cTrunk(VGGTrunk):
       flat = K.nhwc_to_nchw(a).reshape(n, -1)
 
       def finisher(dfeat):
-        return K.nchw_to_nhwc(dfeat.reshape(n, c, h, w).contiguous(), dt)
+        return K.nchw_to_nhwc(dfeat.float().reshape(n, c, h, w).contiguous(), dt)
 
       return flat, finisher
 

@@ -1,0 +1,2 @@
+from .net10a import *
+from .net10a_twohead import *

@@ -39,9 +39,11 @@ struct IidParams {
   float* dzt;
   float* joint_ws;
   float* joint_out;
+  float* h_out;      // optional [S][k][k]: H = d loss / d (raw joint)   (segmentation losses)
   int n, k, kp, tk, ntiles, groups;
   float lamb, eps;
   int phase;
+  int detached;      // 1: the normaliser carries no gradient (collapsed seg loss, seg IID_losses.py:60)
 };
 
 __device__ __forceinline__ void stage_rows(const float* __restrict__ src, float* dst, int row0, int rows, int n,
@@ -238,15 +240,21 @@ __global__ void __launch_bounds__(IID_THREADS, 1) iid_loss_kernel(IidParams p) {
     p.loss[2 * s] = (float)l_lamb;
     p.loss[2 * s + 1] = (float)l_one;
   }
-  if (p.dz == nullptr && p.dzt == nullptr) return;
+  if (p.dz == nullptr && p.dzt == nullptr && p.h_out == nullptr) return;
   // H = ((G - gp) + (G - gp)^T) / (2 s)  -> bufB (symmetric)
-  const float gpf = (float)gp;
+  const float gpf = p.detached ? 0.f : (float)gp;
   const float hs = (float)(0.5 / ssum);
   for (int e = tid; e < kk; e += IID_THREADS) {
     int a = e / kp, b = e - a * kp;
     bufB[e] = (a < k && b < k) ? (bufA[a * kp + b] + bufA[b * kp + a] - 2.f * gpf) * hs : 0.f;
   }
   __syncthreads();
+  if (p.h_out != nullptr && rank == 0)
+    for (int e = tid; e < k * k; e += IID_THREADS) {
+      int a = e / k, b = e - a * k;
+      p.h_out[(size_t)s * k * k + e] = bufB[a * kp + b];
+    }
+  if (p.dz == nullptr && p.dzt == nullptr) return;
   // ---- 4. gradient sweep over this CTA's rows --------------------------------------------
   float* dz = p.dz ? p.dz + (size_t)s * p.n * k : nullptr;
   float* dzt = p.dzt ? p.dzt + (size_t)s * p.n * k : nullptr;
@@ -274,27 +282,18 @@ __global__ void __launch_bounds__(IID_THREADS, 1) iid_loss_kernel(IidParams p) {
 
 }  // namespace iic
 
-extern "C" int iic_iid_loss(const float* z, const float* zt, int S, int n, int k, float lamb, double eps, float* loss,
-                            float* dz, float* dzt, float* joint_ws, float* joint_out, int phase, void* stream) {
-  using namespace iic;
-  IIC_REQUIRE(z && zt && S > 0 && n > 0 && k > 0, IIC_ERR_BAD_ARG, "iic_iid_loss: bad arguments");
-  IIC_REQUIRE(phase == IIC_PHASE_FUSED || phase == IIC_PHASE_PARTIAL || phase == IIC_PHASE_FINISH, IIC_ERR_BAD_ARG,
-              "iic_iid_loss: bad phase %d", phase);
-  IIC_REQUIRE(phase == IIC_PHASE_FUSED || joint_ws, IIC_ERR_BAD_ARG, "iic_iid_loss: joint_ws required for phase %d",
-              phase);
-  IIC_REQUIRE(phase == IIC_PHASE_PARTIAL || loss, IIC_ERR_BAD_ARG, "iic_iid_loss: loss output required");
-  IidParams p;
-  p.z = z; p.zt = zt; p.loss = loss; p.dz = dz; p.dzt = dzt; p.joint_ws = joint_ws; p.joint_out = joint_out;
+using namespace iic;
+
+static int launch_iid(IidParams p, int S, int n, int k, cudaStream_t st) {
   p.n = n; p.k = k; p.kp = (k + 3) & ~3; p.tk = p.kp / 4; p.ntiles = p.tk * p.tk;
   IIC_REQUIRE(p.ntiles <= IID_MAX_TILES * IID_THREADS, IIC_ERR_UNSUPPORTED,
-              "iic_iid_loss: k=%d exceeds the fused kernel's limit (k <= 156)", k);
+              "iic joint/MI kernel: k=%d exceeds the fused kernel's limit (k <= 156)", k);
   p.groups = p.ntiles >= IID_THREADS ? 1 : IID_THREADS / p.ntiles;
   if (p.groups > IID_ROWS) p.groups = IID_ROWS;
-  p.lamb = lamb; p.eps = (float)eps; p.phase = phase;
   const int kk = p.kp * p.kp;
   const int bsz = kk > p.groups * kk ? kk : p.groups * kk;
   size_t smem = (size_t)(kk + bsz + 2 * IID_ROWS * p.kp + 4 * p.kp + 2) * sizeof(float) + 40 * sizeof(double);
-  IIC_REQUIRE(smem <= 220 * 1024, IIC_ERR_UNSUPPORTED, "iic_iid_loss: k=%d needs %zu B of shared memory", k, smem);
+  IIC_REQUIRE(smem <= 220 * 1024, IIC_ERR_UNSUPPORTED, "iic joint/MI kernel: k=%d needs %zu B of shared memory", k, smem);
   IIC_CUDA(cudaFuncSetAttribute(iid_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int C = 8;
   while (C > 1 && (n + C - 1) / C < 8) C >>= 1;  // tiny batches: fewer CTAs per cluster
@@ -302,7 +301,7 @@ extern "C" int iic_iid_loss(const float* z, const float* zt, int S, int n, int k
   cfg.gridDim = dim3(C, S, 1);
   cfg.blockDim = dim3(IID_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
-  cfg.stream = (cudaStream_t)stream;
+  cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = C;
@@ -313,4 +312,31 @@ extern "C" int iic_iid_loss(const float* z, const float* zt, int S, int n, int k
   IIC_CUDA(cudaLaunchKernelEx(&cfg, iid_loss_kernel, p));
   count_launch();
   return IIC_OK;
+}
+
+extern "C" int iic_iid_loss(const float* z, const float* zt, int S, int n, int k, float lamb, double eps, float* loss,
+                            float* dz, float* dzt, float* joint_ws, float* joint_out, int phase, void* stream) {
+  using namespace iic;
+  IIC_REQUIRE(z && zt && S > 0 && n > 0 && k > 0, IIC_ERR_BAD_ARG, "iic_iid_loss: bad arguments");
+  IIC_REQUIRE(phase == IIC_PHASE_FUSED || phase == IIC_PHASE_PARTIAL || phase == IIC_PHASE_FINISH, IIC_ERR_BAD_ARG,
+              "iic_iid_loss: bad phase %d", phase);
+  IIC_REQUIRE(phase == IIC_PHASE_FUSED || joint_ws, IIC_ERR_BAD_ARG, "iic_iid_loss: joint_ws required for phase %d",
+              phase);
+  IIC_REQUIRE(phase == IIC_PHASE_PARTIAL || loss, IIC_ERR_BAD_ARG, "iic_iid_loss: loss output required");
+  IidParams p = {};
+  p.z = z; p.zt = zt; p.loss = loss; p.dz = dz; p.dzt = dzt; p.joint_ws = joint_ws; p.joint_out = joint_out;
+  p.h_out = nullptr; p.detached = 0;
+  p.lamb = lamb; p.eps = (float)eps; p.phase = phase;
+  return launch_iid(p, S, n, k, (cudaStream_t)stream);
+}
+
+extern "C" int iic_joint_mi(const float* joint, int S, int k, float lamb, double eps, int detached_norm, float* loss,
+                            float* h_out, void* stream) {
+  using namespace iic;
+  IIC_REQUIRE(joint && loss && S > 0 && k > 0, IIC_ERR_BAD_ARG, "iic_joint_mi: bad arguments");
+  IidParams p = {};
+  p.z = nullptr; p.zt = nullptr; p.loss = loss; p.dz = nullptr; p.dzt = nullptr;
+  p.joint_ws = const_cast<float*>(joint); p.joint_out = nullptr; p.h_out = h_out; p.detached = detached_norm ? 1 : 0;
+  p.lamb = lamb; p.eps = (float)eps; p.phase = IIC_PHASE_FINISH;
+  return launch_iid(p, S, 0, k, (cudaStream_t)stream);
 }

@@ -99,6 +99,67 @@ def iid_loss(z, zt, lamb, eps, want_grad, phase=_lib.PHASE_FUSED, joint_ws=None,
   return loss, dz, dzt, jout
 
 
+def joint_mi(joint, lamb, eps, detached, want_h):
+  """joint [S,k,k] raw -> (loss [S,2], H [S,k,k] | None)"""
+  S, k, _ = joint.shape
+  loss = torch.empty((S, 2), device=joint.device, dtype=torch.float32)
+  H = torch.empty_like(joint) if want_h else None
+  check(_lib.lib().iic_joint_mi(_p(joint), S, k, float(lamb), float(eps), int(bool(detached)), _p(loss), _p(H),
+                                _stream()), "iic_joint_mi")
+  return loss, H
+
+
+# ---- segmentation objective -------------------------------------------------------------------
+def seg_kp(k):
+  kp = int(_lib.lib().iic_seg_kp(int(k)))
+  assert kp > 0, "segmentation losses support k <= 48"
+  return kp
+
+
+def seg_prepare(x1, x2, theta, mask):
+  n, k, h, w = x1.shape
+  kp = seg_kp(k)
+  x1m = torch.empty((n, h, w, kp), device=x1.device, dtype=torch.float32)
+  x2m = torch.empty_like(x1m)
+  check(_lib.lib().iic_seg_prepare(_p(x1), _p(x2), _p(theta), _p(mask), _p(x1m), _p(x2m), n, k, h, w, _stream()),
+        "iic_seg_prepare")
+  return x1m, x2m
+
+
+def seg_unprepare(dx1m, dx2m, theta, mask, k):
+  n, h, w, _ = dx1m.shape
+  dx1 = torch.empty((n, k, h, w), device=dx1m.device, dtype=torch.float32)
+  dx2 = torch.empty_like(dx1)
+  check(_lib.lib().iic_seg_unprepare(_p(dx1m), _p(dx2m), _p(theta), _p(mask), _p(dx1), _p(dx2), n, k, h, w, _stream()),
+        "iic_seg_unprepare")
+  return dx1, dx2
+
+
+def seg_joint(x1m, x2m, k, T):
+  n, h, w, _ = x1m.shape
+  V = 2 * T + 1
+  nbytes = int(_lib.lib().iic_seg_joint_workspace(n, k, T))
+  ws = torch.empty(max(nbytes // 4, 1), device=x1m.device, dtype=torch.float32)
+  joint = torch.empty((V * V, k, k), device=x1m.device, dtype=torch.float32)
+  check(_lib.lib().iic_seg_joint(_p(x1m), _p(x2m), _p(joint), _p(ws), n, k, h, w, T, _stream()), "iic_seg_joint")
+  return joint
+
+
+def seg_corr_bwd(inp, H, k, T, sgn, scale):
+  n, h, w, _ = inp.shape
+  out = torch.empty_like(inp)
+  check(_lib.lib().iic_seg_corr_bwd(_p(inp), _p(H), _p(out), n, k, h, w, T, sgn, float(scale), _stream()),
+        "iic_seg_corr_bwd")
+  return out
+
+
+def box_filter(x, k, T):
+  n, h, w, _ = x.shape
+  tmp, out = torch.empty_like(x), torch.empty_like(x)
+  check(_lib.lib().iic_box_filter(_p(x), _p(tmp), _p(out), n, k, h, w, T, _stream()), "iic_box_filter")
+  return out
+
+
 def sobel(imgs, include_rgb, using_ir):
   n, c, h, w = imgs.shape
   cout = (3 if include_rgb else 0) + 2 + (1 if using_ir else 0)
@@ -267,6 +328,37 @@ def heads_bwd(feat, w, z, dz, S, k, want_dfeat):
   check(_lib.lib().iic_heads_bwd(_p(feat), _p(w), _p(z), _p(dz), _p(dlog), _p(dw), _p(db), _p(dfeat), n, F, S, k,
                                  _stream()), "iic_heads_bwd")
   return dw, db, dfeat
+
+
+# ---- segmentation sub-head --------------------------------------------------------------------
+def seg_head_fwd(feat, w, H, W):
+  """feat NHWC [n,hf,wf,C]; w [k,C] fp32 -> (out NCHW [n,k,H,W] fp32, zlow)"""
+  n, hf, wf, C = feat.shape
+  k = w.shape[0]
+  dev = feat.device
+  logits = torch.empty((n * hf * wf, k), device=dev, dtype=torch.float32)
+  zlow = torch.empty((n, hf + 2, wf + 2, k), device=dev, dtype=torch.float32)
+  out = torch.empty((n, k, H, W), device=dev, dtype=torch.float32)
+  check(_lib.lib().iic_seg_head_fwd(_p(feat), iic_dtype(feat), _p(w), _p(logits), _p(zlow), _p(out), n, hf, wf, C, k,
+                                    H, W, _stream()), "iic_seg_head_fwd")
+  return out, zlow
+
+
+def seg_head_bwd(feat, w, zlow, dout, dfeat, accumulate):
+  """Returns dw [k,C]; writes (or accumulates) the feature gradient into dfeat (same dtype as feat)."""
+  n, hf, wf, C = feat.shape
+  k = w.shape[0]
+  H, W = dout.shape[2], dout.shape[3]
+  dev = feat.device
+  dzlow = torch.empty_like(zlow)
+  dlog = torch.empty((n * hf * wf, k), device=dev, dtype=torch.float32)
+  dw = torch.empty_like(w)
+  nbytes = int(_lib.lib().iic_seg_head_workspace(n, hf, wf, C, k))
+  ws = torch.empty(max(nbytes // 4, 1), device=dev, dtype=torch.float32)
+  check(_lib.lib().iic_seg_head_bwd(_p(feat), iic_dtype(feat), _p(w), _p(zlow), _p(dout), _p(dzlow), _p(dlog), _p(dw),
+                                    _p(ws), _p(dfeat), int(bool(accumulate)), n, hf, wf, C, k, H, W, _stream()),
+        "iic_seg_head_bwd")
+  return dw
 
 
 # ---- optimiser ------------------------------------------------------------------------------

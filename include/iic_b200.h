@@ -64,6 +64,39 @@ int iic_iid_loss(const float* z, const float* zt, int S, int n, int k, float lam
                  float* loss, float* dz, float* dzt, float* joint_ws, float* joint_out, int phase,
                  void* stream);
 
+/* MI + analytic gradient from given (already reduced) joint matrices: the FINISH half of iic_iid_loss
+ * without rows.  joint [S][k][k] raw (un-normalised) -> loss [S][2]; h_out (optional) [S][k][k] =
+ * d loss / d joint.  detached_norm != 0: the normaliser carries no gradient (collapsed segmentation
+ * loss, code/utils/segmentation/IID_losses.py:60).  Used with S = (2T+1)^2 for the uncollapsed loss. */
+int iic_joint_mi(const float* joint, int S, int k, float lamb, double eps, int detached_norm, float* loss,
+                 float* h_out, void* stream);
+
+/* ---- a9-a11: segmentation objective -- code/utils/segmentation/IID_losses.py:14-159 and
+ *      perform_affine_tf, code/utils/segmentation/transforms.py:131-143.
+ * Pixel-major work layout: [n][h][w][KP] fp32 with KP = iic_seg_kp(k) (k rounded up to 4/8/16/32/48,
+ * zero padded).
+ *   iic_seg_prepare   x1m = x1*mask ; x2m = grid_sample(x2, affine_grid(theta))*mask
+ *                     (bilinear, zeros padding, align_corners=True = torch-0.4.1 semantics);
+ *                     x1,x2 NCHW (n,k,h,w); theta (n,2,3); mask (n,h,w).
+ *   iic_seg_joint     joint[(2T+1)^2][k][k] : A[u][v][c][c'] = sum x1m[n,y+u-T,x+v-T,c]*x2m[n,y,x,c']
+ *                     (what F.conv2d(x1^T, weight=x2^T, padding=T) evaluates, :53/:125); T = 0 gives
+ *                     the plain k x k outer-product sum.  workspace: iic_seg_joint_workspace bytes.
+ *   iic_seg_corr_bwd  out[n,Y,X,c] = scale * sum_{u,v,c'} H[u][v][c][c'] * in[n,Y-sgn(u-T),X-sgn(v-T),c']
+ *                     (sgn=+1, in=x2m -> d x1m ; sgn=-1, in=x1m -> d x2m ; H symmetric in c,c')
+ *   iic_seg_unprepare dx1 = d x1m*mask, dx2 = bilinear adjoint of d x2m*mask, back to NCHW
+ *   iic_box_filter    zero-padded (2T+1)^2 box sum (collapsed loss via SURVEY.md S8 a10 identity) */
+int iic_seg_kp(int k);
+int iic_seg_prepare(const float* x1, const float* x2, const float* theta, const float* mask, float* x1m, float* x2m,
+                    int n, int k, int h, int w, void* stream);
+int iic_seg_unprepare(const float* dx1m, const float* dx2m, const float* theta, const float* mask, float* dx1,
+                      float* dx2, int n, int k, int h, int w, void* stream);
+long long iic_seg_joint_workspace(int n, int k, int T);
+int iic_seg_joint(const float* x1m, const float* x2m, float* joint, void* workspace, int n, int k, int h, int w,
+                  int T, void* stream);
+int iic_seg_corr_bwd(const float* in, const float* H, float* out, int n, int k, int h, int w, int T, int sgn,
+                     float scale, void* stream);
+int iic_box_filter(const float* in, float* tmp, float* out, int n, int k, int h, int w, int T, void* stream);
+
 /* ---- a1: sobel_process -- code/utils/cluster/transforms.py:47-96.
  * imgs NCHW fp32 (n, c_in, h, w) -> out NCHW fp32 (n, c_out, h, w); channel rules of
  * :50-66,:84-94 selected by include_rgb / using_ir. */
@@ -161,6 +194,21 @@ int iic_heads_fwd(const float* feat, const float* w, const float* b, float* logi
  * (overwritten; may be NULL). */
 int iic_heads_bwd(const float* feat, const float* w, const float* z, const float* dz, float* dlogits_ws,
                   float* dw, float* db, float* dfeat, int n, int F, int S, int k, void* stream);
+
+/* ---- a6: segmentation sub-heads -- code/archs/segmentation/net10a.py:34-59:
+ *      Conv2d(C -> k, 1x1, padding=1, bias=False) -> Softmax2d -> F.interpolate(size=(H,W), bilinear,
+ *      align_corners=False), one sub-head per call.
+ * feat [n][hf][wf][C] NHWC (`dtype`); w [k][C] fp32; logits_ws [n*hf*wf][k]; zlow [n][hf+2][wf+2][k]
+ * (saved for backward); out NCHW fp32 (n,k,H,W).
+ * backward: dout NCHW (n,k,H,W) -> dw [k][C] (overwritten), dfeat [n][hf][wf][C] (`dtype`, overwritten or
+ * accumulated; may be NULL).  dzlow_ws [n][hf+2][wf+2][k], dlogits_ws [n*hf*wf][k], dw_workspace of
+ * iic_seg_head_workspace() bytes. */
+long long iic_seg_head_workspace(int n, int hf, int wf, int C, int k);
+int iic_seg_head_fwd(const void* feat, int dtype, const float* w, float* logits_ws, float* zlow, float* out, int n,
+                     int hf, int wf, int C, int k, int H, int W, void* stream);
+int iic_seg_head_bwd(const void* feat, int dtype, const float* w, const float* zlow, const float* dout,
+                     float* dzlow_ws, float* dlogits_ws, float* dw, void* dw_workspace, void* dfeat,
+                     int accumulate_dfeat, int n, int hf, int wf, int C, int k, int H, int W, void* stream);
 
 /* ---- a12: torch.optim.Adam step (utils/cluster/general.py:8-9; defaults of
  *      cluster_sobel_twohead.py:184): one launch over a list of tensors.
