@@ -10,7 +10,7 @@ if [ "${NCU_LIST:-1}" = "1" ]; then
   echo "ncu list rc=$?"; wc -l gpurun_out/launches.csv
 fi
 if [ "${NCU_FULL:-0}" = "1" ]; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s ${NCU_SKIP:-150} -c 3 -o gpurun_out/prof_conv \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc2_kernel -s ${NCU_SKIP:-150} -c ${NCU_COUNT:-4} -o gpurun_out/prof_conv \
      python bench.py --steps 1 --warmup 1 --pairs-per-gpu ${NCU_PAIRS:-176} --no-cpu-baseline --no-roofline > gpurun_out/ncu_full.log 2>&1
   echo "ncu full rc=$?"
 fi
