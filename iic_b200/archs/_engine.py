@@ -101,10 +101,22 @@ def initialize_weights(net, mode):
 class _Ctx(object):
   """Per-forward record of what backward needs."""
 
-  def __init__(self, dt, training, need_grad):
+  def __init__(self, dt, training, need_grad, groups=1):
     self.dt, self.training, self.need_grad = dt, training, need_grad
+    # groups > 1: the batch is the concatenation of `groups` views (x, x_tf) pushed through the trunk in
+    # ONE pass; BatchNorm statistics stay per view, exactly as in the reference's two separate forward
+    # calls (cluster_sobel_twohead.py:320-321), everything else sees one batch of groups*n images.
+    self.groups = groups
     self.saved = []
     self.wcache = {}
+
+  def split(self, t):
+    if t is None:
+      return [None] * self.groups
+    if self.groups == 1:
+      return [t]
+    n = t.shape[0] // self.groups
+    return [t[i * n:(i + 1) * n] for i in range(self.groups)]
 
   def packed(self, conv, kind):
     key = (id(conv), kind)
@@ -114,14 +126,41 @@ class _Ctx(object):
 
 
 def _bn_stats(ctx, bn, y):
+  """Per-view batch statistics -> ([scale_shift per view], [mean_invstd per view])."""
   use_running = (not ctx.training) and bn.track_running_stats
-  rm = bn.running_mean if bn.track_running_stats else None
-  rv = bn.running_var if bn.track_running_stats else None
-  if ctx.training and bn.track_running_stats:
-    bn.num_batches_tracked += 1
   update = ctx.training and bn.track_running_stats
-  return K.bn_stats(y, bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum, rm if (update or use_running) else None,
-                    rv if (update or use_running) else None, use_running)
+  rm = bn.running_mean if (update or use_running) else None
+  rv = bn.running_var if (update or use_running) else None
+  sss, mis = [], []
+  for yg in ctx.split(y):  # running statistics are updated view by view, in call order
+    if update:
+      bn.num_batches_tracked += 1
+    ss, mi = K.bn_stats(yg, bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum, rm, rv, use_running)
+    sss.append(ss)
+    mis.append(mi)
+  return sss, mis
+
+
+def _bn_apply(ctx, y, ss, relu, res=None, rss=None):
+  out = torch.empty_like(y)
+  for yg, og, sg, rg, rsg in zip(ctx.split(y), ctx.split(out), ss, ctx.split(res), rss if rss is not None else [None] * ctx.groups):
+    K.bn_apply(yg, sg, relu, res=rg, rss=rsg, out=og)
+  return out
+
+
+def _bn_relu_maxpool(ctx, y, ss, pad):
+  shape = K.pooled_shape(y, pad)
+  out = torch.empty(shape, device=y.device, dtype=y.dtype)
+  for yg, og, sg in zip(ctx.split(y), ctx.split(out), ss):
+    K.bn_relu_maxpool(yg, sg, pad, out=og)
+  return out
+
+
+def _bn_relu_maxpool_bwd(ctx, y, ss, dpool, pad):
+  g = torch.empty_like(y)
+  for yg, gg, sg, dg in zip(ctx.split(y), ctx.split(g), ss, ctx.split(dpool)):
+    K.bn_relu_maxpool_bwd(yg, sg, dg, pad, out=gg)
+  return g
 
 
 class GradSink(object):
@@ -144,7 +183,13 @@ def _bn_backward(ctx, sink, bn, g_in, act, y, mi, want_g_out):
   dg, acc1 = sink.buf(bn.weight)
   db, acc2 = sink.buf(bn.bias)
   assert acc1 == acc2
-  return K.bn_bwd(g_in, act, y, mi, bn.weight.detach(), dg, db, acc1, want_g_out)
+  dy = torch.empty_like(y)
+  g_out = torch.empty_like(y) if want_g_out else None
+  acc = acc1
+  for gg, ag, yg, mg, dyg, gog in zip(ctx.split(g_in), ctx.split(act), ctx.split(y), mi, ctx.split(dy), ctx.split(g_out)):
+    K.bn_bwd(gg, ag, yg, mg, bn.weight.detach(), dg, db, acc, want_g_out, dy=dyg, g_out=gog)
+    acc = True  # later views add to the same dgamma / dbeta
+  return dy, g_out
 
 
 def _conv_wgrad(ctx, sink, conv, x, dy, g):
@@ -158,7 +203,7 @@ def stem_forward(ctx, conv, bn, x_nchw, pool_pad):
   g = conv.geom(n, h, w)
   y = K.stem_fprop(x_nchw, conv.weight.detach(), g, ctx.dt)
   ss, mi = _bn_stats(ctx, bn, y)
-  out = K.bn_relu_maxpool(y, ss, pool_pad) if pool_pad is not None else K.bn_apply(y, ss, relu=True)
+  out = _bn_relu_maxpool(ctx, y, ss, pool_pad) if pool_pad is not None else _bn_apply(ctx, y, ss, True)
   if ctx.need_grad:
     ctx.saved.append(("stem", conv, bn, x_nchw, g, y, ss, mi, out if pool_pad is None else None, pool_pad))
   return out
@@ -167,7 +212,7 @@ def stem_forward(ctx, conv, bn, x_nchw, pool_pad):
 def stem_backward(ctx, sink, rec, d_out):
   _, conv, bn, x_nchw, g, y, ss, mi, act, pool_pad = rec
   if pool_pad is not None:
-    gmask = K.bn_relu_maxpool_bwd(y, ss, d_out, pool_pad)
+    gmask = _bn_relu_maxpool_bwd(ctx, y, ss, d_out, pool_pad)
     dy, _ = _bn_backward(ctx, sink, bn, gmask, None, y, mi, False)
   else:
     dy, _ = _bn_backward(ctx, sink, bn, d_out, act, y, mi, False)
@@ -182,7 +227,7 @@ def convbn_forward(ctx, conv, bn, x, pool_pad):
   g = conv.geom(n, h, w)
   y = K.conv_fprop(x, ctx.packed(conv, 0), g, ctx.dt)
   ss, mi = _bn_stats(ctx, bn, y)
-  out = K.bn_relu_maxpool(y, ss, pool_pad) if pool_pad is not None else K.bn_apply(y, ss, relu=True)
+  out = _bn_relu_maxpool(ctx, y, ss, pool_pad) if pool_pad is not None else _bn_apply(ctx, y, ss, True)
   if ctx.need_grad:
     ctx.saved.append(("convbn", conv, bn, x, g, y, ss, mi, out if pool_pad is None else None, pool_pad))
   return out
@@ -191,7 +236,7 @@ def convbn_forward(ctx, conv, bn, x, pool_pad):
 def convbn_backward(ctx, sink, rec, d_out):
   _, conv, bn, x, g, y, ss, mi, act, pool_pad = rec
   if pool_pad is not None:
-    gmask = K.bn_relu_maxpool_bwd(y, ss, d_out, pool_pad)
+    gmask = _bn_relu_maxpool_bwd(ctx, y, ss, d_out, pool_pad)
     dy, _ = _bn_backward(ctx, sink, bn, gmask, None, y, mi, False)
   else:
     dy, _ = _bn_backward(ctx, sink, bn, d_out, act, y, mi, False)
@@ -205,7 +250,7 @@ def block_forward(ctx, blk, x):
   g1 = blk.conv1.geom(n, h, w)
   y1 = K.conv_fprop(x, ctx.packed(blk.conv1, 0), g1, ctx.dt)
   ss1, mi1 = _bn_stats(ctx, blk.bn1, y1)
-  a1 = K.bn_apply(y1, ss1, relu=True)
+  a1 = _bn_apply(ctx, y1, ss1, True)
   g2 = blk.conv2.geom(n, g1.oh, g1.ow)
   y2 = K.conv_fprop(a1, ctx.packed(blk.conv2, 0), g2, ctx.dt)
   ss2, mi2 = _bn_stats(ctx, blk.bn2, y2)
@@ -214,10 +259,10 @@ def block_forward(ctx, blk, x):
     gd = dconv.geom(n, h, w)
     yd = K.conv_fprop(x, ctx.packed(dconv, 0), gd, ctx.dt)
     ssd, mid = _bn_stats(ctx, dbn, yd)
-    out = K.bn_apply(y2, ss2, relu=True, res=yd, rss=ssd)
+    out = _bn_apply(ctx, y2, ss2, True, res=yd, rss=ssd)
   else:
     gd = yd = mid = None
-    out = K.bn_apply(y2, ss2, relu=True, res=x)
+    out = _bn_apply(ctx, y2, ss2, True, res=x)
   if ctx.need_grad:
     ctx.saved.append(("block", blk, x, g1, y1, mi1, a1, g2, y2, mi2, gd, yd, mid, out))
   return out
@@ -249,8 +294,8 @@ class TrunkFunction(torch.autograd.Function):
   NHWC activation."""
 
   @staticmethod
-  def forward(ctx, trunk, run, need_grad, x, *params):
-    ectx = _Ctx(_PRECISIONS[trunk.precision], trunk.training, need_grad)
+  def forward(ctx, trunk, run, need_grad, groups, x, *params):
+    ectx = _Ctx(_PRECISIONS[trunk.precision], trunk.training, need_grad, groups)
     feat, finisher = run(ectx, x)
     ctx.ectx, ctx.finisher, ctx.params = ectx, finisher, params
     return feat
@@ -265,10 +310,10 @@ class TrunkFunction(torch.autograd.Function):
     ectx.saved = []
     ectx.wcache = {}
     grads = tuple(sink.get(p) for p in ctx.params)
-    return (None, None, None, None) + grads
+    return (None, None, None, None, None) + grads
 
 
-def run_trunk(trunk, run, x):
+def run_trunk(trunk, run, x, groups=1):
   if not x.is_cuda:
     raise RuntimeError("iic_b200 networks run on CUDA tensors only (no CPU fallback; the CPU restatement in "
                        "oracle/ is a test checker)")
@@ -276,7 +321,8 @@ def run_trunk(trunk, run, x):
   params = [p for p in trunk.parameters()]
   # (inside Function.forward grad mode is off and needs_input_grad ignores torch.no_grad())
   need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-  return TrunkFunction.apply(trunk, run, need_grad, x.detach().float().contiguous(), *params)
+  assert x.shape[0] % groups == 0
+  return TrunkFunction.apply(trunk, run, need_grad, groups, x.detach().float().contiguous(), *params)
 
 
 # ---------------------------------------------------------------------------------------------

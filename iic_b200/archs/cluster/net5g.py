@@ -30,7 +30,7 @@ class ClusterNet5gTrunk(ResNetTrunk):
       avg_pool_sz = 3
     self.avg_pool_sz = avg_pool_sz  # nn.AvgPool2d(avg_pool_sz, stride=1) on an avg_pool_sz^2 map
 
-  def forward(self, x, penultimate_features=False):
+  def forward(self, x, penultimate_features=False, groups=1):
     def run(ctx, xin):
       a = E.stem_forward(ctx, self.conv1, self.bn1, xin, pool_pad=1)  # conv1,bn1,relu,maxpool(2,2,1)
       for layer in (self.layer1, self.layer2, self.layer3):
@@ -46,7 +46,7 @@ class ClusterNet5gTrunk(ResNetTrunk):
       shape, dt = tuple(a.shape), ctx.dt
       return K.avgpool(a), (lambda dfeat: K.avgpool_bwd(dfeat.contiguous().float(), shape, dt))
 
-    return E.run_trunk(self, run, x)
+    return E.run_trunk(self, run, x, groups)
 
 
 class ClusterNet5gHead(E.SubHeads):

@@ -51,3 +51,12 @@ class ClusterNet5gTwoHead(ResNet):
     """Same as forward but returns the [S, bn, k] tensor (no unbind) for IID_loss_subheads."""
     feat = self.trunk(x)
     return (self.head_A if head == "A" else self.head_B).forward_stacked(feat)
+
+  def forward_stacked_pair(self, x, x_tf, head="B"):
+    """Both views in ONE pass through the trunk (BatchNorm statistics per view, identical to two
+    forward calls); returns the two [S, bn, k] softmax stacks."""
+    import torch
+    n = x.shape[0]
+    feat = self.trunk(torch.cat([x, x_tf], dim=0), groups=2)
+    z = (self.head_A if head == "A" else self.head_B).forward_stacked(feat)  # [S, 2n, k]
+    return z[:, :n], z[:, n:]

@@ -33,7 +33,7 @@ class ClusterNet6cTrunk(VGGTrunk):
     self.in_channels = config.in_channels if hasattr(config, 'in_channels') else 3
     self.features = self._make_layers()
 
-  def forward(self, x):
+  def forward(self, x, groups=1):
     def run(ctx, xin):
       a = run_vgg_features(self, ctx, xin)
       n, h, w, c = a.shape
@@ -46,7 +46,7 @@ class ClusterNet6cTrunk(VGGTrunk):
 
       return flat, finisher
 
-    return E.run_trunk(self, run, x)
+    return E.run_trunk(self, run, x, groups)
 
 
 def _feat_size(config, cfg):

@@ -53,7 +53,55 @@ __global__ void __launch_bounds__(256) stem_fprop_kernel(const float* __restrict
   }
 }
 
-constexpr int SW_PC = 32;  // pixels per chunk
+// cout == 64 fast path: one thread per output pixel (a warp reads 32 consecutive pixels of the NCHW input:
+// coalesced), all 64 output channels in registers, weights broadcast from shared memory
+// (1 LDS.128 per 4 FMA, FMA-bound), one 128 B (bf16) / 256 B (fp32) contiguous store per thread.
+template <typename T>
+__global__ void __launch_bounds__(128) stem_fprop64_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           T* __restrict__ y, iic_conv_geom g) {
+  extern __shared__ __align__(16) float ws[];  // [K][64]
+  const int K = g.cin * g.kh * g.kw;
+  for (int i = threadIdx.x; i < K * 64; i += blockDim.x) ws[i] = w[(long long)(i & 63) * K + (i >> 6)];
+  __syncthreads();
+  const long long P = (long long)g.n * g.oh * g.ow;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(p % g.ow);
+    const int oy = (int)((p / g.ow) % g.oh);
+    const int n = (int)(p / ((long long)g.ow * g.oh));
+    float acc[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+    int k = 0;
+    for (int ci = 0; ci < g.cin; ++ci) {
+      const float* xc = x + ((long long)n * g.cin + ci) * g.h * g.w;
+      for (int a = 0; a < g.kh; ++a) {
+        const int iy = oy * g.stride - g.pad + a * g.dil;
+        for (int b = 0; b < g.kw; ++b, ++k) {
+          const int ix = ox * g.stride - g.pad + b * g.dil;
+          const float v = (iy >= 0 && iy < g.h && ix >= 0 && ix < g.w) ? __ldg(xc + (long long)iy * g.w + ix) : 0.f;
+          const float4* wk = reinterpret_cast<const float4*>(ws + k * 64);
+#pragma unroll
+          for (int c4 = 0; c4 < 16; ++c4) {
+            const float4 w4 = wk[c4];
+            acc[c4 * 4] = fmaf(v, w4.x, acc[c4 * 4]);
+            acc[c4 * 4 + 1] = fmaf(v, w4.y, acc[c4 * 4 + 1]);
+            acc[c4 * 4 + 2] = fmaf(v, w4.z, acc[c4 * 4 + 2]);
+            acc[c4 * 4 + 3] = fmaf(v, w4.w, acc[c4 * 4 + 3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = acc[q * 8 + e];
+      store8(y + p * 64 + q * 8, f);
+    }
+  }
+}
+
+constexpr int SW_PC = 64;  // pixels per chunk
 
 template <typename T>
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy,
@@ -63,36 +111,58 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
   const int K = g.cin * g.kh * g.kw, cout = g.cout;
   float* dys = sm;                   // [SW_PC][cout]
   float* pat = dys + SW_PC * cout;   // [SW_PC][Kp]
-  float* red = pat + SW_PC * Kp;     // [G][cout*Kp] (reused at the end)
-  const long long P = (long long)g.n * g.oh * g.ow;
+  float* red = pat + SW_PC * Kp;     // [G][cout*Kp] (used at the end)
+  int* pixb = reinterpret_cast<int*>(red + (size_t)G * cout * Kp);  // [SW_PC][3]: image base offset, iy0, ix0
+  int* ktab = pixb + SW_PC * 3;                                     // [Kp][3]: plane offset, a*dil, b*dil
+  const int P = g.n * g.oh * g.ow;  // (host guarantees < 2^31)
   const int tid = threadIdx.x;
   const int my_g = tid / T_tiles, my_t = tid % T_tiles;
   const bool active = my_g < G;
   const int tc = my_t / tkk, tk = my_t % tkk;
+  const int hw = g.h * g.w;
+  for (int k = tid; k < Kp; k += 256) {
+    const int b = k % g.kw, a = (k / g.kw) % g.kh, ci = k / (g.kw * g.kh);
+    ktab[k * 3] = k < K ? ci * hw : -1;
+    ktab[k * 3 + 1] = a * g.dil;
+    ktab[k * 3 + 2] = b * g.dil;
+  }
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  const long long nchunks = (P + SW_PC - 1) / SW_PC;
-  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-    const long long p0 = ch * SW_PC;
+  const int nchunks = (P + SW_PC - 1) / SW_PC;
+  for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const int p0 = ch * SW_PC;
     __syncthreads();
-    for (int i = tid; i < SW_PC * cout; i += 256) {
-      const long long p = p0 + i / cout;
-      dys[i] = p < P ? to_f(dy[p * cout + (i % cout)]) : 0.f;
+    if (tid < SW_PC) {
+      const int p = p0 + tid;
+      if (p < P) {
+        const int ox = p % g.ow;
+        const int q = p / g.ow;
+        const int oy = q % g.oh;
+        const int n = q / g.oh;
+        pixb[tid * 3] = n * g.cin * hw;
+        pixb[tid * 3 + 1] = oy * g.stride - g.pad;
+        pixb[tid * 3 + 2] = ox * g.stride - g.pad;
+      } else {
+        pixb[tid * 3] = -1;
+      }
     }
+    // dy chunk: contiguous [SW_PC][cout] rows
+    {
+      const long long base = (long long)p0 * cout;
+      const int count = (P - p0 < SW_PC ? P - p0 : SW_PC) * cout;
+      for (int i = tid; i < SW_PC * cout; i += 256) dys[i] = i < count ? to_f(dy[base + i]) : 0.f;
+    }
+    __syncthreads();
     for (int i = tid; i < SW_PC * Kp; i += 256) {
       const int r = i % SW_PC, k = i / SW_PC;  // consecutive threads -> consecutive pixels (coalesced in NCHW)
-      const long long p = p0 + r;
       float v = 0.f;
-      if (p < P && k < K) {
-        const int ox = (int)(p % g.ow);
-        const int oy = (int)((p / g.ow) % g.oh);
-        const int n = (int)(p / ((long long)g.ow * g.oh));
-        const int b = k % g.kw, a = (k / g.kw) % g.kh, ci = k / (g.kw * g.kh);
-        const int iy = oy * g.stride - g.pad + a * g.dil, ix = ox * g.stride - g.pad + b * g.dil;
-        if (iy >= 0 && iy < g.h && ix >= 0 && ix < g.w) v = __ldg(x + (((long long)n * g.cin + ci) * g.h + iy) * g.w + ix);
+      const int pb = pixb[r * 3], kb = ktab[k * 3];
+      if (pb >= 0 && kb >= 0) {
+        const int iy = pixb[r * 3 + 1] + ktab[k * 3 + 1], ix = pixb[r * 3 + 2] + ktab[k * 3 + 2];
+        if ((unsigned)iy < (unsigned)g.h && (unsigned)ix < (unsigned)g.w) v = __ldg(x + (long long)pb + kb + iy * g.w + ix);
       }
       pat[r * Kp + k] = v;
     }
@@ -163,6 +233,18 @@ extern "C" int iic_stem_fprop(const float* x_nchw, const float* w_oihw, void* y,
   const long long cap = (long long)device_sm_count() * 8;
   if (blocks > cap) blocks = cap;
   cudaStream_t st = (cudaStream_t)stream;
+  if (g->cout == 64 && (dtype == IIC_F32 || dtype == IIC_BF16)) {
+    long long b64 = (P + 127) / 128;
+    const long long cap64 = (long long)device_sm_count() * 16;
+    if (b64 > cap64) b64 = cap64;
+    if (dtype == IIC_F32)
+      stem_fprop64_kernel<float><<<(int)b64, 128, smem, st>>>(x_nchw, w_oihw, (float*)y, *g);
+    else
+      stem_fprop64_kernel<__nv_bfloat16><<<(int)b64, 128, smem, st>>>(x_nchw, w_oihw, (__nv_bfloat16*)y, *g);
+    IIC_LAUNCH_CHECK();
+    count_launch();
+    return IIC_OK;
+  }
   if (dtype == IIC_F32) {
     IIC_CUDA(cudaFuncSetAttribute(stem_fprop_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     stem_fprop_kernel<float><<<(int)blocks, 256, smem, st>>>(x_nchw, w_oihw, (float*)y, *g);
@@ -192,12 +274,15 @@ extern "C" int iic_stem_wgrad(const float* x_nchw, const void* dy, float* grad_o
   const long long per_block = (long long)g->cout * K * sizeof(float);
   long long nblk = (long long)device_sm_count() * 4;
   const long long P = (long long)g->n * g->oh * g->ow;
+  IIC_REQUIRE(P < (1ll << 31) && (long long)g->n * g->cin * g->h * g->w < (1ll << 31), IIC_ERR_UNSUPPORTED,
+              "iic_stem_wgrad: more than 2^31 pixels");
   const long long nchunks = (P + SW_PC - 1) / SW_PC;
   if (nblk > nchunks) nblk = nchunks;
   if (nblk > workspace_bytes / per_block) nblk = workspace_bytes / per_block;
   IIC_REQUIRE(nblk >= 1, IIC_ERR_BAD_ARG, "iic_stem_wgrad: workspace too small (%lld B, need >= %lld)", workspace_bytes,
               per_block);
-  const size_t smem = (size_t)(SW_PC * g->cout + SW_PC * Kp + (size_t)G * g->cout * Kp) * sizeof(float);
+  const size_t smem = (size_t)(SW_PC * g->cout + SW_PC * Kp + (size_t)G * g->cout * Kp) * sizeof(float) +
+                      (size_t)(SW_PC * 3 + Kp * 3) * sizeof(int);
   IIC_REQUIRE(smem <= 200 * 1024, IIC_ERR_UNSUPPORTED, "iic_stem_wgrad: needs %zu B smem", smem);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == IIC_F32) {

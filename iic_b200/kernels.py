@@ -253,34 +253,41 @@ def bn_stats(y, gamma, beta, eps, momentum, running_mean, running_var, use_runni
   return ss, mi
 
 
-def bn_apply(y, ss, relu, res=None, rss=None):
+def bn_apply(y, ss, relu, res=None, rss=None, out=None):
   C = y.shape[-1]
   M = y.numel() // C
-  out = torch.empty_like(y)
+  if out is None:
+    out = torch.empty_like(y)
   check(_lib.lib().iic_bn_apply(_p(y), _p(ss), _p(res), _p(rss), _p(out), iic_dtype(y), M, C, int(bool(relu)),
                                 _stream()), "iic_bn_apply")
   return out
 
 
-def bn_relu_maxpool(y, ss, pad):
+def pooled_shape(y, pad):
+  n, h, w, C = y.shape
+  return (n, (h + 2 * pad - 2) // 2 + 1, (w + 2 * pad - 2) // 2 + 1, C)
+
+
+def bn_relu_maxpool(y, ss, pad, out=None):
   n, h, w, C = y.shape
   oh, ow = (h + 2 * pad - 2) // 2 + 1, (w + 2 * pad - 2) // 2 + 1
-  out = torch.empty((n, oh, ow, C), device=y.device, dtype=y.dtype)
+  if out is None:
+    out = torch.empty((n, oh, ow, C), device=y.device, dtype=y.dtype)
   check(_lib.lib().iic_bn_relu_maxpool(_p(y), _p(ss), _p(out), iic_dtype(y), n, h, w, C, pad, oh, ow, _stream()),
         "iic_bn_relu_maxpool")
   return out
 
 
-def bn_relu_maxpool_bwd(y, ss, dpool, pad):
+def bn_relu_maxpool_bwd(y, ss, dpool, pad, out=None):
   n, h, w, C = y.shape
   _, oh, ow, _ = dpool.shape
-  g = torch.empty_like(y)
+  g = torch.empty_like(y) if out is None else out
   check(_lib.lib().iic_bn_relu_maxpool_bwd(_p(y), _p(ss), _p(dpool), _p(g), iic_dtype(y), n, h, w, C, pad, oh, ow,
                                            _stream()), "iic_bn_relu_maxpool_bwd")
   return g
 
 
-def bn_bwd(g_in, act, y, mi, gamma, dgamma, dbeta, accumulate, want_g_out):
+def bn_bwd(g_in, act, y, mi, gamma, dgamma, dbeta, accumulate, want_g_out, dy=None, g_out=None):
   """Returns (dy, g_masked | None); writes/accumulates dgamma, dbeta."""
   C = y.shape[-1]
   M = y.numel() // C
@@ -288,8 +295,12 @@ def bn_bwd(g_in, act, y, mi, gamma, dgamma, dbeta, accumulate, want_g_out):
   sums = torch.empty(2 * C, device=y.device, dtype=torch.float64)
   check(_lib.lib().iic_bn_bwd_reduce(_p(g_in), _p(act), _p(y), _p(mi), dt, M, C, _p(sums), _stream()),
         "iic_bn_bwd_reduce")
-  dy = torch.empty_like(y)
-  g_out = torch.empty_like(y) if want_g_out else None
+  if dy is None:
+    dy = torch.empty_like(y)
+  if want_g_out and g_out is None:
+    g_out = torch.empty_like(y)
+  if not want_g_out:
+    g_out = None
   check(_lib.lib().iic_bn_bwd_apply(_p(g_in), _p(act), _p(y), _p(mi), _p(gamma), _p(sums), _p(dy), _p(g_out),
                                     _p(dgamma), _p(dbeta), int(bool(accumulate)), dt, M, C, _stream()),
         "iic_bn_bwd_apply")

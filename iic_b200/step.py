@@ -14,7 +14,7 @@ from .utils.cluster.transforms import sobel_process
 
 
 def iic_cluster_step(net, optimiser, imgs, imgs_tf, head="B", lamb=1.0, include_rgb=False, sobel=True,
-                     set_to_none=True):
+                     set_to_none=True, pair_batched=True):
   """Returns (avg_loss, avg_loss_no_lamb) as 0-dim device tensors (no host sync)."""
   if optimiser is not None:
     optimiser.zero_grad(set_to_none=set_to_none)
@@ -27,8 +27,9 @@ def iic_cluster_step(net, optimiser, imgs, imgs_tf, head="B", lamb=1.0, include_
   if sobel:
     imgs = sobel_process(imgs, include_rgb)
     imgs_tf = sobel_process(imgs_tf, include_rgb)
-  stacked = hasattr(net, "forward_stacked")
-  if stacked:
+  if hasattr(net, "forward_stacked_pair") and pair_batched:
+    x_outs, x_tf_outs = net.forward_stacked_pair(imgs, imgs_tf, head=head)
+  elif hasattr(net, "forward_stacked"):
     x_outs = net.forward_stacked(imgs, head=head)
     x_tf_outs = net.forward_stacked(imgs_tf, head=head)
   else:

@@ -224,3 +224,35 @@ def test_bf16_block_matches_rounding_oracle(cin, cout, stride, hw, n):
   assert rel(dx.float().permute(0, 3, 1, 2).cpu(), xo.grad) < 3e-2
   for (pn, p), (_, po) in zip(blk.named_parameters(), oblk.named_parameters()):
     assert rel(sink.get(p).cpu(), po.grad) < 3e-2, pn
+
+
+@pytest.mark.parametrize("arch,cfg", [
+  ("ClusterNet5gTwoHead", dict(in_channels=2, input_sz=32, num_sub_heads=3, output_k_A=20, output_k_B=5, batchnorm_track=True)),
+  ("ClusterNet6cTwoHead", dict(in_channels=1, input_sz=24, num_sub_heads=2, output_k_A=12, output_k_B=4, batchnorm_track=True)),
+])
+def test_pair_batched_pass_equals_two_forward_calls(arch, cfg):
+  """forward_stacked_pair pushes both views through the trunk in one pass with per-view BatchNorm
+  statistics: it must reproduce two separate forward calls (outputs, gradients, running stats)."""
+  import iic_b200.archs as archs
+  from iic_b200.utils.cluster.IID_losses import IID_loss_subheads
+  nets_ = []
+  for _ in range(2):
+    net = archs.__dict__[arch](Namespace(precision="fp32", **cfg))
+    weights.fill_state_dict(net, salt=4)
+    nets_.append(net.cuda().train())
+  x = weights.normal("pair.x", (10, cfg["in_channels"], cfg["input_sz"], cfg["input_sz"])).cuda()
+  xt = x + 0.3 * weights.normal("pair.xt", tuple(x.shape)).cuda()
+  za, zta = nets_[0].forward_stacked(x, head="A"), nets_[0].forward_stacked(xt, head="A")
+  zb, ztb = nets_[1].forward_stacked_pair(x, xt, head="A")
+  assert torch.allclose(za, zb, rtol=0, atol=2e-6) and torch.allclose(zta, ztb, rtol=0, atol=2e-6)
+  IID_loss_subheads(za, zta)[0].mean().backward()
+  IID_loss_subheads(zb, ztb)[0].mean().backward()
+  for (n1, p1), (_, p2) in zip(nets_[0].named_parameters(), nets_[1].named_parameters()):
+    if p1.grad is None:
+      assert p2.grad is None
+      continue
+    assert ((p1.grad - p2.grad).norm() / (p1.grad.norm() + 1e-30)).item() < 2e-3, n1
+  sd1, sd2 = nets_[0].state_dict(), nets_[1].state_dict()
+  for key in sd1:
+    if "running" in key or "num_batches" in key:
+      assert torch.allclose(sd1[key].float(), sd2[key].float(), rtol=1e-5, atol=1e-6), key
