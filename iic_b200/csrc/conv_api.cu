@@ -20,6 +20,8 @@ int tc2_conv_gather_gemm(const __nv_bfloat16* src, int srcH, int srcW, int srcC,
                          const __nv_bfloat16* addend, __nv_bfloat16* out, cudaStream_t st);
 long long tc2_conv_wgrad_workspace(const iic_conv_geom* g);
 int tc2_conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* ws, const iic_conv_geom* g, cudaStream_t st);
+int tc2_conv_dgrad_s2(const __nv_bfloat16* dy, const __nv_bfloat16* wpacked_t, const __nv_bfloat16* addend,
+                      __nv_bfloat16* dx, const iic_conv_geom* g, cudaStream_t st);
 }  // namespace iic
 
 using namespace iic;
@@ -70,6 +72,9 @@ extern "C" int iic_conv_dgrad(const void* dy, const void* w_packed_t, const void
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == IIC_F32)
     return simt_conv_dgrad((const float*)dy, (const float*)w_packed_t, (const float*)addend, (float*)dx, g, st);
+  if (dtype == IIC_BF16 && use_tma() && g->stride == 2 && g->dil == 1 && g->kh == g->kw)
+    return tc2_conv_dgrad_s2((const __nv_bfloat16*)dy, (const __nv_bfloat16*)w_packed_t, (const __nv_bfloat16*)addend,
+                             (__nv_bfloat16*)dx, g, st);
   if (dtype == IIC_BF16)
     return ((use_tma() && g->stride == 1) ? tc2_conv_gather_gemm : tc_conv_gather_gemm)(
         (const __nv_bfloat16*)dy, g->oh, g->ow, g->cout, g->h, g->w, g->n, g, 1, (const __nv_bfloat16*)w_packed_t, g->cin,

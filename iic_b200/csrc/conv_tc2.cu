@@ -24,12 +24,20 @@ namespace iic {
 enum { M2_FPROP = 0, M2_WGRAD = 1 };
 constexpr int TC2_THREADS = 192;
 
+constexpr int TC2_MAXTAPS = 25;
+
 struct Tc2Params {
   long long rows;   // pixels enumerated by the gather (n * rowH * rowW)
   int rowH, rowW;
   int KH, KW, s, d;
-  int lower;        // input-space coordinate offset of filter tap 0 (same for h and w)
-  int flip;         // dgrad: tap t reads offset (K-1-t)*d
+  int lower;        // input-space coordinate offset of filter tap 0 (wgrad; fprop uses lower_h / lower_w)
+  int lower_h, lower_w;
+  // fprop / dgrad: the K dimension enumerates (tap index t, channel); per tap: activation offset
+  // (im2col {off_w, off_h}) and the tap's position in the packed weight (K coordinate = wtap*srcC + c)
+  int ntaps;
+  unsigned char offh[TC2_MAXTAPS], offw[TC2_MAXTAPS], wtap[TC2_MAXTAPS];
+  // stride-2 dgrad parity class: tile rows enumerate (n, i, j) and are written to dx pixel (2i+py, 2j+px)
+  int scatter, outH, outW, py, px;
   int srcC, Ktot, N;
   int mtiles, ntiles, splits, kb_per_split, total_kb;
   __nv_bfloat16* out;
@@ -116,21 +124,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const long long q = m0 / P.rowW;
           const int oy = (int)(q % P.rowH);
           const int img = (int)(q / P.rowH);
-          const int cw = ox * P.s + P.lower, ch = oy * P.s + P.lower;
+          const int cw = ox * P.s + P.lower_w, ch = oy * P.s + P.lower_h;
           for (int i = 0; i < nk; ++i, ++it) {
             const int s = it % STAGES;
             mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u);
             const uint32_t sa = base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
             const int j = i * 64;
             const int tap = j / P.srcC, c0 = j - tap * P.srcC;
-            int ta = tap / P.KW, tb = tap - ta * P.KW;
-            if (P.flip) {
-              ta = P.KH - 1 - ta;
-              tb = P.KW - 1 - tb;
-            }
             mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
-            tma_load_im2col(sa, &tmA, full_bar(s), c0, cw, ch, img, (uint16_t)(tb * P.d), (uint16_t)(ta * P.d));
-            tma_load_2d(sb, &tmB, full_bar(s), j, n0);
+            tma_load_im2col(sa, &tmA, full_bar(s), c0, cw, ch, img, (uint16_t)P.offw[tap], (uint16_t)P.offh[tap]);
+            tma_load_2d(sb, &tmB, full_bar(s), (int)P.wtap[tap] * P.srcC + c0, n0);
           }
         } else {
           int a_tap_a[2], a_tap_b[2], a_c0[2];
@@ -227,7 +230,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         if (MODE == M2_FPROP) {
           if (m < P.rows) {
-            __nv_bfloat16* o = P.out + m * P.N + n0 + c0;
+            long long orow = m;
+            if (P.scatter) {
+              const int jj = (int)(m % P.rowW);
+              const long long q = m / P.rowW;
+              const int ii = (int)(q % P.rowH);
+              orow = ((q / P.rowH) * P.outH + 2 * ii + P.py) * P.outW + 2 * jj + P.px;
+            }
+            __nv_bfloat16* o = P.out + orow * P.N + n0 + c0;
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) {
               float f[8];
@@ -235,7 +245,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[qq * 8 + e]);
               if (P.addend != nullptr) {
                 float ad[8];
-                load8(P.addend + m * P.N + n0 + c0 + qq * 8, ad);
+                load8(P.addend + orow * P.N + n0 + c0 + qq * 8, ad);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] += ad[e];
               }
@@ -290,11 +300,20 @@ static int tma_init() {
 }
 
 // NHWC bf16 activation [nimg][H][W][C] as the rank-4 (C, W, H, N) im2col tensor map
+static int make_im2col_map2(CUtensorMap* tm, const void* ptr, int nimg, int H, int W, int C, int lower_w, int lower_h,
+                            int upper_w, int upper_h, int stride, int pixels);
+
 static int make_im2col_map(CUtensorMap* tm, const void* ptr, int nimg, int H, int W, int C, int lower, int upper, int stride,
                            int pixels) {
+  return make_im2col_map2(tm, ptr, nimg, H, W, C, lower, lower, upper, upper, stride, pixels);
+}
+
+static int make_im2col_map2(CUtensorMap* tm, const void* ptr, int nimg, int H, int W, int C, int lower_w, int lower_h,
+                            int upper_w, int upper_h, int stride, int pixels) {
+  const int lower = lower_w, upper = upper_w;
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
   cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  int lo[2] = {lower, lower}, up[2] = {upper, upper};
+  int lo[2] = {lower_w, lower_h}, up[2] = {upper_w, upper_h};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = g_encodeIm2col(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, lo, up, 64,
                               (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -340,13 +359,22 @@ int tc2_conv_gather_gemm(const __nv_bfloat16* src, int srcH, int srcW, int srcC,
   P.rows = (long long)nimg * rowH * rowW;
   P.rowH = rowH; P.rowW = rowW; P.KH = g->kh; P.KW = g->kw; P.d = g->dil;
   const int span = (g->kh - 1) * g->dil;
+  IIC_REQUIRE(g->kh * g->kw <= TC2_MAXTAPS && span <= 255, IIC_ERR_UNSUPPORTED, "tcgen05/TMA conv: filter too large");
   int upper;
   if (!transposed) {
-    P.s = g->stride; P.lower = -g->pad; P.flip = 0;
+    P.s = g->stride; P.lower = -g->pad;
     upper = g->pad - span;
   } else {
-    P.s = 1; P.lower = g->pad - span; P.flip = 1;
+    P.s = 1; P.lower = g->pad - span;
     upper = P.lower + (rowH - srcH);  // number of base positions == rows of dx
+  }
+  P.lower_h = P.lower_w = P.lower;
+  P.ntaps = g->kh * g->kw;
+  for (int t = 0; t < P.ntaps; ++t) {
+    const int ta = t / g->kw, tb = t % g->kw;
+    P.offh[t] = (unsigned char)((transposed ? g->kh - 1 - ta : ta) * g->dil);
+    P.offw[t] = (unsigned char)((transposed ? g->kw - 1 - tb : tb) * g->dil);
+    P.wtap[t] = (unsigned char)t;
   }
   IIC_REQUIRE(P.lower >= -128 && P.lower <= 127 && upper >= -128 && upper <= 127, IIC_ERR_UNSUPPORTED, "im2col corner range");
   P.srcC = srcC; P.Ktot = g->kh * g->kw * srcC; P.N = N;
@@ -393,6 +421,95 @@ static int tc2_wgrad_splits(const iic_conv_geom* g) {
   return (int)want;
 }
 
+// dgrad of a stride-2 convolution, decomposed by output parity: dx[2i+py, 2j+px] only receives the taps a
+// with (py + pad - a) even, read at dy[i + (py + pad - a)/2]; each of the four classes is a stride-1 im2col
+// problem over dy with its own tap subset (1+2+2+4 = 9 taps for 3x3: no wasted MMAs, unlike the zero-filled
+// fractional-stride gather of conv_tc.cu).  w = kind-1 packed weight [cin][kh][kw][cout].
+int tc2_conv_dgrad_s2(const __nv_bfloat16* dy, const __nv_bfloat16* wpacked_t, const __nv_bfloat16* addend,
+                      __nv_bfloat16* dx, const iic_conv_geom* g, cudaStream_t st) {
+  int rc = tma_init();
+  if (rc != IIC_OK) return rc;
+  const int bn = pick_bn2(g->cin);
+  IIC_REQUIRE(bn != 0 && g->cout % 64 == 0 && g->stride == 2 && g->dil == 1 && g->kh == g->kw && g->kh * g->kw <= TC2_MAXTAPS,
+              IIC_ERR_UNSUPPORTED, "tcgen05/TMA stride-2 dgrad: unsupported geometry");
+  alignas(64) CUtensorMap tmB;
+  const int Kw = g->kh * g->kw * g->cout;
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)Kw, (cuuint64_t)g->cin};
+    cuuint64_t gstr[1] = {(cuuint64_t)Kw * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)bn};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encodeTiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(wpacked_t), gdim, gstr, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IIC_REQUIRE(r == CUDA_SUCCESS, IIC_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed (%d)", (int)r);
+  }
+  auto parity_taps = [&](int par, int ksz) {
+    int cnt = 0;
+    for (int a = 0; a < ksz; ++a) cnt += (((par + g->pad - a) % 2) + 2) % 2 == 0;
+    return cnt;
+  };
+  bool need_zero = false;
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px)
+      if (parity_taps(py, g->kh) * parity_taps(px, g->kw) == 0) need_zero = true;
+  if (need_zero) {  // classes that no tap reaches (e.g. 1x1 stride 2): dx = addend or 0 there
+    if (addend != nullptr)
+      IIC_CUDA(cudaMemcpyAsync(dx, addend, sizeof(__nv_bfloat16) * (size_t)g->n * g->h * g->w * g->cin, cudaMemcpyDeviceToDevice, st));
+    else
+      IIC_CUDA(cudaMemsetAsync(dx, 0, sizeof(__nv_bfloat16) * (size_t)g->n * g->h * g->w * g->cin, st));
+  }
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      const int Hc = (g->h - py + 1) / 2, Wc = (g->w - px + 1) / 2;
+      if (Hc <= 0 || Wc <= 0) continue;
+      Tc2Params P = {};
+      // taps and their dy offsets: oy = i + (py + pad - a)/2 ; shift so that the smallest offset is the lower corner
+      int offs_h[8], taps_h[8], nh = 0, offs_w[8], taps_w[8], nw = 0;
+      for (int a = 0; a < g->kh; ++a) {
+        const int tnum = py + g->pad - a;
+        if (((tnum % 2) + 2) % 2 == 0) { offs_h[nh] = tnum / 2; taps_h[nh++] = a; }  // tnum even: exact
+      }
+      for (int b = 0; b < g->kw; ++b) {
+        const int tnum = px + g->pad - b;
+        if (((tnum % 2) + 2) % 2 == 0) { offs_w[nw] = tnum / 2; taps_w[nw++] = b; }
+      }
+      if (nh == 0 || nw == 0) continue;
+      int lo_h = offs_h[0], lo_w = offs_w[0];
+      for (int i = 1; i < nh; ++i) lo_h = offs_h[i] < lo_h ? offs_h[i] : lo_h;
+      for (int i = 1; i < nw; ++i) lo_w = offs_w[i] < lo_w ? offs_w[i] : lo_w;
+      P.rows = (long long)g->n * Hc * Wc;
+      P.rowH = Hc; P.rowW = Wc; P.KH = g->kh; P.KW = g->kw; P.s = 1; P.d = 1;
+      P.lower_h = lo_h; P.lower_w = lo_w; P.lower = 0;
+      P.ntaps = nh * nw;
+      for (int i = 0; i < nh; ++i)
+        for (int j = 0; j < nw; ++j) {
+          const int t = i * nw + j;
+          P.offh[t] = (unsigned char)(offs_h[i] - lo_h);
+          P.offw[t] = (unsigned char)(offs_w[j] - lo_w);
+          P.wtap[t] = (unsigned char)(taps_h[i] * g->kw + taps_w[j]);
+        }
+      P.scatter = 1; P.outH = g->h; P.outW = g->w; P.py = py; P.px = px;
+      P.srcC = g->cout; P.Ktot = P.ntaps * g->cout; P.N = g->cin;
+      P.mtiles = (int)((P.rows + TC_BM - 1) / TC_BM); P.ntiles = g->cin / bn; P.splits = 1; P.total_kb = P.Ktot / 64;
+      P.out = dx; P.addend = addend;  // (classes without taps keep the pre-filled addend / zero)
+      // base positions per dim must number Hc / Wc: upper = lower + (Hc - H_dy)
+      const int up_h = lo_h + (Hc - g->oh), up_w = lo_w + (Wc - g->ow);
+      IIC_REQUIRE(lo_h >= -128 && up_h <= 127 && lo_w >= -128 && up_w <= 127 && up_h >= -128 && up_w >= -128,
+                  IIC_ERR_UNSUPPORTED, "im2col corner range");
+      alignas(64) CUtensorMap tmA;
+      rc = make_im2col_map2(&tmA, dy, g->n, g->oh, g->ow, g->cout, lo_w, lo_h, up_w, up_h, 1, TC_BM);
+      if (rc != IIC_OK) return rc;
+      switch (bn) {
+        case 256: rc = launch_tc2<M2_FPROP, 256>(tmA, tmB, P, 1, st); break;
+        case 128: rc = launch_tc2<M2_FPROP, 128>(tmA, tmB, P, 1, st); break;
+        default: rc = launch_tc2<M2_FPROP, 64>(tmA, tmB, P, 1, st); break;
+      }
+      if (rc != IIC_OK) return rc;
+    }
+  return IIC_OK;
+}
+
 long long tc2_conv_wgrad_workspace(const iic_conv_geom* g) {
   return (long long)tc2_wgrad_splits(g) * g->kh * g->kw * g->cin * g->cout * (long long)sizeof(float);
 }
@@ -416,7 +533,7 @@ int tc2_conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, f
   IIC_REQUIRE(g->kh == g->kw, IIC_ERR_UNSUPPORTED, "tcgen05/TMA wgrad: square filters only");
   Tc2Params P = {};
   P.rows = (long long)g->n * g->oh * g->ow;
-  P.rowH = g->oh; P.rowW = g->ow; P.KH = g->kh; P.KW = g->kw; P.s = g->stride; P.d = g->dil; P.lower = -g->pad; P.flip = 0;
+  P.rowH = g->oh; P.rowW = g->ow; P.KH = g->kh; P.KW = g->kw; P.s = g->stride; P.d = g->dil; P.lower = -g->pad;
   const int upper = g->pad - (g->kh - 1) * g->dil;
   P.srcC = g->cin; P.Ktot = g->kh * g->kw * g->cin; P.N = g->cout;
   P.mtiles = (P.Ktot + TC_BM - 1) / TC_BM; P.ntiles = g->cout / bn;
