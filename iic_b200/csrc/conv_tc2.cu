@@ -113,58 +113,83 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == 5) {
     // =============================== TMA producer ============================================
-    if (lane == 0) {
-      uint32_t it = 0;  // global k-block counter -> stage / phase
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        int z, n0, kb0, nk;
-        long long m0;
-        decode(w, z, m0, n0, kb0, nk);
-        if (MODE == M2_FPROP) {
-          const int ox = (int)(m0 % P.rowW);
-          const long long q = m0 / P.rowW;
-          const int oy = (int)(q % P.rowH);
-          const int img = (int)(q / P.rowH);
-          const int cw = ox * P.s + P.lower_w, ch = oy * P.s + P.lower_h;
-          for (int i = 0; i < nk; ++i, ++it) {
-            const int s = it % STAGES;
-            mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u);
-            const uint32_t sa = base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
-            const int j = i * 64;
-            const int tap = j / P.srcC, c0 = j - tap * P.srcC;
-            mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+    // The whole warp walks the k-blocks (uniform scalar state, no divisions in the loop); lane 0 arms the
+    // barrier, then lane i issues the i-th TMA of the stage, so the 2..6 bulk copies of a stage are
+    // issued in parallel instead of back to back by one thread (the single-thread issue rate, not L2
+    // bandwidth, bounded the 64-channel layers and wgrad: profiles/r01_ncu_wgrad.md).
+    uint32_t it = 0;  // global k-block counter -> stage / phase
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      int z, n0, kb0, nk;
+      long long m0;
+      decode(w, z, m0, n0, kb0, nk);
+      if (MODE == M2_FPROP) {
+        const int ox = (int)(m0 % P.rowW);
+        const long long q = m0 / P.rowW;
+        const int oy = (int)(q % P.rowH);
+        const int img = (int)(q / P.rowH);
+        const int cw = ox * P.s + P.lower_w, ch = oy * P.s + P.lower_h;
+        int tap = 0, c0 = 0;
+        for (int i = 0; i < nk; ++i, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u);
+          const uint32_t sa = base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+          if (lane == 0) mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+          __syncwarp();
+          if (lane == 0)
             tma_load_im2col(sa, &tmA, full_bar(s), c0, cw, ch, img, (uint16_t)P.offw[tap], (uint16_t)P.offh[tap]);
+          else if (lane == 1)
             tma_load_2d(sb, &tmB, full_bar(s), (int)P.wtap[tap] * P.srcC + c0, n0);
+          c0 += 64;
+          if (c0 >= P.srcC) {
+            c0 = 0;
+            ++tap;
           }
-        } else {
-          int a_tap_a[2], a_tap_b[2], a_c0[2];
-          bool a_ok[2];
-#pragma unroll
-          for (int a = 0; a < 2; ++a) {
-            const long long j = m0 + a * 64;
-            a_ok[a] = j < P.Ktot;
-            const int tap = (int)(j / P.srcC);
-            a_c0[a] = (int)(j - (long long)tap * P.srcC);
-            a_tap_a[a] = tap / P.KW;
-            a_tap_b[a] = tap - a_tap_a[a] * P.KW;
+        }
+      } else {
+        int a_off_w = 0, a_off_h = 0, a_c0 = 0;
+        bool a_ok = false;
+        if (lane < 2) {
+          const long long j = m0 + lane * 64;
+          a_ok = j < P.Ktot;
+          const int tap = (int)(j / P.srcC);
+          a_c0 = (int)(j - (long long)tap * P.srcC);
+          const int ta = tap / P.KW;
+          a_off_h = ta * P.d;
+          a_off_w = (tap - ta * P.KW) * P.d;
+        }
+        const bool ok0 = m0 < P.Ktot, ok1 = m0 + 64 < P.Ktot;
+        const uint32_t bytes = (uint32_t)((ok0 ? 8192 : 0) + (ok1 ? 8192 : 0) + Cfg::B_BYTES);
+        // pixel coordinates of the first row of the k-block, advanced by 64 pixels per k-block
+        long long p0 = (long long)kb0 * 64;
+        int ox = (int)(p0 % P.rowW);
+        const long long q = p0 / P.rowW;
+        int oy = (int)(q % P.rowH);
+        int img = (int)(q / P.rowH);
+        const int step_x = 64 % P.rowW, step_y = 64 / P.rowW;
+        for (int i = 0; i < nk; ++i, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u);
+          const uint32_t sa = base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+          if (lane == 0) mbar_expect_tx(full_bar(s), bytes);
+          __syncwarp();
+          if (lane < 2) {
+            if (a_ok)
+              tma_load_im2col(sa + lane * 8192, &tmA, full_bar(s), a_c0, ox * P.s + P.lower, oy * P.s + P.lower, img,
+                              (uint16_t)a_off_w, (uint16_t)a_off_h);
+          } else if (lane < 2 + BN / 64) {
+            const int b = lane - 2;
+            tma_load_2d(sb + b * 8192, &tmB, full_bar(s), n0 + b * 64, (int)p0);
           }
-          const uint32_t bytes = (uint32_t)((a_ok[0] ? 8192 : 0) + (a_ok[1] ? 8192 : 0) + Cfg::B_BYTES);
-          for (int i = 0; i < nk; ++i, ++it) {
-            const int s = it % STAGES;
-            mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u);
-            const uint32_t sa = base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
-            const long long p0 = (long long)(kb0 + i) * 64;
-            const int ox = (int)(p0 % P.rowW);
-            const long long q = p0 / P.rowW;
-            const int oy = (int)(q % P.rowH);
-            const int img = (int)(q / P.rowH);
-            mbar_expect_tx(full_bar(s), bytes);
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-              if (a_ok[a])
-                tma_load_im2col(sa + a * 8192, &tmA, full_bar(s), a_c0[a], ox * P.s + P.lower, oy * P.s + P.lower, img,
-                                (uint16_t)(a_tap_b[a] * P.d), (uint16_t)(a_tap_a[a] * P.d));
-#pragma unroll
-            for (int b = 0; b < BN / 64; ++b) tma_load_2d(sb + b * 8192, &tmB, full_bar(s), n0 + b * 64, (int)p0);
+          p0 += 64;
+          ox += step_x;
+          oy += step_y;
+          if (ox >= P.rowW) {
+            ox -= P.rowW;
+            ++oy;
+          }
+          while (oy >= P.rowH) {
+            oy -= P.rowH;
+            ++img;
           }
         }
       }
