@@ -251,6 +251,8 @@ def run_ours(args):
     summ = kernels.conv_timing_summary()
     kernels.conv_timing(False)
     pk = peaks()
+    other = {k: {"launches": v[0] // 2, "ms_per_step": v[2] / 2} for k, v in summ.items() if v[1] == 0.0}
+    summ = {k: v for k, v in summ.items() if v[1] > 0.0}
     flops = sum(v[1] for v in summ.values())
     ms = sum(v[2] for v in summ.values())
     nl = sum(v[0] for v in summ.values())
@@ -261,7 +263,7 @@ def run_ours(args):
             "flop_per_launch_avg": flops / max(nl, 1), "ms_per_launch_avg": ms / max(nl, 1),
             "by_kind": {k: {"launches": v[0], "tflops": v[1] / (v[2] * 1e-3) / 1e12 if v[2] > 0 else 0.0,
                             "ms_per_step": v[2] / 2} for k, v in summ.items()},
-            "conv_share_of_step": (ms / 2) / (sec / args.steps * 1e3),
+            "conv_share_of_step": (ms / 2) / (sec / args.steps * 1e3), "other_kernels_ms_per_step": other,
             "whole_step_frac": value / world * CONV_FLOP_PER_PAIR_96 / 1e12 / pk["tflops"]}
 
   cpu = None

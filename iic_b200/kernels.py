@@ -81,11 +81,30 @@ class _timed(object):
     return False
 
 
+def _cat(name):
+  """Times a whole wrapper under category `name` when conv_timing is on (bench.py breakdown)."""
+  def deco(fn):
+    def wrapped(*a, **kw):
+      if not _conv_timing["on"]:
+        return fn(*a, **kw)
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      r = fn(*a, **kw)
+      e1.record()
+      _conv_timing["records"].append((name, 0.0, e0, e1))
+      return r
+    wrapped.__name__ = fn.__name__
+    wrapped.__doc__ = fn.__doc__
+    return wrapped
+  return deco
+
+
 def launch_count(reset=False):
   return int(_lib.lib().iic_launch_count(1 if reset else 0))
 
 
 # ---- losses ---------------------------------------------------------------------------------
+@_cat("iid_loss")
 def iid_loss(z, zt, lamb, eps, want_grad, phase=_lib.PHASE_FUSED, joint_ws=None, want_joint=False):
   """z, zt: [S, n, k] fp32.  Returns (loss[S,2] | None, dz | None, dzt | None, joint_out | None)."""
   S, n, k = z.shape
@@ -160,6 +179,7 @@ def box_filter(x, k, T):
   return out
 
 
+@_cat("sobel")
 def sobel(imgs, include_rgb, using_ir):
   n, c, h, w = imgs.shape
   cout = (3 if include_rgb else 0) + 2 + (1 if using_ir else 0)
@@ -191,6 +211,7 @@ def cast(x, dt):
 
 
 # ---- convolution ----------------------------------------------------------------------------
+@_cat("pack_weight")
 def pack_weight(w, dt, kind):
   cout, cin, kh, kw = w.shape
   shape = (cout, kh, kw, cin) if kind == 0 else (cin, kh, kw, cout)
@@ -226,12 +247,14 @@ def conv_wgrad(x, dy, g, dt, grad_out, accumulate):
   return grad_out
 
 
+@_cat("stem_fprop")
 def stem_fprop(x_nchw, w, g, dt):
   y = torch.empty((g.n, g.oh, g.ow, g.cout), device=x_nchw.device, dtype=_TORCH_DT[dt])
   check(_lib.lib().iic_stem_fprop(_p(x_nchw), _p(w), _p(y), ctypes.byref(g), dt, _stream()), "iic_stem_fprop")
   return y
 
 
+@_cat("stem_wgrad")
 def stem_wgrad(x_nchw, dy, g, dt, grad_out, accumulate):
   ws = torch.empty(2 * 1024 * 1024, device=dy.device, dtype=torch.float32)  # 8 MB of per-block partials
   check(_lib.lib().iic_stem_wgrad(_p(x_nchw), _p(dy), _p(grad_out), int(bool(accumulate)), _p(ws), ws.numel() * 4,
@@ -240,6 +263,7 @@ def stem_wgrad(x_nchw, dy, g, dt, grad_out, accumulate):
 
 
 # ---- batch norm / pooling ----------------------------------------------------------------------
+@_cat("bn_stats")
 def bn_stats(y, gamma, beta, eps, momentum, running_mean, running_var, use_running):
   C = y.shape[-1]
   M = y.numel() // C
@@ -253,6 +277,7 @@ def bn_stats(y, gamma, beta, eps, momentum, running_mean, running_var, use_runni
   return ss, mi
 
 
+@_cat("bn_apply")
 def bn_apply(y, ss, relu, res=None, rss=None, out=None):
   C = y.shape[-1]
   M = y.numel() // C
@@ -268,6 +293,7 @@ def pooled_shape(y, pad):
   return (n, (h + 2 * pad - 2) // 2 + 1, (w + 2 * pad - 2) // 2 + 1, C)
 
 
+@_cat("bn_pool")
 def bn_relu_maxpool(y, ss, pad, out=None):
   n, h, w, C = y.shape
   oh, ow = (h + 2 * pad - 2) // 2 + 1, (w + 2 * pad - 2) // 2 + 1
@@ -278,6 +304,7 @@ def bn_relu_maxpool(y, ss, pad, out=None):
   return out
 
 
+@_cat("bn_pool_bwd")
 def bn_relu_maxpool_bwd(y, ss, dpool, pad, out=None):
   n, h, w, C = y.shape
   _, oh, ow, _ = dpool.shape
@@ -287,6 +314,7 @@ def bn_relu_maxpool_bwd(y, ss, dpool, pad, out=None):
   return g
 
 
+@_cat("bn_bwd")
 def bn_bwd(g_in, act, y, mi, gamma, dgamma, dbeta, accumulate, want_g_out, dy=None, g_out=None):
   """Returns (dy, g_masked | None); writes/accumulates dgamma, dbeta."""
   C = y.shape[-1]
@@ -307,6 +335,7 @@ def bn_bwd(g_in, act, y, mi, gamma, dgamma, dbeta, accumulate, want_g_out, dy=No
   return dy, g_out
 
 
+@_cat("avgpool")
 def avgpool(x):
   n, h, w, C = x.shape
   feat = torch.empty((n, C), device=x.device, dtype=torch.float32)
@@ -314,6 +343,7 @@ def avgpool(x):
   return feat
 
 
+@_cat("avgpool")
 def avgpool_bwd(dfeat, shape, dt):
   n, h, w, C = shape
   dx = torch.empty(shape, device=dfeat.device, dtype=_TORCH_DT[dt])
@@ -322,6 +352,7 @@ def avgpool_bwd(dfeat, shape, dt):
 
 
 # ---- heads ----------------------------------------------------------------------------------
+@_cat("heads")
 def heads_fwd(feat, w, b, S, k):
   n, F = feat.shape
   logits = torch.empty((n, S * k), device=feat.device, dtype=torch.float32)
@@ -330,6 +361,7 @@ def heads_fwd(feat, w, b, S, k):
   return z
 
 
+@_cat("heads")
 def heads_bwd(feat, w, z, dz, S, k, want_dfeat):
   n, F = feat.shape
   dlog = torch.empty((n, S * k), device=feat.device, dtype=torch.float32)
@@ -373,6 +405,7 @@ def seg_head_bwd(feat, w, zlow, dout, dfeat, accumulate):
 
 
 # ---- optimiser ------------------------------------------------------------------------------
+@_cat("adam")
 def adam_step(params, grads, exp_avgs, exp_avg_sqs, lr, beta1, beta2, eps, weight_decay, step):
   T = len(params)
   ptrs = (ctypes.c_void_p * (4 * T))()

@@ -10,4 +10,5 @@ import json
 d = json.load(open("gpurun_out/bench_quick.json"))
 r = d.get("roofline", {})
 print("pairs/s %.0f  ms/step %.1f  e2e %.0f  conv TF/s %.0f frac %.3f share %.2f  by_kind %s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], r.get("achieved", 0), r.get("frac", 0), r.get("conv_share_of_step", 0), {k: (round(v["tflops"]), round(v["ms_per_step"], 1)) for k, v in r.get("by_kind", {}).items()}))
+print("other:", {k: round(v["ms_per_step"], 2) for k, v in sorted(r.get("other_kernels_ms_per_step", {}).items(), key=lambda kv: -kv[1]["ms_per_step"])})
 PY
