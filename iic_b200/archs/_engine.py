@@ -179,15 +179,19 @@ class GradSink(object):
     return self.g.get(id(p))
 
 
-def _bn_backward(ctx, sink, bn, g_in, act, y, mi, want_g_out):
+def _bn_backward(ctx, sink, bn, g_in, act, y, mi, want_g_out, mask_ss=None):
+  """act: activation whose sign is the ReLU mask (residual blocks); mask_ss: per-view scale/shift when the
+  ReLU directly follows the BN (the mask is then recomputed from y instead of reading the activation)."""
   dg, acc1 = sink.buf(bn.weight)
   db, acc2 = sink.buf(bn.bias)
   assert acc1 == acc2
   dy = torch.empty_like(y)
   g_out = torch.empty_like(y) if want_g_out else None
   acc = acc1
-  for gg, ag, yg, mg, dyg, gog in zip(ctx.split(g_in), ctx.split(act), ctx.split(y), mi, ctx.split(dy), ctx.split(g_out)):
-    K.bn_bwd(gg, ag, yg, mg, bn.weight.detach(), dg, db, acc, want_g_out, dy=dyg, g_out=gog)
+  mss = mask_ss if mask_ss is not None else [None] * ctx.groups
+  for gg, ag, yg, mg, dyg, gog, ms in zip(ctx.split(g_in), ctx.split(act), ctx.split(y), mi, ctx.split(dy),
+                                          ctx.split(g_out), mss):
+    K.bn_bwd(gg, ag, yg, mg, bn.weight.detach(), dg, db, acc, want_g_out, dy=dyg, g_out=gog, mask_ss=ms)
     acc = True  # later views add to the same dgamma / dbeta
   return dy, g_out
 
@@ -205,7 +209,7 @@ def stem_forward(ctx, conv, bn, x_nchw, pool_pad):
   ss, mi = _bn_stats(ctx, bn, y)
   out = _bn_relu_maxpool(ctx, y, ss, pool_pad) if pool_pad is not None else _bn_apply(ctx, y, ss, True)
   if ctx.need_grad:
-    ctx.saved.append(("stem", conv, bn, x_nchw, g, y, ss, mi, out if pool_pad is None else None, pool_pad))
+    ctx.saved.append(("stem", conv, bn, x_nchw, g, y, ss, mi, None, pool_pad))
   return out
 
 
@@ -215,7 +219,7 @@ def stem_backward(ctx, sink, rec, d_out):
     gmask = _bn_relu_maxpool_bwd(ctx, y, ss, d_out, pool_pad)
     dy, _ = _bn_backward(ctx, sink, bn, gmask, None, y, mi, False)
   else:
-    dy, _ = _bn_backward(ctx, sink, bn, d_out, act, y, mi, False)
+    dy, _ = _bn_backward(ctx, sink, bn, d_out, None, y, mi, False, mask_ss=ss)
   gw, acc = sink.buf(conv.weight)
   K.stem_wgrad(x_nchw, dy, g, ctx.dt, gw, acc)
   return None
@@ -229,7 +233,7 @@ def convbn_forward(ctx, conv, bn, x, pool_pad):
   ss, mi = _bn_stats(ctx, bn, y)
   out = _bn_relu_maxpool(ctx, y, ss, pool_pad) if pool_pad is not None else _bn_apply(ctx, y, ss, True)
   if ctx.need_grad:
-    ctx.saved.append(("convbn", conv, bn, x, g, y, ss, mi, out if pool_pad is None else None, pool_pad))
+    ctx.saved.append(("convbn", conv, bn, x, g, y, ss, mi, None, pool_pad))
   return out
 
 
@@ -239,7 +243,7 @@ def convbn_backward(ctx, sink, rec, d_out):
     gmask = _bn_relu_maxpool_bwd(ctx, y, ss, d_out, pool_pad)
     dy, _ = _bn_backward(ctx, sink, bn, gmask, None, y, mi, False)
   else:
-    dy, _ = _bn_backward(ctx, sink, bn, d_out, act, y, mi, False)
+    dy, _ = _bn_backward(ctx, sink, bn, d_out, None, y, mi, False, mask_ss=ss)
   _conv_wgrad(ctx, sink, conv, x, dy, g)
   return K.conv_dgrad(dy, ctx.packed(conv, 1), g, ctx.dt)
 
@@ -264,17 +268,17 @@ def block_forward(ctx, blk, x):
     gd = yd = mid = None
     out = _bn_apply(ctx, y2, ss2, True, res=x)
   if ctx.need_grad:
-    ctx.saved.append(("block", blk, x, g1, y1, mi1, a1, g2, y2, mi2, gd, yd, mid, out))
+    ctx.saved.append(("block", blk, x, g1, y1, mi1, a1, g2, y2, mi2, gd, yd, mid, out, ss1))
   return out
 
 
 def block_backward(ctx, sink, rec, d_out):
-  _, blk, x, g1, y1, mi1, a1, g2, y2, mi2, gd, yd, mid, out = rec
+  _, blk, x, g1, y1, mi1, a1, g2, y2, mi2, gd, yd, mid, out, ss1 = rec
   # out = relu(bn2(y2) + r): g = d_out * (out > 0) goes both into bn2 and the residual branch
   dy2, gres = _bn_backward(ctx, sink, blk.bn2, d_out, out, y2, mi2, True)
   _conv_wgrad(ctx, sink, blk.conv2, a1, dy2, g2)
   da1 = K.conv_dgrad(dy2, ctx.packed(blk.conv2, 1), g2, ctx.dt)
-  dy1, _ = _bn_backward(ctx, sink, blk.bn1, da1, a1, y1, mi1, False)
+  dy1, _ = _bn_backward(ctx, sink, blk.bn1, da1, None, y1, mi1, False, mask_ss=ss1)  # a1 = relu(bn1(y1))
   _conv_wgrad(ctx, sink, blk.conv1, x, dy1, g1)
   if blk.downsample is not None:
     dconv, dbn = blk.downsample[0], blk.downsample[1]

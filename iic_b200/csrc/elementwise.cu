@@ -86,10 +86,13 @@ __global__ void sobel_kernel(const float* __restrict__ in, float* __restrict__ o
 template <typename T, bool BWD>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ y, const T* __restrict__ gin,
                                                         const T* __restrict__ act,
+                                                        const float* __restrict__ mask_ss,
                                                         const float* __restrict__ mean_invstd, long long M, int C,
                                                         float* __restrict__ partial /* [gridDim.x][2C] */) {
   // BWD=false: sum y, sum y*y
-  // BWD=true : g = gin * (act > 0 if act) ; yhat = (y-mean)*invstd ; sum g ; sum g*yhat
+  // BWD=true : g = gin * relu_mask ; yhat = (y-mean)*invstd ; sum g ; sum g*yhat
+  //            relu_mask = (act > 0) if act, else (y*scale+shift > 0) if mask_ss (BN directly followed by ReLU:
+  //            the mask is recomputed from y, which is read anyway, instead of reading the activation)
   __shared__ float sh[256 * 17];
   const int cg = C >> 3;                // channel groups per row (C <= 2048)
   const int tpr = cg;                   // threads per row
@@ -100,12 +103,14 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ y,
   for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
   if (my_r < rows_per_it) {
     const int c8 = my_cg;
-    float mean[8], istd[8];
+    float mean[8], istd[8], msc[8], msh[8];
     if (BWD) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         mean[j] = mean_invstd[c8 * 8 + j];
         istd[j] = mean_invstd[C + c8 * 8 + j];
+        msc[j] = mask_ss ? mask_ss[c8 * 8 + j] : 0.f;
+        msh[j] = mask_ss ? mask_ss[C + c8 * 8 + j] : 0.f;
       }
     }
     const long long stride = (long long)gridDim.x * rows_per_it;
@@ -125,6 +130,12 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ y,
           for (int j = 0; j < 8; ++j) {
             g[j] = a[j] > 0.f ? g[j] : 0.f;
             if (two) g2[j] = a2[j] > 0.f ? g2[j] : 0.f;
+          }
+        } else if (mask_ss != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            g[j] = fmaf(v[j], msc[j], msh[j]) > 0.f ? g[j] : 0.f;
+            if (two) g2[j] = fmaf(v2[j], msc[j], msh[j]) > 0.f ? g2[j] : 0.f;
           }
         }
       }
@@ -332,12 +343,13 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_bwd_kernel(const T* __res
 template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ gin, const T* __restrict__ act,
                                                            const T* __restrict__ y,
+                                                           const float* __restrict__ mask_ss,
                                                            const float* __restrict__ mean_invstd,
                                                            const float* __restrict__ gamma,
                                                            const double* __restrict__ sums, T* __restrict__ dy,
                                                            T* __restrict__ g_out, float* dgamma, float* dbeta,
                                                            int accumulate, long long M, int C) {
-  extern __shared__ __align__(16) float coef[];  // [3][C]
+  extern __shared__ __align__(16) float coef[];  // [5][C]: A, B, C, mask scale, mask shift
   const int cg = C >> 3;
   const long long total = M * cg;
   const double invM = 1.0 / (double)M;
@@ -348,6 +360,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
     coef[c] = A;
     coef[C + c] = -A * m2 * istd;
     coef[2 * C + c] = -A * m1 + A * m2 * istd * mean;
+    coef[3 * C + c] = mask_ss ? mask_ss[c] : 0.f;
+    coef[4 * C + c] = mask_ss ? mask_ss[C + c] : 0.f;
     if (blockIdx.x == 0) {
       const float db = (float)sums[c], dg = (float)sums[C + c];
       if (dgamma) dgamma[c] = accumulate ? dgamma[c] + dg : dg;
@@ -365,6 +379,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
       load8(act + i * 8, a);
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
+    } else if (mask_ss != nullptr) {
+      float ms[8], mh[8];
+      load8(coef + 3 * C + c8 * 8, ms);
+      load8(coef + 4 * C + c8 * 8, mh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = fmaf(v[j], ms[j], mh[j]) > 0.f ? g[j] : 0.f;
     }
     if (g_out != nullptr) store8(g_out + i * 8, g);
     float cA[8], cB[8], cC[8], o[8];
@@ -543,7 +563,7 @@ extern "C" int iic_bn_stats(const void* y, int dtype, long long M, int C, const 
     const int blocks = bn_reduce_blocks(M, C);
     float* partial = bn_partial_scratch((size_t)device_sm_count() * 4 * 2 * 2048 * sizeof(float));
     IIC_REQUIRE(partial != nullptr, IIC_ERR_CUDA, "iic_bn_stats: scratch allocation failed");
-    DISPATCH_T(dtype, bn_reduce_kernel<T, false><<<blocks, 256, 0, st>>>((const T*)y, nullptr, nullptr, nullptr, M, C, partial);)
+    DISPATCH_T(dtype, bn_reduce_kernel<T, false><<<blocks, 256, 0, st>>>((const T*)y, nullptr, nullptr, nullptr, nullptr, M, C, partial);)
     IIC_LAUNCH_CHECK();
     count_launch();
     bn_sum_partials_kernel<<<cdiv(2 * C * 32, 256), 256, 0, st>>>(partial, blocks, 2 * C, stats_ws);
@@ -598,15 +618,15 @@ extern "C" int iic_bn_relu_maxpool_bwd(const void* y, const float* scale_shift, 
   return IIC_OK;
 }
 
-extern "C" int iic_bn_bwd_reduce(const void* g_in, const void* act, const void* y, const float* mean_invstd, int dtype,
-                                 long long M, int C, double* sums, void* stream) {
+extern "C" int iic_bn_bwd_reduce(const void* g_in, const void* act, const float* mask_scale_shift, const void* y,
+                                 const float* mean_invstd, int dtype, long long M, int C, double* sums, void* stream) {
   IIC_REQUIRE(g_in && y && mean_invstd && sums && M > 0, IIC_ERR_BAD_ARG, "iic_bn_bwd_reduce: bad arguments");
   IIC_REQUIRE(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, IIC_ERR_UNSUPPORTED, "iic_bn_bwd_reduce: C=%d unsupported", C);
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = bn_reduce_blocks(M, C);
   float* partial = bn_partial_scratch((size_t)device_sm_count() * 4 * 2 * 2048 * sizeof(float));
   IIC_REQUIRE(partial != nullptr, IIC_ERR_CUDA, "iic_bn_bwd_reduce: scratch allocation failed");
-  DISPATCH_T(dtype, bn_reduce_kernel<T, true><<<blocks, 256, 0, st>>>((const T*)y, (const T*)g_in, (const T*)act, mean_invstd, M, C, partial);)
+  DISPATCH_T(dtype, bn_reduce_kernel<T, true><<<blocks, 256, 0, st>>>((const T*)y, (const T*)g_in, (const T*)act, mask_scale_shift, mean_invstd, M, C, partial);)
   IIC_LAUNCH_CHECK();
   count_launch();
   bn_sum_partials_kernel<<<cdiv(2 * C * 32, 256), 256, 0, st>>>(partial, blocks, 2 * C, sums);
@@ -615,15 +635,16 @@ extern "C" int iic_bn_bwd_reduce(const void* g_in, const void* act, const void* 
   return IIC_OK;
 }
 
-extern "C" int iic_bn_bwd_apply(const void* g_in, const void* act, const void* y, const float* mean_invstd,
-                                const float* gamma, const double* sums, void* dy, void* g_out, float* dgamma,
+extern "C" int iic_bn_bwd_apply(const void* g_in, const void* act, const float* mask_scale_shift, const void* y,
+                                const float* mean_invstd, const float* gamma, const double* sums, void* dy, void* g_out,
+                                float* dgamma,
                                 float* dbeta, int accumulate, int dtype, long long M, int C, void* stream) {
   IIC_REQUIRE(g_in && y && mean_invstd && gamma && sums && dy && M > 0 && C % 8 == 0, IIC_ERR_BAD_ARG,
               "iic_bn_bwd_apply: bad arguments");
   const long long total = M * (C / 8);
-  const size_t smem = (size_t)3 * C * sizeof(float);
+  const size_t smem = (size_t)5 * C * sizeof(float);
   DISPATCH_T(dtype, bn_bwd_apply_kernel<T><<<ew_grid(total, 256), 256, smem, (cudaStream_t)stream>>>(
-      (const T*)g_in, (const T*)act, (const T*)y, mean_invstd, gamma, sums, (T*)dy, (T*)g_out, dgamma, dbeta,
+      (const T*)g_in, (const T*)act, (const T*)y, mask_scale_shift, mean_invstd, gamma, sums, (T*)dy, (T*)g_out, dgamma, dbeta,
       accumulate, M, C);)
   IIC_LAUNCH_CHECK();
   count_launch();

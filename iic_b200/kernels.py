@@ -315,13 +315,14 @@ def bn_relu_maxpool_bwd(y, ss, dpool, pad, out=None):
 
 
 @_cat("bn_bwd")
-def bn_bwd(g_in, act, y, mi, gamma, dgamma, dbeta, accumulate, want_g_out, dy=None, g_out=None):
+def bn_bwd(g_in, act, y, mi, gamma, dgamma, dbeta, accumulate, want_g_out, dy=None, g_out=None, mask_ss=None):
   """Returns (dy, g_masked | None); writes/accumulates dgamma, dbeta."""
   C = y.shape[-1]
   M = y.numel() // C
   dt = iic_dtype(y)
   sums = torch.empty(2 * C, device=y.device, dtype=torch.float64)
-  check(_lib.lib().iic_bn_bwd_reduce(_p(g_in), _p(act), _p(y), _p(mi), dt, M, C, _p(sums), _stream()),
+  assert act is None or mask_ss is None
+  check(_lib.lib().iic_bn_bwd_reduce(_p(g_in), _p(act), _p(mask_ss), _p(y), _p(mi), dt, M, C, _p(sums), _stream()),
         "iic_bn_bwd_reduce")
   if dy is None:
     dy = torch.empty_like(y)
@@ -329,7 +330,7 @@ def bn_bwd(g_in, act, y, mi, gamma, dgamma, dbeta, accumulate, want_g_out, dy=No
     g_out = torch.empty_like(y)
   if not want_g_out:
     g_out = None
-  check(_lib.lib().iic_bn_bwd_apply(_p(g_in), _p(act), _p(y), _p(mi), _p(gamma), _p(sums), _p(dy), _p(g_out),
+  check(_lib.lib().iic_bn_bwd_apply(_p(g_in), _p(act), _p(mask_ss), _p(y), _p(mi), _p(gamma), _p(sums), _p(dy), _p(g_out),
                                     _p(dgamma), _p(dbeta), int(bool(accumulate)), dt, M, C, _stream()),
         "iic_bn_bwd_apply")
   return dy, g_out

@@ -169,16 +169,17 @@ int iic_bn_relu_maxpool(const void* y, const float* scale_shift, void* out, int 
  * gradient w.r.t. the BN output. */
 int iic_bn_relu_maxpool_bwd(const void* y, const float* scale_shift, const void* dpool, void* g, int dtype,
                             int n, int h, int w, int C, int pad, int oh, int ow, void* stream);
-/* BN backward.  g_in = dL/d(out of the BN [+res] [relu]) ; if `act` != NULL the ReLU mask
- * (act > 0) is applied first.  Pass 1 (reduce): sums[2*C] double (sum g, sum g*yhat),
+/* BN backward.  g_in = dL/d(out of the BN [+res] [relu]).  ReLU mask: (act > 0) if `act` != NULL (needed when a
+ * residual was added before the ReLU); else (y*scale+shift > 0) recomputed from y if `mask_scale_shift` != NULL
+ * (BN directly followed by ReLU: saves reading the activation); else no mask.  Pass 1 (reduce): sums[2*C] double (sum g, sum g*yhat),
  * zeroed by the call.  Pass 2 (apply): dy = scale*(g - mean(g) - yhat*mean(g*yhat)); also
  * writes dgamma/dbeta (accumulate ? += : =) and, if g_out != NULL, the masked g
  * (gradient for the residual branch). */
-int iic_bn_bwd_reduce(const void* g_in, const void* act, const void* y, const float* mean_invstd, int dtype,
-                      long long M, int C, double* sums, void* stream);
-int iic_bn_bwd_apply(const void* g_in, const void* act, const void* y, const float* mean_invstd,
-                     const float* gamma, const double* sums, void* dy, void* g_out, float* dgamma,
-                     float* dbeta, int accumulate, int dtype, long long M, int C, void* stream);
+int iic_bn_bwd_reduce(const void* g_in, const void* act, const float* mask_scale_shift, const void* y,
+                      const float* mean_invstd, int dtype, long long M, int C, double* sums, void* stream);
+int iic_bn_bwd_apply(const void* g_in, const void* act, const float* mask_scale_shift, const void* y,
+                     const float* mean_invstd, const float* gamma, const double* sums, void* dy, void* g_out,
+                     float* dgamma, float* dbeta, int accumulate, int dtype, long long M, int C, void* stream);
 
 /* AvgPool2d(full extent) + flatten (net5g.py:31-39,:56): x (n,hw,C) -> feat fp32 (n,C) */
 int iic_avgpool(const void* x, int dtype, float* feat, int n, int hw, int C, void* stream);

@@ -174,6 +174,14 @@ def test_bn_forward_backward(mode, shape):
     far = (o.detach().abs() > 0.05) | (o.detach() == 0)
     assert ((from_nhwc(dy) - yr.grad).abs()[far] < 0.05 * yr.grad.abs().max()).float().mean() > 0.995
     assert torch.allclose(dg, gr.grad, rtol=5e-2, atol=0.5) and torch.allclose(db, br.grad, rtol=5e-2, atol=0.5)
+  # BN directly followed by ReLU: the mask is recomputed from y instead of reading the activation
+  o3 = F.relu(F.batch_norm(yr2 := y.clone().requires_grad_(True), None, None, gamma, beta, True, 0.1, 1e-5))
+  o3.backward(dout)
+  dy3, _ = K.bn_bwd(to_nhwc(dout, tdt), None, yh, mi, gamma, dg, db, False, False, mask_ss=ss)
+  if mode == "fp32":
+    assert torch.allclose(from_nhwc(dy3), yr2.grad, rtol=1e-3, atol=1e-4)
+  else:
+    assert ((from_nhwc(dy3) - yr2.grad).abs() < 0.05 * yr2.grad.abs().max()).float().mean() > 0.99
   # eval mode uses the running statistics
   ss_e, _ = K.bn_stats(yh, gamma, beta, 1e-5, 0.1, rm, rv, True)
   oe = F.batch_norm(y, rm_r, rv_r, gamma, beta, False, 0.1, 1e-5)
