@@ -141,6 +141,32 @@ def _bn_stats(ctx, bn, y):
   return sss, mis
 
 
+def _conv_bn(ctx, conv, bn, x, g):
+  """y = conv(x) and the per-view BN statistics of y.  On the tensor-core path in training mode the
+  statistics are accumulated in the conv epilogue (no separate pass over y)."""
+  fused = None
+  if ctx.dt == BF16 and (ctx.training or not bn.track_running_stats):
+    fused = K.conv_fprop_stats(x, ctx.packed(conv, 0), g, ctx.dt, ctx.groups)
+  if fused is None:
+    y = K.conv_fprop(x, ctx.packed(conv, 0), g, ctx.dt)
+    ss, mi = _bn_stats(ctx, bn, y)
+    return y, ss, mi
+  y, partial, nblk = fused
+  update = ctx.training and bn.track_running_stats
+  rm = bn.running_mean if update else None
+  rv = bn.running_var if update else None
+  M = (y.numel() // y.shape[-1]) // ctx.groups
+  sss, mis = [], []
+  for v in range(ctx.groups):
+    if update:
+      bn.num_batches_tracked += 1
+    ss, mi = K.bn_stats_from_partials(partial, nblk, ctx.groups, v, M, bn.weight.detach(), bn.bias.detach(), bn.eps,
+                                      bn.momentum, rm, rv)
+    sss.append(ss)
+    mis.append(mi)
+  return y, sss, mis
+
+
 def _bn_apply(ctx, y, ss, relu, res=None, rss=None):
   out = torch.empty_like(y)
   for yg, og, sg, rg, rsg in zip(ctx.split(y), ctx.split(out), ss, ctx.split(res), rss if rss is not None else [None] * ctx.groups):
@@ -229,8 +255,7 @@ def stem_backward(ctx, sink, rec, d_out):
 def convbn_forward(ctx, conv, bn, x, pool_pad):
   n, h, w, _ = x.shape
   g = conv.geom(n, h, w)
-  y = K.conv_fprop(x, ctx.packed(conv, 0), g, ctx.dt)
-  ss, mi = _bn_stats(ctx, bn, y)
+  y, ss, mi = _conv_bn(ctx, conv, bn, x, g)
   out = _bn_relu_maxpool(ctx, y, ss, pool_pad) if pool_pad is not None else _bn_apply(ctx, y, ss, True)
   if ctx.need_grad:
     ctx.saved.append(("convbn", conv, bn, x, g, y, ss, mi, None, pool_pad))
@@ -252,17 +277,14 @@ def convbn_backward(ctx, sink, rec, d_out):
 def block_forward(ctx, blk, x):
   n, h, w, _ = x.shape
   g1 = blk.conv1.geom(n, h, w)
-  y1 = K.conv_fprop(x, ctx.packed(blk.conv1, 0), g1, ctx.dt)
-  ss1, mi1 = _bn_stats(ctx, blk.bn1, y1)
+  y1, ss1, mi1 = _conv_bn(ctx, blk.conv1, blk.bn1, x, g1)
   a1 = _bn_apply(ctx, y1, ss1, True)
   g2 = blk.conv2.geom(n, g1.oh, g1.ow)
-  y2 = K.conv_fprop(a1, ctx.packed(blk.conv2, 0), g2, ctx.dt)
-  ss2, mi2 = _bn_stats(ctx, blk.bn2, y2)
+  y2, ss2, mi2 = _conv_bn(ctx, blk.conv2, blk.bn2, a1, g2)
   if blk.downsample is not None:
     dconv, dbn = blk.downsample[0], blk.downsample[1]
     gd = dconv.geom(n, h, w)
-    yd = K.conv_fprop(x, ctx.packed(dconv, 0), gd, ctx.dt)
-    ssd, mid = _bn_stats(ctx, dbn, yd)
+    yd, ssd, mid = _conv_bn(ctx, dconv, dbn, x, gd)
     out = _bn_apply(ctx, y2, ss2, True, res=yd, rss=ssd)
   else:
     gd = yd = mid = None

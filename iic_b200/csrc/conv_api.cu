@@ -20,6 +20,11 @@ int tc2_conv_gather_gemm(const __nv_bfloat16* src, int srcH, int srcW, int srcC,
                          const __nv_bfloat16* addend, __nv_bfloat16* out, cudaStream_t st);
 long long tc2_conv_wgrad_workspace(const iic_conv_geom* g);
 int tc2_conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* ws, const iic_conv_geom* g, cudaStream_t st);
+int tc2_conv_fprop_blocks(const iic_conv_geom* g);
+int tc2_conv_gather_gemm_stats(const __nv_bfloat16* src, int srcH, int srcW, int srcC, int rowH, int rowW, int nimg,
+                               const iic_conv_geom* g, int transposed, const __nv_bfloat16* wpacked, int N,
+                               const __nv_bfloat16* addend, __nv_bfloat16* out, float* stat_partial, int stat_groups,
+                               cudaStream_t st);
 int tc2_conv_dgrad_s2(const __nv_bfloat16* dy, const __nv_bfloat16* wpacked_t, const __nv_bfloat16* addend,
                       __nv_bfloat16* dx, const iic_conv_geom* g, cudaStream_t st);
 }  // namespace iic
@@ -101,4 +106,22 @@ extern "C" int iic_conv_wgrad(const void* x, const void* dy, float* dw_packed, v
                                                         (float*)workspace, g, st);
   set_error("iic_conv_wgrad: bad dtype %d", dtype);
   return IIC_ERR_BAD_ARG;
+}
+
+// fprop with the BatchNorm statistics of the output fused into the epilogue (tensor-core path only): the
+// separate statistics pass (one full read of y) disappears.  Returns the number of partial rows written.
+extern "C" int iic_conv_fprop_stats_blocks(const iic_conv_geom* g, int dtype) {
+  if (g == nullptr || dtype != IIC_BF16 || !use_tma()) return 0;
+  return tc2_conv_fprop_blocks(g);
+}
+
+extern "C" int iic_conv_fprop_stats(const void* x, const void* w_packed, void* y, const iic_conv_geom* g, int dtype,
+                                    int views, float* stat_partial, void* stream) {
+  int rc = geom_check(g, "iic_conv_fprop_stats");
+  if (rc != IIC_OK) return rc;
+  IIC_REQUIRE(x && w_packed && y && stat_partial, IIC_ERR_BAD_ARG, "iic_conv_fprop_stats: null pointer");
+  IIC_REQUIRE(dtype == IIC_BF16 && use_tma(), IIC_ERR_UNSUPPORTED, "iic_conv_fprop_stats: tensor-core (bf16) path only");
+  return tc2_conv_gather_gemm_stats((const __nv_bfloat16*)x, g->h, g->w, g->cin, g->oh, g->ow, g->n, g, 0,
+                                    (const __nv_bfloat16*)w_packed, g->cout, nullptr, (__nv_bfloat16*)y, stat_partial, views,
+                                    (cudaStream_t)stream);
 }

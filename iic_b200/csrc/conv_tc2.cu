@@ -43,14 +43,32 @@ struct Tc2Params {
   __nv_bfloat16* out;
   const __nv_bfloat16* addend;
   float* partial;
+  // fused BatchNorm statistics (fprop only): per-CTA partial column sums of the fp32 accumulators,
+  // stat_partial[cta][group][{sum, sum of squares}][N]; rows < stat_half belong to view 0, the rest to view 1
+  float* stat_partial;
+  long long stat_half;
 };
+
+// Transpose-reduce: on return t[0] of lane l holds sum over the 32 lanes of (their) t[l]  (31 shuffles).
+__device__ __forceinline__ void warp_col_reduce(float (&t)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? t[i] : t[i + off];
+      const float keep = up ? t[i + off] : t[i];
+      t[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
 
 template <int BN> struct Tc2Cfg {
   static constexpr int A_BYTES = TC_BM * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;  // (+ 64 B x N for fused BN statistics)
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
@@ -69,6 +87,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + STAGES * Cfg::STAGE_BYTES + (2 * STAGES + 4) * 8);
+  float* stat = reinterpret_cast<float*>(base_ptr + STAGES * Cfg::STAGE_BYTES + 256);  // [4 warps][2 views][2][N]
+  const bool do_stats = (MODE == M2_FPROP) && P.stat_partial != nullptr;
+  if (do_stats)
+    for (int i = threadIdx.x; i < 16 * P.N; i += TC2_THREADS) stat[i] = 0.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -254,6 +276,27 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int qq = 0; qq < 32; ++qq) v[qq] = 0u;
         }
         if (MODE == M2_FPROP) {
+          if (do_stats) {
+            // per-column sums over this warp's 32 rows (rows >= P.rows are exact zeros: TMA zero fill)
+            const bool lo1 = m0 >= P.stat_half, hi1 = (m0 + TC_BM - 1) >= P.stat_half;
+            for (int grp = lo1 ? 1 : 0; grp <= (hi1 ? 1 : 0); ++grp) {
+              const bool mine = (m >= P.stat_half) == (grp == 1);
+              float t[32];
+#pragma unroll
+              for (int e = 0; e < 32; ++e) t[e] = mine ? __uint_as_float(v[e]) : 0.f;
+              warp_col_reduce(t, lane);
+              const float s1 = t[0];
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                const float f = mine ? __uint_as_float(v[e]) : 0.f;
+                t[e] = f * f;
+              }
+              warp_col_reduce(t, lane);
+              float* sp = stat + ((warp * 2 + grp) * 2) * P.N + n0 + c0 + lane;
+              sp[0] += s1;
+              sp[P.N] += t[0];
+            }
+          }
           if (m < P.rows) {
             long long orow = m;
             if (P.scatter) {
@@ -295,6 +338,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (do_stats)
+    for (int i = threadIdx.x; i < 4 * P.N; i += TC2_THREADS)  // i = (view, q, col); fixed warp order
+      P.stat_partial[(long long)blockIdx.x * 4 * P.N + i] = stat[i] + stat[4 * P.N + i] + stat[8 * P.N + i] + stat[12 * P.N + i];
 }
 
 // ---- host side: tensor-map construction through the driver entry points ----------------------
@@ -351,13 +397,17 @@ static int make_im2col_map2(CUtensorMap* tm, const void* ptr, int nimg, int H, i
   return IIC_OK;
 }
 
+static int tc2_grid(long long work) { return (int)(work < device_sm_count() ? work : device_sm_count()); }
+
 template <int MODE, int BN>
 static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc2Params& P, int splits, cudaStream_t st) {
   using Cfg = Tc2Cfg<BN>;
-  IIC_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  const int smem = Cfg::SMEM + (P.stat_partial ? 64 * P.N : 0);
+  IIC_REQUIRE(smem <= 232448, IIC_ERR_UNSUPPORTED, "conv_tc2: shared memory budget exceeded (%d B)", smem);
+  IIC_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   long long work = (long long)P.mtiles * P.ntiles * splits;
-  int grid = (int)(work < device_sm_count() ? work : device_sm_count());
-  conv_tc2_kernel<MODE, BN><<<grid, TC2_THREADS, Cfg::SMEM, st>>>(tmA, tmB, P);
+  int grid = tc2_grid(work);
+  conv_tc2_kernel<MODE, BN><<<grid, TC2_THREADS, smem, st>>>(tmA, tmB, P);
   IIC_LAUNCH_CHECK();
   count_launch();
   return IIC_OK;
@@ -371,9 +421,29 @@ static int pick_bn2(int N) {
 }
 
 // fprop (transposed == 0) or dgrad of a stride-1 conv (transposed == 1; src = dy, N = cin)
+int tc2_conv_fprop_blocks(const iic_conv_geom* g) {
+  const int bn = pick_bn2(g->cout);
+  if (bn == 0) return 0;
+  const long long rows = (long long)g->n * g->oh * g->ow;
+  return tc2_grid(((rows + TC_BM - 1) / TC_BM) * (g->cout / bn));
+}
+
+int tc2_conv_gather_gemm_stats(const __nv_bfloat16* src, int srcH, int srcW, int srcC, int rowH, int rowW, int nimg,
+                               const iic_conv_geom* g, int transposed, const __nv_bfloat16* wpacked, int N,
+                               const __nv_bfloat16* addend, __nv_bfloat16* out, float* stat_partial, int stat_groups,
+                               cudaStream_t st);
+
 int tc2_conv_gather_gemm(const __nv_bfloat16* src, int srcH, int srcW, int srcC, int rowH, int rowW, int nimg,
                          const iic_conv_geom* g, int transposed, const __nv_bfloat16* wpacked, int N,
                          const __nv_bfloat16* addend, __nv_bfloat16* out, cudaStream_t st) {
+  return tc2_conv_gather_gemm_stats(src, srcH, srcW, srcC, rowH, rowW, nimg, g, transposed, wpacked, N, addend, out, nullptr, 1,
+                                    st);
+}
+
+int tc2_conv_gather_gemm_stats(const __nv_bfloat16* src, int srcH, int srcW, int srcC, int rowH, int rowW, int nimg,
+                               const iic_conv_geom* g, int transposed, const __nv_bfloat16* wpacked, int N,
+                               const __nv_bfloat16* addend, __nv_bfloat16* out, float* stat_partial, int stat_groups,
+                               cudaStream_t st) {
   int rc = tma_init();
   if (rc != IIC_OK) return rc;
   const int bn = pick_bn2(N);
@@ -405,6 +475,9 @@ int tc2_conv_gather_gemm(const __nv_bfloat16* src, int srcH, int srcW, int srcC,
   P.srcC = srcC; P.Ktot = g->kh * g->kw * srcC; P.N = N;
   P.mtiles = (int)((P.rows + TC_BM - 1) / TC_BM); P.ntiles = N / bn; P.splits = 1; P.total_kb = P.Ktot / 64;
   P.out = out; P.addend = addend;
+  P.stat_partial = stat_partial;
+  IIC_REQUIRE(stat_groups == 1 || (stat_groups == 2 && nimg % 2 == 0), IIC_ERR_BAD_ARG, "conv stats: 1 or 2 views");
+  P.stat_half = stat_groups == 2 ? P.rows / 2 : P.rows;
   alignas(64) CUtensorMap tmA, tmB;
   rc = make_im2col_map(&tmA, src, nimg, srcH, srcW, srcC, P.lower, upper, P.s, TC_BM);
   if (rc != IIC_OK) return rc;

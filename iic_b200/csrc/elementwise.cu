@@ -174,11 +174,12 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ y,
 }
 
 // sums[i] = sum_b partial[b][i]  (double, fixed order => deterministic); one warp per entry
-__global__ void bn_sum_partials_kernel(const float* __restrict__ partial, int nblk, int n2c, double* __restrict__ sums) {
+__global__ void bn_sum_partials_kernel(const float* __restrict__ partial, int nblk, int n2c, long long stride,
+                                       double* __restrict__ sums) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n2c) return;
   double t = 0.0;
-  for (int b = lane; b < nblk; b += 32) t += (double)partial[(long long)b * n2c + warp];
+  for (int b = lane; b < nblk; b += 32) t += (double)partial[(long long)b * stride + warp];
   t = warp_sum(t);
   if (lane == 0) sums[warp] = t;
 }
@@ -566,12 +567,32 @@ extern "C" int iic_bn_stats(const void* y, int dtype, long long M, int C, const 
     DISPATCH_T(dtype, bn_reduce_kernel<T, false><<<blocks, 256, 0, st>>>((const T*)y, nullptr, nullptr, nullptr, nullptr, M, C, partial);)
     IIC_LAUNCH_CHECK();
     count_launch();
-    bn_sum_partials_kernel<<<cdiv(2 * C * 32, 256), 256, 0, st>>>(partial, blocks, 2 * C, stats_ws);
+    bn_sum_partials_kernel<<<cdiv(2 * C * 32, 256), 256, 0, st>>>(partial, blocks, 2 * C, 2 * C, stats_ws);
     IIC_LAUNCH_CHECK();
     count_launch();
   }
   bn_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(stats_ws, M, C, gamma, beta, eps, momentum, running_mean,
                                                     running_var, use_running, scale_shift, mean_invstd);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
+// statistics from the per-CTA partials written by iic_conv_fprop_stats: partial[blk][views][2][C]
+extern "C" int iic_bn_stats_from_partials(const float* stat_partial, int nblk, int views, int view, long long M, int C,
+                                          const float* gamma, const float* beta, float eps, float momentum,
+                                          float* running_mean, float* running_var, double* stats_ws, float* scale_shift,
+                                          float* mean_invstd, void* stream) {
+  IIC_REQUIRE(stat_partial && nblk > 0 && views >= 1 && view >= 0 && view < views && gamma && beta && stats_ws &&
+                  scale_shift && mean_invstd && M > 0 && C > 0,
+              IIC_ERR_BAD_ARG, "iic_bn_stats_from_partials: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  bn_sum_partials_kernel<<<cdiv(2 * C * 32, 256), 256, 0, st>>>(stat_partial + (long long)view * 2 * C, nblk, 2 * C,
+                                                                 (long long)views * 2 * C, stats_ws);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(stats_ws, M, C, gamma, beta, eps, momentum, running_mean, running_var, 0,
+                                                    scale_shift, mean_invstd);
   IIC_LAUNCH_CHECK();
   count_launch();
   return IIC_OK;
@@ -629,7 +650,7 @@ extern "C" int iic_bn_bwd_reduce(const void* g_in, const void* act, const float*
   DISPATCH_T(dtype, bn_reduce_kernel<T, true><<<blocks, 256, 0, st>>>((const T*)y, (const T*)g_in, (const T*)act, mask_scale_shift, mean_invstd, M, C, partial);)
   IIC_LAUNCH_CHECK();
   count_launch();
-  bn_sum_partials_kernel<<<cdiv(2 * C * 32, 256), 256, 0, st>>>(partial, blocks, 2 * C, sums);
+  bn_sum_partials_kernel<<<cdiv(2 * C * 32, 256), 256, 0, st>>>(partial, blocks, 2 * C, 2 * C, sums);
   IIC_LAUNCH_CHECK();
   count_launch();
   return IIC_OK;

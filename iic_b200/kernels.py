@@ -227,6 +227,32 @@ def conv_fprop(x, wp, g, dt):
   return y
 
 
+def conv_fprop_stats(x, wp, g, dt, views):
+  """fprop + fused per-view BN statistics partials.  Returns (y, partial, nblk) or None if unsupported."""
+  nblk = int(_lib.lib().iic_conv_fprop_stats_blocks(ctypes.byref(g), dt))
+  if nblk <= 0:
+    return None
+  y = torch.empty((g.n, g.oh, g.ow, g.cout), device=x.device, dtype=_TORCH_DT[dt])
+  partial = torch.empty((nblk, views, 2, g.cout), device=x.device, dtype=torch.float32)
+  with _timed("fprop", g):
+    check(_lib.lib().iic_conv_fprop_stats(_p(x), _p(wp), _p(y), ctypes.byref(g), dt, views, _p(partial), _stream()),
+          "iic_conv_fprop_stats")
+  return y, partial, nblk
+
+
+@_cat("bn_stats")
+def bn_stats_from_partials(partial, nblk, views, view, M, gamma, beta, eps, momentum, running_mean, running_var):
+  C = gamma.numel()
+  dev = partial.device
+  ws = torch.empty(2 * C, device=dev, dtype=torch.float64)
+  ss = torch.empty(2 * C, device=dev, dtype=torch.float32)
+  mi = torch.empty(2 * C, device=dev, dtype=torch.float32)
+  check(_lib.lib().iic_bn_stats_from_partials(_p(partial), nblk, views, view, M, C, _p(gamma), _p(beta), float(eps),
+                                              float(momentum), _p(running_mean), _p(running_var), _p(ws), _p(ss), _p(mi),
+                                              _stream()), "iic_bn_stats_from_partials")
+  return ss, mi
+
+
 def conv_dgrad(dy, wpt, g, dt, addend=None):
   dx = torch.empty((g.n, g.h, g.w, g.cin), device=dy.device, dtype=_TORCH_DT[dt])
   with _timed("dgrad", g):

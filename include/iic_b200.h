@@ -130,6 +130,19 @@ int iic_unpack_wgrad(const float* dw_packed, float* grad_oihw, int accumulate, i
  * w is the kind-0 packed weight in the same dtype.  y has dtype `dtype`. */
 int iic_conv_fprop(const void* x, const void* w_packed, void* y, const iic_conv_geom* g, int dtype,
                    void* stream);
+/* fprop with the BatchNorm batch statistics of y fused into the epilogue (IIC_BF16 only; otherwise
+ * IIC_ERR_UNSUPPORTED and the caller uses iic_conv_fprop + iic_bn_stats).  `views` = 1 or 2: the batch is the
+ * concatenation of that many equally sized views whose statistics stay separate.  stat_partial receives
+ * iic_conv_fprop_stats_blocks() rows of [views][2][cout] fp32 (per-CTA column sums / sums of squares of the
+ * fp32 accumulators); iic_bn_stats_from_partials folds them (fixed order) into scale/shift, mean/invstd and the
+ * running statistics of one view. */
+int iic_conv_fprop_stats_blocks(const iic_conv_geom* g, int dtype);
+int iic_conv_fprop_stats(const void* x, const void* w_packed, void* y, const iic_conv_geom* g, int dtype, int views,
+                         float* stat_partial, void* stream);
+int iic_bn_stats_from_partials(const float* stat_partial, int nblk, int views, int view, long long M, int C,
+                               const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                               float* running_var, double* stats_ws, float* scale_shift, float* mean_invstd,
+                               void* stream);
 /* dgrad: dx[n,h,w,cin] = conv_transpose(dy, w) (+ addend, same shape/dtype as dx, may be NULL).
  * w is the kind-1 packed weight. */
 int iic_conv_dgrad(const void* dy, const void* w_packed_t, const void* addend, void* dx,

@@ -321,3 +321,58 @@ def test_adam_matches_torch():
     K.adam_step(ps, gs, ms, vs, 1e-3, 0.9, 0.999, 1e-8, 0.0, step)
   for p, r in zip(ps, ref):
     assert torch.allclose(p, r.detach(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("h,cin,cout,k,s,p", [(49, 64, 64, 3, 1, 1), (49, 64, 128, 3, 2, 1), (25, 128, 128, 3, 1, 1),
+                                               (13, 256, 256, 3, 1, 1), (13, 256, 512, 1, 2, 0), (7, 512, 512, 3, 1, 1)])
+def test_full_size_conv_adjoint_identities(h, cin, cout, k, s, p):
+  """BASELINE size (88 pairs per GPU x 2 views = 176 images, ClusterNet5g layer shapes): the three
+  tensor-core kernels must be mutually adjoint, <conv(x,w), dy> == <x, dgrad(dy,w)> == <w, wgrad(x,dy)>,
+  a size-independent property that needs no oracle run."""
+  K = _K()
+  from iic_b200._lib import BF16
+  n = 176
+  g = torch.Generator().manual_seed(11)
+  x = torch.randn(n, h, h, cin, generator=g).cuda().bfloat16()
+  w = (torch.randn(cout, cin, k, k, generator=g) * math.sqrt(2.0 / (cin * k * k))).cuda().bfloat16().float()
+  geo = K.conv_geom(n, h, h, cin, cout, k, k, s, p, 1)
+  dy = torch.randn(n, geo.oh, geo.ow, cout, generator=g).cuda().bfloat16()
+  y = K.conv_fprop(x, K.pack_weight(w, BF16, 0), geo, BF16)
+  dx = K.conv_dgrad(dy, K.pack_weight(w, BF16, 1), geo, BF16)
+  dw = torch.zeros_like(w)
+  K.conv_wgrad(x, dy, geo, BF16, dw, False)
+  a = (y.double() * dy.double()).sum().item()
+  b = (x.double() * dx.double()).sum().item()
+  c = (w.double() * dw.double()).sum().item()
+  scale = (y.double().norm() * dy.double().norm()).item()
+  assert abs(a - c) <= 2e-3 * scale and abs(b - c) <= 2e-3 * scale, (a, b, c, scale)
+
+
+@pytest.mark.parametrize("n,h,cin,cout,k,s,p", [(6, 13, 64, 64, 3, 1, 1), (4, 25, 64, 128, 3, 2, 1), (10, 7, 256, 512, 3, 1, 1),
+                                                 (2, 49, 64, 64, 3, 1, 1)])
+def test_conv_epilogue_bn_statistics(n, h, cin, cout, k, s, p):
+  """BN statistics accumulated in the tcgen05 conv epilogue (two views in one launch, statistics kept
+  per view) == statistics of a separate pass over the stored output."""
+  K = _K()
+  from iic_b200._lib import BF16
+  g = torch.Generator().manual_seed(21)
+  x = torch.randn(n, h, h, cin, generator=g).cuda().bfloat16()
+  x[n // 2:] = x[n // 2:] * 2.0 + 0.5  # make the two views' statistics clearly different
+  w = (torch.randn(cout, cin, k, k, generator=g) * math.sqrt(2.0 / (cin * k * k))).cuda()
+  gamma = (torch.rand(cout, generator=g) + 0.5).cuda()
+  beta = (torch.randn(cout, generator=g) * 0.1).cuda()
+  geo = K.conv_geom(n, h, h, cin, cout, k, k, s, p, 1)
+  wp = K.pack_weight(w, BF16, 0)
+  y, partial, nblk = K.conv_fprop_stats(x, wp, geo, BF16, 2)
+  y_ref = K.conv_fprop(x, wp, geo, BF16)
+  assert torch.equal(y, y_ref)
+  M = (n // 2) * geo.oh * geo.ow
+  for v in range(2):
+    rm, rv = torch.zeros(cout).cuda(), torch.ones(cout).cuda()
+    rm2, rv2 = torch.zeros(cout).cuda(), torch.ones(cout).cuda()
+    ss, mi = K.bn_stats_from_partials(partial, nblk, 2, v, M, gamma, beta, 1e-5, 0.1, rm, rv)
+    ss2, mi2 = K.bn_stats(y[v * (n // 2):(v + 1) * (n // 2)], gamma, beta, 1e-5, 0.1, rm2, rv2, False)
+    assert torch.allclose(mi[:cout], mi2[:cout], rtol=0, atol=3e-3 * mi2[:cout].abs().max().item() + 1e-3)  # mean
+    assert torch.allclose(mi[cout:], mi2[cout:], rtol=5e-3, atol=0)  # invstd
+    assert torch.allclose(ss, ss2, rtol=1e-2, atol=5e-3)
+    assert torch.allclose(rv, rv2, rtol=1e-2, atol=1e-4)
