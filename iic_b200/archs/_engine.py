@@ -160,7 +160,7 @@ def _conv_bn(ctx, conv, bn, x, g):
   for v in range(ctx.groups):
     if update:
       bn.num_batches_tracked += 1
-    ss, mi = K.bn_stats_from_partials(partial, nblk, ctx.groups, v, M, bn.weight.detach(), bn.bias.detach(), bn.eps,
+    ss, mi = K.bn_stats_from_partials(partial, nblk, 2, v, M, bn.weight.detach(), bn.bias.detach(), bn.eps,
                                       bn.momentum, rm, rv)
     sss.append(ss)
     mis.append(mi)

@@ -233,7 +233,7 @@ def conv_fprop_stats(x, wp, g, dt, views):
   if nblk <= 0:
     return None
   y = torch.empty((g.n, g.oh, g.ow, g.cout), device=x.device, dtype=_TORCH_DT[dt])
-  partial = torch.empty((nblk, views, 2, g.cout), device=x.device, dtype=torch.float32)
+  partial = torch.empty((nblk, 2, 2, g.cout), device=x.device, dtype=torch.float32)  # rows are always [2 views][2][C]
   with _timed("fprop", g):
     check(_lib.lib().iic_conv_fprop_stats(_p(x), _p(wp), _p(y), ctypes.byref(g), dt, views, _p(partial), _stream()),
           "iic_conv_fprop_stats")

@@ -133,9 +133,10 @@ int iic_conv_fprop(const void* x, const void* w_packed, void* y, const iic_conv_
 /* fprop with the BatchNorm batch statistics of y fused into the epilogue (IIC_BF16 only; otherwise
  * IIC_ERR_UNSUPPORTED and the caller uses iic_conv_fprop + iic_bn_stats).  `views` = 1 or 2: the batch is the
  * concatenation of that many equally sized views whose statistics stay separate.  stat_partial receives
- * iic_conv_fprop_stats_blocks() rows of [views][2][cout] fp32 (per-CTA column sums / sums of squares of the
- * fp32 accumulators); iic_bn_stats_from_partials folds them (fixed order) into scale/shift, mean/invstd and the
- * running statistics of one view. */
+ * iic_conv_fprop_stats_blocks() rows of [2][2][cout] fp32 (per-CTA column sums / sums of squares of the fp32
+ * accumulators; the row layout always has two view slots, the second is zero when views == 1);
+ * iic_bn_stats_from_partials(…, views = 2 (row layout), view, …) folds them (fixed order) into scale/shift,
+ * mean/invstd and the running statistics of one view. */
 int iic_conv_fprop_stats_blocks(const iic_conv_geom* g, int dtype);
 int iic_conv_fprop_stats(const void* x, const void* w_packed, void* y, const iic_conv_geom* g, int dtype, int views,
                          float* stat_partial, void* stream);

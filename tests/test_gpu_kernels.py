@@ -376,3 +376,9 @@ def test_conv_epilogue_bn_statistics(n, h, cin, cout, k, s, p):
     assert torch.allclose(mi[cout:], mi2[cout:], rtol=5e-3, atol=0)  # invstd
     assert torch.allclose(ss, ss2, rtol=1e-2, atol=5e-3)
     assert torch.allclose(rv, rv2, rtol=1e-2, atol=1e-4)
+  # one view: second slot of every partial row is zero, first holds the whole batch
+  y1, partial1, nblk1 = K.conv_fprop_stats(x, wp, geo, BF16, 1)
+  assert partial1.shape[1] == 2 and float(partial1[:, 1].abs().max()) == 0.0
+  ss, mi = K.bn_stats_from_partials(partial1, nblk1, 2, 0, 2 * M, gamma, beta, 1e-5, 0.1, None, None)
+  ss2, mi2 = K.bn_stats(y, gamma, beta, 1e-5, 0.1, None, None, False)
+  assert torch.allclose(ss, ss2, rtol=1e-2, atol=5e-3)
