@@ -69,6 +69,31 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   *reinterpret_cast<uint4*>(p) = v;
 }
+// raw (unconverted) 8-element vectors: keep several loads in flight without paying fp32 registers for bf16 data
+struct Raw8f { float4 a, b; };
+struct Raw8h { uint4 v; };
+__device__ __forceinline__ void load_raw(const float* p, Raw8f& r) {
+  r.a = *reinterpret_cast<const float4*>(p);
+  r.b = *reinterpret_cast<const float4*>(p + 4);
+}
+__device__ __forceinline__ void load_raw(const __nv_bfloat16* p, Raw8h& r) { r.v = *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void cvt_raw(const Raw8f& r, float (&f)[8]) {
+  f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w;
+  f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+}
+__device__ __forceinline__ void cvt_raw(const Raw8h& r, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+template <typename T> struct RawOf;
+template <> struct RawOf<float> { using type = Raw8f; };
+template <> struct RawOf<__nv_bfloat16> { using type = Raw8h; };
+
 __device__ __forceinline__ float to_f(float x) { return x; }
 __device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float(x); }
 template <typename T> __device__ __forceinline__ T from_f(float x);

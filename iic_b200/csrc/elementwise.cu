@@ -114,46 +114,43 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const T* __restrict__ y,
       }
     }
     const long long stride = (long long)gridDim.x * rows_per_it;
-    for (long long r = (long long)blockIdx.x * rows_per_it + my_r; r < M; r += 2 * stride) {
-      const long long r2 = r + stride;
-      const bool two = r2 < M;
-      float v[8], v2[8], g[8], g2[8], a[8], a2[8];
-      load8(y + r * C + c8 * 8, v);
-      if (two) load8(y + r2 * C + c8 * 8, v2);
-      if (BWD) {
-        load8(gin + r * C + c8 * 8, g);
-        if (two) load8(gin + r2 * C + c8 * 8, g2);
-        if (act != nullptr) {
-          load8(act + r * C + c8 * 8, a);
-          if (two) load8(act + r2 * C + c8 * 8, a2);
+    constexpr int U = 4;  // rows in flight per thread: all (raw, unconverted) loads are issued before any arithmetic
+    using Raw = typename RawOf<T>::type;
+    for (long long r = (long long)blockIdx.x * rows_per_it + my_r; r < M; r += U * stride) {
+      Raw rv[U], rg[U], ra[U];
+      bool ok[U];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            g[j] = a[j] > 0.f ? g[j] : 0.f;
-            if (two) g2[j] = a2[j] > 0.f ? g2[j] : 0.f;
-          }
-        } else if (mask_ss != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            g[j] = fmaf(v[j], msc[j], msh[j]) > 0.f ? g[j] : 0.f;
-            if (two) g2[j] = fmaf(v2[j], msc[j], msh[j]) > 0.f ? g2[j] : 0.f;
+      for (int u = 0; u < U; ++u) {
+        const long long ru = r + u * stride;
+        ok[u] = ru < M;
+        if (ok[u]) {
+          load_raw(y + ru * C + c8 * 8, rv[u]);
+          if (BWD) {
+            load_raw(gin + ru * C + c8 * 8, rg[u]);
+            if (act != nullptr) load_raw(act + ru * C + c8 * 8, ra[u]);
           }
         }
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (!BWD) {
-          a0[j] += v[j];
-          a1[j] = fmaf(v[j], v[j], a1[j]);
-          if (two) {
-            a0[j] += v2[j];
-            a1[j] = fmaf(v2[j], v2[j], a1[j]);
-          }
-        } else {
-          a0[j] += g[j];
-          a1[j] = fmaf(g[j], (v[j] - mean[j]) * istd[j], a1[j]);
-          if (two) {
-            a0[j] += g2[j];
-            a1[j] = fmaf(g2[j], (v2[j] - mean[j]) * istd[j], a1[j]);
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        float v[8], g[8], a[8];
+        cvt_raw(rv[u], v);
+        if (BWD) {
+          cvt_raw(rg[u], g);
+          if (act != nullptr) cvt_raw(ra[u], a);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (!BWD) {
+            a0[j] += v[j];
+            a1[j] = fmaf(v[j], v[j], a1[j]);
+          } else {
+            float gj = g[j];
+            if (act != nullptr) gj = a[j] > 0.f ? gj : 0.f;
+            else if (mask_ss != nullptr) gj = fmaf(v[j], msc[j], msh[j]) > 0.f ? gj : 0.f;
+            a0[j] += gj;
+            a1[j] = fmaf(gj, (v[j] - mean[j]) * istd[j], a1[j]);
           }
         }
       }
@@ -526,8 +523,8 @@ extern "C" int iic_sobel(const float* imgs, float* out, int n, int c_in, int h, 
 
 static int bn_reduce_blocks(long long M, int C) {
   const int rpi = 256 / (C / 8);
-  long long blocks = (M + 2 * rpi - 1) / (2 * rpi);
-  const long long cap = (long long)device_sm_count() * 4;
+  long long blocks = (M + 4 * rpi - 1) / (4 * rpi);
+  const long long cap = (long long)device_sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
@@ -562,7 +559,7 @@ extern "C" int iic_bn_stats(const void* y, int dtype, long long M, int C, const 
   cudaStream_t st = (cudaStream_t)stream;
   if (!use_running) {
     const int blocks = bn_reduce_blocks(M, C);
-    float* partial = bn_partial_scratch((size_t)device_sm_count() * 4 * 2 * 2048 * sizeof(float));
+    float* partial = bn_partial_scratch((size_t)device_sm_count() * 8 * 2 * 2048 * sizeof(float));
     IIC_REQUIRE(partial != nullptr, IIC_ERR_CUDA, "iic_bn_stats: scratch allocation failed");
     DISPATCH_T(dtype, bn_reduce_kernel<T, false><<<blocks, 256, 0, st>>>((const T*)y, nullptr, nullptr, nullptr, nullptr, M, C, partial);)
     IIC_LAUNCH_CHECK();
@@ -645,7 +642,7 @@ extern "C" int iic_bn_bwd_reduce(const void* g_in, const void* act, const float*
   IIC_REQUIRE(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, IIC_ERR_UNSUPPORTED, "iic_bn_bwd_reduce: C=%d unsupported", C);
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = bn_reduce_blocks(M, C);
-  float* partial = bn_partial_scratch((size_t)device_sm_count() * 4 * 2 * 2048 * sizeof(float));
+  float* partial = bn_partial_scratch((size_t)device_sm_count() * 8 * 2 * 2048 * sizeof(float));
   IIC_REQUIRE(partial != nullptr, IIC_ERR_CUDA, "iic_bn_bwd_reduce: scratch allocation failed");
   DISPATCH_T(dtype, bn_reduce_kernel<T, true><<<blocks, 256, 0, st>>>((const T*)y, (const T*)g_in, (const T*)act, mask_scale_shift, mean_invstd, M, C, partial);)
   IIC_LAUNCH_CHECK();
