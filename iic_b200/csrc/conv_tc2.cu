@@ -63,30 +63,37 @@ __device__ __forceinline__ void warp_col_reduce(float (&t)[32], int lane) {
   }
 }
 
-template <int BN> struct Tc2Cfg {
+// RESB: the whole dense operand (all k-blocks of the packed weight for this N tile) stays resident in shared
+// memory for the lifetime of the persistent CTA; the ring then carries only the activation tile.  Used for
+// the 64-channel layers (3x3x64x64 weights = 72 KB), where re-fetching the weight tile for every 128-pixel
+// tile was a third of the L2->SM traffic that bounds them.
+template <int BN, bool RESB = false> struct Tc2Cfg {
   static constexpr int A_BYTES = TC_BM * 128;
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int STAGE_BYTES = A_BYTES + (RESB ? 0 : B_BYTES);
+  static constexpr int STAGES = RESB ? 8 : ((BN >= 256) ? 4 : (BN >= 128 ? 6 : 8));
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;  // (+ 64 B x N for fused BN statistics)
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
-template <int MODE, int BN>
+template <int MODE, int BN, bool RESB = false>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Tc2Params P) {
-  using Cfg = Tc2Cfg<BN>;
+  using Cfg = Tc2Cfg<BN, RESB>;
   constexpr int STAGES = Cfg::STAGES;
+  static_assert(!RESB || MODE == M2_FPROP, "resident dense operand: fprop/dgrad only");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t resb = (raw + 1023u) & ~1023u;  // [total_kb][BN x 128 B] resident weights (RESB), else empty
+  const uint32_t base = resb + (RESB ? (uint32_t)P.total_kb * Cfg::B_BYTES : 0u);
   uint8_t* base_ptr = smem_raw + (base - raw);
   const uint32_t bars = base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bres_bar = bars + 8u * (2 * STAGES + 4);
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + STAGES * Cfg::STAGE_BYTES + (2 * STAGES + 4) * 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + STAGES * Cfg::STAGE_BYTES + (2 * STAGES + 5) * 8);
   float* stat = reinterpret_cast<float*>(base_ptr + STAGES * Cfg::STAGE_BYTES + 256);  // [4 warps][2 views][2][N]
   const bool do_stats = (MODE == M2_FPROP) && P.stat_partial != nullptr;
   if (do_stats)
@@ -102,6 +109,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 128);
     }
+    mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 5 && lane == 0) {
@@ -140,6 +148,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // issued in parallel instead of back to back by one thread (the single-thread issue rate, not L2
     // bandwidth, bounded the 64-channel layers and wgrad: profiles/r01_ncu_wgrad.md).
     uint32_t it = 0;  // global k-block counter -> stage / phase
+    if (RESB && blockIdx.x < total_work) {
+      // one-off: the whole packed weight of this (single) N tile, k-block by k-block
+      if (lane == 0) mbar_expect_tx(bres_bar, (uint32_t)P.total_kb * Cfg::B_BYTES);
+      __syncwarp();
+      int tap = 0, c0 = 0;
+      for (int i = 0; i < P.total_kb; ++i) {
+        if (lane == (i & 31)) tma_load_2d(resb + i * Cfg::B_BYTES, &tmB, bres_bar, (int)P.wtap[tap] * P.srcC + c0, 0);
+        c0 += 64;
+        if (c0 >= P.srcC) {
+          c0 = 0;
+          ++tap;
+        }
+      }
+    }
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       int z, n0, kb0, nk;
       long long m0;
@@ -159,7 +181,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
           if (lane == 0)
             tma_load_im2col(sa, &tmA, full_bar(s), c0, cw, ch, img, (uint16_t)P.offw[tap], (uint16_t)P.offh[tap]);
-          else if (lane == 1)
+          else if (lane == 1 && !RESB)
             tma_load_2d(sb, &tmB, full_bar(s), (int)P.wtap[tap] * P.srcC + c0, n0);
           c0 += 64;
           if (c0 >= P.srcC) {
@@ -220,6 +242,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // =============================== MMA issuer ==============================================
     constexpr uint32_t idesc = (MODE == M2_FPROP) ? make_idesc(BN, 0, 0) : make_idesc(BN, 1, 1);
     uint32_t it = 0, tile_it = 0;
+    if (RESB && blockIdx.x < total_work) mbar_wait(bres_bar, 0);
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tile_it) {
       int z, n0, kb0, nk;
       long long m0;
@@ -233,7 +256,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(full_bar(s), (it / STAGES) & 1u);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t sa = base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+          const uint32_t sa = base + s * Cfg::STAGE_BYTES;
+          const uint32_t sb = RESB ? resb + (uint32_t)i * Cfg::B_BYTES : sa + Cfg::A_BYTES;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             uint64_t ad, bd;
@@ -399,18 +423,25 @@ static int make_im2col_map2(CUtensorMap* tm, const void* ptr, int nimg, int H, i
 
 static int tc2_grid(long long work) { return (int)(work < device_sm_count() ? work : device_sm_count()); }
 
-template <int MODE, int BN>
-static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc2Params& P, int splits, cudaStream_t st) {
-  using Cfg = Tc2Cfg<BN>;
-  const int smem = Cfg::SMEM + (P.stat_partial ? 64 * P.N : 0);
+template <int MODE, int BN, bool RESB>
+static int launch_tc2_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc2Params& P, int splits, cudaStream_t st) {
+  using Cfg = Tc2Cfg<BN, RESB>;
+  const int smem = Cfg::SMEM + (P.stat_partial ? 64 * P.N : 0) + (RESB ? P.total_kb * Cfg::B_BYTES : 0);
   IIC_REQUIRE(smem <= 232448, IIC_ERR_UNSUPPORTED, "conv_tc2: shared memory budget exceeded (%d B)", smem);
-  IIC_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  IIC_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<MODE, BN, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   long long work = (long long)P.mtiles * P.ntiles * splits;
   int grid = tc2_grid(work);
-  conv_tc2_kernel<MODE, BN><<<grid, TC2_THREADS, smem, st>>>(tmA, tmB, P);
+  conv_tc2_kernel<MODE, BN, RESB><<<grid, TC2_THREADS, smem, st>>>(tmA, tmB, P);
   IIC_LAUNCH_CHECK();
   count_launch();
   return IIC_OK;
+}
+
+template <int MODE, int BN>
+static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc2Params& P, int splits, cudaStream_t st) {
+  if (MODE == M2_FPROP && BN == 64 && P.ntiles == 1 && P.total_kb * (BN * 128) <= 80 * 1024 && P.mtiles > device_sm_count())
+    return launch_tc2_impl<M2_FPROP, 64, true>(tmA, tmB, P, splits, st);
+  return launch_tc2_impl<MODE, BN, false>(tmA, tmB, P, splits, st);
 }
 
 static int pick_bn2(int N) {

@@ -217,23 +217,26 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, 
                                                        T* __restrict__ out, long long M, int C, int relu) {
   const int cg = C >> 3;
   const long long total = M * cg;
+  // a thread's channel group is loop invariant (blockDim.x is a multiple of C/8): keep the coefficients in registers
+  const int c8 = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) % cg);
+  float sc[8], sh[8], rsc[8], rsh[8];
+  load8(ss + c8 * 8, sc);
+  load8(ss + C + c8 * 8, sh);
+  if (rss != nullptr) {
+    load8(rss + c8 * 8, rsc);
+    load8(rss + C + c8 * 8, rsh);
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % cg);
     float v[8];
     load8(y + i * 8, v);
-    float sc[8], sh[8];
-    load8(ss + c8 * 8, sc);
-    load8(ss + C + c8 * 8, sh);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
     if (res != nullptr) {
       float r[8];
       load8(res + i * 8, r);
       if (rss != nullptr) {
-        load8(rss + c8 * 8, sc);
-        load8(rss + C + c8 * 8, sh);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = fmaf(r[j], sc[j], sh[j]);
+        for (int j = 0; j < 8; ++j) r[j] = fmaf(r[j], rsc[j], rsh[j]);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += r[j];
@@ -367,8 +370,15 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
     }
   }
   __syncthreads();
+  // blockDim.x (256) is a multiple of C/8 (<= 64 groups... up to 256), so a thread's channel group never changes
+  const int c8 = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) % cg);
+  float cA[8], cB[8], cC[8], ms[8], mh[8];
+  load8(coef + c8 * 8, cA);
+  load8(coef + C + c8 * 8, cB);
+  load8(coef + 2 * C + c8 * 8, cC);
+  load8(coef + 3 * C + c8 * 8, ms);
+  load8(coef + 4 * C + c8 * 8, mh);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % cg);
     float g[8], v[8];
     load8(gin + i * 8, g);
     load8(y + i * 8, v);
@@ -378,17 +388,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
     } else if (mask_ss != nullptr) {
-      float ms[8], mh[8];
-      load8(coef + 3 * C + c8 * 8, ms);
-      load8(coef + 4 * C + c8 * 8, mh);
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] = fmaf(v[j], ms[j], mh[j]) > 0.f ? g[j] : 0.f;
     }
     if (g_out != nullptr) store8(g_out + i * 8, g);
-    float cA[8], cB[8], cC[8], o[8];
-    load8(coef + c8 * 8, cA);
-    load8(coef + C + c8 * 8, cB);
-    load8(coef + 2 * C + c8 * 8, cC);
+    float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = fmaf(cA[j], g[j], fmaf(cB[j], v[j], cC[j]));
     store8(dy + i * 8, o);
@@ -598,6 +602,7 @@ extern "C" int iic_bn_stats_from_partials(const float* stat_partial, int nblk, i
 extern "C" int iic_bn_apply(const void* y, const float* scale_shift, const void* res, const float* res_scale_shift,
                             void* out, int dtype, long long M, int C, int relu, void* stream) {
   IIC_REQUIRE(y && scale_shift && out && M > 0 && C % 8 == 0, IIC_ERR_BAD_ARG, "iic_bn_apply: bad arguments");
+  IIC_REQUIRE(256 % (C / 8) == 0, IIC_ERR_UNSUPPORTED, "iic_bn_apply: C=%d must be 8 * (a divisor of 256)", C);
   const long long total = M * (C / 8);
   DISPATCH_T(dtype, bn_apply_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const T*)y, scale_shift, (const T*)res, res_scale_shift, (T*)out, M, C, relu);)
@@ -659,6 +664,7 @@ extern "C" int iic_bn_bwd_apply(const void* g_in, const void* act, const float* 
                                 float* dbeta, int accumulate, int dtype, long long M, int C, void* stream) {
   IIC_REQUIRE(g_in && y && mean_invstd && gamma && sums && dy && M > 0 && C % 8 == 0, IIC_ERR_BAD_ARG,
               "iic_bn_bwd_apply: bad arguments");
+  IIC_REQUIRE(256 % (C / 8) == 0, IIC_ERR_UNSUPPORTED, "iic_bn_bwd_apply: C=%d must be 8 * (a divisor of 256)", C);
   const long long total = M * (C / 8);
   const size_t smem = (size_t)5 * C * sizeof(float);
   DISPATCH_T(dtype, bn_bwd_apply_kernel<T><<<ew_grid(total, 256), 256, smem, (cudaStream_t)stream>>>(
