@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
   const int tid = threadIdx.x;
   const int my_g = tid / T_tiles, my_t = tid % T_tiles;
   const bool active = my_g < G;
-  const int tc = my_t / tkk, tk = my_t % tkk;  // tile = 8 output channels x 4 taps
+  const int tc = my_t / tkk, tk = my_t % tkk;  // tile = 4 output channels x 4 taps
   const int hw = g.h * g.w;
   for (int k = tid; k < Kp; k += 256) {
     const int b = k % g.kw, a = (k / g.kw) % g.kh, ci = k / (g.kw * g.kh);
@@ -126,9 +126,9 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
     ktab[k * 3 + 1] = a * g.dil;
     ktab[k * 3 + 2] = b * g.dil;
   }
-  float acc[8][4];
+  float acc[4][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const int nchunks = (P + SW_PC - 1) / SW_PC;
@@ -179,12 +179,11 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
     __syncthreads();
     if (active) {
       for (int r = my_g; r < SW_PC; r += G) {
-        const float4 a0 = *reinterpret_cast<const float4*>(dys + r * cout + 8 * tc);
-        const float4 a1 = *reinterpret_cast<const float4*>(dys + r * cout + 8 * tc + 4);
+        const float4 a = *reinterpret_cast<const float4*>(dys + r * cout + 4 * tc);
         const float4 b = *reinterpret_cast<const float4*>(pat + r * Kp + 4 * tk);
-        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[4] = {b.x, b.y, b.z, b.w};
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
       }
@@ -193,9 +192,9 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
   __syncthreads();
   if (active) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) red[(long long)my_g * cout * Kp + (8 * tc + i) * Kp + 4 * tk + j] = acc[i][j];
+      for (int j = 0; j < 4; ++j) red[(long long)my_g * cout * Kp + (4 * tc + i) * Kp + 4 * tk + j] = acc[i][j];
   }
   __syncthreads();
   for (int e = tid; e < cout * K; e += 256) {
@@ -278,7 +277,7 @@ extern "C" int iic_stem_wgrad(const float* x_nchw, const void* dy, float* grad_o
   IIC_REQUIRE(x_nchw && dy && grad_oihw && workspace, IIC_ERR_BAD_ARG, "iic_stem_wgrad: null pointer");
   IIC_REQUIRE(g->cout % 8 == 0, IIC_ERR_UNSUPPORTED, "iic_stem_wgrad: cout must be a multiple of 8");
   const int K = g->cin * g->kh * g->kw, Kp = (K + 3) & ~3, tkk = Kp / 4;
-  const int T_tiles = (g->cout / 8) * tkk;
+  const int T_tiles = (g->cout / 4) * tkk;
   IIC_REQUIRE(T_tiles <= 256, IIC_ERR_UNSUPPORTED, "iic_stem_wgrad: cout*K too large (%d tiles)", T_tiles);
   int G = 256 / T_tiles;
   if (G > SW_PC) G = SW_PC;
