@@ -175,13 +175,11 @@ __global__ void __launch_bounds__(IID_THREADS, 1) iid_loss_kernel(IidParams p) {
   double part = 0.0;
   for (int e = tid; e < kk; e += IID_THREADS) part += (double)bufA[e];
   const double ssum = block_sum(part, red);
-  const float inv2s = (float)(0.5 / ssum);
   // P = (A + A^T)/2 / s   -> bufB     (reference :44-45)
   for (int e = tid; e < kk; e += IID_THREADS) {
     int a = e / kp, b = e - a * kp;
     bufB[e] = (a < k && b < k) ? (bufA[a * kp + b] + bufA[b * kp + a]) * 0.5f / (float)ssum : 0.f;
   }
-  (void)inv2s;
   __syncthreads();
   float* pi = marg;            // row sums of the un-clamped P (:12)
   float* pj = marg + kp;       // col sums (:13-14)
