@@ -67,13 +67,16 @@ __device__ __forceinline__ void warp_col_reduce(float (&t)[32], int lane) {
 // memory for the lifetime of the persistent CTA; the ring then carries only the activation tile.  Used for
 // the 64-channel layers (3x3x64x64 weights = 72 KB), where re-fetching the weight tile for every 128-pixel
 // tile was a third of the L2->SM traffic that bounds them.
+// With RESB a work item is TWO 128-row tiles (MT = 2): one 256-pixel TMA box and one barrier round-trip feed eight
+// MMAs, halving the per-byte producer / barrier overhead that bounds N = 64 tiles (128 MMA cycles per k-block).
 template <int BN, bool RESB = false> struct Tc2Cfg {
-  static constexpr int A_BYTES = TC_BM * 128;
+  static constexpr int MT = RESB ? 2 : 1;
+  static constexpr int A_BYTES = MT * TC_BM * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + (RESB ? 0 : B_BYTES);
-  static constexpr int STAGES = RESB ? 8 : ((BN >= 256) ? 4 : (BN >= 128 ? 6 : 8));
+  static constexpr int STAGES = RESB ? 4 : ((BN >= 256) ? 4 : (BN >= 128 ? 6 : 8));
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;  // (+ 64 B x N for fused BN statistics)
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int TMEM_COLS = 2 * MT * BN;
 };
 
 template <int MODE, int BN, bool RESB = false>
@@ -81,6 +84,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Tc2Params P) {
   using Cfg = Tc2Cfg<BN, RESB>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int MT = Cfg::MT;
   static_assert(!RESB || MODE == M2_FPROP, "resident dense operand: fprop/dgrad only");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -130,7 +134,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     z = w / tiles_mn;
     const int r = w - z * tiles_mn;
     n0 = (r % P.ntiles) * BN;
-    m0 = (long long)(r / P.ntiles) * TC_BM;
+    m0 = (long long)(r / P.ntiles) * (MT * TC_BM);
     if (MODE == M2_FPROP) {
       kb0 = 0;
       nk = P.total_kb;
@@ -250,7 +254,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t as = tile_it & 1u;
       mbar_wait(tempty_bar(as), ((tile_it >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
       tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + as * BN;
+      const uint32_t tmem_acc = tmem_base + as * (MT * BN);
       for (int i = 0; i < nk; ++i, ++it) {
         const int s = it % STAGES;
         mbar_wait(full_bar(s), (it / STAGES) & 1u);
@@ -259,16 +263,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t sa = base + s * Cfg::STAGE_BYTES;
           const uint32_t sb = RESB ? resb + (uint32_t)i * Cfg::B_BYTES : sa + Cfg::A_BYTES;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            uint64_t ad, bd;
-            if (MODE == M2_FPROP) {
-              ad = make_desc(sa + kk * 32, 16, 1024);
-              bd = make_desc(sb + kk * 32, 16, 1024);
-            } else {
-              ad = make_desc(sa + kk * 2048, 8192, 1024);
-              bd = make_desc(sb + kk * 2048, 8192, 1024);
+          for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              uint64_t ad, bd;
+              if (MODE == M2_FPROP) {
+                ad = make_desc(sa + mt * (TC_BM * 128) + kk * 32, 16, 1024);
+                bd = make_desc(sb + kk * 32, 16, 1024);
+              } else {
+                ad = make_desc(sa + kk * 2048, 8192, 1024);
+                bd = make_desc(sb + kk * 2048, 8192, 1024);
+              }
+              umma_bf16(tmem_acc + mt * BN, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
             }
-            umma_bf16(tmem_acc, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(s));
         }
@@ -287,8 +294,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t as = tile_it & 1u;
       mbar_wait(tfull_bar(as), (tile_it >> 1) & 1u);
       tc_fence_after();
-      const long long m = m0 + warp * 32 + lane;  // TMEM lane == tile row
-      const uint32_t tmem_acc = tmem_base + as * BN + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+      const long long mtile0 = m0 + (long long)mt * TC_BM;
+      const long long m = mtile0 + warp * 32 + lane;  // TMEM lane == tile row
+      const uint32_t tmem_acc = tmem_base + as * (MT * BN) + mt * BN + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
@@ -302,7 +312,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (MODE == M2_FPROP) {
           if (do_stats) {
             // per-column sums over this warp's 32 rows (rows >= P.rows are exact zeros: TMA zero fill)
-            const bool lo1 = m0 >= P.stat_half, hi1 = (m0 + TC_BM - 1) >= P.stat_half;
+            const bool lo1 = mtile0 >= P.stat_half, hi1 = (mtile0 + TC_BM - 1) >= P.stat_half;
             for (int grp = lo1 ? 1 : 0; grp <= (hi1 ? 1 : 0); ++grp) {
               const bool mine = (m >= P.stat_half) == (grp == 1);
               float t[32];
@@ -354,6 +364,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                               __uint_as_float(v[qq * 4 + 3]));
           }
         }
+      }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(as));
@@ -439,9 +450,12 @@ static int launch_tc2_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const
 
 template <int MODE, int BN>
 static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc2Params& P, int splits, cudaStream_t st) {
-  if (MODE == M2_FPROP && BN == 64 && P.ntiles == 1 && P.total_kb * (BN * 128) <= 80 * 1024 && P.mtiles > device_sm_count())
-    return launch_tc2_impl<M2_FPROP, 64, true>(tmA, tmB, P, splits, st);
   return launch_tc2_impl<MODE, BN, false>(tmA, tmB, P, splits, st);
+}
+
+// resident-weights / two-tile variant: N == 64 (one N tile), whole packed weight <= 80 KB, many tiles per CTA
+static bool tc2_use_resb(int bn, int N, int total_kb, long long rows) {
+  return bn == 64 && N == 64 && total_kb * (64 * 128) <= 80 * 1024 && (rows + TC_BM - 1) / TC_BM > 2ll * device_sm_count();
 }
 
 static int pick_bn2(int N) {
@@ -456,7 +470,8 @@ int tc2_conv_fprop_blocks(const iic_conv_geom* g) {
   const int bn = pick_bn2(g->cout);
   if (bn == 0) return 0;
   const long long rows = (long long)g->n * g->oh * g->ow;
-  return tc2_grid(((rows + TC_BM - 1) / TC_BM) * (g->cout / bn));
+  const int tile_rows = tc2_use_resb(bn, g->cout, g->kh * g->kw * g->cin / 64, rows) ? 2 * TC_BM : TC_BM;
+  return tc2_grid(((rows + tile_rows - 1) / tile_rows) * (g->cout / bn));
 }
 
 int tc2_conv_gather_gemm_stats(const __nv_bfloat16* src, int srcH, int srcW, int srcC, int rowH, int rowW, int nimg,
@@ -504,13 +519,16 @@ int tc2_conv_gather_gemm_stats(const __nv_bfloat16* src, int srcH, int srcW, int
   }
   IIC_REQUIRE(P.lower >= -128 && P.lower <= 127 && upper >= -128 && upper <= 127, IIC_ERR_UNSUPPORTED, "im2col corner range");
   P.srcC = srcC; P.Ktot = g->kh * g->kw * srcC; P.N = N;
-  P.mtiles = (int)((P.rows + TC_BM - 1) / TC_BM); P.ntiles = N / bn; P.splits = 1; P.total_kb = P.Ktot / 64;
+  P.ntiles = N / bn; P.splits = 1; P.total_kb = P.Ktot / 64;
+  const bool resb = tc2_use_resb(bn, N, P.total_kb, P.rows);
+  const int tile_rows = resb ? 2 * TC_BM : TC_BM;
+  P.mtiles = (int)((P.rows + tile_rows - 1) / tile_rows);
   P.out = out; P.addend = addend;
   P.stat_partial = stat_partial;
   IIC_REQUIRE(stat_groups == 1 || (stat_groups == 2 && nimg % 2 == 0), IIC_ERR_BAD_ARG, "conv stats: 1 or 2 views");
   P.stat_half = stat_groups == 2 ? P.rows / 2 : P.rows;
   alignas(64) CUtensorMap tmA, tmB;
-  rc = make_im2col_map(&tmA, src, nimg, srcH, srcW, srcC, P.lower, upper, P.s, TC_BM);
+  rc = make_im2col_map(&tmA, src, nimg, srcH, srcW, srcC, P.lower, upper, P.s, tile_rows);
   if (rc != IIC_OK) return rc;
   {
     cuuint64_t gdim[2] = {(cuuint64_t)P.Ktot, (cuuint64_t)N};
@@ -522,6 +540,7 @@ int tc2_conv_gather_gemm_stats(const __nv_bfloat16* src, int srcH, int srcW, int
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     IIC_REQUIRE(r == CUDA_SUCCESS, IIC_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed (%d)", (int)r);
   }
+  if (resb) return launch_tc2_impl<M2_FPROP, 64, true>(tmA, tmB, P, 1, st);
   switch (bn) {
     case 256: return launch_tc2<M2_FPROP, 256>(tmA, tmB, P, 1, st);
     case 128: return launch_tc2<M2_FPROP, 128>(tmA, tmB, P, 1, st);

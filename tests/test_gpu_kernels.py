@@ -51,6 +51,7 @@ CONV_CASES = [
   (2, 12, 64, 128, 5, 1, 2, 1),
   (2, 16, 256, 512, 3, 1, 1, 2),
   (1, 5, 128, 128, 3, 1, 1, 1),
+  (32, 49, 64, 64, 3, 1, 1, 1),  # > 2 tiles per SM: resident-weights / two-tile variant of the TMA kernel
 ]
 
 
@@ -349,7 +350,7 @@ def test_full_size_conv_adjoint_identities(h, cin, cout, k, s, p):
 
 
 @pytest.mark.parametrize("n,h,cin,cout,k,s,p", [(6, 13, 64, 64, 3, 1, 1), (4, 25, 64, 128, 3, 2, 1), (10, 7, 256, 512, 3, 1, 1),
-                                                 (2, 49, 64, 64, 3, 1, 1)])
+                                                 (2, 49, 64, 64, 3, 1, 1), (32, 49, 64, 64, 3, 1, 1)])
 def test_conv_epilogue_bn_statistics(n, h, cin, cout, k, s, p):
   """BN statistics accumulated in the tcgen05 conv epilogue (two views in one launch, statistics kept
   per view) == statistics of a separate pass over the stored output."""
