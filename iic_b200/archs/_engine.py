@@ -13,6 +13,8 @@ Precision modes (``net.precision``):
 """
 import math
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -125,19 +127,32 @@ class _Ctx(object):
     return self.wcache[key]
 
 
+class _ViewStats(list):
+  """Per-view [2C] coefficient tensors that are rows of one contiguous [views, 2C] tensor (`stacked`), so the
+  multi-view kernels take one base pointer."""
+
+  def __init__(self, stacked):
+    super(_ViewStats, self).__init__(stacked[i] for i in range(stacked.shape[0]))
+    self.stacked = stacked
+
+
+# one launch per BatchNorm pass for all views (IIC_BN_MERGED=0: one launch chain per view, the first implementation)
+_MERGED = os.environ.get("IIC_BN_MERGED", "1") != "0"
+
+
 def _bn_stats(ctx, bn, y):
   """Per-view batch statistics -> ([scale_shift per view], [mean_invstd per view])."""
   use_running = (not ctx.training) and bn.track_running_stats
   update = ctx.training and bn.track_running_stats
   rm = bn.running_mean if (update or use_running) else None
   rv = bn.running_var if (update or use_running) else None
-  sss, mis = [], []
-  for yg in ctx.split(y):  # running statistics are updated view by view, in call order
+  C = y.shape[-1]
+  sss = _ViewStats(torch.empty((ctx.groups, 2 * C), device=y.device, dtype=torch.float32))
+  mis = _ViewStats(torch.empty((ctx.groups, 2 * C), device=y.device, dtype=torch.float32))
+  for yg, ss, mi in zip(ctx.split(y), sss, mis):  # running statistics are updated view by view, in call order
     if update:
       bn.num_batches_tracked += 1
-    ss, mi = K.bn_stats(yg, bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum, rm, rv, use_running)
-    sss.append(ss)
-    mis.append(mi)
+    K.bn_stats(yg, bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum, rm, rv, use_running, ss=ss, mi=mi)
   return sss, mis
 
 
@@ -156,6 +171,12 @@ def _conv_bn(ctx, conv, bn, x, g):
   rm = bn.running_mean if update else None
   rv = bn.running_var if update else None
   M = (y.numel() // y.shape[-1]) // ctx.groups
+  if _MERGED:
+    if update:
+      bn.num_batches_tracked += ctx.groups
+    ss, mi = K.bn_stats_from_partials_views(partial, nblk, 2, ctx.groups, M, bn.weight.detach(), bn.bias.detach(),
+                                            bn.eps, bn.momentum, rm, rv)
+    return y, _ViewStats(ss), _ViewStats(mi)
   sss, mis = [], []
   for v in range(ctx.groups):
     if update:
@@ -169,6 +190,8 @@ def _conv_bn(ctx, conv, bn, x, g):
 
 def _bn_apply(ctx, y, ss, relu, res=None, rss=None):
   out = torch.empty_like(y)
+  if _MERGED and hasattr(ss, "stacked") and (rss is None or hasattr(rss, "stacked")):
+    return K.bn_apply_views(y, ss.stacked, relu, ctx.groups, res=res, rss=None if rss is None else rss.stacked, out=out)
   for yg, og, sg, rg, rsg in zip(ctx.split(y), ctx.split(out), ss, ctx.split(res), rss if rss is not None else [None] * ctx.groups):
     K.bn_apply(yg, sg, relu, res=rg, rss=rsg, out=og)
   return out
@@ -211,6 +234,8 @@ def _bn_backward(ctx, sink, bn, g_in, act, y, mi, want_g_out, mask_ss=None):
   dg, acc1 = sink.buf(bn.weight)
   db, acc2 = sink.buf(bn.bias)
   assert acc1 == acc2
+  if _MERGED and ctx.groups <= 2:
+    return K.bn_bwd_fused(g_in, act, y, mi, bn.weight.detach(), dg, db, acc1, want_g_out, mask_sss=mask_ss)
   dy = torch.empty_like(y)
   g_out = torch.empty_like(y) if want_g_out else None
   acc = acc1

@@ -2,6 +2,8 @@
 // layout plumbing, sobel, BatchNorm statistics / apply / backward, ReLU, residual add, max / avg
 // pooling, weight repacking.  Each kernel cites the reference op it replaces.
 #include "common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace iic {
 
@@ -210,15 +212,62 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, long long M,
   mean_invstd[C + c] = invstd;
 }
 
+// conv-epilogue partials [nblk][views][2C] -> per-view scale/shift and mean/invstd in ONE launch: one warp per
+// channel folds both sums of every view (fixed order, fp64) and finalises; running statistics are
+// updated view after view, like the reference's consecutive forward calls.
+__global__ void bn_fold_finalize_kernel(const float* __restrict__ partial, int nblk, int slots, int views, long long M, int C,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                        float momentum, float* running_mean, float* running_var,
+                                        float* __restrict__ scale_shift, float* __restrict__ mean_invstd) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= C) return;
+  const long long stride = (long long)slots * 2 * C;  // a CTA's partial row holds `slots` views
+  for (int v = 0; v < views; ++v) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = lane; b < nblk; b += 32) {
+      s1 += (double)partial[b * stride + (long long)v * 2 * C + c];
+      s2 += (double)partial[b * stride + (long long)v * 2 * C + C + c];
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      const double m = s1 / (double)M;
+      double var = s2 / (double)M - m * m;
+      if (var < 0.0) var = 0.0;
+      const float mean = (float)m, invstd = (float)(1.0 / sqrt(var + (double)eps));
+      if (running_mean != nullptr) {
+        const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+      }
+      const float sc = gamma[c] * invstd;
+      float* ss = scale_shift + (long long)v * 2 * C;
+      float* mi = mean_invstd + (long long)v * 2 * C;
+      ss[c] = sc;
+      ss[C + c] = beta[c] - mean * sc;
+      mi[c] = mean;
+      mi[C + c] = invstd;
+    }
+  }
+}
+
 // out = relu?( y*scale+shift [+ res | + res*rscale + rshift] )   (residual.py:27-43)
 template <typename T>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ ss,
                                                        const T* __restrict__ res, const float* __restrict__ rss,
-                                                       T* __restrict__ out, long long M, int C, int relu) {
+                                                       T* __restrict__ out, long long M, int C, int relu, int views) {
+  // views > 1: the tensor is `views` stacked batches of M rows with their own coefficients ([views][2C]);
+  // the grid is split evenly between them
   const int cg = C >> 3;
   const long long total = M * cg;
+  const int Gv = gridDim.x / views, v = blockIdx.x / Gv, lb = blockIdx.x % Gv;
+  y += (long long)v * M * C;
+  out += (long long)v * M * C;
+  ss += (long long)v * 2 * C;
+  if (res != nullptr) res += (long long)v * M * C;
+  if (rss != nullptr) rss += (long long)v * 2 * C;
   // a thread's channel group is loop invariant (blockDim.x is a multiple of C/8): keep the coefficients in registers
-  const int c8 = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) % cg);
+  const int c8 = (int)((lb * (long long)blockDim.x + threadIdx.x) % cg);
   float sc[8], sh[8], rsc[8], rsh[8];
   load8(ss + c8 * 8, sc);
   load8(ss + C + c8 * 8, sh);
@@ -226,7 +275,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, 
     load8(rss + c8 * 8, rsc);
     load8(rss + C + c8 * 8, rsh);
   }
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  for (long long i = lb * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)Gv * blockDim.x) {
     float v[8];
     load8(y + i * 8, v);
 #pragma unroll
@@ -396,6 +445,170 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = fmaf(cA[j], g[j], fmaf(cB[j], v[j], cC[j]));
     store8(dy + i * 8, o);
+  }
+}
+
+// ---- whole BatchNorm backward of up to two views in ONE cooperative launch ------------------------
+// phase 1: per-CTA partial sums of g and g*yhat over the CTA's own rows; grid barrier; fixed-order fp64
+// fold of the partials; grid barrier; phase 2: dy = A*g + B*y + C over the SAME rows in reverse order
+// (the tail of phase 1 is still in the 126 MB L2).  Replaces 3 launches per view (reduce, fold, apply);
+// the arithmetic per element is the one of bn_reduce_kernel<.,true> / bn_bwd_apply_kernel.
+struct BnBwdFusedArgs {
+  const void *gin, *act, *y;
+  void *dy, *gout;
+  const float* mi[2];   // per view [2C]: mean, invstd
+  const float* mss[2];  // per view [2C] scale, shift of the ReLU mask (or null)
+  const float* gamma;
+  float *dgamma, *dbeta;
+  int accumulate, views, C;
+  long long Mv;         // rows per view
+  float* partial;       // [gridDim.x][2C]
+  double* sums;         // [views][2C]
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_fused_kernel(BnBwdFusedArgs p) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) float fsm[];  // max(256*17, 5*C) floats
+  const int C = p.C, tpr = C >> 3, rpi = 256 / tpr;
+  const int Gv = gridDim.x / p.views, v = blockIdx.x / Gv, lb = blockIdx.x % Gv;
+  const int c8 = threadIdx.x % tpr, my_r = threadIdx.x / tpr;
+  const long long Mv = p.Mv, voff = (long long)v * Mv * C;
+  const T* y = (const T*)p.y + voff;
+  const T* gin = (const T*)p.gin + voff;
+  const T* act = p.act ? (const T*)p.act + voff : nullptr;
+  const float* mss = p.mss[v];
+  const float* mi = p.mi[v];
+  const long long stride = (long long)Gv * rpi, r0 = (long long)lb * rpi + my_r;
+  const long long nk = r0 < Mv ? (Mv - r0 + stride - 1) / stride : 0;
+  using Raw = typename RawOf<T>::type;
+  constexpr int U = 4;
+  float msc[8], msh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    msc[j] = mss ? mss[c8 * 8 + j] : 0.f;
+    msh[j] = mss ? mss[C + c8 * 8 + j] : 0.f;
+  }
+  {
+    float a0[8], a1[8], mean[8], istd[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a0[j] = a1[j] = 0.f;
+      mean[j] = mi[c8 * 8 + j];
+      istd[j] = mi[C + c8 * 8 + j];
+    }
+    for (long long k = 0; k < nk; k += U) {
+      Raw rv[U], rg[U], ra[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (k + u < nk) {
+          const long long off = (r0 + (k + u) * stride) * C + c8 * 8;
+          load_raw(y + off, rv[u]);
+          load_raw(gin + off, rg[u]);
+          if (act != nullptr) load_raw(act + off, ra[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (k + u >= nk) continue;
+        float vv[8], g[8], a[8];
+        cvt_raw(rv[u], vv);
+        cvt_raw(rg[u], g);
+        if (act != nullptr) cvt_raw(ra[u], a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float gj = g[j];
+          if (act != nullptr) gj = a[j] > 0.f ? gj : 0.f;
+          else if (mss != nullptr) gj = fmaf(vv[j], msc[j], msh[j]) > 0.f ? gj : 0.f;
+          a0[j] += gj;
+          a1[j] = fmaf(gj, (vv[j] - mean[j]) * istd[j], a1[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      fsm[threadIdx.x * 17 + j] = a0[j];
+      fsm[threadIdx.x * 17 + 8 + j] = a1[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < tpr * 16; i += 256) {
+    const int g = i / 16, j = i % 16;
+    float t = 0.f;
+    for (int r = 0; r < rpi; ++r) t += fsm[(r * tpr + g) * 17 + j];
+    p.partial[(long long)blockIdx.x * 2 * C + (j >> 3) * C + g * 8 + (j & 7)] = t;
+  }
+  grid.sync();
+  {  // fold: one warp per (view, entry), fixed order
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * 8, n2c = 2 * C;
+    for (int e = blockIdx.x * 8 + (threadIdx.x >> 5); e < p.views * n2c; e += nwarps) {
+      const int vv = e / n2c, idx = e % n2c;
+      double t = 0.0;
+      for (int b = lane; b < Gv; b += 32) t += (double)p.partial[(long long)(vv * Gv + b) * n2c + idx];
+      t = warp_sum(t);
+      if (lane == 0) p.sums[e] = t;
+    }
+  }
+  grid.sync();
+  const double invM = 1.0 / (double)Mv;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const double* sv = p.sums + (long long)v * 2 * C;
+    const float mean = mi[c], istd = mi[C + c];
+    const float m1 = (float)(sv[c] * invM), m2 = (float)(sv[C + c] * invM);
+    const float A = p.gamma[c] * istd;
+    fsm[c] = A;
+    fsm[C + c] = -A * m2 * istd;
+    fsm[2 * C + c] = -A * m1 + A * m2 * istd * mean;
+    if (blockIdx.x == 0) {
+      double db = 0.0, dg = 0.0;
+      for (int q = 0; q < p.views; ++q) {
+        db += p.sums[(long long)q * 2 * C + c];
+        dg += p.sums[(long long)q * 2 * C + C + c];
+      }
+      if (p.dgamma) p.dgamma[c] = p.accumulate ? p.dgamma[c] + (float)dg : (float)dg;
+      if (p.dbeta) p.dbeta[c] = p.accumulate ? p.dbeta[c] + (float)db : (float)db;
+    }
+  }
+  __syncthreads();
+  float cA[8], cB[8], cC[8];
+  load8(fsm + c8 * 8, cA);
+  load8(fsm + C + c8 * 8, cB);
+  load8(fsm + 2 * C + c8 * 8, cC);
+  T* dy = (T*)p.dy + voff;
+  T* gout = p.gout ? (T*)p.gout + voff : nullptr;
+  constexpr int U2 = 2;
+  for (long long k = nk - 1; k >= 0; k -= U2) {
+    Raw rv[U2], rg[U2], ra[U2];
+#pragma unroll
+    for (int u = 0; u < U2; ++u) {
+      if (k - u >= 0) {
+        const long long off = (r0 + (k - u) * stride) * C + c8 * 8;
+        load_raw(y + off, rv[u]);
+        load_raw(gin + off, rg[u]);
+        if (act != nullptr) load_raw(act + off, ra[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U2; ++u) {
+      if (k - u < 0) continue;
+      const long long off = (r0 + (k - u) * stride) * C + c8 * 8;
+      float vv[8], g[8], a[8], o[8];
+      cvt_raw(rv[u], vv);
+      cvt_raw(rg[u], g);
+      if (act != nullptr) {
+        cvt_raw(ra[u], a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
+      } else if (mss != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = fmaf(vv[j], msc[j], msh[j]) > 0.f ? g[j] : 0.f;
+      }
+      if (gout != nullptr) store8(gout + off, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(cA[j], g[j], fmaf(cB[j], vv[j], cC[j]));
+      store8(dy + off, o);
+    }
   }
 }
 
@@ -580,6 +793,21 @@ extern "C" int iic_bn_stats(const void* y, int dtype, long long M, int C, const 
 }
 
 // statistics from the per-CTA partials written by iic_conv_fprop_stats: partial[blk][views][2][C]
+extern "C" int iic_bn_stats_from_partials_views(const float* stat_partial, int nblk, int slots, int views, long long M_per_view,
+                                                int C, const float* gamma, const float* beta, float eps,
+                                                float momentum, float* running_mean, float* running_var,
+                                                float* scale_shift, float* mean_invstd, void* stream) {
+  IIC_REQUIRE(stat_partial && nblk > 0 && views >= 1 && slots >= views && gamma && beta && scale_shift && mean_invstd && M_per_view > 0 &&
+                  C > 0,
+              IIC_ERR_BAD_ARG, "iic_bn_stats_from_partials_views: bad arguments");
+  bn_fold_finalize_kernel<<<cdiv((long long)C * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      stat_partial, nblk, slots, views, M_per_view, C, gamma, beta, eps, momentum, running_mean, running_var,
+      scale_shift, mean_invstd);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
 extern "C" int iic_bn_stats_from_partials(const float* stat_partial, int nblk, int views, int view, long long M, int C,
                                           const float* gamma, const float* beta, float eps, float momentum,
                                           float* running_mean, float* running_var, double* stats_ws, float* scale_shift,
@@ -599,16 +827,24 @@ extern "C" int iic_bn_stats_from_partials(const float* stat_partial, int nblk, i
   return IIC_OK;
 }
 
-extern "C" int iic_bn_apply(const void* y, const float* scale_shift, const void* res, const float* res_scale_shift,
-                            void* out, int dtype, long long M, int C, int relu, void* stream) {
-  IIC_REQUIRE(y && scale_shift && out && M > 0 && C % 8 == 0, IIC_ERR_BAD_ARG, "iic_bn_apply: bad arguments");
+extern "C" int iic_bn_apply_views(const void* y, const float* scale_shift, const void* res,
+                                  const float* res_scale_shift, void* out, int dtype, long long M_per_view, int C,
+                                  int relu, int views, void* stream) {
+  IIC_REQUIRE(y && scale_shift && out && M_per_view > 0 && C % 8 == 0 && views >= 1 && views <= 8, IIC_ERR_BAD_ARG,
+              "iic_bn_apply: bad arguments");
   IIC_REQUIRE(256 % (C / 8) == 0, IIC_ERR_UNSUPPORTED, "iic_bn_apply: C=%d must be 8 * (a divisor of 256)", C);
-  const long long total = M * (C / 8);
-  DISPATCH_T(dtype, bn_apply_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const T*)y, scale_shift, (const T*)res, res_scale_shift, (T*)out, M, C, relu);)
+  const long long total = M_per_view * (C / 8);
+  const int grid = ew_grid(total, 256) * views;  // ew_grid caps at 16 CTAs per SM per view
+  DISPATCH_T(dtype, bn_apply_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (const T*)y, scale_shift, (const T*)res, res_scale_shift, (T*)out, M_per_view, C, relu, views);)
   IIC_LAUNCH_CHECK();
   count_launch();
   return IIC_OK;
+}
+
+extern "C" int iic_bn_apply(const void* y, const float* scale_shift, const void* res, const float* res_scale_shift,
+                            void* out, int dtype, long long M, int C, int relu, void* stream) {
+  return iic_bn_apply_views(y, scale_shift, res, res_scale_shift, out, dtype, M, C, relu, 1, stream);
 }
 
 extern "C" int iic_bn_relu_maxpool(const void* y, const float* scale_shift, void* out, int dtype, int n, int h, int w,
@@ -671,6 +907,69 @@ extern "C" int iic_bn_bwd_apply(const void* g_in, const void* act, const float* 
       (const T*)g_in, (const T*)act, (const T*)y, mask_scale_shift, mean_invstd, gamma, sums, (T*)dy, (T*)g_out, dgamma, dbeta,
       accumulate, M, C);)
   IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
+static double* bn_sums_scratch() {
+  static double* buf[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!buf[dev] && cudaMalloc(&buf[dev], 2 * 2 * 2048 * sizeof(double)) != cudaSuccess) buf[dev] = nullptr;
+  return buf[dev];
+}
+
+template <typename T>
+static int bn_bwd_fused_grid(size_t smem, int views) {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (!cached[dev]) {
+    int occ = 0;  // worst-case dynamic smem (C = 2048) so one answer serves every C
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T>, 256, 5 * 2048 * sizeof(float)) != cudaSuccess)
+      return 0;
+    if (occ > 4) occ = 4;
+    cached[dev] = occ > 0 ? occ : -1;
+  }
+  if (cached[dev] < 0) return 0;
+  int g = device_sm_count() * cached[dev];
+  g -= g % views;
+  return g;
+}
+
+extern "C" int iic_bn_bwd_fused(const void* g_in, const void* act, const void* y, int views, const float* mean_invstd0,
+                                const float* mean_invstd1, const float* mask_ss0, const float* mask_ss1,
+                                const float* gamma, void* dy, void* g_out, float* dgamma, float* dbeta, int accumulate,
+                                int dtype, long long M_per_view, int C, void* stream) {
+  IIC_REQUIRE(g_in && y && mean_invstd0 && gamma && dy && M_per_view > 0 && (views == 1 || (views == 2 && mean_invstd1)),
+              IIC_ERR_BAD_ARG, "iic_bn_bwd_fused: bad arguments");
+  IIC_REQUIRE(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, IIC_ERR_UNSUPPORTED, "iic_bn_bwd_fused: C=%d unsupported", C);
+  IIC_REQUIRE(views == 1 || ((mask_ss0 == nullptr) == (mask_ss1 == nullptr)), IIC_ERR_BAD_ARG,
+              "iic_bn_bwd_fused: mask scale/shift must be given for both views or neither");
+  BnBwdFusedArgs a;
+  a.gin = g_in; a.act = act; a.y = y; a.dy = dy; a.gout = g_out;
+  a.mi[0] = mean_invstd0; a.mi[1] = mean_invstd1; a.mss[0] = mask_ss0; a.mss[1] = mask_ss1;
+  a.gamma = gamma; a.dgamma = dgamma; a.dbeta = dbeta; a.accumulate = accumulate; a.views = views; a.C = C;
+  a.Mv = M_per_view;
+  a.partial = bn_partial_scratch((size_t)device_sm_count() * 8 * 2 * 2048 * sizeof(float));
+  a.sums = bn_sums_scratch();
+  IIC_REQUIRE(a.partial && a.sums, IIC_ERR_CUDA, "iic_bn_bwd_fused: scratch allocation failed");
+  const size_t smem = sizeof(float) * (size_t)(5 * C > 256 * 17 ? 5 * C : 256 * 17);
+  void* args[] = {&a};
+  int grid = 0;
+  cudaError_t e = cudaSuccess;
+  if (dtype == IIC_BF16) {
+    grid = bn_bwd_fused_grid<__nv_bfloat16>(smem, views);
+    IIC_REQUIRE(grid >= views, IIC_ERR_CUDA, "iic_bn_bwd_fused: occupancy query failed");
+    e = cudaLaunchCooperativeKernel((void*)bn_bwd_fused_kernel<__nv_bfloat16>, dim3(grid), dim3(256), args, smem, (cudaStream_t)stream);
+  } else if (dtype == IIC_F32) {
+    grid = bn_bwd_fused_grid<float>(smem, views);
+    IIC_REQUIRE(grid >= views, IIC_ERR_CUDA, "iic_bn_bwd_fused: occupancy query failed");
+    e = cudaLaunchCooperativeKernel((void*)bn_bwd_fused_kernel<float>, dim3(grid), dim3(256), args, smem, (cudaStream_t)stream);
+  } else {
+    IIC_REQUIRE(false, IIC_ERR_BAD_ARG, "iic_bn_bwd_fused: bad dtype %d", dtype);
+  }
+  IIC_REQUIRE(e == cudaSuccess, IIC_ERR_CUDA, "iic_bn_bwd_fused: cooperative launch failed: %s", cudaGetErrorString(e));
   count_launch();
   return IIC_OK;
 }

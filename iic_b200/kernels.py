@@ -290,17 +290,61 @@ def stem_wgrad(x_nchw, dy, g, dt, grad_out, accumulate):
 
 # ---- batch norm / pooling ----------------------------------------------------------------------
 @_cat("bn_stats")
-def bn_stats(y, gamma, beta, eps, momentum, running_mean, running_var, use_running):
+def bn_stats(y, gamma, beta, eps, momentum, running_mean, running_var, use_running, ss=None, mi=None):
   C = y.shape[-1]
   M = y.numel() // C
   dev = y.device
   ws = torch.empty(2 * C, device=dev, dtype=torch.float64)
-  ss = torch.empty(2 * C, device=dev, dtype=torch.float32)
-  mi = torch.empty(2 * C, device=dev, dtype=torch.float32)
+  ss = torch.empty(2 * C, device=dev, dtype=torch.float32) if ss is None else ss
+  mi = torch.empty(2 * C, device=dev, dtype=torch.float32) if mi is None else mi
   check(_lib.lib().iic_bn_stats(_p(y), iic_dtype(y), M, C, _p(gamma), _p(beta), float(eps), float(momentum),
                                 _p(running_mean), _p(running_var), int(bool(use_running)), _p(ws), _p(ss), _p(mi),
                                 _stream()), "iic_bn_stats")
   return ss, mi
+
+
+@_cat("bn_stats")
+def bn_stats_from_partials_views(partial, nblk, slots, views, M, gamma, beta, eps, momentum, running_mean, running_var):
+  """All views in one launch -> (scale_shift [views, 2C], mean_invstd [views, 2C])."""
+  C = gamma.numel()
+  ss = torch.empty((views, 2 * C), device=partial.device, dtype=torch.float32)
+  mi = torch.empty((views, 2 * C), device=partial.device, dtype=torch.float32)
+  check(_lib.lib().iic_bn_stats_from_partials_views(_p(partial), nblk, slots, views, M, C, _p(gamma), _p(beta), float(eps),
+                                                    float(momentum), _p(running_mean), _p(running_var), _p(ss), _p(mi),
+                                                    _stream()), "iic_bn_stats_from_partials_views")
+  return ss, mi
+
+
+@_cat("bn_apply")
+def bn_apply_views(y, ss, relu, views, res=None, rss=None, out=None):
+  """y: `views` stacked batches; ss / rss: [views, 2C] contiguous."""
+  C = y.shape[-1]
+  M = y.numel() // C
+  assert M % views == 0 and ss.is_contiguous() and (rss is None or rss.is_contiguous())
+  if out is None:
+    out = torch.empty_like(y)
+  check(_lib.lib().iic_bn_apply_views(_p(y), _p(ss), _p(res), _p(rss), _p(out), iic_dtype(y), M // views, C,
+                                      int(bool(relu)), views, _stream()), "iic_bn_apply_views")
+  return out
+
+
+@_cat("bn_bwd")
+def bn_bwd_fused(g_in, act, y, mis, gamma, dgamma, dbeta, accumulate, want_g_out, mask_sss=None):
+  """BatchNorm backward of 1 or 2 stacked views in one cooperative launch.  mis / mask_sss: per-view tensors."""
+  views = len(mis)
+  assert views in (1, 2)
+  C = y.shape[-1]
+  M = y.numel() // C
+  assert M % views == 0 and (act is None or mask_sss is None)
+  dy = torch.empty_like(y)
+  g_out = torch.empty_like(y) if want_g_out else None
+  ms = list(mask_sss) if mask_sss is not None else [None] * views
+  mi1 = mis[1] if views == 2 else None
+  ms1 = ms[1] if views == 2 else None
+  check(_lib.lib().iic_bn_bwd_fused(_p(g_in), _p(act), _p(y), views, _p(mis[0]), _p(mi1), _p(ms[0]), _p(ms1), _p(gamma),
+                                    _p(dy), _p(g_out), _p(dgamma), _p(dbeta), int(bool(accumulate)), iic_dtype(y),
+                                    M // views, C, _stream()), "iic_bn_bwd_fused")
+  return dy, g_out
 
 
 @_cat("bn_apply")

@@ -144,6 +144,12 @@ int iic_bn_stats_from_partials(const float* stat_partial, int nblk, int views, i
                                const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
                                float* running_var, double* stats_ws, float* scale_shift, float* mean_invstd,
                                void* stream);
+/* All views in one launch: stat_partial rows hold `slots` (= 2) view slots of which the first `views` are
+ * folded; scale_shift / mean_invstd are [views][2*C]; the running statistics are updated view after view. */
+int iic_bn_stats_from_partials_views(const float* stat_partial, int nblk, int slots, int views, long long M_per_view,
+                                     int C, const float* gamma, const float* beta, float eps, float momentum,
+                                     float* running_mean, float* running_var, float* scale_shift, float* mean_invstd,
+                                     void* stream);
 /* dgrad: dx[n,h,w,cin] = conv_transpose(dy, w) (+ addend, same shape/dtype as dx, may be NULL).
  * w is the kind-1 packed weight. */
 int iic_conv_dgrad(const void* dy, const void* w_packed_t, const void* addend, void* dx,
@@ -176,6 +182,9 @@ int iic_bn_stats(const void* y, int dtype, long long M, int C, const float* gamm
 /* out = relu?( y*scale+shift  [+ res  | + res*rscale+rshift] ) */
 int iic_bn_apply(const void* y, const float* scale_shift, const void* res, const float* res_scale_shift,
                  void* out, int dtype, long long M, int C, int relu, void* stream);
+/* the same over `views` stacked batches of M_per_view rows; scale_shift / res_scale_shift are [views][2*C] */
+int iic_bn_apply_views(const void* y, const float* scale_shift, const void* res, const float* res_scale_shift,
+                       void* out, int dtype, long long M_per_view, int C, int relu, int views, void* stream);
 /* fused BN + ReLU + MaxPool2d(k=2, s=2, pad) (net5g.py:24-26; vgg.py 'M'): y (n,h,w,C) -> out (n,oh,ow,C) */
 int iic_bn_relu_maxpool(const void* y, const float* scale_shift, void* out, int dtype, int n, int h, int w,
                         int C, int pad, int oh, int ow, void* stream);
@@ -194,6 +203,14 @@ int iic_bn_bwd_reduce(const void* g_in, const void* act, const float* mask_scale
 int iic_bn_bwd_apply(const void* g_in, const void* act, const float* mask_scale_shift, const void* y,
                      const float* mean_invstd, const float* gamma, const double* sums, void* dy, void* g_out,
                      float* dgamma, float* dbeta, int accumulate, int dtype, long long M, int C, void* stream);
+/* The same backward for `views` (1 or 2) stacked batches of M_per_view rows, each with its own statistics, in ONE
+ * cooperative launch: partial sums, grid barrier, fp64 fold, grid barrier, apply over the same rows in reverse
+ * order (L2 reuse).  dgamma/dbeta receive the sum over the views (the two forward calls of
+ * cluster_sobel_twohead.py:320-321 share the BatchNorm parameters). */
+int iic_bn_bwd_fused(const void* g_in, const void* act, const void* y, int views, const float* mean_invstd0,
+                     const float* mean_invstd1, const float* mask_scale_shift0, const float* mask_scale_shift1,
+                     const float* gamma, void* dy, void* g_out, float* dgamma, float* dbeta, int accumulate, int dtype,
+                     long long M_per_view, int C, void* stream);
 
 /* AvgPool2d(full extent) + flatten (net5g.py:31-39,:56): x (n,hw,C) -> feat fp32 (n,C) */
 int iic_avgpool(const void* x, int dtype, float* feat, int n, int hw, int C, void* stream);

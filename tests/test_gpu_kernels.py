@@ -383,3 +383,75 @@ def test_conv_epilogue_bn_statistics(n, h, cin, cout, k, s, p):
   ss, mi = K.bn_stats_from_partials(partial1, nblk1, 2, 0, 2 * M, gamma, beta, 1e-5, 0.1, None, None)
   ss2, mi2 = K.bn_stats(y, gamma, beta, 1e-5, 0.1, None, None, False)
   assert torch.allclose(ss, ss2, rtol=1e-2, atol=5e-3)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(6, 13, 13, 64), (4, 7, 7, 512), (2, 5, 5, 2048), (64, 25, 25, 128)])
+@pytest.mark.parametrize("views", [1, 2])
+def test_bn_multi_view_kernels_match_per_view_chain(mode, shape, views):
+  """One-launch-for-all-views kernels (bn_apply_views, the cooperative bn_bwd_fused, bn_stats_from_partials_views'
+  consumer layout) against the per-view launch chain they replace: same arithmetic per element, so the
+  tolerance only covers the different partial-sum grouping."""
+  K = _K()
+  tdt = torch.float32 if mode == "fp32" else torch.bfloat16
+  n, h, w, C = shape
+  g = torch.Generator().manual_seed(31)
+  y = (torch.randn(n, h, w, C, generator=g) * 2 + 0.5).cuda().to(tdt)
+  y[n // 2:] = (y[n // 2:].float() * 0.5 - 1.0).to(tdt)
+  res = torch.randn(n, h, w, C, generator=g).cuda().to(tdt)
+  dout = torch.randn(n, h, w, C, generator=g).cuda().to(tdt)
+  gamma = (torch.rand(C, generator=g) + 0.5).cuda()
+  beta = (torch.randn(C, generator=g) * 0.1).cuda()
+  nv = n // views
+  ss = torch.empty(views, 2 * C).cuda()
+  mi = torch.empty(views, 2 * C).cuda()
+  for v in range(views):
+    K.bn_stats(y[v * nv:(v + 1) * nv], gamma, beta, 1e-5, 0.1, None, None, False, ss=ss[v], mi=mi[v])
+  # forward
+  out = K.bn_apply_views(y, ss, True, views, res=res, rss=ss)
+  out_ref = torch.empty_like(y)
+  for v in range(views):
+    sl = slice(v * nv, (v + 1) * nv)
+    K.bn_apply(y[sl], ss[v], True, res=res[sl], rss=ss[v], out=out_ref[sl])
+  assert torch.equal(out, out_ref)
+  # backward, both mask flavours
+  for act, mss in ((out, None), (None, [ss[v] for v in range(views)]), (None, None)):
+    dg, db = torch.full((C,), 3.0).cuda(), torch.full((C,), -2.0).cuda()
+    dy, go = K.bn_bwd_fused(dout, act, y, [mi[v] for v in range(views)], gamma, dg, db, True, act is not None, mask_sss=mss)
+    dg_r, db_r = torch.full((C,), 3.0).cuda(), torch.full((C,), -2.0).cuda()
+    dy_r, go_r = torch.empty_like(y), torch.empty_like(y)
+    for v in range(views):
+      sl = slice(v * nv, (v + 1) * nv)
+      K.bn_bwd(dout[sl], None if act is None else act[sl], y[sl], mi[v], gamma, dg_r, db_r, True, act is not None,
+               dy=dy_r[sl], g_out=go_r[sl], mask_ss=None if mss is None else mss[v])
+    scale = dy_r.float().abs().max().item()
+    assert (dy.float() - dy_r.float()).abs().max().item() <= (1e-5 if mode == "fp32" else 1e-2) * scale
+    assert torch.allclose(dg, dg_r, rtol=1e-4, atol=1e-3 * dg_r.abs().max().item())
+    assert torch.allclose(db, db_r, rtol=1e-4, atol=1e-3 * db_r.abs().max().item())
+    if act is not None:
+      assert torch.equal(go, go_r)
+    else:
+      assert go is None
+
+
+def test_bn_stats_from_partials_all_views_in_one_launch():
+  K = _K()
+  from iic_b200._lib import BF16
+  g = torch.Generator().manual_seed(22)
+  n, h, cin, cout = 6, 13, 64, 128
+  x = torch.randn(n, h, h, cin, generator=g).cuda().bfloat16()
+  x[n // 2:] = x[n // 2:] * 2.0 + 0.5
+  w = (torch.randn(cout, cin, 3, 3, generator=g) * math.sqrt(2.0 / (cin * 9))).cuda()
+  gamma = (torch.rand(cout, generator=g) + 0.5).cuda()
+  beta = (torch.randn(cout, generator=g) * 0.1).cuda()
+  geo = K.conv_geom(n, h, h, cin, cout, 3, 3, 1, 1, 1)
+  for views in (1, 2):
+    y, partial, nblk = K.conv_fprop_stats(x, K.pack_weight(w, BF16, 0), geo, BF16, views)
+    M = (n // views) * geo.oh * geo.ow
+    rm, rv = torch.zeros(cout).cuda(), torch.ones(cout).cuda()
+    rm2, rv2 = torch.zeros(cout).cuda(), torch.ones(cout).cuda()
+    ss, mi = K.bn_stats_from_partials_views(partial, nblk, 2, views, M, gamma, beta, 1e-5, 0.1, rm, rv)
+    for v in range(views):  # same fold order => identical to the per-view call; running stats chained view by view
+      ss1, mi1 = K.bn_stats_from_partials(partial, nblk, 2, v, M, gamma, beta, 1e-5, 0.1, rm2, rv2)
+      assert torch.equal(ss[v], ss1) and torch.equal(mi[v], mi1)
+    assert torch.equal(rm, rm2) and torch.equal(rv, rv2)
