@@ -467,7 +467,7 @@ struct BnBwdFusedArgs {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_fused_kernel(BnBwdFusedArgs p) {
+__global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnBwdFusedArgs p) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) float fsm[];  // max(256*17, 5*C) floats
   const int C = p.C, tpr = C >> 3, rpi = 256 / tpr;
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(BnBwdFusedArgs p) {
   const long long stride = (long long)Gv * rpi, r0 = (long long)lb * rpi + my_r;
   const long long nk = r0 < Mv ? (Mv - r0 + stride - 1) / stride : 0;
   using Raw = typename RawOf<T>::type;
-  constexpr int U = 4;
+  constexpr int U = sizeof(T) == 2 ? 4 : 2;  // rows in flight per thread (2 CTAs / SM => <= 128 registers)
   float msc[8], msh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(256) bn_bwd_fused_kernel(BnBwdFusedArgs p) {
   load8(fsm + 2 * C + c8 * 8, cC);
   T* dy = (T*)p.dy + voff;
   T* gout = p.gout ? (T*)p.gout + voff : nullptr;
-  constexpr int U2 = 2;
+  constexpr int U2 = sizeof(T) == 2 ? 4 : 2;
   for (long long k = nk - 1; k >= 0; k -= U2) {
     Raw rv[U2], rg[U2], ra[U2];
 #pragma unroll

@@ -30,5 +30,13 @@ for name, h, C in SHAPES:
   t_apply = timeit(lambda: K.bn_apply(y, ss, True, res=act, out=out))
   t_b1 = timeit(lambda: K.bn_bwd(g, None, y, mi, gamma, dg, db, False, False, dy=dy, mask_ss=ss))
   t_b2 = timeit(lambda: K.bn_bwd(g, act, y, mi, gamma, dg, db, False, True, dy=dy, g_out=go))
+  mi2 = [mi, mi.clone()]
+  ss2 = [ss, ss.clone()]
+  y2, g2, act2 = torch.cat([y, y]), torch.cat([g, g]), torch.cat([act, act])
+  t_f1 = timeit(lambda: K.bn_bwd_fused(g2, None, y2, mi2, gamma, dg, db, False, False, mask_sss=ss2)) / 2
+  t_f2 = timeit(lambda: K.bn_bwd_fused(g2, act2, y2, mi2, gamma, dg, db, False, True)) / 2
+  print("%-16s fused (2 views in one launch, per view): bwd(bn1) %.3f ms %5.0f GB/s | bwd(bn2+gout) %.3f ms %5.0f GB/s" % (
+    name, t_f1, 5 * nb / t_f1 / 1e6, t_f2, 8 * nb / t_f2 / 1e6))
+  del y2, g2, act2
   print("%-16s %6.1f MB/tensor | stats %.3f ms %5.0f GB/s | apply+res %.3f ms %5.0f GB/s | bwd(bn1) %.3f ms %5.0f GB/s | bwd(bn2+gout) %.3f ms %5.0f GB/s" % (
     name, nb / 1e6, t_stats, nb / t_stats / 1e6, t_apply, 3 * nb / t_apply / 1e6, t_b1, 5 * nb / t_b1 / 1e6, t_b2, 8 * nb / t_b2 / 1e6))
