@@ -17,11 +17,16 @@
 // im2col access pattern).
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "tc_ptx.cuh"
 
 namespace iic {
 
 enum { M2_FPROP = 0, M2_WGRAD = 1 };
+#ifndef IIC_CONV_HALO_DEFAULT
+#define IIC_CONV_HALO_DEFAULT 0  // halo variant of the 64-channel 3x3 layers: opt-in until validated on hardware
+#endif
 constexpr int TC2_THREADS = 192;
 
 constexpr int TC2_MAXTAPS = 25;
@@ -378,6 +383,198 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       P.stat_partial[(long long)blockIdx.x * 4 * P.N + i] = stat[i] + stat[4 * P.N + i] + stat[8 * P.N + i] + stat[12 * P.N + i];
 }
 
+
+// =================================================================================================
+// Halo variant for 3x3 / stride 1 / pad 1 / 64 -> 64 channels (ClusterNet5g layer1 fprop and dgrad).
+//
+// The im2col kernel above re-reads every input pixel nine times from L2 (one 128-pixel box per filter
+// tap): at N = 64 that is 128 B of shared-memory fill per MMA cycle and the L2 -> SM path, not the tensor
+// pipe, bounds the layer (profiles/r01_conv_sweep.md).  Here ONE tiled TMA box per work item brings
+// R+2 input rows of an image, padded to width Wp = W+2 by the TMA zero fill, into shared memory as
+// consecutive 128-byte rows (row = (iy - y0 + 1) * Wp + ix + 1).  On that padded grid the A operand of
+// filter tap (a, b) is the SAME buffer started a*Wp + b rows later, so all nine taps (72 MMAs for a
+// 256-row tile) are fed from one 45 KB load.  A UMMA descriptor may start at any 128-byte row of a
+// 1024-byte aligned SWIZZLE_128B buffer with base_offset = 0 (the swizzle is a function of the absolute
+// shared-memory address; measured with tools/umma_shift_probe.cu).  Tile rows m = r*Wp + x with x >= W
+// or y0 + r >= H are padding positions: computed, never stored, excluded from the statistics.
+// Warps: 0-7 epilogue (TMEM lane quadrant = warp % 4, column half = warp / 4), 8 MMA issuer, 9 TMA producer.
+constexpr int HALO_THREADS = 320;
+constexpr int HALO_TILE = 256;  // accumulator rows per work item (two M = 128 MMA tiles)
+
+struct HaloParams {
+  int nimg, H, W, Wp, R;
+  int tiles_per_img, total_tiles;
+  int stage_bytes, box_bytes, stages;
+  unsigned short shift[9];
+  unsigned char wtap[9];
+  __nv_bfloat16* out;
+  const __nv_bfloat16* addend;
+  float* stat_partial;  // [cta][view][{sum, sum of squares}][64] or null
+  int img_half;         // images >= img_half belong to view 1
+};
+
+__global__ void __launch_bounds__(HALO_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, HaloParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t resb = (raw + 1023u) & ~1023u;           // [9][64 x 128 B] resident weights
+  const uint32_t base = resb + 9u * 8192u;                // stages
+  const uint32_t bars = base + (uint32_t)P.stages * (uint32_t)P.stage_bytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };          // s < 4
+  auto empty_bar = [&](int s) { return bars + 8u * (4 + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (8 + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (10 + a); };
+  const uint32_t bres_bar = bars + 8u * 12;
+  uint8_t* bars_ptr = smem_raw + (bars - raw);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_ptr + 8 * 13);
+  float* stat = reinterpret_cast<float*>(bars_ptr + 128);  // [8 warps][2 views][2][32]
+  const bool do_stats = P.stat_partial != nullptr;
+  if (do_stats)
+    for (int i = threadIdx.x; i < 8 * 2 * 2 * 32; i += HALO_THREADS) stat[i] = 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 256);
+    }
+    mbar_init(bres_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 9) {
+    // =============================== TMA producer ============================================
+    if (blockIdx.x < P.total_tiles) {
+      if (lane == 0) mbar_expect_tx(bres_bar, 9u * 8192u);
+      __syncwarp();
+      if (lane < 9) tma_load_2d(resb + lane * 8192u, &tmB, bres_bar, (int)P.wtap[lane] * 64, 0);
+    }
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int w = blockIdx.x; w < P.total_tiles; w += gridDim.x, ++it) {
+        const int img = w / P.tiles_per_img;
+        const int y0 = (w - img * P.tiles_per_img) * P.R;
+        const int s = it % P.stages;
+        mbar_wait(empty_bar(s), ((it / P.stages) & 1u) ^ 1u);
+        mbar_expect_tx(full_bar(s), (uint32_t)P.box_bytes);
+        tma_load_4d(base + (uint32_t)s * (uint32_t)P.stage_bytes, &tmA, full_bar(s), 0, -1, y0 - 1, img);
+      }
+    }
+  } else if (warp == 8) {
+    // =============================== MMA issuer ==============================================
+    constexpr uint32_t idesc = make_idesc(64, 0, 0);
+    uint32_t it = 0;
+    if (blockIdx.x < P.total_tiles) mbar_wait(bres_bar, 0);
+    for (int w = blockIdx.x; w < P.total_tiles; w += gridDim.x, ++it) {
+      const uint32_t as = it & 1u;
+      mbar_wait(tempty_bar(as), ((it >> 1) & 1u) ^ 1u);
+      const int s = it % P.stages;
+      mbar_wait(full_bar(s), (it / P.stages) & 1u);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = base + (uint32_t)s * (uint32_t)P.stage_bytes;
+        const uint32_t tmem_acc = tmem_base + as * 128u;
+#pragma unroll 1
+        for (int t = 0; t < 9; ++t) {
+          const uint32_t a_t = sa + (uint32_t)P.shift[t] * 128u;
+          const uint32_t b_t = resb + (uint32_t)t * 8192u;
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t ad = make_desc(a_t + mt * (TC_BM * 128) + kk * 32, 16, 1024);
+              const uint64_t bd = make_desc(b_t + kk * 32, 16, 1024);
+              umma_bf16(tmem_acc + mt * 64, ad, bd, idesc, (t > 0 || kk > 0) ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(empty_bar(s));
+        umma_commit(tfull_bar(as));
+      }
+      __syncwarp();
+    }
+  } else {
+    // =============================== epilogue (warps 0-7) ======================================
+    const int quad = warp & 3, hsel = warp >> 2;
+    uint32_t it = 0;
+    for (int w = blockIdx.x; w < P.total_tiles; w += gridDim.x, ++it) {
+      const int img = w / P.tiles_per_img;
+      const int y0 = (w - img * P.tiles_per_img) * P.R;
+      const int view = img >= P.img_half ? 1 : 0;
+      const uint32_t as = it & 1u;
+      mbar_wait(tfull_bar(as), (it >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int mt = 0; mt < 2; ++mt) {
+        const int m = mt * TC_BM + quad * 32 + lane;  // accumulator row == TMEM lane (+128 for the second MMA tile)
+        const int r = m / P.Wp, x = m - r * P.Wp;
+        const bool valid = r < P.R && x < P.W && y0 + r < P.H;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + as * 128u + mt * 64 + hsel * 32 + ((uint32_t)(quad * 32) << 16), v);
+        tmem_ld_wait();
+        if (do_stats) {
+          float t[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) t[e] = valid ? __uint_as_float(v[e]) : 0.f;
+          warp_col_reduce(t, lane);
+          const float s1 = t[0];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float f = valid ? __uint_as_float(v[e]) : 0.f;
+            t[e] = f * f;
+          }
+          warp_col_reduce(t, lane);
+          float* sp = stat + ((warp * 2 + view) * 2) * 32 + lane;
+          sp[0] += s1;
+          sp[32] += t[0];
+        }
+        if (valid) {
+          const long long pix = ((long long)img * P.H + y0 + r) * P.W + x;
+          __nv_bfloat16* o = P.out + pix * 64 + hsel * 32;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[qq * 8 + e]);
+            if (P.addend != nullptr) {
+              float ad[8];
+              load8(P.addend + pix * 64 + hsel * 32 + qq * 8, ad);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] += ad[e];
+            }
+            store8(o + qq * 8, f);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(as));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 256);
+  if (do_stats)
+    for (int i = threadIdx.x; i < 4 * 64; i += HALO_THREADS) {  // i = (view, q, col); fixed warp order
+      const int col = i & 63, q = (i >> 6) & 1, view = i >> 7;
+      const int h = col >> 5, l = col & 31;
+      float t = 0.f;
+      for (int qd = 0; qd < 4; ++qd) t += stat[(((h * 4 + qd) * 2 + view) * 2 + q) * 32 + l];
+      P.stat_partial[(long long)blockIdx.x * 4 * 64 + i] = t;
+    }
+}
+
 // ---- host side: tensor-map construction through the driver entry points ----------------------
 typedef CUresult (*PFN_tmEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -465,11 +662,88 @@ static int pick_bn2(int N) {
   return 0;
 }
 
+
+// ---- halo variant: plan + launch -----------------------------------------------------------------
+struct HaloPlan {
+  bool ok;
+  int Wp, R, tiles_per_img, total_tiles, stage_bytes, box_bytes, stages, smem;
+};
+
+// IIC_CONV_HALO: 0 never, 1 (default) when the geometry fits and the tile efficiency is good, 2 whenever the geometry fits
+static int halo_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("IIC_CONV_HALO");
+    mode = e ? atoi(e) : IIC_CONV_HALO_DEFAULT;
+  }
+  return mode;
+}
+
+static HaloPlan halo_plan(const iic_conv_geom* g, int srcC, int N, int H, int W, int nimg) {
+  HaloPlan p = {};
+  if (halo_mode() == 0) return p;
+  if (!(g->kh == 3 && g->kw == 3 && g->stride == 1 && g->pad == 1 && g->dil == 1 && srcC == 64 && N == 64)) return p;
+  p.Wp = W + 2;
+  p.R = HALO_TILE / p.Wp;
+  if (p.R < 1) return p;
+  p.tiles_per_img = (H + p.R - 1) / p.R;
+  const long long total = (long long)nimg * p.tiles_per_img;
+  if (total > 0x7fffffffll) return p;
+  p.total_tiles = (int)total;
+  p.box_bytes = p.Wp * (p.R + 2) * 128;
+  p.stage_bytes = ((HALO_TILE + 2 * p.Wp + 2) * 128 + 1023) / 1024 * 1024;
+  if (p.box_bytes > p.stage_bytes || p.R + 2 > 256) return p;
+  const int fixed = 1024 + 9 * 8192 + 128 + 8 * 2 * 2 * 32 * 4;
+  p.stages = (232448 - fixed) / p.stage_bytes;
+  if (p.stages > 4) p.stages = 4;
+  if (p.stages < 2) return p;
+  p.smem = fixed + p.stages * p.stage_bytes;
+  if (halo_mode() == 1) {
+    const double eff = (double)H * W / ((double)p.tiles_per_img * HALO_TILE);
+    if (eff < 0.80 || p.total_tiles < 2 * device_sm_count()) return p;
+  }
+  p.ok = true;
+  return p;
+}
+
+static int launch_halo(const HaloPlan& hp, const __nv_bfloat16* src, int H, int W, int nimg, const Tc2Params& P,
+                       const CUtensorMap& tmB, cudaStream_t st) {
+  alignas(64) CUtensorMap tmA;
+  {
+    cuuint64_t gdim[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
+    cuuint64_t gstr[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
+    cuuint32_t box[4] = {64, (cuuint32_t)hp.Wp, (cuuint32_t)(hp.R + 2), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encodeTiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(src), gdim, gstr, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IIC_REQUIRE(r == CUDA_SUCCESS, IIC_ERR_CUDA, "cuTensorMapEncodeTiled(halo) failed (%d) H=%d W=%d box %dx%d", (int)r, H, W,
+                hp.Wp, hp.R + 2);
+  }
+  HaloParams Q = {};
+  Q.nimg = nimg; Q.H = H; Q.W = W; Q.Wp = hp.Wp; Q.R = hp.R;
+  Q.tiles_per_img = hp.tiles_per_img; Q.total_tiles = hp.total_tiles;
+  Q.stage_bytes = hp.stage_bytes; Q.box_bytes = hp.box_bytes; Q.stages = hp.stages;
+  for (int t = 0; t < 9; ++t) {
+    Q.shift[t] = (unsigned short)((int)P.offh[t] * hp.Wp + (int)P.offw[t]);
+    Q.wtap[t] = P.wtap[t];
+  }
+  Q.out = P.out; Q.addend = P.addend; Q.stat_partial = P.stat_partial;
+  Q.img_half = (P.stat_half < P.rows) ? nimg / 2 : nimg;
+  IIC_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hp.smem));
+  conv_halo_kernel<<<tc2_grid(hp.total_tiles), HALO_THREADS, hp.smem, st>>>(tmA, tmB, Q);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
 // fprop (transposed == 0) or dgrad of a stride-1 conv (transposed == 1; src = dy, N = cin)
 int tc2_conv_fprop_blocks(const iic_conv_geom* g) {
   const int bn = pick_bn2(g->cout);
   if (bn == 0) return 0;
   const long long rows = (long long)g->n * g->oh * g->ow;
+  const HaloPlan hp = halo_plan(g, g->cin, g->cout, g->h, g->w, g->n);
+  if (hp.ok) return tc2_grid(hp.total_tiles);
   const int tile_rows = tc2_use_resb(bn, g->cout, g->kh * g->kw * g->cin / 64, rows) ? 2 * TC_BM : TC_BM;
   return tc2_grid(((rows + tile_rows - 1) / tile_rows) * (g->cout / bn));
 }
@@ -528,8 +802,11 @@ int tc2_conv_gather_gemm_stats(const __nv_bfloat16* src, int srcH, int srcW, int
   IIC_REQUIRE(stat_groups == 1 || (stat_groups == 2 && nimg % 2 == 0), IIC_ERR_BAD_ARG, "conv stats: 1 or 2 views");
   P.stat_half = stat_groups == 2 ? P.rows / 2 : P.rows;
   alignas(64) CUtensorMap tmA, tmB;
-  rc = make_im2col_map(&tmA, src, nimg, srcH, srcW, srcC, P.lower, upper, P.s, tile_rows);
-  if (rc != IIC_OK) return rc;
+  const HaloPlan hp = halo_plan(g, srcC, N, srcH, srcW, nimg);
+  if (!hp.ok) {
+    rc = make_im2col_map(&tmA, src, nimg, srcH, srcW, srcC, P.lower, upper, P.s, tile_rows);
+    if (rc != IIC_OK) return rc;
+  }
   {
     cuuint64_t gdim[2] = {(cuuint64_t)P.Ktot, (cuuint64_t)N};
     cuuint64_t gstr[1] = {(cuuint64_t)P.Ktot * 2};
@@ -540,6 +817,7 @@ int tc2_conv_gather_gemm_stats(const __nv_bfloat16* src, int srcH, int srcW, int
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     IIC_REQUIRE(r == CUDA_SUCCESS, IIC_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed (%d)", (int)r);
   }
+  if (hp.ok) return launch_halo(hp, src, srcH, srcW, nimg, P, tmB, st);
   if (resb) return launch_tc2_impl<M2_FPROP, 64, true>(tmA, tmB, P, 1, st);
   switch (bn) {
     case 256: return launch_tc2<M2_FPROP, 256>(tmA, tmB, P, 1, st);

@@ -466,7 +466,8 @@ struct BnBwdFusedArgs {
   double* sums;         // [views][2C]
 };
 
-template <typename T>
+// MASK: 0 none, 1 activation sign (three input streams), 2 recomputed from y*scale+shift.
+template <typename T, int MASK>
 __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnBwdFusedArgs p) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) float fsm[];  // max(256*17, 5*C) floats
@@ -476,26 +477,28 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnBwdFusedArgs p) 
   const long long Mv = p.Mv, voff = (long long)v * Mv * C;
   const T* y = (const T*)p.y + voff;
   const T* gin = (const T*)p.gin + voff;
-  const T* act = p.act ? (const T*)p.act + voff : nullptr;
-  const float* mss = p.mss[v];
+  const T* act = MASK == 1 ? (const T*)p.act + voff : nullptr;
+  const float* mss = MASK == 2 ? p.mss[v] : nullptr;
   const float* mi = p.mi[v];
   const long long stride = (long long)Gv * rpi, r0 = (long long)lb * rpi + my_r;
   const long long nk = r0 < Mv ? (Mv - r0 + stride - 1) / stride : 0;
   using Raw = typename RawOf<T>::type;
-  constexpr int U = sizeof(T) == 2 ? 4 : 2;  // rows in flight per thread (2 CTAs / SM => <= 128 registers)
+  // rows in flight per thread: 2 CTAs / SM (<= 128 registers) leave 48-64 registers for raw loads, and ~100 KB
+  // per SM must be in flight to cover the HBM latency (two input streams need more rows than three); the
+  // values below are the largest that do not spill
+  constexpr int U = sizeof(T) == 2 ? (MASK == 1 ? 5 : (MASK == 2 ? 6 : 8)) : 2;
   float msc[8], msh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    msc[j] = mss ? mss[c8 * 8 + j] : 0.f;
-    msh[j] = mss ? mss[C + c8 * 8 + j] : 0.f;
+    msc[j] = MASK == 2 ? mss[c8 * 8 + j] : 0.f;
+    msh[j] = MASK == 2 ? mss[C + c8 * 8 + j] : 0.f;
   }
   {
-    float a0[8], a1[8], mean[8], istd[8];
+    float a0[8], a1[8], mean[8];  // a1 accumulates g*(y-mean); the common factor invstd is applied once at the end
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       a0[j] = a1[j] = 0.f;
       mean[j] = mi[c8 * 8 + j];
-      istd[j] = mi[C + c8 * 8 + j];
     }
     for (long long k = 0; k < nk; k += U) {
       Raw rv[U], rg[U], ra[U];
@@ -505,7 +508,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnBwdFusedArgs p) 
           const long long off = (r0 + (k + u) * stride) * C + c8 * 8;
           load_raw(y + off, rv[u]);
           load_raw(gin + off, rg[u]);
-          if (act != nullptr) load_raw(act + off, ra[u]);
+          if (MASK == 1) load_raw(act + off, ra[u]);
         }
       }
 #pragma unroll
@@ -514,21 +517,21 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnBwdFusedArgs p) 
         float vv[8], g[8], a[8];
         cvt_raw(rv[u], vv);
         cvt_raw(rg[u], g);
-        if (act != nullptr) cvt_raw(ra[u], a);
+        if (MASK == 1) cvt_raw(ra[u], a);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float gj = g[j];
-          if (act != nullptr) gj = a[j] > 0.f ? gj : 0.f;
-          else if (mss != nullptr) gj = fmaf(vv[j], msc[j], msh[j]) > 0.f ? gj : 0.f;
+          if (MASK == 1) gj = a[j] > 0.f ? gj : 0.f;
+          else if (MASK == 2) gj = fmaf(vv[j], msc[j], msh[j]) > 0.f ? gj : 0.f;
           a0[j] += gj;
-          a1[j] = fmaf(gj, (vv[j] - mean[j]) * istd[j], a1[j]);
+          a1[j] = fmaf(gj, vv[j] - mean[j], a1[j]);
         }
       }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       fsm[threadIdx.x * 17 + j] = a0[j];
-      fsm[threadIdx.x * 17 + 8 + j] = a1[j];
+      fsm[threadIdx.x * 17 + 8 + j] = a1[j] * mi[C + c8 * 8 + j];
     }
   }
   __syncthreads();
@@ -577,7 +580,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnBwdFusedArgs p) 
   load8(fsm + 2 * C + c8 * 8, cC);
   T* dy = (T*)p.dy + voff;
   T* gout = p.gout ? (T*)p.gout + voff : nullptr;
-  constexpr int U2 = sizeof(T) == 2 ? 4 : 2;
+  constexpr int U2 = U;
   for (long long k = nk - 1; k >= 0; k -= U2) {
     Raw rv[U2], rg[U2], ra[U2];
 #pragma unroll
@@ -586,7 +589,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnBwdFusedArgs p) 
         const long long off = (r0 + (k - u) * stride) * C + c8 * 8;
         load_raw(y + off, rv[u]);
         load_raw(gin + off, rg[u]);
-        if (act != nullptr) load_raw(act + off, ra[u]);
+        if (MASK == 1) load_raw(act + off, ra[u]);
       }
     }
 #pragma unroll
@@ -596,11 +599,11 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnBwdFusedArgs p) 
       float vv[8], g[8], a[8], o[8];
       cvt_raw(rv[u], vv);
       cvt_raw(rg[u], g);
-      if (act != nullptr) {
+      if (MASK == 1) {
         cvt_raw(ra[u], a);
 #pragma unroll
         for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
-      } else if (mss != nullptr) {
+      } else if (MASK == 2) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) g[j] = fmaf(vv[j], msc[j], msh[j]) > 0.f ? g[j] : 0.f;
       }
@@ -919,22 +922,32 @@ static double* bn_sums_scratch() {
   return buf[dev];
 }
 
-template <typename T>
-static int bn_bwd_fused_grid(size_t smem, int views) {
+template <typename T, int MASK>
+static int bn_bwd_fused_launch(BnBwdFusedArgs& a, size_t smem, cudaStream_t st) {
   static int cached[64] = {0};
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  IIC_CUDA(cudaGetDevice(&dev));
+  IIC_REQUIRE(dev >= 0 && dev < 64, IIC_ERR_CUDA, "iic_bn_bwd_fused: device index");
   if (!cached[dev]) {
     int occ = 0;  // worst-case dynamic smem (C = 2048) so one answer serves every C
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T>, 256, 5 * 2048 * sizeof(float)) != cudaSuccess)
-      return 0;
-    if (occ > 4) occ = 4;
-    cached[dev] = occ > 0 ? occ : -1;
+    IIC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T, MASK>, 256, 5 * 2048 * sizeof(float)));
+    cached[dev] = occ > 2 ? 2 : occ;
+    IIC_REQUIRE(cached[dev] > 0, IIC_ERR_CUDA, "iic_bn_bwd_fused: kernel does not fit");
   }
-  if (cached[dev] < 0) return 0;
-  int g = device_sm_count() * cached[dev];
-  g -= g % views;
-  return g;
+  int grid = device_sm_count() * cached[dev];
+  grid -= grid % a.views;
+  void* args[] = {&a};
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)bn_bwd_fused_kernel<T, MASK>, dim3(grid), dim3(256), args, smem, st);
+  IIC_REQUIRE(e == cudaSuccess, IIC_ERR_CUDA, "iic_bn_bwd_fused: cooperative launch failed: %s", cudaGetErrorString(e));
+  count_launch();
+  return IIC_OK;
+}
+
+template <typename T>
+static int bn_bwd_fused_dispatch(BnBwdFusedArgs& a, size_t smem, cudaStream_t st) {
+  if (a.act != nullptr) return bn_bwd_fused_launch<T, 1>(a, smem, st);
+  if (a.mss[0] != nullptr) return bn_bwd_fused_launch<T, 2>(a, smem, st);
+  return bn_bwd_fused_launch<T, 0>(a, smem, st);
 }
 
 extern "C" int iic_bn_bwd_fused(const void* g_in, const void* act, const void* y, int views, const float* mean_invstd0,
@@ -946,6 +959,8 @@ extern "C" int iic_bn_bwd_fused(const void* g_in, const void* act, const void* y
   IIC_REQUIRE(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, IIC_ERR_UNSUPPORTED, "iic_bn_bwd_fused: C=%d unsupported", C);
   IIC_REQUIRE(views == 1 || ((mask_ss0 == nullptr) == (mask_ss1 == nullptr)), IIC_ERR_BAD_ARG,
               "iic_bn_bwd_fused: mask scale/shift must be given for both views or neither");
+  IIC_REQUIRE(!(act && mask_ss0), IIC_ERR_BAD_ARG, "iic_bn_bwd_fused: one ReLU mask source at most");
+  IIC_REQUIRE(dtype == IIC_BF16 || dtype == IIC_F32, IIC_ERR_BAD_ARG, "iic_bn_bwd_fused: bad dtype %d", dtype);
   BnBwdFusedArgs a;
   a.gin = g_in; a.act = act; a.y = y; a.dy = dy; a.gout = g_out;
   a.mi[0] = mean_invstd0; a.mi[1] = mean_invstd1; a.mss[0] = mask_ss0; a.mss[1] = mask_ss1;
@@ -955,23 +970,8 @@ extern "C" int iic_bn_bwd_fused(const void* g_in, const void* act, const void* y
   a.sums = bn_sums_scratch();
   IIC_REQUIRE(a.partial && a.sums, IIC_ERR_CUDA, "iic_bn_bwd_fused: scratch allocation failed");
   const size_t smem = sizeof(float) * (size_t)(5 * C > 256 * 17 ? 5 * C : 256 * 17);
-  void* args[] = {&a};
-  int grid = 0;
-  cudaError_t e = cudaSuccess;
-  if (dtype == IIC_BF16) {
-    grid = bn_bwd_fused_grid<__nv_bfloat16>(smem, views);
-    IIC_REQUIRE(grid >= views, IIC_ERR_CUDA, "iic_bn_bwd_fused: occupancy query failed");
-    e = cudaLaunchCooperativeKernel((void*)bn_bwd_fused_kernel<__nv_bfloat16>, dim3(grid), dim3(256), args, smem, (cudaStream_t)stream);
-  } else if (dtype == IIC_F32) {
-    grid = bn_bwd_fused_grid<float>(smem, views);
-    IIC_REQUIRE(grid >= views, IIC_ERR_CUDA, "iic_bn_bwd_fused: occupancy query failed");
-    e = cudaLaunchCooperativeKernel((void*)bn_bwd_fused_kernel<float>, dim3(grid), dim3(256), args, smem, (cudaStream_t)stream);
-  } else {
-    IIC_REQUIRE(false, IIC_ERR_BAD_ARG, "iic_bn_bwd_fused: bad dtype %d", dtype);
-  }
-  IIC_REQUIRE(e == cudaSuccess, IIC_ERR_CUDA, "iic_bn_bwd_fused: cooperative launch failed: %s", cudaGetErrorString(e));
-  count_launch();
-  return IIC_OK;
+  if (dtype == IIC_BF16) return bn_bwd_fused_dispatch<__nv_bfloat16>(a, smem, (cudaStream_t)stream);
+  return bn_bwd_fused_dispatch<float>(a, smem, (cudaStream_t)stream);
 }
 
 extern "C" int iic_avgpool(const void* x, int dtype, float* feat, int n, int hw, int C, void* stream) {

@@ -110,6 +110,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* desc, uint
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// tiled mode, rank 4 (out-of-bounds elements, including negative coordinates, are zero-filled)
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 // im2col mode, NHWC activation as a (C, W, H, N) tensor: {c, w, h, n} = channel offset and the input-space
 // coordinate of the first pixel's receptive-field corner; {off_w, off_h} = filter tap * dilation.
 __device__ __forceinline__ void tma_load_im2col(uint32_t dst, const void* desc, uint32_t bar, int c, int w, int h, int n,
