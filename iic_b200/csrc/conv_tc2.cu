@@ -249,9 +249,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 4) {
     // =============================== MMA issuer ==============================================
+    // The issue path is kept warp-uniform (wrapping stage counter, descriptors = one base + immediate adds, the
+    // issuing lane chosen by elect.sync): ptxas then holds the descriptors in uniform registers and emits
+    // UTCHMMA back to back.  With `if (lane == 0)` and descriptors rebuilt from vector registers every MMA cost an
+    // ELECT / R2UR round trip (~15 instructions), which bounded the N = 64 tiles (32 tensor cycles per MMA).
     constexpr uint32_t idesc = (MODE == M2_FPROP) ? make_idesc(BN, 0, 0) : make_idesc(BN, 1, 1);
-    uint32_t it = 0, tile_it = 0;
+    uint32_t s = 0, sphase = 0, tile_it = 0;
     if (RESB && blockIdx.x < total_work) mbar_wait(bres_bar, 0);
+    const uint64_t desc_base = (MODE == M2_FPROP) ? make_desc(base, 16, 1024) : make_desc(base, 8192, 1024);
+    const uint64_t desc_resb = make_desc(resb, 16, 1024);
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tile_it) {
       int z, n0, kb0, nk;
       long long m0;
@@ -260,33 +266,33 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(tempty_bar(as), ((tile_it >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + as * (MT * BN);
-      for (int i = 0; i < nk; ++i, ++it) {
-        const int s = it % STAGES;
-        mbar_wait(full_bar(s), (it / STAGES) & 1u);
+      for (int i = 0; i < nk; ++i) {
+        mbar_wait(full_bar(s), sphase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = base + s * Cfg::STAGE_BYTES;
-          const uint32_t sb = RESB ? resb + (uint32_t)i * Cfg::B_BYTES : sa + Cfg::A_BYTES;
+        if (elect_one_sync()) {
+          const uint64_t ad0 = desc_base + (uint64_t)((s * (uint32_t)Cfg::STAGE_BYTES) >> 4);
+          const uint64_t bd0 = RESB ? desc_resb + (uint64_t)(((uint32_t)i * (uint32_t)Cfg::B_BYTES) >> 4)
+                                    : ad0 + (uint64_t)(Cfg::A_BYTES >> 4);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              uint64_t ad, bd;
-              if (MODE == M2_FPROP) {
-                ad = make_desc(sa + mt * (TC_BM * 128) + kk * 32, 16, 1024);
-                bd = make_desc(sb + kk * 32, 16, 1024);
-              } else {
-                ad = make_desc(sa + kk * 2048, 8192, 1024);
-                bd = make_desc(sb + kk * 2048, 8192, 1024);
-              }
+              // K-major: 32 B per K = 16 step inside the 128 B swizzle row; MN-major: 16 K-rows x 128 B
+              const uint32_t koff = (MODE == M2_FPROP) ? kk * 32 : kk * 2048;
+              const uint64_t ad = ad0 + (uint64_t)((mt * (TC_BM * 128) + koff) >> 4);
+              const uint64_t bd = bd0 + (uint64_t)(koff >> 4);
               umma_bf16(tmem_acc + mt * BN, ad, bd, idesc, (i > 0 || kk > 0) ? 1u : 0u);
             }
           }
           umma_commit(empty_bar(s));
         }
         __syncwarp();
+        if (++s == (uint32_t)STAGES) {
+          s = 0;
+          sphase ^= 1u;
+        }
       }
-      if (lane == 0) umma_commit(tfull_bar(as));  // (also correct for nk == 0: arrives immediately)
+      if (elect_one_sync()) umma_commit(tfull_bar(as));  // (also correct for nk == 0: arrives immediately)
       __syncwarp();
     }
   } else {
@@ -474,28 +480,34 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 8) {
     // =============================== MMA issuer ==============================================
+    // Everything that feeds a descriptor stays warp-uniform (wrapping stage counter instead of a modulo, the
+    // nine tap shifts read from the kernel parameters by a fully unrolled loop): ptxas then keeps the
+    // descriptors in uniform registers and issues UTCHMMA back to back; a descriptor that passes through a
+    // vector register costs an ELECT / R2UR round trip per MMA, which at N = 64 (32 MMA cycles) is the bound.
     constexpr uint32_t idesc = make_idesc(64, 0, 0);
-    uint32_t it = 0;
+    uint32_t it = 0, s = 0, sphase = 0;
     if (blockIdx.x < P.total_tiles) mbar_wait(bres_bar, 0);
+    const uint64_t bdesc_res = make_desc(resb, 16, 1024);
     for (int w = blockIdx.x; w < P.total_tiles; w += gridDim.x, ++it) {
       const uint32_t as = it & 1u;
       mbar_wait(tempty_bar(as), ((it >> 1) & 1u) ^ 1u);
-      const int s = it % P.stages;
-      mbar_wait(full_bar(s), (it / P.stages) & 1u);
+      mbar_wait(full_bar(s), sphase);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = base + (uint32_t)s * (uint32_t)P.stage_bytes;
+      if (elect_one_sync()) {
+        const uint64_t adesc0 = make_desc(base + s * (uint32_t)P.stage_bytes, 16, 1024);
         const uint32_t tmem_acc = tmem_base + as * 128u;
-#pragma unroll 1
+        uint64_t bdesc0 = bdesc_res;
+        asm volatile("" : "+l"(bdesc0));  // opaque per tile: the 36 weight descriptors are rebuilt from one uniform
+                                          // base by immediate adds instead of living in 72 hoisted vector registers
+#pragma unroll
         for (int t = 0; t < 9; ++t) {
-          const uint32_t a_t = sa + (uint32_t)P.shift[t] * 128u;
-          const uint32_t b_t = resb + (uint32_t)t * 8192u;
+          const uint64_t a_t = adesc0 + (uint64_t)((uint32_t)P.shift[t] * 8u);  // descriptor address unit = 16 B
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t ad = make_desc(a_t + mt * (TC_BM * 128) + kk * 32, 16, 1024);
-              const uint64_t bd = make_desc(b_t + kk * 32, 16, 1024);
+              const uint64_t ad = a_t + (uint64_t)((mt * (TC_BM * 128) + kk * 32) >> 4);
+              const uint64_t bd = bdesc0 + (uint64_t)((t * 8192 + kk * 32) >> 4);
               umma_bf16(tmem_acc + mt * 64, ad, bd, idesc, (t > 0 || kk > 0) ? 1u : 0u);
             }
           }
@@ -504,6 +516,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         umma_commit(tfull_bar(as));
       }
       __syncwarp();
+      if (++s == (uint32_t)P.stages) {
+        s = 0;
+        sphase ^= 1u;
+      }
     }
   } else {
     // =============================== epilogue (warps 0-7) ======================================
