@@ -19,6 +19,10 @@ class ConvGeom(Structure):
   _fields_ = [(n, c_int) for n in ("n", "h", "w", "cin", "oh", "ow", "cout", "kh", "kw", "stride", "pad", "dil")]
 
 
+class PackJob(Structure):
+  _fields_ = [("w", c_void_p), ("dst", c_void_p)] + [(n, c_int) for n in ("kind", "cout", "cin", "kh", "kw", "reserved")]
+
+
 _P = c_void_p
 _SIGS = {
   "iic_abi_version": (c_int, []),
@@ -58,6 +62,9 @@ _SIGS = {
   "iic_bn_bwd_fused": (c_int, [_P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_longlong, c_int, _P]),
   "iic_bn_apply_views": (c_int, [_P, _P, _P, _P, _P, c_int, c_longlong, c_int, c_int, c_int, _P]),
   "iic_bn_stats_from_partials_views": (c_int, [_P, c_int, c_int, c_int, c_longlong, c_int, _P, _P, c_float, c_float, _P, _P, _P, _P, _P]),
+  "iic_pack_weights_batched": (c_int, [_P, c_int, c_int, _P]),
+  "iic_stem_fprop_stats_blocks": (c_int, [POINTER(ConvGeom), c_int, c_int]),
+  "iic_stem_fprop_stats": (c_int, [_P, _P, _P, POINTER(ConvGeom), c_int, c_int, _P, _P]),
   "iic_avgpool": (c_int, [_P, c_int, _P, c_int, c_int, c_int, _P]),
   "iic_avgpool_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
   "iic_heads_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),

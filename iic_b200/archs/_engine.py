@@ -167,6 +167,12 @@ def _conv_bn(ctx, conv, bn, x, g):
     ss, mi = _bn_stats(ctx, bn, y)
     return y, ss, mi
   y, partial, nblk = fused
+  ss, mi = _stats_from_partials(ctx, bn, y, partial, nblk)
+  return y, ss, mi
+
+
+def _stats_from_partials(ctx, bn, y, partial, nblk):
+  """Per-CTA partial sums written by a producing kernel's epilogue -> per-view scale/shift and mean/invstd."""
   update = ctx.training and bn.track_running_stats
   rm = bn.running_mean if update else None
   rv = bn.running_var if update else None
@@ -176,7 +182,7 @@ def _conv_bn(ctx, conv, bn, x, g):
       bn.num_batches_tracked += ctx.groups
     ss, mi = K.bn_stats_from_partials_views(partial, nblk, 2, ctx.groups, M, bn.weight.detach(), bn.bias.detach(),
                                             bn.eps, bn.momentum, rm, rv)
-    return y, _ViewStats(ss), _ViewStats(mi)
+    return _ViewStats(ss), _ViewStats(mi)
   sss, mis = [], []
   for v in range(ctx.groups):
     if update:
@@ -185,7 +191,7 @@ def _conv_bn(ctx, conv, bn, x, g):
                                       bn.momentum, rm, rv)
     sss.append(ss)
     mis.append(mi)
-  return y, sss, mis
+  return sss, mis
 
 
 def _bn_apply(ctx, y, ss, relu, res=None, rss=None):
@@ -256,8 +262,15 @@ def _conv_wgrad(ctx, sink, conv, x, dy, g):
 def stem_forward(ctx, conv, bn, x_nchw, pool_pad):
   n, c, h, w = x_nchw.shape
   g = conv.geom(n, h, w)
-  y = K.stem_fprop(x_nchw, conv.weight.detach(), g, ctx.dt)
-  ss, mi = _bn_stats(ctx, bn, y)
+  fused = None
+  if ctx.dt == BF16 and (ctx.training or not bn.track_running_stats):  # statistics in the conv kernel, like _conv_bn
+    fused = K.stem_fprop_stats(x_nchw, conv.weight.detach(), g, ctx.dt, ctx.groups)
+  if fused is None:
+    y = K.stem_fprop(x_nchw, conv.weight.detach(), g, ctx.dt)
+    ss, mi = _bn_stats(ctx, bn, y)
+  else:
+    y, partial, nblk = fused
+    ss, mi = _stats_from_partials(ctx, bn, y, partial, nblk)
   out = _bn_relu_maxpool(ctx, y, ss, pool_pad) if pool_pad is not None else _bn_apply(ctx, y, ss, True)
   if ctx.need_grad:
     ctx.saved.append(("stem", conv, bn, x_nchw, g, y, ss, mi, None, pool_pad))
@@ -336,6 +349,27 @@ def block_backward(ctx, sink, rec, d_out):
   return K.conv_dgrad(dy1, ctx.packed(blk.conv1, 1), g1, ctx.dt, addend=gres)
 
 
+def _prepack(trunk, ectx):
+  """All tensor-core weight layouts of the trunk (fprop, and dgrad when a backward follows) in one launch.  The
+  job table and the destination buffers persist on the module; they are rebuilt if a weight was re-allocated."""
+  if os.environ.get("IIC_PACK_BATCHED", "1") == "0":
+    return
+  convs = [m for m in trunk.modules() if isinstance(m, ConvParams) and m.cin % 8 == 0]  # (the stem reads fp32 weights)
+  if not convs:
+    return
+  weights = [c.weight.detach() for c in convs]
+  kinds = (0, 1) if ectx.need_grad else (0,)
+  key = K.PackPlan.make_key(weights, kinds, ectx.dt)
+  plans = trunk.__dict__.setdefault("_iic_pack_plans", {})
+  plan = plans.get((kinds, ectx.dt))
+  if plan is None or plan.key != key:
+    plan = plans[(kinds, ectx.dt)] = K.PackPlan(weights, kinds, ectx.dt)
+  out = plan.run()
+  for wi, c in enumerate(convs):
+    for kind in kinds:
+      ectx.wcache[(id(c), kind)] = out[(wi, kind)]
+
+
 _BACKWARD = {"stem": stem_backward, "convbn": convbn_backward, "block": block_backward}
 
 
@@ -347,6 +381,7 @@ class TrunkFunction(torch.autograd.Function):
   @staticmethod
   def forward(ctx, trunk, run, need_grad, groups, x, *params):
     ectx = _Ctx(_PRECISIONS[trunk.precision], trunk.training, need_grad, groups)
+    _prepack(trunk, ectx)
     feat, finisher = run(ectx, x)
     ctx.ectx, ctx.finisher, ctx.params = ectx, finisher, params
     return feat

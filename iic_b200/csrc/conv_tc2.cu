@@ -25,7 +25,7 @@ namespace iic {
 
 enum { M2_FPROP = 0, M2_WGRAD = 1 };
 #ifndef IIC_CONV_HALO_DEFAULT
-#define IIC_CONV_HALO_DEFAULT 0  // halo variant of the 64-channel 3x3 layers: opt-in until validated on hardware
+#define IIC_CONV_HALO_DEFAULT 1  // halo variant of the 64-channel 3x3 layers (validated: profiles/r01_conv_sweep.md)
 #endif
 constexpr int TC2_THREADS = 192;
 
@@ -591,6 +591,126 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
+
+// ---- halo wgrad: dW[tap][ci][co] = sum_p x[p + tap shift][ci] * dy[p][co] on the padded grid ----------------
+// One work item = R output rows of one image: the x box (R+2 rows x Wp, zero-filled borders) and the dy box
+// (R rows x Wp; its two padding columns are zero-filled, so padding positions contribute nothing) are loaded
+// ONCE and all nine taps are accumulated from them: the A operand (MN-major, K = pixel) of an MMA holds two taps
+// as its two 64-column blocks -- two shifted views of the x tile, LBO = their distance -- so five M = 128 MMAs
+// per K step cover the nine taps (the tenth block is discarded).  Each persistent CTA keeps its 576 x 64 fp32
+// partial in TMEM (5 x 64 columns) over all its work items and writes it once; wgrad2_reduce_kernel folds the
+// per-CTA partials.  (The im2col kernel re-loads x nine times and dy five times: 192 B of shared-memory fill
+// per tensor cycle at N = 64, which pinned this layer at ~0.3 of the tensor peak.)
+__global__ void __launch_bounds__(TC2_THREADS, 1)
+conv_halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy, HaloParams P,
+                       float* __restrict__ partial) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  constexpr uint32_t DY_BYTES = HALO_TILE * 128;
+  const uint32_t stage_stride = (uint32_t)P.stage_bytes + DY_BYTES;  // [x tile | dy tile]
+  const uint32_t bars = base + 2u * stage_stride;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (2 + s); };
+  const uint32_t done_bar = bars + 8u * 4;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + 2u * stage_stride + 8 * 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // rows the TMA boxes never write but the MMAs read (K is padded to 256 pixels, the last taps look 2*Wp+2 rows
+  // ahead): zero once -- dy = 0 there, and x must at least be finite
+  for (int s = 0; s < 2; ++s) {
+    uint4* xs = reinterpret_cast<uint4*>(base_ptr + s * stage_stride);
+    for (int i = P.box_bytes / 16 + threadIdx.x; i < P.stage_bytes / 16; i += TC2_THREADS) xs[i] = make_uint4(0, 0, 0, 0);
+    uint4* ds = reinterpret_cast<uint4*>(base_ptr + s * stage_stride + P.stage_bytes);
+    for (int i = P.R * P.Wp * 8 + threadIdx.x; i < (int)(DY_BYTES / 16); i += TC2_THREADS) ds[i] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDy);
+  }
+  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 5) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      const uint32_t bytes = (uint32_t)P.box_bytes + (uint32_t)(P.R * P.Wp * 128);
+      for (int w = blockIdx.x; w < P.total_tiles; w += gridDim.x, ++it) {
+        const int img = w / P.tiles_per_img;
+        const int y0 = (w - img * P.tiles_per_img) * P.R;
+        const uint32_t s = it & 1u;
+        mbar_wait(empty_bar(s), ((it >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(full_bar(s), bytes);
+        tma_load_4d(base + s * stage_stride, &tmX, full_bar(s), 0, -1, y0 - 1, img);
+        tma_load_4d(base + s * stage_stride + (uint32_t)P.stage_bytes, &tmDy, full_bar(s), 0, 0, y0, img);
+      }
+    }
+  } else if (warp == 4) {
+    constexpr uint32_t idesc = make_idesc(64, 1, 1);
+    uint32_t it = 0;
+    for (int w = blockIdx.x; w < P.total_tiles; w += gridDim.x, ++it) {
+      const uint32_t s = it & 1u;
+      mbar_wait(full_bar(s), (it >> 1) & 1u);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t xs = base + s * stage_stride;
+        const uint64_t bd0 = make_desc(xs + (uint32_t)P.stage_bytes, 8192, 1024);
+#pragma unroll
+        for (int g = 0; g < 5; ++g) {
+          // column blocks = taps 2g and 2g+1 (the "tap 9" of the last group is a dummy: rows >= 576 are dropped)
+          const uint32_t sh0 = P.shift[2 * g];
+          const uint32_t lbo = (g < 4 ? (uint32_t)P.shift[2 * g + 1] - sh0 : 1u) * 128u;
+          const uint64_t ad0 = make_desc(xs + sh0 * 128u, lbo, 1024);
+#pragma unroll
+          for (int kk = 0; kk < HALO_TILE / 16; ++kk)
+            umma_bf16(tmem_base + g * 64, ad0 + (uint64_t)(kk * 2048 >> 4), bd0 + (uint64_t)(kk * 2048 >> 4), idesc,
+                      (it > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));
+      }
+      __syncwarp();
+    }
+    if (elect_one_sync()) umma_commit(done_bar);
+    __syncwarp();
+  } else {
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+#pragma unroll 1
+    for (int g = 0; g < 5; ++g) {
+      const int j = g * 128 + row;  // row of the [576][64] partial = tap * 64 + ci
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + g * 64 + c0 + ((uint32_t)(warp * 32) << 16), v);
+        tmem_ld_wait();
+        if (j < 576) {
+          float* o = partial + ((long long)blockIdx.x * 576 + j) * 64 + c0;
+#pragma unroll
+          for (int qq = 0; qq < 8; ++qq)
+            *reinterpret_cast<float4*>(o + qq * 4) = make_float4(__uint_as_float(v[qq * 4]), __uint_as_float(v[qq * 4 + 1]),
+                                                                 __uint_as_float(v[qq * 4 + 2]), __uint_as_float(v[qq * 4 + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
 // ---- host side: tensor-map construction through the driver entry points ----------------------
 typedef CUresult (*PFN_tmEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -722,19 +842,35 @@ static HaloPlan halo_plan(const iic_conv_geom* g, int srcC, int N, int H, int W,
   return p;
 }
 
+static int make_halo_map(CUtensorMap* tm, const __nv_bfloat16* src, int H, int W, int nimg, int box_w, int box_h) {
+  cuuint64_t gdim[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
+  cuuint64_t gstr[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(src), gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IIC_REQUIRE(r == CUDA_SUCCESS, IIC_ERR_CUDA, "cuTensorMapEncodeTiled(halo) failed (%d) H=%d W=%d box %dx%d", (int)r, H, W, box_w,
+              box_h);
+  return IIC_OK;
+}
+
+// wgrad flavour of the plan: two [x tile | dy tile] stages; the per-CTA partials are the split-K workspace
+static HaloPlan halo_wgrad_plan(const iic_conv_geom* g) {
+  HaloPlan p = halo_plan(g, g->cin, g->cout, g->h, g->w, g->n);
+  if (!p.ok) return p;
+  p.stages = 2;
+  p.smem = 1024 + 2 * (p.stage_bytes + HALO_TILE * 128) + 256;
+  if (p.smem > 232448) p.ok = false;
+  return p;
+}
+
 static int launch_halo(const HaloPlan& hp, const __nv_bfloat16* src, int H, int W, int nimg, const Tc2Params& P,
                        const CUtensorMap& tmB, cudaStream_t st) {
   alignas(64) CUtensorMap tmA;
   {
-    cuuint64_t gdim[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg};
-    cuuint64_t gstr[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
-    cuuint32_t box[4] = {64, (cuuint32_t)hp.Wp, (cuuint32_t)(hp.R + 2), 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_encodeTiled(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(src), gdim, gstr, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    IIC_REQUIRE(r == CUDA_SUCCESS, IIC_ERR_CUDA, "cuTensorMapEncodeTiled(halo) failed (%d) H=%d W=%d box %dx%d", (int)r, H, W,
-                hp.Wp, hp.R + 2);
+    const int rc = make_halo_map(&tmA, src, H, W, nimg, hp.Wp, hp.R + 2);
+    if (rc != IIC_OK) return rc;
   }
   HaloParams Q = {};
   Q.nimg = nimg; Q.H = H; Q.W = W; Q.Wp = hp.Wp; Q.R = hp.R;
@@ -953,7 +1089,9 @@ int tc2_conv_dgrad_s2(const __nv_bfloat16* dy, const __nv_bfloat16* wpacked_t, c
 }
 
 long long tc2_conv_wgrad_workspace(const iic_conv_geom* g) {
-  return (long long)tc2_wgrad_splits(g) * g->kh * g->kw * g->cin * g->cout * (long long)sizeof(float);
+  const HaloPlan hp = halo_wgrad_plan(g);
+  const long long splits = hp.ok ? tc2_grid(hp.total_tiles) : tc2_wgrad_splits(g);
+  return splits * g->kh * g->kw * g->cin * g->cout * (long long)sizeof(float);
 }
 
 __global__ void wgrad2_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Ktot, int N, int splits) {
@@ -973,6 +1111,29 @@ int tc2_conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, f
   const int bn = pick_bn2(g->cout);
   IIC_REQUIRE(bn != 0 && g->cin % 64 == 0, IIC_ERR_UNSUPPORTED, "tcgen05/TMA wgrad: channels must be multiples of 64");
   IIC_REQUIRE(g->kh == g->kw, IIC_ERR_UNSUPPORTED, "tcgen05/TMA wgrad: square filters only");
+  const HaloPlan hp = halo_wgrad_plan(g);
+  if (hp.ok) {
+    alignas(64) CUtensorMap tmX, tmDy;
+    rc = make_halo_map(&tmX, x, g->h, g->w, g->n, hp.Wp, hp.R + 2);
+    if (rc != IIC_OK) return rc;
+    rc = make_halo_map(&tmDy, dy, g->h, g->w, g->n, hp.Wp, hp.R);
+    if (rc != IIC_OK) return rc;
+    HaloParams Q = {};
+    Q.nimg = g->n; Q.H = g->h; Q.W = g->w; Q.Wp = hp.Wp; Q.R = hp.R;
+    Q.tiles_per_img = hp.tiles_per_img; Q.total_tiles = hp.total_tiles;
+    Q.stage_bytes = hp.stage_bytes; Q.box_bytes = hp.box_bytes; Q.stages = 2;
+    for (int t = 0; t < 9; ++t) Q.shift[t] = (unsigned short)((t / 3) * hp.Wp + t % 3);
+    const int grid = tc2_grid(hp.total_tiles);
+    IIC_CUDA(cudaFuncSetAttribute(conv_halo_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hp.smem));
+    conv_halo_wgrad_kernel<<<grid, TC2_THREADS, hp.smem, st>>>(tmX, tmDy, Q, ws);
+    IIC_LAUNCH_CHECK();
+    count_launch();
+    const long long total = 576ll * 64;
+    wgrad2_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(ws, dw, 576, 64, grid);
+    IIC_LAUNCH_CHECK();
+    count_launch();
+    return IIC_OK;
+  }
   Tc2Params P = {};
   P.rows = (long long)g->n * g->oh * g->ow;
   P.rowH = g->oh; P.rowW = g->ow; P.KH = g->kh; P.KW = g->kw; P.s = g->stride; P.d = g->dil; P.lower = -g->pad;

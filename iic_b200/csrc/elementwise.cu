@@ -659,6 +659,25 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
     }
   }
 }
+// all convolutions of a trunk in one launch: blockIdx.y = job, blockIdx.x strides over the job's elements
+template <typename T>
+__global__ void pack_weights_batched_kernel(const iic_pack_job* __restrict__ jobs) {
+  const iic_pack_job j = jobs[blockIdx.y];
+  const float* __restrict__ w = j.w;
+  T* __restrict__ dst = (T*)j.dst;
+  const int cin = j.cin, cout = j.cout, kh = j.kh, kw = j.kw;
+  const int total = cout * cin * kh * kw;
+  const int inner_n = j.kind == 0 ? cin : cout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int t = i;
+    const int inner = t % inner_n; t /= inner_n;
+    const int b = t % kw; t /= kw;
+    const int a = t % kh;
+    const int outer = t / kh;
+    const int co = j.kind == 0 ? outer : inner, ci = j.kind == 0 ? inner : outer;
+    dst[i] = from_f<T>(w[((co * cin + ci) * kh + a) * kw + b]);
+  }
+}
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ grad, int accumulate, int cout,
                                     int cin, int kh, int kw) {
   const long long total = (long long)cout * cin * kh * kw;
@@ -995,6 +1014,13 @@ extern "C" int iic_pack_weight(const float* w_oihw, void* dst, int dst_dtype, in
               "iic_pack_weight: bad arguments");
   const long long total = (long long)cout * cin * kh * kw;
   DISPATCH_T(dst_dtype, pack_weight_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, (T*)dst, kind, cout, cin, kh, kw);)
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+extern "C" int iic_pack_weights_batched(const iic_pack_job* jobs_device, int njobs, int dst_dtype, void* stream) {
+  IIC_REQUIRE(jobs_device && njobs > 0 && njobs <= 65535, IIC_ERR_BAD_ARG, "iic_pack_weights_batched: bad arguments");
+  DISPATCH_T(dst_dtype, pack_weights_batched_kernel<T><<<dim3(32, njobs), 256, 0, (cudaStream_t)stream>>>(jobs_device);)
   IIC_LAUNCH_CHECK();
   count_launch();
   return IIC_OK;

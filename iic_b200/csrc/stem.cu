@@ -101,6 +101,110 @@ __global__ void __launch_bounds__(128) stem_fprop64_kernel(const float* __restri
   }
 }
 
+// cout == 64, stride 1, dilation 1, ow % 4 == 0: a thread computes 4 consecutive output pixels x 16 channels
+// (64 FMA per 4 LDS.128 and per ~2 global loads; the one-pixel-per-thread kernel above issues one LDS.128 per
+// 4 FMA and is bound by the shared-memory pipe).  Warp = 32 consecutive pixel quads x one channel quarter, so the
+// weight reads are warp broadcasts.  Optionally accumulates the BatchNorm batch statistics of the fp32
+// results (per-thread sums over its pixels, shuffle reduction at the end, one partial row per block in the
+// layout of the tcgen05 conv epilogue: [block][2 view slots][{sum, sum of squares}][64]); the grid is split
+// evenly between the `views` stacked batches.
+template <typename T, int KS>
+__global__ void __launch_bounds__(256, 2) stem_fprop64q_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               T* __restrict__ y, iic_conv_geom g,
+                                                               float* __restrict__ stat_partial, int views) {
+  extern __shared__ __align__(16) float ws[];  // [K][64]
+  __shared__ float red[8][32];
+  const int K = g.cin * KS * KS;
+  for (int i = threadIdx.x; i < K * 64; i += blockDim.x) ws[i] = w[(long long)(i & 63) * K + (i >> 6)];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cq = warp & 3, qg = warp >> 2;
+  const int qpr = g.ow >> 2;
+  const long long Qv = (long long)(g.n / views) * g.oh * qpr;  // quads per view
+  const int Gv = gridDim.x / views, v = blockIdx.x / Gv, lb = blockIdx.x % Gv;
+  float s1[16], s2[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) s1[c] = s2[c] = 0.f;
+  for (long long ql = (long long)(lb * 2 + qg) * 32 + lane; ql < Qv; ql += (long long)Gv * 64) {
+    const long long q = (long long)v * Qv + ql;
+    const int ox0 = (int)(q % qpr) * 4;
+    const long long t = q / qpr;
+    const int oy = (int)(t % g.oh);
+    const int n = (int)(t / g.oh);
+    float acc[4][16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc[j][c] = 0.f;
+    for (int ci = 0; ci < g.cin; ++ci) {
+      const float* xc = x + ((long long)n * g.cin + ci) * g.h * g.w;
+#pragma unroll
+      for (int a = 0; a < KS; ++a) {
+        const int iy = oy - g.pad + a;
+        const bool rowok = (unsigned)iy < (unsigned)g.h;
+        float xv[KS + 3];
+#pragma unroll
+        for (int j = 0; j < KS + 3; ++j) {
+          const int ix = ox0 - g.pad + j;
+          xv[j] = (rowok && (unsigned)ix < (unsigned)g.w) ? __ldg(xc + (long long)iy * g.w + ix) : 0.f;
+        }
+#pragma unroll
+        for (int b = 0; b < KS; ++b) {
+          const float4* wk = reinterpret_cast<const float4*>(ws + ((ci * KS + a) * KS + b) * 64 + cq * 16);
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 w4 = wk[c4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc[j][c4 * 4] = fmaf(xv[j + b], w4.x, acc[j][c4 * 4]);
+              acc[j][c4 * 4 + 1] = fmaf(xv[j + b], w4.y, acc[j][c4 * 4 + 1]);
+              acc[j][c4 * 4 + 2] = fmaf(xv[j + b], w4.z, acc[j][c4 * 4 + 2]);
+              acc[j][c4 * 4 + 3] = fmaf(xv[j + b], w4.w, acc[j][c4 * 4 + 3]);
+            }
+          }
+        }
+      }
+    }
+    const long long p0 = ((long long)n * g.oh + oy) * g.ow + ox0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f[8];
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = acc[j][h2 * 8 + e];
+        store8(y + (p0 + j) * 64 + cq * 16 + h2 * 8, f);
+      }
+      if (stat_partial != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          s1[c] += acc[j][c];
+          s2[c] = fmaf(acc[j][c], acc[j][c], s2[c]);
+        }
+      }
+    }
+  }
+  if (stat_partial == nullptr) return;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    s1[c] = warp_sum(s1[c]);
+    s2[c] = warp_sum(s2[c]);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      red[warp][c] = s1[c];
+      red[warp][16 + c] = s2[c];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 256) {  // (slot, stat, channel)
+    const int ch = threadIdx.x & 63, q2 = (threadIdx.x >> 6) & 1, slot = threadIdx.x >> 7;
+    const int wq = ch >> 4, c = ch & 15;
+    const float val = slot == v ? red[wq][q2 * 16 + c] + red[wq + 4][q2 * 16 + c] : 0.f;
+    stat_partial[(long long)blockIdx.x * 256 + threadIdx.x] = val;
+  }
+}
+
 constexpr int SW_PC = 64;  // pixels per chunk
 
 template <typename T>
@@ -230,11 +334,58 @@ static int stem_check(const iic_conv_geom* g, const char* who) {
   return IIC_OK;
 }
 
+static bool stem_quad_ok(const iic_conv_geom* g) {
+  return g->cout == 64 && g->stride == 1 && g->dil == 1 && g->ow % 4 == 0 && g->kh == g->kw && (g->kh == 3 || g->kh == 5);
+}
+static int stem_quad_blocks(const iic_conv_geom* g, int views) {
+  const long long quads = (long long)g->n * g->oh * (g->ow / 4);
+  long long blocks = (quads / views + 63) / 64;
+  const long long cap = (long long)device_sm_count() * 4;  // 2 resident blocks per SM, two rounds
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks * views;
+}
+template <typename T>
+static int stem_quad_launch(const float* x, const float* w, T* y, const iic_conv_geom* g, float* stat_partial, int views,
+                            cudaStream_t st) {
+  const size_t smem = (size_t)g->cin * g->kh * g->kw * 64 * sizeof(float);
+  const int blocks = stem_quad_blocks(g, views);
+  if (g->kh == 3)
+    stem_fprop64q_kernel<T, 3><<<blocks, 256, smem, st>>>(x, w, y, *g, stat_partial, views);
+  else
+    stem_fprop64q_kernel<T, 5><<<blocks, 256, smem, st>>>(x, w, y, *g, stat_partial, views);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
+extern "C" int iic_stem_fprop_stats_blocks(const iic_conv_geom* g, int dtype, int views) {
+  if (g == nullptr || !stem_quad_ok(g) || (dtype != IIC_F32 && dtype != IIC_BF16) || views < 1 || views > 2 ||
+      g->n % views != 0)
+    return 0;
+  return stem_quad_blocks(g, views);
+}
+
+extern "C" int iic_stem_fprop_stats(const float* x_nchw, const float* w_oihw, void* y, const iic_conv_geom* g, int dtype,
+                                    int views, float* stat_partial, void* stream) {
+  int rc = stem_check(g, "iic_stem_fprop_stats");
+  if (rc != IIC_OK) return rc;
+  IIC_REQUIRE(x_nchw && w_oihw && y && stat_partial, IIC_ERR_BAD_ARG, "iic_stem_fprop_stats: null pointer");
+  IIC_REQUIRE(iic_stem_fprop_stats_blocks(g, dtype, views) > 0, IIC_ERR_UNSUPPORTED,
+              "iic_stem_fprop_stats: needs cout 64, stride 1, dilation 1, 3x3 or 5x5, ow %% 4 == 0, 1 or 2 views");
+  if (dtype == IIC_F32) return stem_quad_launch<float>(x_nchw, w_oihw, (float*)y, g, stat_partial, views, (cudaStream_t)stream);
+  return stem_quad_launch<__nv_bfloat16>(x_nchw, w_oihw, (__nv_bfloat16*)y, g, stat_partial, views, (cudaStream_t)stream);
+}
+
 extern "C" int iic_stem_fprop(const float* x_nchw, const float* w_oihw, void* y, const iic_conv_geom* g, int dtype,
                               void* stream) {
   int rc = stem_check(g, "iic_stem_fprop");
   if (rc != IIC_OK) return rc;
   IIC_REQUIRE(x_nchw && w_oihw && y, IIC_ERR_BAD_ARG, "iic_stem_fprop: null pointer");
+  if (stem_quad_ok(g) && (dtype == IIC_F32 || dtype == IIC_BF16)) {
+    if (dtype == IIC_F32) return stem_quad_launch<float>(x_nchw, w_oihw, (float*)y, g, nullptr, 1, (cudaStream_t)stream);
+    return stem_quad_launch<__nv_bfloat16>(x_nchw, w_oihw, (__nv_bfloat16*)y, g, nullptr, 1, (cudaStream_t)stream);
+  }
   const int K = g->cin * g->kh * g->kw;
   const size_t smem = (size_t)K * g->cout * sizeof(float);
   const int ppb = 256 / (g->cout / 8);

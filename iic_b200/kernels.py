@@ -220,6 +220,41 @@ def pack_weight(w, dt, kind):
   return out
 
 
+class PackPlan(object):
+  """Device job table + persistent destination buffers for iic_pack_weights_batched.  Built once per set of
+  weight tensors (keyed by their storage addresses) and replayed every step: one launch instead of one per
+  convolution and layout."""
+
+  def __init__(self, weights, kinds, dt):
+    import numpy as np
+    self.key = PackPlan.make_key(weights, kinds, dt)
+    self.dt = dt
+    self.out = {}
+    jobs = (_lib.PackJob * (len(weights) * len(kinds)))()
+    i = 0
+    for wi, w in enumerate(weights):
+      assert w.is_cuda and w.is_contiguous() and w.dtype == torch.float32
+      cout, cin, kh, kw = w.shape
+      for kind in kinds:
+        shape = (cout, kh, kw, cin) if kind == 0 else (cin, kh, kw, cout)
+        dst = torch.empty(shape, device=w.device, dtype=_TORCH_DT[dt])
+        self.out[(wi, kind)] = dst
+        jobs[i] = _lib.PackJob(w.data_ptr(), dst.data_ptr(), kind, cout, cin, kh, kw, 0)
+        i += 1
+    self.njobs = i
+    raw = np.frombuffer(bytes(jobs), dtype=np.uint8).copy()
+    self.table = torch.from_numpy(raw).to(weights[0].device)
+
+  @staticmethod
+  def make_key(weights, kinds, dt):
+    return (tuple(w.data_ptr() for w in weights), tuple(kinds), dt)
+
+  @_cat("pack_weight")
+  def run(self):
+    check(_lib.lib().iic_pack_weights_batched(_p(self.table), self.njobs, self.dt, _stream()), "iic_pack_weights_batched")
+    return self.out
+
+
 def conv_fprop(x, wp, g, dt):
   y = torch.empty((g.n, g.oh, g.ow, g.cout), device=x.device, dtype=_TORCH_DT[dt])
   with _timed("fprop", g):
@@ -278,6 +313,19 @@ def stem_fprop(x_nchw, w, g, dt):
   y = torch.empty((g.n, g.oh, g.ow, g.cout), device=x_nchw.device, dtype=_TORCH_DT[dt])
   check(_lib.lib().iic_stem_fprop(_p(x_nchw), _p(w), _p(y), ctypes.byref(g), dt, _stream()), "iic_stem_fprop")
   return y
+
+
+@_cat("stem_fprop")
+def stem_fprop_stats(x_nchw, w, g, dt, views):
+  """Stem conv + fused per-view BN statistics partials.  Returns (y, partial, nblk) or None if unsupported."""
+  nblk = int(_lib.lib().iic_stem_fprop_stats_blocks(ctypes.byref(g), dt, views))
+  if nblk <= 0:
+    return None
+  y = torch.empty((g.n, g.oh, g.ow, g.cout), device=x_nchw.device, dtype=_TORCH_DT[dt])
+  partial = torch.empty((nblk, 2, 2, g.cout), device=x_nchw.device, dtype=torch.float32)
+  check(_lib.lib().iic_stem_fprop_stats(_p(x_nchw), _p(w), _p(y), ctypes.byref(g), dt, views, _p(partial), _stream()),
+        "iic_stem_fprop_stats")
+  return y, partial, nblk
 
 
 @_cat("stem_wgrad")

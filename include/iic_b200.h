@@ -122,6 +122,15 @@ typedef struct {
  *   kind 1 (dgrad layout):       [cin][kh][kw][cout]                                   */
 int iic_pack_weight(const float* w_oihw, void* dst, int dst_dtype, int kind, int cout, int cin, int kh,
                     int kw, void* stream);
+/* Every convolution weight of a trunk repacked in ONE launch (the per-step repacking of ~70 small tensors was
+ * launch-latency bound).  `jobs_device` is a DEVICE array; each job is one iic_pack_weight call (all weights must
+ * have fewer than 2^31 elements). */
+typedef struct iic_pack_job {
+  const float* w; /* torch layout [cout][cin][kh][kw] fp32 */
+  void* dst;      /* kind 0: [cout][kh][kw][cin], kind 1: [cin][kh][kw][cout], in dst_dtype */
+  int kind, cout, cin, kh, kw, reserved;
+} iic_pack_job;
+int iic_pack_weights_batched(const iic_pack_job* jobs_device, int njobs, int dst_dtype, void* stream);
 /* dw_packed fp32 [cout][kh][kw][cin] -> (accumulate ? += : =) torch-layout grad [cout][cin][kh][kw] */
 int iic_unpack_wgrad(const float* dw_packed, float* grad_oihw, int accumulate, int cout, int cin, int kh,
                      int kw, void* stream);
@@ -165,6 +174,14 @@ int iic_conv_wgrad(const void* x, const void* dy, float* dw_packed, void* worksp
  *      w: torch layout [cout][cin][kh][kw] fp32.  y: NHWC `dtype`. */
 int iic_stem_fprop(const float* x_nchw, const float* w_oihw, void* y, const iic_conv_geom* g, int dtype,
                    void* stream);
+/* The same with the BatchNorm batch statistics of y accumulated in the kernel (fp32 results, before rounding to
+ * the storage type), for `views` = 1 or 2 stacked batches.  stat_partial receives
+ * iic_stem_fprop_stats_blocks() rows of [2 view slots][{sum, sum of squares}][64] -- the layout of
+ * iic_conv_fprop_stats, folded by iic_bn_stats_from_partials(_views).  _blocks() returns 0 when the geometry is
+ * not supported (needs cout 64, stride 1, dilation 1, 3x3 or 5x5, ow % 4 == 0): use iic_stem_fprop + iic_bn_stats. */
+int iic_stem_fprop_stats_blocks(const iic_conv_geom* g, int dtype, int views);
+int iic_stem_fprop_stats(const float* x_nchw, const float* w_oihw, void* y, const iic_conv_geom* g, int dtype, int views,
+                         float* stat_partial, void* stream);
 int iic_stem_wgrad(const float* x_nchw, const void* dy, float* grad_oihw, int accumulate, void* workspace,
                    long long workspace_bytes, const iic_conv_geom* g, int dtype, void* stream);
 

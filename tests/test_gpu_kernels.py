@@ -455,3 +455,51 @@ def test_bn_stats_from_partials_all_views_in_one_launch():
       ss1, mi1 = K.bn_stats_from_partials(partial, nblk, 2, v, M, gamma, beta, 1e-5, 0.1, rm2, rv2)
       assert torch.equal(ss[v], ss1) and torch.equal(mi[v], mi1)
     assert torch.equal(rm, rm2) and torch.equal(rv, rv2)
+
+
+@pytest.mark.parametrize("cin,k,pad,hw", [(2, 3, 1, 24), (1, 5, 2, 24), (5, 3, 1, 16), (2, 3, 1, 96)])
+@pytest.mark.parametrize("views", [1, 2])
+def test_stem_fprop_with_fused_bn_statistics(cin, k, pad, hw, views):
+  """Quad stem kernel: same output as the plain entry point, statistics == a separate pass (fp32 accumulators vs
+  bf16-rounded storage: loose tolerance), per view."""
+  K = _K()
+  from iic_b200._lib import BF16
+  g = torch.Generator().manual_seed(41)
+  n = 6
+  x = torch.randn(n, cin, hw, hw, generator=g).cuda()
+  x[n // 2:] = x[n // 2:] * 1.5 + 0.3
+  w = (torch.randn(64, cin, k, k, generator=g) * math.sqrt(2.0 / (cin * k * k))).cuda()
+  gamma = (torch.rand(64, generator=g) + 0.5).cuda()
+  beta = (torch.randn(64, generator=g) * 0.1).cuda()
+  geo = K.conv_geom(n, hw, hw, cin, 64, k, k, 1, pad, 1)
+  y_ref = F.conv2d(x.double().cpu(), w.double().cpu(), None, 1, pad).permute(0, 2, 3, 1).float().cuda()
+  fused = K.stem_fprop_stats(x, w, geo, BF16, views)
+  assert fused is not None
+  y, partial, nblk = fused
+  assert torch.equal(y, K.stem_fprop(x, w, geo, BF16))
+  assert torch.allclose(y.float(), y_ref, rtol=1e-2, atol=1e-2)
+  M = (n // views) * hw * hw
+  ss, mi = K.bn_stats_from_partials_views(partial, nblk, 2, views, M, gamma, beta, 1e-5, 0.1, None, None)
+  for v in range(views):
+    sl = slice(v * (n // views), (v + 1) * (n // views))
+    mean = y_ref[sl].mean(dim=(0, 1, 2))
+    var = y_ref[sl].var(dim=(0, 1, 2), unbiased=False)
+    assert torch.allclose(mi[v, :64], mean, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(mi[v, 64:], 1.0 / torch.sqrt(var + 1e-5), rtol=1e-4)
+  # fp32 storage takes the same kernel
+  from iic_b200._lib import F32
+  y32 = K.stem_fprop(x, w, geo, F32)
+  assert torch.allclose(y32, y_ref, rtol=1e-4, atol=1e-5)
+
+
+def test_batched_weight_packing_matches_single_calls():
+  K = _K()
+  from iic_b200._lib import BF16, F32
+  g = torch.Generator().manual_seed(42)
+  ws = [torch.randn(co, ci, k, k, generator=g).cuda() for co, ci, k in ((64, 64, 3), (128, 64, 1), (128, 64, 3), (512, 256, 3))]
+  for dt in (BF16, F32):
+    plan = K.PackPlan(ws, (0, 1), dt)
+    out = plan.run()
+    for i, w in enumerate(ws):
+      for kind in (0, 1):
+        assert torch.equal(out[(i, kind)], K.pack_weight(w, dt, kind))
