@@ -271,13 +271,16 @@ def run_ours(args):
     cpu, _, _ = time_cpu_reference(args.cpu_pairs, args.head, 3, 1, budget_s=20.0)
 
   if rank == 0:
+    from iic_b200.archs import _engine
+    variants = {k: kernels.get_option(k) for k in ("conv_halo", "conv_halo_wgrad", "stem_quad", "tc_cpasync")}
+    variants.update({k: int(v) for k, v in _engine.OPTIONS.items()})
     line = {"metric": METRIC, "value": value, "unit": "img-pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": workload_config(args, B, world), "clocks": clocks,
             "e2e": {"value": e2e, "unit": "img-pairs/s", "h2d_bytes_per_step": 2 * B * 96 * 96 * 4 * world,
                     "d2h_bytes_per_step": 8 * world, "ms_per_step": sec_e / args.steps * 1e3},
-            "gpu_launches": launches, "loss": float(last[0]), "wall_s": wall}
+            "gpu_launches": launches, "loss": float(last[0]), "wall_s": wall, "kernel_variants": variants}
     if roof is not None:
       line["roofline"] = roof
     if cpu is not None:

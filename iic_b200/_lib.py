@@ -28,6 +28,8 @@ _SIGS = {
   "iic_abi_version": (c_int, []),
   "iic_last_error": (c_char_p, []),
   "iic_launch_count": (c_longlong, [c_int]),
+  "iic_get_option": (c_int, [c_char_p]),
+  "iic_set_option": (c_int, [c_char_p, c_int]),
   "iic_iid_loss": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_double, _P, _P, _P, _P, _P, c_int, _P]),
   "iic_joint_mi": (c_int, [_P, c_int, c_int, c_float, c_double, c_int, _P, _P, _P]),
   "iic_seg_kp": (c_int, [c_int]),

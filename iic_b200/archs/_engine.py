@@ -136,8 +136,15 @@ class _ViewStats(list):
     self.stacked = stacked
 
 
-# one launch per BatchNorm pass for all views (IIC_BN_MERGED=0: one launch chain per view, the first implementation)
-_MERGED = os.environ.get("IIC_BN_MERGED", "1") != "0"
+# Host-side variant switches (A/B measurement; defaults from the environment, tests may flip them in place):
+#   bn_merged    one launch per BatchNorm pass for all views (0: one launch chain per view, the first implementation)
+#   stem_stats   BatchNorm statistics of the stem accumulated inside the stem conv kernel (0: separate pass over y)
+#   pack_batched all tensor-core weight layouts of a trunk repacked by one launch (0: one launch per conv and layout)
+OPTIONS = {
+  "bn_merged": os.environ.get("IIC_BN_MERGED", "1") != "0",
+  "stem_stats": os.environ.get("IIC_STEM_STATS", "1") != "0",
+  "pack_batched": os.environ.get("IIC_PACK_BATCHED", "1") != "0",
+}
 
 
 def _bn_stats(ctx, bn, y):
@@ -177,7 +184,7 @@ def _stats_from_partials(ctx, bn, y, partial, nblk):
   rm = bn.running_mean if update else None
   rv = bn.running_var if update else None
   M = (y.numel() // y.shape[-1]) // ctx.groups
-  if _MERGED:
+  if OPTIONS["bn_merged"]:
     if update:
       bn.num_batches_tracked += ctx.groups
     ss, mi = K.bn_stats_from_partials_views(partial, nblk, 2, ctx.groups, M, bn.weight.detach(), bn.bias.detach(),
@@ -196,7 +203,7 @@ def _stats_from_partials(ctx, bn, y, partial, nblk):
 
 def _bn_apply(ctx, y, ss, relu, res=None, rss=None):
   out = torch.empty_like(y)
-  if _MERGED and hasattr(ss, "stacked") and (rss is None or hasattr(rss, "stacked")):
+  if OPTIONS["bn_merged"] and hasattr(ss, "stacked") and (rss is None or hasattr(rss, "stacked")):
     return K.bn_apply_views(y, ss.stacked, relu, ctx.groups, res=res, rss=None if rss is None else rss.stacked, out=out)
   for yg, og, sg, rg, rsg in zip(ctx.split(y), ctx.split(out), ss, ctx.split(res), rss if rss is not None else [None] * ctx.groups):
     K.bn_apply(yg, sg, relu, res=rg, rss=rsg, out=og)
@@ -240,7 +247,7 @@ def _bn_backward(ctx, sink, bn, g_in, act, y, mi, want_g_out, mask_ss=None):
   dg, acc1 = sink.buf(bn.weight)
   db, acc2 = sink.buf(bn.bias)
   assert acc1 == acc2
-  if _MERGED and ctx.groups <= 2:
+  if OPTIONS["bn_merged"] and ctx.groups <= 2:
     return K.bn_bwd_fused(g_in, act, y, mi, bn.weight.detach(), dg, db, acc1, want_g_out, mask_sss=mask_ss)
   dy = torch.empty_like(y)
   g_out = torch.empty_like(y) if want_g_out else None
@@ -263,7 +270,8 @@ def stem_forward(ctx, conv, bn, x_nchw, pool_pad):
   n, c, h, w = x_nchw.shape
   g = conv.geom(n, h, w)
   fused = None
-  if ctx.dt == BF16 and (ctx.training or not bn.track_running_stats):  # statistics in the conv kernel, like _conv_bn
+  if OPTIONS["stem_stats"] and ctx.dt == BF16 and (ctx.training or not bn.track_running_stats):
+    # statistics in the conv kernel, like _conv_bn
     fused = K.stem_fprop_stats(x_nchw, conv.weight.detach(), g, ctx.dt, ctx.groups)
   if fused is None:
     y = K.stem_fprop(x_nchw, conv.weight.detach(), g, ctx.dt)
@@ -352,7 +360,7 @@ def block_backward(ctx, sink, rec, d_out):
 def _prepack(trunk, ectx):
   """All tensor-core weight layouts of the trunk (fprop, and dgrad when a backward follows) in one launch.  The
   job table and the destination buffers persist on the module; they are rebuilt if a weight was re-allocated."""
-  if os.environ.get("IIC_PACK_BATCHED", "1") == "0":
+  if not OPTIONS["pack_batched"]:
     return
   convs = [m for m in trunk.modules() if isinstance(m, ConvParams) and m.cin % 8 == 0]  # (the stem reads fp32 weights)
   if not convs:

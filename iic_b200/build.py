@@ -30,7 +30,7 @@ def _newer(a, b):
 def _compile(src):
   s = os.path.join(CSRC, src)
   o = os.path.join(OBJDIR, src[:-3] + ".o")
-  deps = [s, os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "iic_b200.h")]
+  deps = [s, os.path.join(ROOT, "include", "iic_b200.h")] + [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".cuh")]
   if not any(_newer(d, o) for d in deps):
     return o, ""
   r = subprocess.run([NVCC] + FLAGS + ["-c", s, "-o", o], capture_output=True, text=True)

@@ -1,5 +1,7 @@
 // Library-level plumbing: error string, launch counter, device properties.
 #include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -16,6 +18,44 @@ void set_error(const char* fmt, ...) {
 }
 
 void count_launch() { ++g_launches; }
+
+// ---- runtime options: kernel-variant switches (A/B measurement, tests); defaults come from the environment -----
+struct Option {
+  const char* name;
+  const char* env;
+  int def;
+  int value;
+  bool init;
+};
+static Option g_opts[OPT_COUNT] = {
+    // conv_halo: halo variant of the 3x3 / stride-1 / 64->64 fprop+dgrad: 0 never, 1 when the geometry fits and the
+    // tile efficiency is good, 2 whenever the geometry fits
+    {"conv_halo", "IIC_CONV_HALO", 1, 0, false},
+    // conv_halo_wgrad: same switch for the halo wgrad kernel (needs conv_halo's geometry test to pass as well)
+    {"conv_halo_wgrad", "IIC_CONV_HALO_WGRAD", 1, 0, false},
+    // tc_cpasync: 1 = cp.async-fed tcgen05 kernel (conv_tc.cu) instead of the TMA-fed one
+    {"tc_cpasync", "IIC_TC_CPASYNC", 0, 0, false},
+    // stem_quad: 4-pixels-per-thread stem conv kernel (with optional fused BN statistics); 0 = one pixel per thread
+    {"stem_quad", "IIC_STEM_QUAD", 1, 0, false},
+};
+
+int option(int id) {
+  if (id < 0 || id >= OPT_COUNT) return 0;
+  Option& o = g_opts[id];
+  if (!o.init) {
+    const char* e = getenv(o.env);
+    o.value = (e != nullptr && e[0] != 0) ? atoi(e) : o.def;
+    o.init = true;
+  }
+  return o.value;
+}
+
+static int option_id(const char* name) {
+  if (name == nullptr) return -1;
+  for (int i = 0; i < OPT_COUNT; ++i)
+    if (strcmp(name, g_opts[i].name) == 0) return i;
+  return -1;
+}
 
 int device_sm_count() {
   static int cached[64] = {0};
@@ -37,4 +77,24 @@ extern "C" long long iic_launch_count(int reset) {
   long long v = iic::g_launches;
   if (reset) iic::g_launches = 0;
   return v;
+}
+
+extern "C" int iic_get_option(const char* name) {
+  const int id = iic::option_id(name);
+  if (id < 0) {
+    iic::set_error("iic_get_option: unknown option '%s'", name ? name : "(null)");
+    return IIC_ERR_BAD_ARG;
+  }
+  return iic::option(id);
+}
+extern "C" int iic_set_option(const char* name, int value) {
+  const int id = iic::option_id(name);
+  if (id < 0 || value < 0) {
+    iic::set_error("iic_set_option: unknown option '%s' or negative value", name ? name : "(null)");
+    return IIC_ERR_BAD_ARG;
+  }
+  iic::option(id);  // resolve the default first, so that the return value is the previous setting
+  const int prev = iic::g_opts[id].value;
+  iic::g_opts[id].value = value;
+  return prev;
 }

@@ -33,14 +33,7 @@ using namespace iic;
 
 // The TMA-fed persistent kernel (conv_tc2.cu) is the default tensor-core path; IIC_TC_CPASYNC=1 selects the
 // cp.async-fed kernel (conv_tc.cu) everywhere (kept for stride-2 dgrad and for A/B measurements).
-static bool use_tma() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("IIC_TC_CPASYNC");
-    v = (e != nullptr && e[0] == '1') ? 0 : 1;
-  }
-  return v == 1;
-}
+static bool use_tma() { return option(OPT_TC_CPASYNC) != 1; }
 
 static int geom_check(const iic_conv_geom* g, const char* who) {
   IIC_REQUIRE(g != nullptr, IIC_ERR_BAD_ARG, "%s: null geometry", who);

@@ -24,9 +24,6 @@
 namespace iic {
 
 enum { M2_FPROP = 0, M2_WGRAD = 1 };
-#ifndef IIC_CONV_HALO_DEFAULT
-#define IIC_CONV_HALO_DEFAULT 1  // halo variant of the 64-channel 3x3 layers (validated: profiles/r01_conv_sweep.md)
-#endif
 constexpr int TC2_THREADS = 192;
 
 constexpr int TC2_MAXTAPS = 25;
@@ -805,15 +802,9 @@ struct HaloPlan {
   int Wp, R, tiles_per_img, total_tiles, stage_bytes, box_bytes, stages, smem;
 };
 
-// IIC_CONV_HALO: 0 never, 1 (default) when the geometry fits and the tile efficiency is good, 2 whenever the geometry fits
-static int halo_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("IIC_CONV_HALO");
-    mode = e ? atoi(e) : IIC_CONV_HALO_DEFAULT;
-  }
-  return mode;
-}
+// option conv_halo / IIC_CONV_HALO: 0 never, 1 (default) when the geometry fits and the tile efficiency is good,
+// 2 whenever the geometry fits (tests)
+static int halo_mode() { return option(OPT_CONV_HALO); }
 
 static HaloPlan halo_plan(const iic_conv_geom* g, int srcC, int N, int H, int W, int nimg) {
   HaloPlan p = {};
@@ -859,6 +850,10 @@ static int make_halo_map(CUtensorMap* tm, const __nv_bfloat16* src, int H, int W
 static HaloPlan halo_wgrad_plan(const iic_conv_geom* g) {
   HaloPlan p = halo_plan(g, g->cin, g->cout, g->h, g->w, g->n);
   if (!p.ok) return p;
+  if (option(OPT_CONV_HALO_WGRAD) == 0) {
+    p.ok = false;
+    return p;
+  }
   p.stages = 2;
   p.smem = 1024 + 2 * (p.stage_bytes + HALO_TILE * 128) + 256;
   if (p.smem > 232448) p.ok = false;

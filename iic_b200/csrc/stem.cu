@@ -335,7 +335,7 @@ static int stem_check(const iic_conv_geom* g, const char* who) {
 }
 
 static bool stem_quad_ok(const iic_conv_geom* g) {
-  return g->cout == 64 && g->stride == 1 && g->dil == 1 && g->ow % 4 == 0 && g->kh == g->kw && (g->kh == 3 || g->kh == 5);
+  return option(OPT_STEM_QUAD) != 0 && g->cout == 64 && g->stride == 1 && g->dil == 1 && g->ow % 4 == 0 && g->kh == g->kw && (g->kh == 3 || g->kh == 5);
 }
 static int stem_quad_blocks(const iic_conv_geom* g, int views) {
   const long long quads = (long long)g->n * g->oh * (g->ow / 4);

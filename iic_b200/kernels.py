@@ -103,6 +103,39 @@ def launch_count(reset=False):
   return int(_lib.lib().iic_launch_count(1 if reset else 0))
 
 
+def get_option(name):
+  """Kernel-variant switch of the library (include/iic_b200.h: iic_get_option)."""
+  v = _lib.lib().iic_get_option(name.encode())
+  if v < 0:
+    _lib.check(v, "iic_get_option")
+  return v
+
+
+def set_option(name, value):
+  """Sets a kernel-variant switch; returns the previous value."""
+  v = _lib.lib().iic_set_option(name.encode(), int(value))
+  if v < 0:
+    _lib.check(v, "iic_set_option")
+  return v
+
+
+class options:
+  """`with kernels.options(conv_halo=2): ...` -- scoped override of kernel-variant switches (tests, A/B runs)."""
+
+  def __init__(self, **kw):
+    self.kw, self.prev = kw, {}
+
+  def __enter__(self):
+    for k, v in self.kw.items():
+      self.prev[k] = set_option(k, v)
+    return self
+
+  def __exit__(self, *exc):
+    for k, v in self.prev.items():
+      set_option(k, v)
+    return False
+
+
 # ---- losses ---------------------------------------------------------------------------------
 @_cat("iid_loss")
 def iid_loss(z, zt, lamb, eps, want_grad, phase=_lib.PHASE_FUSED, joint_ws=None, want_joint=False):

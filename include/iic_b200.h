@@ -48,6 +48,16 @@ int iic_abi_version(void);
 const char* iic_last_error(void);
 /* number of kernels launched by this library on the calling thread since the last reset */
 long long iic_launch_count(int reset);
+/* Kernel-variant switches of this sm_100a code base (A/B measurement and tests; not backends).  Defaults come from
+ * the environment variable in brackets.  iic_set_option returns the previous value (>= 0) or IIC_ERR_BAD_ARG.
+ *   "conv_halo"       [IIC_CONV_HALO=1]        halo kernel for 3x3/s1/p1 64->64 fprop+dgrad: 0 never, 1 when it pays,
+ *                                              2 whenever the geometry fits
+ *   "conv_halo_wgrad" [IIC_CONV_HALO_WGRAD=1]  halo kernel for the wgrad of the same layers (0 = im2col split-K kernel)
+ *   "tc_cpasync"      [IIC_TC_CPASYNC=0]       1 = cp.async-fed tcgen05 kernel instead of the TMA-fed one
+ *   "stem_quad"       [IIC_STEM_QUAD=1]        stem conv: 4 pixels x 16 channels per thread (and the fused-statistics
+ *                                              entry point); 0 = the one-pixel-per-thread kernel                    */
+int iic_get_option(const char* name);
+int iic_set_option(const char* name, int value);
 
 /* ---- a7/a8: clustering objective -- code/utils/cluster/IID_losses.py:6-33 (IID_loss) and
  *      :36-47 (compute_joint).

@@ -43,3 +43,22 @@ def golden_seg():
 @pytest.fixture(scope="session")
 def golden_nets():
   return load_golden("nets.npz")
+
+
+@pytest.fixture(autouse=True)
+def _fresh_worker_after_a_device_fault(request):
+  """A kernel fault (e.g. the mbarrier watchdog trap in the tcgen05 kernels) poisons the CUDA context of the process:
+  every later test in it would fail for no reason of its own.  Under pytest-xdist the worker is ended instead, xdist
+  reports the faulting test as crashed and carries on with a fresh worker, so one broken kernel costs one test."""
+  yield
+  if request.node.get_closest_marker("gpu") is None or "PYTEST_XDIST_WORKER" not in os.environ:
+    return
+  torch = sys.modules.get("torch")
+  if torch is None or not torch.cuda.is_initialized():
+    return
+  try:
+    torch.cuda.synchronize()
+  except Exception as e:  # noqa: BLE001
+    sys.stderr.write("device fault after %s: %s -- ending this xdist worker\n" % (request.node.nodeid, e))
+    sys.stderr.flush()
+    os._exit(3)

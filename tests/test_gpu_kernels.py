@@ -503,3 +503,91 @@ def test_batched_weight_packing_matches_single_calls():
     for i, w in enumerate(ws):
       for kind in (0, 1):
         assert torch.equal(out[(i, kind)], K.pack_weight(w, dt, kind))
+
+
+HALO_GEOMS = [
+  # n, h: Wp = h + 2, R = 256 // Wp output rows per work item; covers R > H (one item per image, box taller than
+  # the image), ragged last item (H % R != 0), R == 1 (Wp = 162) and a row too wide for two pipeline stages (h = 200: im2col fallback)
+  (3, 5), (5, 13), (2, 30), (3, 49), (2, 96), (1, 126), (1, 160), (1, 200),
+]
+
+
+@pytest.mark.parametrize("n,h", HALO_GEOMS)
+@pytest.mark.parametrize("halo_wgrad", [1, 0])
+def test_halo_kernels_forced_exact_small_integers(n, h, halo_wgrad):
+  """The halo kernels (3x3 / stride 1 / pad 1 / 64 -> 64: fprop, dgrad, wgrad) forced on every geometry they accept
+  (option conv_halo = 2; by default they only run where they pay): EXACT on small-integer operands against CPU fp64,
+  and bit-identical to the im2col kernels (conv_halo = 0), including the dgrad addend and the fused BN statistics."""
+  K = _K()
+  from iic_b200._lib import BF16
+  if halo_wgrad == 0 and h not in (13, 49):
+    pytest.skip("im2col wgrad beside the halo fprop/dgrad: two geometries are enough")
+  g = torch.Generator().manual_seed(100 + h)
+  x = torch.randint(-1, 2, (n, 64, h, h), generator=g).float()
+  w = torch.randint(-1, 2, (64, 64, 3, 3), generator=g).float()
+  dy = torch.randint(-1, 2, (n, 64, h, h), generator=g).float()
+  add = torch.randint(-2, 3, (n, 64, h, h), generator=g).float()
+  geo = K.conv_geom(n, h, h, 64, 64, 3, 3, 1, 1, 1)
+  xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+  ref = F.conv2d(xr, wr, None, 1, 1)
+  ref.backward(dy.double())
+  assert ref.abs().max() <= 256 and xr.grad.abs().max() <= 250
+  xh, dyh, addh = [to_nhwc(t.cuda(), torch.bfloat16) for t in (x, dy, add)]
+  wp0, wp1 = K.pack_weight(w.cuda(), BF16, 0), K.pack_weight(w.cuda(), BF16, 1)
+
+  def run():
+    y = K.conv_fprop(xh, wp0, geo, BF16)
+    dx = K.conv_dgrad(dyh, wp1, geo, BF16)
+    dx2 = K.conv_dgrad(dyh, wp1, geo, BF16, addend=addh)
+    gw = torch.zeros_like(w).cuda()
+    K.conv_wgrad(xh, dyh, geo, BF16, gw, False)
+    st = K.conv_fprop_stats(xh, wp0, geo, BF16, 2) if n % 2 == 0 else K.conv_fprop_stats(xh, wp0, geo, BF16, 1)
+    torch.cuda.synchronize()
+    return y, dx, dx2, gw, st
+
+  with K.options(conv_halo=2, conv_halo_wgrad=halo_wgrad):
+    y, dx, dx2, gw, st = run()
+  with K.options(conv_halo=0):
+    y0, dx0, dx20, gw0, st0 = run()
+  assert torch.equal(from_nhwc(y).cpu(), ref.detach().float()), "halo fprop"
+  assert torch.equal(from_nhwc(dx).cpu(), xr.grad.float()), "halo dgrad"
+  assert torch.equal(from_nhwc(dx2).cpu(), (xr.grad + add.double()).float()), "halo dgrad + addend"
+  assert torch.equal(gw.cpu(), wr.grad.float()), "halo wgrad"
+  for a, b in ((y, y0), (dx, dx0), (dx2, dx20), (gw, gw0), (st[0], st0[0])):
+    assert torch.equal(a, b)
+  # statistics: integer sums, exact in fp32 whatever the partition into per-CTA partial rows
+  views = 2 if n % 2 == 0 else 1
+  tot = st[1][:st[2]].double().sum(0).cpu()  # [2 slots][{sum, sumsq}][64]
+  yr = ref.detach()
+  for v in range(views):
+    sl = yr[v * (n // views):(v + 1) * (n // views)]
+    assert torch.equal(tot[v, 0], sl.sum(dim=(0, 2, 3))) and torch.equal(tot[v, 1], (sl * sl).sum(dim=(0, 2, 3)))
+  if views == 1:
+    assert float(tot[1].abs().max()) == 0.0
+
+
+def test_runtime_options_roundtrip():
+  K = _K()
+  for name in ("conv_halo", "conv_halo_wgrad", "tc_cpasync", "stem_quad"):
+    v = K.get_option(name)
+    with K.options(**{name: 0}):
+      assert K.get_option(name) == 0
+    assert K.get_option(name) == v
+  with pytest.raises(AssertionError):
+    K.get_option("no_such_option")
+
+
+@pytest.mark.parametrize("cin,k,pad,hw", [(2, 3, 1, 24), (1, 5, 2, 24), (5, 3, 1, 16)])
+def test_stem_quad_kernel_equals_one_pixel_kernel(cin, k, pad, hw):
+  """The two stem conv kernels accumulate in the same (ci, a, b) order: bit-identical fp32 results."""
+  K = _K()
+  from iic_b200._lib import F32
+  g = torch.Generator().manual_seed(43)
+  x = torch.randn(4, cin, hw, hw, generator=g).cuda()
+  w = (torch.randn(64, cin, k, k, generator=g) * math.sqrt(2.0 / (cin * k * k))).cuda()
+  geo = K.conv_geom(4, hw, hw, cin, 64, k, k, 1, pad, 1)
+  with K.options(stem_quad=1):
+    yq = K.stem_fprop(x, w, geo, F32)
+  with K.options(stem_quad=0):
+    y1 = K.stem_fprop(x, w, geo, F32)
+  assert torch.allclose(yq, y1, rtol=1e-6, atol=1e-6)

@@ -186,9 +186,18 @@ def test_shard_equivalence_per_rank_batchnorm():
     assert ((p.grad.cpu() - want).norm() / want.norm()).item() <= 5e-2, pn
 
 
+@pytest.fixture(params=[1, 2], ids=["halo-auto", "halo-forced"])
+def halo_mode(request):
+  """conv_halo = 2 pushes the 64-channel 3x3 convs through the halo kernels (fprop with fused BN statistics, dgrad
+  with the residual addend, wgrad) at test sizes; by default they only take over at production sizes."""
+  from iic_b200 import kernels
+  with kernels.options(conv_halo=request.param):
+    yield request.param
+
+
 @pytest.mark.parametrize("cin,cout,stride,hw,n", [(64, 64, 1, 17, 5), (64, 128, 2, 17, 6), (128, 256, 2, 9, 8),
-                                                  (256, 512, 2, 13, 4), (512, 512, 1, 7, 9)])
-def test_bf16_block_matches_rounding_oracle(cin, cout, stride, hw, n):
+                                                  (256, 512, 2, 13, 4), (512, 512, 1, 7, 9), (64, 64, 1, 49, 2)])
+def test_bf16_block_matches_rounding_oracle(cin, cout, stride, hw, n, halo_mode):
   """One BasicBlock (2 tcgen05 convs, 2-3 BNs, residual) forward + backward in bf16 mode against the
   oracle block with bf16 rounding emulated at the product's storage points (oracle/nets.py q/qw).
   A single block is not chaotic, so this is a tight check of every bf16 kernel in composition."""
@@ -196,6 +205,8 @@ def test_bf16_block_matches_rounding_oracle(cin, cout, stride, hw, n):
   from iic_b200.archs import _engine as E
   from iic_b200.archs.cluster.residual import BasicBlock
   from iic_b200._lib import BF16
+  if halo_mode == 2 and cin != 64:
+    pytest.skip("no 64 -> 64 conv in this block")
   ds = None
   if stride != 1 or cin != cout:
     ds = nn.Sequential(E.ConvParams(cin, cout, 1, stride, 0), E.BNParams(cout, False))
