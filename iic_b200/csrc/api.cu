@@ -1,5 +1,7 @@
 // Library-level plumbing: error string, launch counter, device properties.
 #include <stdarg.h>
+
+#include <atomic>
 #include <stdlib.h>
 #include <string.h>
 
@@ -8,7 +10,7 @@
 namespace iic {
 
 static thread_local char g_err[512] = "";
-static thread_local long long g_launches = 0;
+static std::atomic<long long> g_launches{0};  // process-wide: backward runs on autograd's own threads
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -17,7 +19,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-void count_launch() { ++g_launches; }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // ---- runtime options: kernel-variant switches (A/B measurement, tests); defaults come from the environment -----
 struct Option {
@@ -35,8 +37,11 @@ static Option g_opts[OPT_COUNT] = {
     {"conv_halo_wgrad", "IIC_CONV_HALO_WGRAD", 1, 0, false},
     // tc_cpasync: 1 = cp.async-fed tcgen05 kernel (conv_tc.cu) instead of the TMA-fed one
     {"tc_cpasync", "IIC_TC_CPASYNC", 0, 0, false},
-    // stem_quad: 4-pixels-per-thread stem conv kernel (with optional fused BN statistics); 0 = one pixel per thread
-    {"stem_quad", "IIC_STEM_QUAD", 1, 0, false},
+    // stem_quad: 4-pixels-per-thread stem conv kernel (with optional fused BN statistics): 2 = channel-interleaved thread
+    // layout (whole-sector stores), 1 = 16 consecutive channels per thread, 0 = the one-pixel-per-thread kernel
+    {"stem_quad", "IIC_STEM_QUAD", 2, 0, false},
+    // dgrad_prefetch: the dgrad epilogues request the residual-gradient addend ahead of its use (0 = on demand)
+    {"dgrad_prefetch", "IIC_DGRAD_PREFETCH", 1, 0, false},
 };
 
 int option(int id) {
@@ -74,9 +79,7 @@ int device_sm_count() {
 extern "C" int iic_abi_version(void) { return 1; }
 extern "C" const char* iic_last_error(void) { return iic::g_err; }
 extern "C" long long iic_launch_count(int reset) {
-  long long v = iic::g_launches;
-  if (reset) iic::g_launches = 0;
-  return v;
+  return reset ? iic::g_launches.exchange(0) : iic::g_launches.load();
 }
 
 extern "C" int iic_get_option(const char* name) {

@@ -44,6 +44,7 @@ struct Tc2Params {
   int mtiles, ntiles, splits, kb_per_split, total_kb;
   __nv_bfloat16* out;
   const __nv_bfloat16* addend;
+  int addend_prefetch;  // fetch the addend one 32-column chunk ahead of its use (option dgrad_prefetch)
   float* partial;
   // fused BatchNorm statistics (fprop only): per-CTA partial column sums of the fp32 accumulators,
   // stat_partial[cta][group][{sum, sum of squares}][N]; rows < stat_half belong to view 0, the rest to view 1
@@ -295,29 +296,63 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     // =============================== epilogue (warps 0-3) ======================================
     uint32_t tile_it = 0;
+    constexpr int CH = BN / 32;  // 32-column chunks per 128-row accumulator tile
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tile_it) {
       int z, n0, kb0, nk;
       long long m0;
       decode(w, z, m0, n0, kb0, nk);
       const uint32_t as = tile_it & 1u;
-      mbar_wait(tfull_bar(as), (tile_it >> 1) & 1u);
-      tc_fence_after();
-#pragma unroll 1
-      for (int mt = 0; mt < MT; ++mt) {
-      const long long mtile0 = m0 + (long long)mt * TC_BM;
-      const long long m = mtile0 + warp * 32 + lane;  // TMEM lane == tile row
-      const uint32_t tmem_acc = tmem_base + as * (MT * BN) + mt * BN + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        if (nk > 0) {
-          tmem_ld32(tmem_acc + (uint32_t)c0, v);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int qq = 0; qq < 32; ++qq) v[qq] = 0u;
+      if constexpr (MODE == M2_FPROP) {
+        // this thread's row in each of the MT accumulator tiles (TMEM lane == tile row) and where it is written
+        const long long mrow0 = m0 + warp * 32 + lane, mrow1 = mrow0 + TC_BM;
+        long long orow0 = mrow0, orow1 = mrow1;
+        if (P.scatter) {
+          auto scat = [&](long long m) {
+            const int jj = (int)(m % P.rowW);
+            const long long q = m / P.rowW;
+            const int ii = (int)(q % P.rowH);
+            return ((q / P.rowH) * P.outH + 2 * ii + P.py) * P.outW + 2 * jj + P.px;
+          };
+          if (mrow0 < P.rows) orow0 = scat(mrow0);
+          if (MT == 2 && mrow1 < P.rows) orow1 = scat(mrow1);
         }
-        if (MODE == M2_FPROP) {
+        // dgrad adds the residual-branch gradient (`addend`) in the epilogue.  Its 64 B per thread and chunk are fetched
+        // one chunk ahead (the first one before the accumulator is even complete): fetched on demand, the global-load
+        // latency sat between every tcgen05.ld and its stores and cost the dgrad launches with an addend ~50 % of
+        // their time (profiles/r01_ncu_halo.md).
+        const bool has_add = P.addend != nullptr;
+        const bool pre = has_add && P.addend_prefetch != 0;
+        uint4 acur[4], anxt[4];
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) acur[qq] = anxt[qq] = make_uint4(0u, 0u, 0u, 0u);
+        auto fetch = [&](uint4(&dst)[4], int mt, int c0) {
+          const long long mr = (MT == 2 && mt == 1) ? mrow1 : mrow0;
+          const long long orow = (MT == 2 && mt == 1) ? orow1 : orow0;
+          if (mr < P.rows) {
+            const uint4* src = reinterpret_cast<const uint4*>(P.addend + orow * P.N + n0 + c0);
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) dst[qq] = src[qq];
+          }
+        };
+        if (pre) fetch(acur, 0, 0);
+        mbar_wait(tfull_bar(as), (tile_it >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int j = 0; j < MT * CH; ++j) {
+          const int mt = j / CH, c0 = (j % CH) * 32;
+          const long long mtile0 = m0 + (long long)mt * TC_BM;
+          const long long m = (MT == 2 && mt == 1) ? mrow1 : mrow0;
+          const long long orow = (MT == 2 && mt == 1) ? orow1 : orow0;
+          const uint32_t tmem_acc = tmem_base + as * (MT * BN) + mt * BN + ((uint32_t)(warp * 32) << 16);
+          uint32_t v[32];
+          if (nk > 0) {
+            tmem_ld32(tmem_acc + (uint32_t)c0, v);
+          } else {
+#pragma unroll
+            for (int qq = 0; qq < 32; ++qq) v[qq] = 0u;
+          }
+          if (pre && j + 1 < MT * CH) fetch(anxt, (j + 1) / CH, ((j + 1) % CH) * 32);
+          if (nk > 0) tmem_ld_wait();
           if (do_stats) {
             // per-column sums over this warp's 32 rows (rows >= P.rows are exact zeros: TMA zero fill)
             const bool lo1 = mtile0 >= P.stat_half, hi1 = (mtile0 + TC_BM - 1) >= P.stat_half;
@@ -340,29 +375,44 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
           if (m < P.rows) {
-            long long orow = m;
-            if (P.scatter) {
-              const int jj = (int)(m % P.rowW);
-              const long long q = m / P.rowW;
-              const int ii = (int)(q % P.rowH);
-              orow = ((q / P.rowH) * P.outH + 2 * ii + P.py) * P.outW + 2 * jj + P.px;
-            }
+            if (has_add && !pre) fetch(acur, mt, c0);
             __nv_bfloat16* o = P.out + orow * P.N + n0 + c0;
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) {
               float f[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[qq * 8 + e]);
-              if (P.addend != nullptr) {
+              if (has_add) {
                 float ad[8];
-                load8(P.addend + orow * P.N + n0 + c0 + qq * 8, ad);
+                Raw8h raw;
+                raw.v = acur[qq];
+                cvt_raw(raw, ad);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] += ad[e];
               }
               store8(o + qq * 8, f);
             }
           }
-        } else {
+          if (pre) {
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) acur[qq] = anxt[qq];
+          }
+        }
+      } else {
+        mbar_wait(tfull_bar(as), (tile_it >> 1) & 1u);
+        tc_fence_after();
+        const long long m = m0 + warp * 32 + lane;  // TMEM lane == tile row
+        const uint32_t tmem_acc = tmem_base + as * (MT * BN) + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          if (nk > 0) {
+            tmem_ld32(tmem_acc + (uint32_t)c0, v);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int qq = 0; qq < 32; ++qq) v[qq] = 0u;
+          }
           if (m < P.Ktot) {
             float* o = P.partial + ((long long)z * P.Ktot + m) * P.N + n0 + c0;
 #pragma unroll
@@ -372,7 +422,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                               __uint_as_float(v[qq * 4 + 3]));
           }
         }
-      }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(as));
@@ -414,6 +463,7 @@ struct HaloParams {
   const __nv_bfloat16* addend;
   float* stat_partial;  // [cta][view][{sum, sum of squares}][64] or null
   int img_half;         // images >= img_half belong to view 1
+  int addend_prefetch;  // request the addend before waiting for the accumulator (option dgrad_prefetch)
 };
 
 __global__ void __launch_bounds__(HALO_THREADS, 1)
@@ -521,19 +571,45 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // =============================== epilogue (warps 0-7) ======================================
     const int quad = warp & 3, hsel = warp >> 2;
+    const bool has_add = P.addend != nullptr;
+    const bool pre = has_add && P.addend_prefetch != 0;
     uint32_t it = 0;
     for (int w = blockIdx.x; w < P.total_tiles; w += gridDim.x, ++it) {
       const int img = w / P.tiles_per_img;
       const int y0 = (w - img * P.tiles_per_img) * P.R;
       const int view = img >= P.img_half ? 1 : 0;
       const uint32_t as = it & 1u;
+      // this thread's two accumulator rows (TMEM lane, +128 for the second MMA tile) -> output pixels
+      bool valid2[2];
+      long long pix2[2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int m = mt * TC_BM + quad * 32 + lane;
+        const int r = m / P.Wp, x = m - r * P.Wp;
+        valid2[mt] = r < P.R && x < P.W && y0 + r < P.H;
+        pix2[mt] = ((long long)img * P.H + y0 + r) * P.W + x;
+      }
+      // residual-gradient addend (dgrad): both rows' 64 B are requested before the accumulator is complete, so the
+      // global-load latency overlaps the MMAs instead of sitting between tcgen05.ld and the stores
+      uint4 add2[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) add2[mt][qq] = make_uint4(0u, 0u, 0u, 0u);
+      if (pre) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+          if (valid2[mt]) {
+            const uint4* src = reinterpret_cast<const uint4*>(P.addend + pix2[mt] * 64 + hsel * 32);
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) add2[mt][qq] = src[qq];
+          }
+      }
       mbar_wait(tfull_bar(as), (it >> 1) & 1u);
       tc_fence_after();
-#pragma unroll 1
+#pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        const int m = mt * TC_BM + quad * 32 + lane;  // accumulator row == TMEM lane (+128 for the second MMA tile)
-        const int r = m / P.Wp, x = m - r * P.Wp;
-        const bool valid = r < P.R && x < P.W && y0 + r < P.H;
+        const bool valid = valid2[mt];
         uint32_t v[32];
         tmem_ld32(tmem_base + as * 128u + mt * 64 + hsel * 32 + ((uint32_t)(quad * 32) << 16), v);
         tmem_ld_wait();
@@ -554,16 +630,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           sp[32] += t[0];
         }
         if (valid) {
-          const long long pix = ((long long)img * P.H + y0 + r) * P.W + x;
+          const long long pix = pix2[mt];
           __nv_bfloat16* o = P.out + pix * 64 + hsel * 32;
+          if (has_add && !pre) {
+            const uint4* src = reinterpret_cast<const uint4*>(P.addend + pix * 64 + hsel * 32);
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) add2[mt][qq] = src[qq];
+          }
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) {
             float f[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[qq * 8 + e]);
-            if (P.addend != nullptr) {
+            if (has_add) {
               float ad[8];
-              load8(P.addend + pix * 64 + hsel * 32 + qq * 8, ad);
+              Raw8h raw;
+              raw.v = add2[mt][qq];
+              cvt_raw(raw, ad);
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] += ad[e];
             }
@@ -876,6 +959,7 @@ static int launch_halo(const HaloPlan& hp, const __nv_bfloat16* src, int H, int 
     Q.wtap[t] = P.wtap[t];
   }
   Q.out = P.out; Q.addend = P.addend; Q.stat_partial = P.stat_partial;
+  Q.addend_prefetch = P.addend_prefetch;
   Q.img_half = (P.stat_half < P.rows) ? nimg / 2 : nimg;
   IIC_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hp.smem));
   conv_halo_kernel<<<tc2_grid(hp.total_tiles), HALO_THREADS, hp.smem, st>>>(tmA, tmB, Q);
@@ -945,6 +1029,7 @@ int tc2_conv_gather_gemm_stats(const __nv_bfloat16* src, int srcH, int srcW, int
   const int tile_rows = resb ? 2 * TC_BM : TC_BM;
   P.mtiles = (int)((P.rows + tile_rows - 1) / tile_rows);
   P.out = out; P.addend = addend;
+  P.addend_prefetch = option(OPT_DGRAD_PREFETCH);
   P.stat_partial = stat_partial;
   IIC_REQUIRE(stat_groups == 1 || (stat_groups == 2 && nimg % 2 == 0), IIC_ERR_BAD_ARG, "conv stats: 1 or 2 views");
   P.stat_half = stat_groups == 2 ? P.rows / 2 : P.rows;
@@ -1066,6 +1151,7 @@ int tc2_conv_dgrad_s2(const __nv_bfloat16* dy, const __nv_bfloat16* wpacked_t, c
       P.srcC = g->cout; P.Ktot = P.ntaps * g->cout; P.N = g->cin;
       P.mtiles = (int)((P.rows + TC_BM - 1) / TC_BM); P.ntiles = g->cin / bn; P.splits = 1; P.total_kb = P.Ktot / 64;
       P.out = dx; P.addend = addend;  // (classes without taps keep the pre-filled addend / zero)
+      P.addend_prefetch = option(OPT_DGRAD_PREFETCH);
       // base positions per dim must number Hc / Wc: upper = lower + (Hc - H_dy)
       const int up_h = lo_h + (Hc - g->oh), up_w = lo_w + (Wc - g->ow);
       IIC_REQUIRE(lo_h >= -128 && up_h <= 127 && lo_w >= -128 && up_w <= 127 && up_h >= -128 && up_w >= -128,

@@ -103,28 +103,36 @@ __global__ void __launch_bounds__(128) stem_fprop64_kernel(const float* __restri
 
 // cout == 64, stride 1, dilation 1, ow % 4 == 0: a thread computes 4 consecutive output pixels x 16 channels
 // (64 FMA per 4 LDS.128 and per ~2 global loads; the one-pixel-per-thread kernel above issues one LDS.128 per
-// 4 FMA and is bound by the shared-memory pipe).  Warp = 32 consecutive pixel quads x one channel quarter, so the
-// weight reads are warp broadcasts.  Optionally accumulates the BatchNorm batch statistics of the fp32
-// results (per-thread sums over its pixels, shuffle reduction at the end, one partial row per block in the
-// layout of the tcgen05 conv epilogue: [block][2 view slots][{sum, sum of squares}][64]); the grid is split
-// evenly between the `views` stacked batches.
-template <typename T, int KS>
+// 4 FMA and is bound by the shared-memory pipe).  Two thread layouts:
+//   ILV = 0  warp = 32 consecutive pixel quads x one channel quarter (16 consecutive channels per thread): every
+//            store instruction of a warp writes 16 B pieces 512 B apart -- half sectors;
+//   ILV = 1  warp = 8 consecutive pixel quads x 4 channel slices; a thread owns channels [8s, 8s+8) and [32+8s, 32+8s+8),
+//            so the four lanes of a quad write 64 (bf16) / 128 (fp32) contiguous bytes per store instruction: whole
+//            sectors.  The output write (1.7 GB per step at the bench shape) is what bounds this kernel.
+// The weight reads are warp broadcasts in both (ILV = 1: four distinct 16 B chunks per LDS.128, conflict free).
+// Optionally accumulates the BatchNorm batch statistics of the fp32 results (per-thread sums over its pixels,
+// shuffle reduction at the end, one partial row per block in the layout of the tcgen05 conv epilogue:
+// [block][2 view slots][{sum, sum of squares}][64]); the grid is split evenly between the `views` stacked batches.
+template <typename T, int KS, int ILV>
 __global__ void __launch_bounds__(256, 2) stem_fprop64q_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                T* __restrict__ y, iic_conv_geom g,
                                                                float* __restrict__ stat_partial, int views) {
   extern __shared__ __align__(16) float ws[];  // [K][64]
-  __shared__ float red[8][32];
+  __shared__ float red[8][4][32];              // [warp][channel slice][{sum, sum of squares} x 16]
   const int K = g.cin * KS * KS;
   for (int i = threadIdx.x; i < K * 64; i += blockDim.x) ws[i] = w[(long long)(i & 63) * K + (i >> 6)];
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cq = warp & 3, qg = warp >> 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cq = ILV ? (lane & 3) : (warp & 3);                                // channel slice
+  const int qslot = ILV ? warp * 8 + (lane >> 2) : (warp >> 2) * 32 + lane;    // quad of the block's 64 per iteration
+  const int cb0 = ILV ? cq * 8 : cq * 16, cb1 = ILV ? 32 + cq * 8 : cq * 16 + 8;  // the thread's two 8-channel groups
   const int qpr = g.ow >> 2;
   const long long Qv = (long long)(g.n / views) * g.oh * qpr;  // quads per view
   const int Gv = gridDim.x / views, v = blockIdx.x / Gv, lb = blockIdx.x % Gv;
   float s1[16], s2[16];
 #pragma unroll
   for (int c = 0; c < 16; ++c) s1[c] = s2[c] = 0.f;
-  for (long long ql = (long long)(lb * 2 + qg) * 32 + lane; ql < Qv; ql += (long long)Gv * 64) {
+  for (long long ql = (long long)lb * 64 + qslot; ql < Qv; ql += (long long)Gv * 64) {
     const long long q = (long long)v * Qv + ql;
     const int ox0 = (int)(q % qpr) * 4;
     const long long t = q / qpr;
@@ -149,10 +157,10 @@ __global__ void __launch_bounds__(256, 2) stem_fprop64q_kernel(const float* __re
         }
 #pragma unroll
         for (int b = 0; b < KS; ++b) {
-          const float4* wk = reinterpret_cast<const float4*>(ws + ((ci * KS + a) * KS + b) * 64 + cq * 16);
+          const float* wk = ws + ((ci * KS + a) * KS + b) * 64;
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
-            const float4 w4 = wk[c4];
+            const float4 w4 = *reinterpret_cast<const float4*>(wk + (c4 < 2 ? cb0 + c4 * 4 : cb1 + (c4 - 2) * 4));
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               acc[j][c4 * 4] = fmaf(xv[j + b], w4.x, acc[j][c4 * 4]);
@@ -172,7 +180,7 @@ __global__ void __launch_bounds__(256, 2) stem_fprop64q_kernel(const float* __re
       for (int h2 = 0; h2 < 2; ++h2) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) f[e] = acc[j][h2 * 8 + e];
-        store8(y + (p0 + j) * 64 + cq * 16 + h2 * 8, f);
+        store8(y + (p0 + j) * 64 + (h2 ? cb1 : cb0), f);
       }
       if (stat_partial != nullptr) {
 #pragma unroll
@@ -184,23 +192,35 @@ __global__ void __launch_bounds__(256, 2) stem_fprop64q_kernel(const float* __re
     }
   }
   if (stat_partial == nullptr) return;
+  // lanes that share a channel slice: all 32 (ILV = 0) or those with equal lane & 3 (ILV = 1)
 #pragma unroll
   for (int c = 0; c < 16; ++c) {
-    s1[c] = warp_sum(s1[c]);
-    s2[c] = warp_sum(s2[c]);
+#pragma unroll
+    for (int o = 16; o >= (ILV ? 4 : 1); o >>= 1) {
+      s1[c] += __shfl_xor_sync(0xffffffffu, s1[c], o);
+      s2[c] += __shfl_xor_sync(0xffffffffu, s2[c], o);
+    }
   }
-  if (lane == 0) {
+  for (int i = threadIdx.x; i < 8 * 4 * 32; i += blockDim.x) (&red[0][0][0])[i] = 0.f;
+  __syncthreads();
+  if (ILV ? (lane < 4) : (lane == 0)) {
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
-      red[warp][c] = s1[c];
-      red[warp][16 + c] = s2[c];
+      red[warp][cq][c] = s1[c];
+      red[warp][cq][16 + c] = s2[c];
     }
   }
   __syncthreads();
   if (threadIdx.x < 256) {  // (slot, stat, channel)
     const int ch = threadIdx.x & 63, q2 = (threadIdx.x >> 6) & 1, slot = threadIdx.x >> 7;
-    const int wq = ch >> 4, c = ch & 15;
-    const float val = slot == v ? red[wq][q2 * 16 + c] + red[wq + 4][q2 * 16 + c] : 0.f;
+    // channel -> (slice, index among the thread's 16 accumulators)
+    const int sl = ILV ? ((ch & 31) >> 3) : (ch >> 4);
+    const int c = ILV ? ((ch >> 5) * 8 + (ch & 7)) : (ch & 15);
+    float val = 0.f;
+    if (slot == v) {
+#pragma unroll
+      for (int wp = 0; wp < 8; ++wp) val += red[wp][sl][q2 * 16 + c];
+    }
     stat_partial[(long long)blockIdx.x * 256 + threadIdx.x] = val;
   }
 }
@@ -350,10 +370,18 @@ static int stem_quad_launch(const float* x, const float* w, T* y, const iic_conv
                             cudaStream_t st) {
   const size_t smem = (size_t)g->cin * g->kh * g->kw * 64 * sizeof(float);
   const int blocks = stem_quad_blocks(g, views);
-  if (g->kh == 3)
-    stem_fprop64q_kernel<T, 3><<<blocks, 256, smem, st>>>(x, w, y, *g, stat_partial, views);
-  else
-    stem_fprop64q_kernel<T, 5><<<blocks, 256, smem, st>>>(x, w, y, *g, stat_partial, views);
+  const bool ilv = option(OPT_STEM_QUAD) >= 2;
+  if (g->kh == 3) {
+    if (ilv)
+      stem_fprop64q_kernel<T, 3, 1><<<blocks, 256, smem, st>>>(x, w, y, *g, stat_partial, views);
+    else
+      stem_fprop64q_kernel<T, 3, 0><<<blocks, 256, smem, st>>>(x, w, y, *g, stat_partial, views);
+  } else {
+    if (ilv)
+      stem_fprop64q_kernel<T, 5, 1><<<blocks, 256, smem, st>>>(x, w, y, *g, stat_partial, views);
+    else
+      stem_fprop64q_kernel<T, 5, 0><<<blocks, 256, smem, st>>>(x, w, y, *g, stat_partial, views);
+  }
   IIC_LAUNCH_CHECK();
   count_launch();
   return IIC_OK;

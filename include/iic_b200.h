@@ -46,7 +46,8 @@ extern "C" {
 
 int iic_abi_version(void);
 const char* iic_last_error(void);
-/* number of kernels launched by this library on the calling thread since the last reset */
+/* number of kernels launched by this library (all host threads of the process: autograd runs backward on its own
+ * threads) since the last reset */
 long long iic_launch_count(int reset);
 /* Kernel-variant switches of this sm_100a code base (A/B measurement and tests; not backends).  Defaults come from
  * the environment variable in brackets.  iic_set_option returns the previous value (>= 0) or IIC_ERR_BAD_ARG.
@@ -54,8 +55,10 @@ long long iic_launch_count(int reset);
  *                                              2 whenever the geometry fits
  *   "conv_halo_wgrad" [IIC_CONV_HALO_WGRAD=1]  halo kernel for the wgrad of the same layers (0 = im2col split-K kernel)
  *   "tc_cpasync"      [IIC_TC_CPASYNC=0]       1 = cp.async-fed tcgen05 kernel instead of the TMA-fed one
- *   "stem_quad"       [IIC_STEM_QUAD=1]        stem conv: 4 pixels x 16 channels per thread (and the fused-statistics
- *                                              entry point); 0 = the one-pixel-per-thread kernel                    */
+ *   "stem_quad"       [IIC_STEM_QUAD=2]        stem conv: 4 pixels x 16 channels per thread (and the fused-statistics
+ *                                              entry point): 2 = channel-interleaved lanes (whole-sector stores),
+ *                                              1 = 16 consecutive channels per thread; 0 = one pixel per thread
+ *   "dgrad_prefetch"  [IIC_DGRAD_PREFETCH=1]   dgrad epilogues fetch the residual-gradient addend ahead of its use    */
 int iic_get_option(const char* name);
 int iic_set_option(const char* name, int value);
 

@@ -457,9 +457,18 @@ def test_bn_stats_from_partials_all_views_in_one_launch():
     assert torch.equal(rm, rm2) and torch.equal(rv, rv2)
 
 
+@pytest.fixture(params=[1, 2], ids=["quad-consecutive", "quad-interleaved"])
+def quad_stem(request):
+  """The fused-statistics entry point belongs to the quad stem kernels; both thread layouts are checked whatever the
+  process default (IIC_STEM_QUAD) is."""
+  K = _K()
+  with K.options(stem_quad=request.param):
+    yield
+
+
 @pytest.mark.parametrize("cin,k,pad,hw", [(2, 3, 1, 24), (1, 5, 2, 24), (5, 3, 1, 16), (2, 3, 1, 96)])
 @pytest.mark.parametrize("views", [1, 2])
-def test_stem_fprop_with_fused_bn_statistics(cin, k, pad, hw, views):
+def test_stem_fprop_with_fused_bn_statistics(cin, k, pad, hw, views, quad_stem):
   """Quad stem kernel: same output as the plain entry point, statistics == a separate pass (fp32 accumulators vs
   bf16-rounded storage: loose tolerance), per view."""
   K = _K()
@@ -568,7 +577,7 @@ def test_halo_kernels_forced_exact_small_integers(n, h, halo_wgrad):
 
 def test_runtime_options_roundtrip():
   K = _K()
-  for name in ("conv_halo", "conv_halo_wgrad", "tc_cpasync", "stem_quad"):
+  for name in ("conv_halo", "conv_halo_wgrad", "tc_cpasync", "stem_quad", "dgrad_prefetch"):
     v = K.get_option(name)
     with K.options(**{name: 0}):
       assert K.get_option(name) == 0
@@ -586,8 +595,9 @@ def test_stem_quad_kernel_equals_one_pixel_kernel(cin, k, pad, hw):
   x = torch.randn(4, cin, hw, hw, generator=g).cuda()
   w = (torch.randn(64, cin, k, k, generator=g) * math.sqrt(2.0 / (cin * k * k))).cuda()
   geo = K.conv_geom(4, hw, hw, cin, 64, k, k, 1, pad, 1)
-  with K.options(stem_quad=1):
-    yq = K.stem_fprop(x, w, geo, F32)
-  with K.options(stem_quad=0):
-    y1 = K.stem_fprop(x, w, geo, F32)
-  assert torch.allclose(yq, y1, rtol=1e-6, atol=1e-6)
+  ys = []
+  for mode in (0, 1, 2):
+    with K.options(stem_quad=mode):
+      ys.append(K.stem_fprop(x, w, geo, F32))
+  assert torch.allclose(ys[1], ys[0], rtol=1e-6, atol=1e-6)
+  assert torch.equal(ys[2], ys[1])  # the two quad layouts differ only in which thread owns which channel
