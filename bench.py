@@ -272,7 +272,7 @@ def run_ours(args):
 
   if rank == 0:
     from iic_b200.archs import _engine
-    variants = {k: kernels.get_option(k) for k in ("conv_halo", "conv_halo_wgrad", "stem_quad", "dgrad_prefetch", "tc_cpasync")}
+    variants = {k: kernels.get_option(k) for k in ("conv_halo", "conv_halo_wgrad", "conv_halo_store", "stem_quad", "dgrad_prefetch", "tc2_mt2", "tc_cpasync")}
     variants.update({k: int(v) for k, v in _engine.OPTIONS.items()})
     line = {"metric": METRIC, "value": value, "unit": "img-pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",

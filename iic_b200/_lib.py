@@ -65,6 +65,9 @@ _SIGS = {
   "iic_bn_apply_views": (c_int, [_P, _P, _P, _P, _P, c_int, c_longlong, c_int, c_int, c_int, _P]),
   "iic_bn_stats_from_partials_views": (c_int, [_P, c_int, c_int, c_int, c_longlong, c_int, _P, _P, c_float, c_float, _P, _P, _P, _P, _P]),
   "iic_pack_weights_batched": (c_int, [_P, c_int, c_int, _P]),
+  "iic_stem_bwd_fused_workspace": (c_longlong, [POINTER(ConvGeom), c_int, c_int, c_int]),
+  "iic_stem_bwd_fused": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, c_int, POINTER(ConvGeom), c_int, c_int, c_int, _P,
+                                 c_longlong, _P]),
   "iic_stem_fprop_stats_blocks": (c_int, [POINTER(ConvGeom), c_int, c_int]),
   "iic_stem_fprop_stats": (c_int, [_P, _P, _P, POINTER(ConvGeom), c_int, c_int, _P, _P]),
   "iic_avgpool": (c_int, [_P, c_int, _P, c_int, c_int, c_int, _P]),

@@ -140,10 +140,13 @@ class _ViewStats(list):
 #   bn_merged    one launch per BatchNorm pass for all views (0: one launch chain per view, the first implementation)
 #   stem_stats   BatchNorm statistics of the stem accumulated inside the stem conv kernel (0: separate pass over y)
 #   pack_batched all tensor-core weight layouts of a trunk repacked by one launch (0: one launch per conv and layout)
+#   stem_bwd_fused  backward of the 5g stem (conv3x3 -> BN -> ReLU -> MaxPool) in two passes over (y, dpool)
+#                (0: max-pool backward, BatchNorm backward and stem wgrad as separate passes)
 OPTIONS = {
   "bn_merged": os.environ.get("IIC_BN_MERGED", "1") != "0",
   "stem_stats": os.environ.get("IIC_STEM_STATS", "1") != "0",
   "pack_batched": os.environ.get("IIC_PACK_BATCHED", "1") != "0",
+  "stem_bwd_fused": os.environ.get("IIC_STEM_BWD_FUSED", "1") != "0",
 }
 
 
@@ -287,6 +290,16 @@ def stem_forward(ctx, conv, bn, x_nchw, pool_pad):
 
 def stem_backward(ctx, sink, rec, d_out):
   _, conv, bn, x_nchw, g, y, ss, mi, act, pool_pad = rec
+  if (pool_pad is not None and OPTIONS["stem_bwd_fused"] and hasattr(ss, "stacked") and hasattr(mi, "stacked")
+      and d_out.is_contiguous() and K.stem_bwd_fused_workspace(g, pool_pad, ss.stacked.shape[0], ctx.dt) > 0):
+    dg, acc1 = sink.buf(bn.weight)
+    db, acc2 = sink.buf(bn.bias)
+    gw, accw = sink.buf(conv.weight)
+    assert acc1 == acc2
+    done = K.stem_bwd_fused(x_nchw, y, d_out, ss.stacked, mi.stacked, bn.weight.detach(), dg, db, acc1, gw, accw, g,
+                            pool_pad, ctx.dt)
+    assert done
+    return None
   if pool_pad is not None:
     gmask = _bn_relu_maxpool_bwd(ctx, y, ss, d_out, pool_pad)
     dy, _ = _bn_backward(ctx, sink, bn, gmask, None, y, mi, False)

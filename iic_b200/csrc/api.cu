@@ -42,6 +42,11 @@ static Option g_opts[OPT_COUNT] = {
     {"stem_quad", "IIC_STEM_QUAD", 2, 0, false},
     // dgrad_prefetch: the dgrad epilogues request the residual-gradient addend ahead of its use (0 = on demand)
     {"dgrad_prefetch", "IIC_DGRAD_PREFETCH", 1, 0, false},
+    // tc2_mt2: N = 128 fprop/dgrad tiles of the TMA kernel take two 128-row tiles per weight k-block (0 = one)
+    {"tc2_mt2", "IIC_TC2_MT2", 1, 0, false},
+    // conv_halo_store: halo fprop/dgrad write their output tile with one TMA store out of a shared-memory staging
+    // buffer (0 = 16-byte stores from the epilogue threads, one accumulator row per lane)
+    {"conv_halo_store", "IIC_CONV_HALO_STORE", 1, 0, false},
 };
 
 int option(int id) {

@@ -72,23 +72,27 @@ __device__ __forceinline__ void warp_col_reduce(float (&t)[32], int lane) {
 // tile was a third of the L2->SM traffic that bounds them.
 // With RESB a work item is TWO 128-row tiles (MT = 2): one 256-pixel TMA box and one barrier round-trip feed eight
 // MMAs, halving the per-byte producer / barrier overhead that bounds N = 64 tiles (128 MMA cycles per k-block).
-template <int BN, bool RESB = false> struct Tc2Cfg {
-  static constexpr int MT = RESB ? 2 : 1;
+// MTP = 2 without RESB (N = 128 tiles, option tc2_mt2): one weight k-block (16 KB) feeds two 128-row activation tiles, so
+// the shared-memory fill per tensor cycle drops from 128 to 96 B and a barrier round trip covers eight MMAs.
+template <int BN, bool RESB = false, int MTP = (RESB ? 2 : 1)> struct Tc2Cfg {
+  static constexpr int MT = MTP;
   static constexpr int A_BYTES = MT * TC_BM * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + (RESB ? 0 : B_BYTES);
-  static constexpr int STAGES = RESB ? 4 : ((BN >= 256) ? 4 : (BN >= 128 ? 6 : 8));
+  static constexpr int STAGES = (RESB || MT == 2) ? 4 : ((BN >= 256) ? 4 : (BN >= 128 ? 6 : 8));
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;  // (+ 64 B x N for fused BN statistics)
   static constexpr int TMEM_COLS = 2 * MT * BN;
 };
 
-template <int MODE, int BN, bool RESB = false>
+template <int MODE, int BN, bool RESB = false, int MTP = (RESB ? 2 : 1)>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Tc2Params P) {
-  using Cfg = Tc2Cfg<BN, RESB>;
+  using Cfg = Tc2Cfg<BN, RESB, MTP>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int MT = Cfg::MT;
   static_assert(!RESB || MODE == M2_FPROP, "resident dense operand: fprop/dgrad only");
+  static_assert(MT == 1 || MODE == M2_FPROP, "two-tile work items: fprop/dgrad only");
+  static_assert(Cfg::TMEM_COLS <= 512 && (!RESB || MT == 2), "TMEM budget / RESB implies two-tile work items");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t resb = (raw + 1023u) & ~1023u;  // [total_kb][BN x 128 B] resident weights (RESB), else empty
@@ -464,14 +468,26 @@ struct HaloParams {
   float* stat_partial;  // [cta][view][{sum, sum of squares}][64] or null
   int img_half;         // images >= img_half belong to view 1
   int addend_prefetch;  // request the addend before waiting for the accumulator (option dgrad_prefetch)
+  int tma_store;        // output tile staged in shared memory and written by one TMA store (option conv_halo_store)
 };
 
+// Output path (fprop / dgrad).  With one accumulator row per lane, a warp's 16-byte global stores hit 32 different
+// 128-byte lines per instruction: 2048 LSU wavefronts per 256 x 64 tile against 2304 tensor cycles of MMAs -- the
+// epilogue, not the tensor pipe, paced this kernel (profiles/r01_ncu_halo.md: 41-47 % tensor active).  tma_store != 0:
+// the epilogue warps write the bf16 tile into a SWIZZLE_128B staging buffer (conflict-free 16-byte STS) and ONE
+// cp.async.bulk.tensor store per work item writes it out; the box is the load box without the halo rows (64 x Wp x R),
+// so the padding columns x >= W and the rows below the image are clipped by the TMA unit like they were zero-filled
+// on the way in.
+constexpr uint32_t HALO_STAGING_BYTES = HALO_TILE * 128;
+
 __global__ void __launch_bounds__(HALO_THREADS, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, HaloParams P) {
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, HaloParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t resb = (raw + 1023u) & ~1023u;           // [9][64 x 128 B] resident weights
-  const uint32_t base = resb + 9u * 8192u;                // stages
+  const uint32_t staging = resb + 9u * 8192u;             // [256][128 B] bf16 output tile (tma_store only)
+  const uint32_t base = staging + (P.tma_store ? HALO_STAGING_BYTES : 0u);  // stages
   const uint32_t bars = base + (uint32_t)P.stages * (uint32_t)P.stage_bytes;
   auto full_bar = [&](int s) { return bars + 8u * s; };          // s < 4
   auto empty_bar = [&](int s) { return bars + 8u * (4 + s); };
@@ -500,6 +516,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 9 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (P.tma_store) tma_prefetch_desc(&tmO);
   }
   if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 256);
   tc_fence_before();
@@ -573,12 +590,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quad = warp & 3, hsel = warp >> 2;
     const bool has_add = P.addend != nullptr;
     const bool pre = has_add && P.addend_prefetch != 0;
+    const bool ts = P.tma_store != 0;
+    uint8_t* staging_ptr = smem_raw + (staging - raw);
     uint32_t it = 0;
     for (int w = blockIdx.x; w < P.total_tiles; w += gridDim.x, ++it) {
       const int img = w / P.tiles_per_img;
       const int y0 = (w - img * P.tiles_per_img) * P.R;
       const int view = img >= P.img_half ? 1 : 0;
       const uint32_t as = it & 1u;
+      if (ts) {  // the previous work item's TMA store must have read the staging buffer before it is rewritten
+        if (threadIdx.x == 0) bulk_wait_read0();
+        named_bar_sync(1, 256);
+      }
       // this thread's two accumulator rows (TMEM lane, +128 for the second MMA tile) -> output pixels
       bool valid2[2];
       long long pix2[2];
@@ -629,10 +652,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           sp[0] += s1;
           sp[32] += t[0];
         }
-        if (valid) {
+        if (valid || ts) {
           const long long pix = pix2[mt];
+          const int m = mt * TC_BM + quad * 32 + lane;
           __nv_bfloat16* o = P.out + pix * 64 + hsel * 32;
-          if (has_add && !pre) {
+          if (has_add && !pre && valid) {
             const uint4* src = reinterpret_cast<const uint4*>(P.addend + pix * 64 + hsel * 32);
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) add2[mt][qq] = src[qq];
@@ -650,13 +674,25 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] += ad[e];
             }
-            store8(o + qq * 8, f);
+            if (ts)  // staging row m, 16-byte chunk (hsel * 4 + qq) at its SWIZZLE_128B position
+              store8(reinterpret_cast<__nv_bfloat16*>(staging_ptr + m * 128 + (((hsel * 4 + qq) ^ (m & 7)) << 4)), f);
+            else
+              store8(o + qq * 8, f);
           }
         }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(as));
+      if (ts) {
+        fence_proxy_async();  // the generic-proxy writes above -> visible to the TMA unit
+        named_bar_sync(1, 256);
+        if (threadIdx.x == 0) {
+          tma_store_4d(&tmO, staging, 0, 0, y0, img);
+          bulk_commit();
+        }
+      }
     }
+    if (ts && threadIdx.x == 0) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -847,15 +883,15 @@ static int make_im2col_map2(CUtensorMap* tm, const void* ptr, int nimg, int H, i
 
 static int tc2_grid(long long work) { return (int)(work < device_sm_count() ? work : device_sm_count()); }
 
-template <int MODE, int BN, bool RESB>
+template <int MODE, int BN, bool RESB, int MTP = (RESB ? 2 : 1)>
 static int launch_tc2_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc2Params& P, int splits, cudaStream_t st) {
-  using Cfg = Tc2Cfg<BN, RESB>;
+  using Cfg = Tc2Cfg<BN, RESB, MTP>;
   const int smem = Cfg::SMEM + (P.stat_partial ? 64 * P.N : 0) + (RESB ? P.total_kb * Cfg::B_BYTES : 0);
   IIC_REQUIRE(smem <= 232448, IIC_ERR_UNSUPPORTED, "conv_tc2: shared memory budget exceeded (%d B)", smem);
-  IIC_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<MODE, BN, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  IIC_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<MODE, BN, RESB, MTP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   long long work = (long long)P.mtiles * P.ntiles * splits;
   int grid = tc2_grid(work);
-  conv_tc2_kernel<MODE, BN, RESB><<<grid, TC2_THREADS, smem, st>>>(tmA, tmB, P);
+  conv_tc2_kernel<MODE, BN, RESB, MTP><<<grid, TC2_THREADS, smem, st>>>(tmA, tmB, P);
   IIC_LAUNCH_CHECK();
   count_launch();
   return IIC_OK;
@@ -878,11 +914,20 @@ static int pick_bn2(int N) {
   return 0;
 }
 
+// two 128-row tiles per work item with streamed weights (option tc2_mt2): N = 128 tiles with enough work per CTA
+// (1 = when every CTA gets at least two such work items, 2 = always: tests)
+static bool tc2_use_mt2(int bn, int N, long long rows) {
+  const int mode = option(OPT_TC2_MT2);
+  if (mode == 0 || bn != 128) return false;
+  return mode >= 2 || ((rows + 2 * TC_BM - 1) / (2 * TC_BM)) * (N / bn) >= 2ll * device_sm_count();
+}
+
 
 // ---- halo variant: plan + launch -----------------------------------------------------------------
 struct HaloPlan {
   bool ok;
   int Wp, R, tiles_per_img, total_tiles, stage_bytes, box_bytes, stages, smem;
+  int tma_store;  // fprop / dgrad: output tile through a shared-memory staging buffer and one TMA store
 };
 
 // option conv_halo / IIC_CONV_HALO: 0 never, 1 (default) when the geometry fits and the tile efficiency is good,
@@ -904,10 +949,13 @@ static HaloPlan halo_plan(const iic_conv_geom* g, int srcC, int N, int H, int W,
   p.stage_bytes = ((HALO_TILE + 2 * p.Wp + 2) * 128 + 1023) / 1024 * 1024;
   if (p.box_bytes > p.stage_bytes || p.R + 2 > 256) return p;
   const int fixed = 1024 + 9 * 8192 + 128 + 8 * 2 * 2 * 32 * 4;
-  p.stages = (232448 - fixed) / p.stage_bytes;
+  // with the staging buffer of the TMA-store epilogue (option conv_halo_store) if two pipeline stages still fit
+  p.tma_store = option(OPT_HALO_STORE) != 0 && (232448 - fixed - (int)HALO_STAGING_BYTES) / p.stage_bytes >= 2;
+  const int fixed_all = fixed + (p.tma_store ? (int)HALO_STAGING_BYTES : 0);
+  p.stages = (232448 - fixed_all) / p.stage_bytes;
   if (p.stages > 4) p.stages = 4;
   if (p.stages < 2) return p;
-  p.smem = fixed + p.stages * p.stage_bytes;
+  p.smem = fixed_all + p.stages * p.stage_bytes;
   if (halo_mode() == 1) {
     const double eff = (double)H * W / ((double)p.tiles_per_img * HALO_TILE);
     if (eff < 0.80 || p.total_tiles < 2 * device_sm_count()) return p;
@@ -945,9 +993,12 @@ static HaloPlan halo_wgrad_plan(const iic_conv_geom* g) {
 
 static int launch_halo(const HaloPlan& hp, const __nv_bfloat16* src, int H, int W, int nimg, const Tc2Params& P,
                        const CUtensorMap& tmB, cudaStream_t st) {
-  alignas(64) CUtensorMap tmA;
+  alignas(64) CUtensorMap tmA, tmO;
   {
-    const int rc = make_halo_map(&tmA, src, H, W, nimg, hp.Wp, hp.R + 2);
+    int rc = make_halo_map(&tmA, src, H, W, nimg, hp.Wp, hp.R + 2);
+    if (rc != IIC_OK) return rc;
+    // output map: the load box without the two halo rows; unused (but valid) when the epilogue stores directly
+    rc = make_halo_map(&tmO, P.out, H, W, nimg, hp.Wp, hp.R);
     if (rc != IIC_OK) return rc;
   }
   HaloParams Q = {};
@@ -960,9 +1011,10 @@ static int launch_halo(const HaloPlan& hp, const __nv_bfloat16* src, int H, int 
   }
   Q.out = P.out; Q.addend = P.addend; Q.stat_partial = P.stat_partial;
   Q.addend_prefetch = P.addend_prefetch;
+  Q.tma_store = hp.tma_store;
   Q.img_half = (P.stat_half < P.rows) ? nimg / 2 : nimg;
   IIC_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hp.smem));
-  conv_halo_kernel<<<tc2_grid(hp.total_tiles), HALO_THREADS, hp.smem, st>>>(tmA, tmB, Q);
+  conv_halo_kernel<<<tc2_grid(hp.total_tiles), HALO_THREADS, hp.smem, st>>>(tmA, tmB, tmO, Q);
   IIC_LAUNCH_CHECK();
   count_launch();
   return IIC_OK;
@@ -975,7 +1027,8 @@ int tc2_conv_fprop_blocks(const iic_conv_geom* g) {
   const long long rows = (long long)g->n * g->oh * g->ow;
   const HaloPlan hp = halo_plan(g, g->cin, g->cout, g->h, g->w, g->n);
   if (hp.ok) return tc2_grid(hp.total_tiles);
-  const int tile_rows = tc2_use_resb(bn, g->cout, g->kh * g->kw * g->cin / 64, rows) ? 2 * TC_BM : TC_BM;
+  const int tile_rows =
+      (tc2_use_resb(bn, g->cout, g->kh * g->kw * g->cin / 64, rows) || tc2_use_mt2(bn, g->cout, rows)) ? 2 * TC_BM : TC_BM;
   return tc2_grid(((rows + tile_rows - 1) / tile_rows) * (g->cout / bn));
 }
 
@@ -1026,7 +1079,8 @@ int tc2_conv_gather_gemm_stats(const __nv_bfloat16* src, int srcH, int srcW, int
   P.srcC = srcC; P.Ktot = g->kh * g->kw * srcC; P.N = N;
   P.ntiles = N / bn; P.splits = 1; P.total_kb = P.Ktot / 64;
   const bool resb = tc2_use_resb(bn, N, P.total_kb, P.rows);
-  const int tile_rows = resb ? 2 * TC_BM : TC_BM;
+  const bool mt2 = !resb && tc2_use_mt2(bn, N, P.rows);
+  const int tile_rows = (resb || mt2) ? 2 * TC_BM : TC_BM;
   P.mtiles = (int)((P.rows + tile_rows - 1) / tile_rows);
   P.out = out; P.addend = addend;
   P.addend_prefetch = option(OPT_DGRAD_PREFETCH);
@@ -1051,6 +1105,7 @@ int tc2_conv_gather_gemm_stats(const __nv_bfloat16* src, int srcH, int srcW, int
   }
   if (hp.ok) return launch_halo(hp, src, srcH, srcW, nimg, P, tmB, st);
   if (resb) return launch_tc2_impl<M2_FPROP, 64, true>(tmA, tmB, P, 1, st);
+  if (mt2) return launch_tc2_impl<M2_FPROP, 128, false, 2>(tmA, tmB, P, 1, st);
   switch (bn) {
     case 256: return launch_tc2<M2_FPROP, 256>(tmA, tmB, P, 1, st);
     case 128: return launch_tc2<M2_FPROP, 128>(tmA, tmB, P, 1, st);

@@ -123,6 +123,18 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* desc, uint
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// TMA store, tiled mode, rank 4: shared -> global (elements outside the tensor are clipped), bulk async-group completion
+__device__ __forceinline__ void tma_store_4d(const void* desc, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk groups of this thread have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // im2col mode, NHWC activation as a (C, W, H, N) tensor: {c, w, h, n} = channel offset and the input-space
 // coordinate of the first pixel's receptive-field corner; {off_w, off_h} = filter tap * dilation.
 __device__ __forceinline__ void tma_load_im2col(uint32_t dst, const void* desc, uint32_t bar, int c, int w, int h, int n,

@@ -361,6 +361,28 @@ def stem_fprop_stats(x_nchw, w, g, dt, views):
   return y, partial, nblk
 
 
+def stem_bwd_fused_workspace(g, pool_pad, views, dt):
+  """Scratch bytes of iic_stem_bwd_fused, 0 if the geometry is not supported."""
+  return int(_lib.lib().iic_stem_bwd_fused_workspace(ctypes.byref(g), pool_pad, views, dt))
+
+
+@_cat("stem_bwd_fused")
+def stem_bwd_fused(x_nchw, y, dpool, ss, mi, gamma, dgamma, dbeta, bn_accumulate, grad_w, w_accumulate, g, pool_pad, dt):
+  """Backward of conv3x3 -> BN -> ReLU -> MaxPool(2,2,pool_pad) of the stem in two passes (csrc/stem_bwd.cu).
+  ss, mi: [views, 128] stacked per-view BN coefficients.  Returns False (nothing done) if the geometry is unsupported."""
+  views = ss.shape[0]
+  nbytes = stem_bwd_fused_workspace(g, pool_pad, views, dt)
+  if nbytes <= 0:
+    return False
+  assert ss.is_contiguous() and mi.is_contiguous() and ss.shape == mi.shape == (views, 128)
+  assert y.is_contiguous() and dpool.is_contiguous() and x_nchw.is_contiguous() and iic_dtype(y) == dt == iic_dtype(dpool)
+  ws = torch.empty(nbytes, device=y.device, dtype=torch.uint8)
+  check(_lib.lib().iic_stem_bwd_fused(_p(x_nchw), _p(y), _p(dpool), _p(ss), _p(mi), _p(gamma), _p(dgamma), _p(dbeta),
+                                      int(bool(bn_accumulate)), _p(grad_w), int(bool(w_accumulate)), ctypes.byref(g),
+                                      pool_pad, views, dt, _p(ws), nbytes, _stream()), "iic_stem_bwd_fused")
+  return True
+
+
 @_cat("stem_wgrad")
 def stem_wgrad(x_nchw, dy, g, dt, grad_out, accumulate):
   ws = torch.empty(2 * 1024 * 1024, device=dy.device, dtype=torch.float32)  # 8 MB of per-block partials

@@ -58,7 +58,10 @@ long long iic_launch_count(int reset);
  *   "stem_quad"       [IIC_STEM_QUAD=2]        stem conv: 4 pixels x 16 channels per thread (and the fused-statistics
  *                                              entry point): 2 = channel-interleaved lanes (whole-sector stores),
  *                                              1 = 16 consecutive channels per thread; 0 = one pixel per thread
- *   "dgrad_prefetch"  [IIC_DGRAD_PREFETCH=1]   dgrad epilogues fetch the residual-gradient addend ahead of its use    */
+ *   "dgrad_prefetch"  [IIC_DGRAD_PREFETCH=1]   dgrad epilogues fetch the residual-gradient addend ahead of its use
+ *   "tc2_mt2"         [IIC_TC2_MT2=1]          128-channel fprop/dgrad: two 128-row tiles per weight k-block (0 = one)
+ *   "conv_halo_store" [IIC_CONV_HALO_STORE=1]  halo fprop/dgrad: output tile staged in shared memory, one TMA store per
+ *                                              work item (0 = per-thread 16-byte global stores)                      */
 int iic_get_option(const char* name);
 int iic_set_option(const char* name, int value);
 
@@ -197,6 +200,20 @@ int iic_stem_fprop_stats(const float* x_nchw, const float* w_oihw, void* y, cons
                          float* stat_partial, void* stream);
 int iic_stem_wgrad(const float* x_nchw, const void* dy, float* grad_oihw, int accumulate, void* workspace,
                    long long workspace_bytes, const iic_conv_geom* g, int dtype, void* stream);
+/* Whole backward of the ClusterNet5g stem, conv3x3(cin 1|2 -> 64, pad 1) -> BatchNorm -> ReLU -> MaxPool(2, 2, pool_pad)
+ * (net5g.py:21-26), in two passes over (y, dpool) instead of six over y-sized tensors: the pooled gradient is routed
+ * and ReLU-masked on the fly, reduced for the BatchNorm backward, and the BatchNorm input gradient is consumed by the
+ * weight gradient without being stored (the network input takes no gradient).
+ *   x_nchw [n][cin][h][w] fp32; y [n][h][w][64] conv output and dpool [n][oh][ow][64] in `dtype`;
+ *   ss, mi [views][2*64]: per-view BatchNorm scale/shift and mean/invstd of the forward pass; views = 1 or 2 stacked
+ *   batches with their own statistics; dgamma/dbeta [64] and dw_oihw [64][cin][3][3] are written or accumulated.
+ * _workspace() returns the scratch bytes needed, or 0 when the geometry is not supported (then use
+ * iic_bn_relu_maxpool_bwd + iic_bn_bwd_fused + iic_stem_wgrad).                                                  */
+long long iic_stem_bwd_fused_workspace(const iic_conv_geom* g, int pool_pad, int views, int dtype);
+int iic_stem_bwd_fused(const float* x_nchw, const void* y, const void* dpool, const float* ss, const float* mi,
+                       const float* gamma, float* dgamma, float* dbeta, int bn_accumulate, float* dw_oihw,
+                       int w_accumulate, const iic_conv_geom* g, int pool_pad, int views, int dtype, void* workspace,
+                       long long workspace_bytes, void* stream);
 
 /* ---- BatchNorm2d, train mode (net5g.py:24, residual.py:20,23,56, vgg.py:28-29): statistics
  *      are per forward call over all M = n*h*w rows.

@@ -522,13 +522,15 @@ HALO_GEOMS = [
 
 
 @pytest.mark.parametrize("n,h", HALO_GEOMS)
-@pytest.mark.parametrize("halo_wgrad", [1, 0])
-def test_halo_kernels_forced_exact_small_integers(n, h, halo_wgrad):
+@pytest.mark.parametrize("variant", ["tma-store", "direct-store", "im2col-wgrad"])
+def test_halo_kernels_forced_exact_small_integers(n, h, variant):
   """The halo kernels (3x3 / stride 1 / pad 1 / 64 -> 64: fprop, dgrad, wgrad) forced on every geometry they accept
   (option conv_halo = 2; by default they only run where they pay): EXACT on small-integer operands against CPU fp64,
   and bit-identical to the im2col kernels (conv_halo = 0), including the dgrad addend and the fused BN statistics."""
   K = _K()
   from iic_b200._lib import BF16
+  halo_wgrad = 0 if variant == "im2col-wgrad" else 1
+  halo_store = 0 if variant == "direct-store" else 1
   if halo_wgrad == 0 and h not in (13, 49):
     pytest.skip("im2col wgrad beside the halo fprop/dgrad: two geometries are enough")
   g = torch.Generator().manual_seed(100 + h)
@@ -554,7 +556,7 @@ def test_halo_kernels_forced_exact_small_integers(n, h, halo_wgrad):
     torch.cuda.synchronize()
     return y, dx, dx2, gw, st
 
-  with K.options(conv_halo=2, conv_halo_wgrad=halo_wgrad):
+  with K.options(conv_halo=2, conv_halo_wgrad=halo_wgrad, conv_halo_store=halo_store):
     y, dx, dx2, gw, st = run()
   with K.options(conv_halo=0):
     y0, dx0, dx20, gw0, st0 = run()
@@ -577,7 +579,7 @@ def test_halo_kernels_forced_exact_small_integers(n, h, halo_wgrad):
 
 def test_runtime_options_roundtrip():
   K = _K()
-  for name in ("conv_halo", "conv_halo_wgrad", "tc_cpasync", "stem_quad", "dgrad_prefetch"):
+  for name in ("conv_halo", "conv_halo_wgrad", "tc_cpasync", "stem_quad", "dgrad_prefetch", "tc2_mt2", "conv_halo_store"):
     v = K.get_option(name)
     with K.options(**{name: 0}):
       assert K.get_option(name) == 0
@@ -601,3 +603,120 @@ def test_stem_quad_kernel_equals_one_pixel_kernel(cin, k, pad, hw):
       ys.append(K.stem_fprop(x, w, geo, F32))
   assert torch.allclose(ys[1], ys[0], rtol=1e-6, atol=1e-6)
   assert torch.equal(ys[2], ys[1])  # the two quad layouts differ only in which thread owns which channel
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("cin,hw,pool_pad,views,n", [(2, 32, 1, 2, 6), (2, 96, 1, 2, 4), (1, 24, 0, 1, 3), (2, 20, 0, 2, 2),
+                                                     (2, 18, 1, 1, 5)])
+def test_stem_backward_fused_matches_chain_and_autograd(mode, cin, hw, pool_pad, views, n):
+  """iic_stem_bwd_fused (conv3x3 -> BN -> ReLU -> MaxPool backward in two passes over (y, dpool)) against the
+  three-kernel chain it replaces (max-pool backward, BatchNorm backward, stem wgrad) and, in fp32 mode, against
+  torch autograd in double precision -- per-view BatchNorm statistics, both pool paddings, accumulate flags."""
+  K = _K()
+  from iic_b200._lib import BF16, F32
+  dt, tdt = (F32, torch.float32) if mode == "fp32" else (BF16, torch.bfloat16)
+  g = torch.Generator().manual_seed(77)
+  x = torch.randn(n, cin, hw, hw, generator=g).cuda()
+  if views == 2:
+    x[n // 2:] = x[n // 2:] * 1.7 + 0.4
+  w = (torch.randn(64, cin, 3, 3, generator=g) * math.sqrt(2.0 / (cin * 9))).cuda()
+  gamma = (torch.rand(64, generator=g) + 0.5).cuda()
+  beta = (torch.randn(64, generator=g) * 0.2).cuda()
+  geo = K.conv_geom(n, hw, hw, cin, 64, 3, 3, 1, 1, 1)
+  y = K.stem_fprop(x, w, geo, dt)
+  nv = n // views
+  ss = torch.empty(views, 128, device="cuda")
+  mi = torch.empty(views, 128, device="cuda")
+  for v in range(views):
+    K.bn_stats(y[v * nv:(v + 1) * nv], gamma, beta, 1e-5, 0.1, None, None, False, ss=ss[v], mi=mi[v])
+  oh = (hw + 2 * pool_pad - 2) // 2 + 1
+  dpool = torch.randn(n, oh, oh, 64, generator=g).cuda().to(tdt)
+  # the chain
+  gmask = torch.empty_like(y)
+  for v in range(views):
+    K.bn_relu_maxpool_bwd(y[v * nv:(v + 1) * nv], ss[v], dpool[v * nv:(v + 1) * nv], pool_pad, out=gmask[v * nv:(v + 1) * nv])
+  dg1, db1 = torch.zeros(64).cuda(), torch.zeros(64).cuda()
+  dy, _ = K.bn_bwd_fused(gmask, None, y, [mi[v] for v in range(views)], gamma, dg1, db1, False, False)
+  gw1 = torch.zeros_like(w)
+  K.stem_wgrad(x, dy, geo, dt, gw1, False)
+  # fused
+  assert K.stem_bwd_fused_workspace(geo, pool_pad, views, dt) > 0
+  dg2, db2, gw2 = torch.full((64,), 7.0).cuda(), torch.full((64,), 7.0).cuda(), torch.full_like(w, 7.0)
+  assert K.stem_bwd_fused(x, y, dpool, ss, mi, gamma, dg2, db2, False, gw2, False, geo, pool_pad, dt)
+  torch.cuda.synchronize()
+  sg, sb, sw = dg1.abs().max().item(), db1.abs().max().item(), gw1.abs().max().item()
+  assert (dg2 - dg1).abs().max().item() <= 2e-4 * sg + 1e-5
+  assert (db2 - db1).abs().max().item() <= 2e-4 * sb + 1e-5
+  wtol = 2e-4 if mode == "fp32" else 1e-2  # the chain rounds dy to bf16 before the wgrad, the fused pass keeps fp32
+  assert (gw2 - gw1).abs().max().item() <= wtol * sw + 1e-5
+  # accumulate flags
+  assert K.stem_bwd_fused(x, y, dpool, ss, mi, gamma, dg2, db2, True, gw2, True, geo, pool_pad, dt)
+  assert (dg2 - 2 * dg1).abs().max().item() <= 4e-4 * sg + 2e-5
+  assert (gw2 - 2 * gw1).abs().max().item() <= 2 * wtol * sw + 2e-5
+  if mode == "fp32":
+    xr, wr = x.double().cpu(), w.double().cpu().requires_grad_(True)
+    gr, br = gamma.double().cpu().requires_grad_(True), beta.double().cpu().requires_grad_(True)
+    yr = F.conv2d(xr, wr, None, 1, 1)
+    outs = [F.max_pool2d(torch.relu(F.batch_norm(yr[v * nv:(v + 1) * nv], None, None, gr, br, True, 0.1, 1e-5)), 2, 2, pool_pad)
+            for v in range(views)]
+    torch.cat(outs).backward(dpool.double().cpu().permute(0, 3, 1, 2))
+    K.stem_bwd_fused(x, y, dpool, ss, mi, gamma, dg2, db2, False, gw2, False, geo, pool_pad, dt)
+    assert torch.allclose(gw2.cpu().double(), wr.grad, rtol=0, atol=1e-3 * wr.grad.abs().max().item())
+    assert torch.allclose(dg2.cpu().double(), gr.grad, rtol=0, atol=1e-3 * gr.grad.abs().max().item())
+    assert torch.allclose(db2.cpu().double(), br.grad, rtol=0, atol=1e-3 * br.grad.abs().max().item())
+
+
+def test_stem_backward_fused_reports_unsupported_geometries():
+  K = _K()
+  from iic_b200._lib import BF16
+  assert K.stem_bwd_fused_workspace(K.conv_geom(2, 24, 24, 1, 64, 5, 5, 1, 2, 1), 0, 1, BF16) == 0  # 5x5 (ClusterNet6c)
+  assert K.stem_bwd_fused_workspace(K.conv_geom(2, 32, 32, 5, 64, 3, 3, 1, 1, 1), 1, 1, BF16) == 0  # cin 5 (net10a)
+  assert K.stem_bwd_fused_workspace(K.conv_geom(2, 33, 33, 2, 64, 3, 3, 1, 1, 1), 0, 1, BF16) == 0  # a row no window covers
+  assert K.stem_bwd_fused_workspace(K.conv_geom(3, 32, 32, 2, 64, 3, 3, 1, 1, 1), 1, 2, BF16) == 0  # 3 images, 2 views
+  assert K.stem_bwd_fused_workspace(K.conv_geom(4, 32, 32, 2, 64, 3, 3, 1, 1, 1), 1, 2, BF16) > 0
+
+
+@pytest.mark.parametrize("n,h,cin,cout,k,s,p", [(2, 9, 128, 128, 3, 1, 1), (5, 13, 128, 128, 3, 1, 1), (4, 25, 64, 128, 3, 2, 1),
+                                                 (3, 25, 64, 128, 1, 2, 0), (2, 30, 128, 128, 3, 1, 1)])
+def test_tc2_two_tile_work_items_forced_exact_small_integers(n, h, cin, cout, k, s, p):
+  """N = 128 tiles of the TMA kernel with two 128-row accumulator tiles per weight k-block (option tc2_mt2 = 2 forces the
+  variant at test sizes; by default it needs two work items per SM): exact on small integers, bit-identical to the
+  one-tile variant, fused BN statistics and dgrad addend included."""
+  K = _K()
+  from iic_b200._lib import BF16
+  g = torch.Generator().manual_seed(200 + h + cin)
+  x = torch.randint(-1, 2, (n, cin, h, h), generator=g).float()
+  w = torch.randint(-1, 2, (cout, cin, k, k), generator=g).float()
+  geo = K.conv_geom(n, h, h, cin, cout, k, k, s, p, 1)
+  dy = torch.randint(-1, 2, (n, cout, geo.oh, geo.ow), generator=g).float()
+  add = torch.randint(-2, 3, (n, cin, h, h), generator=g).float()
+  xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+  ref = F.conv2d(xr, wr, None, s, p)
+  ref.backward(dy.double())
+  assert ref.abs().max() <= 256 and xr.grad.abs().max() <= 250
+  xh, dyh, addh = [to_nhwc(t.cuda(), torch.bfloat16) for t in (x, dy, add)]
+  wp0, wp1 = K.pack_weight(w.cuda(), BF16, 0), K.pack_weight(w.cuda(), BF16, 1)
+
+  def run():
+    y = K.conv_fprop(xh, wp0, geo, BF16)
+    st = K.conv_fprop_stats(xh, wp0, geo, BF16, 2 if n % 2 == 0 else 1)
+    dx = K.conv_dgrad(dyh, wp1, geo, BF16)
+    dx2 = K.conv_dgrad(dyh, wp1, geo, BF16, addend=addh)
+    torch.cuda.synchronize()
+    return y, st, dx, dx2
+
+  with K.options(tc2_mt2=2):
+    y, st, dx, dx2 = run()
+  with K.options(tc2_mt2=0):
+    y0, st0, dx0, dx20 = run()
+  assert torch.equal(from_nhwc(y).cpu(), ref.detach().float()), "fprop"
+  assert torch.equal(from_nhwc(dx).cpu(), xr.grad.float()), "dgrad"
+  assert torch.equal(from_nhwc(dx2).cpu(), (xr.grad + add.double()).float()), "dgrad + addend"
+  for a, b in ((y, y0), (st[0], st0[0]), (dx, dx0), (dx2, dx20)):
+    assert torch.equal(a, b)
+  views = 2 if n % 2 == 0 else 1
+  tot = st[1][:st[2]].double().sum(0).cpu()
+  yr = ref.detach()
+  for v in range(views):
+    sl = yr[v * (n // views):(v + 1) * (n // views)]
+    assert torch.equal(tot[v, 0], sl.sum(dim=(0, 2, 3))) and torch.equal(tot[v, 1], (sl * sl).sum(dim=(0, 2, 3)))
