@@ -388,9 +388,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[qq * 8 + e]);
               if (has_add) {
                 float ad[8];
-                Raw8h raw;
-                raw.v = acur[qq];
-                cvt_raw(raw, ad);
+                Raw8h rw;
+                rw.v = acur[qq];
+                cvt_raw(rw, ad);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] += ad[e];
               }
@@ -668,9 +668,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[qq * 8 + e]);
             if (has_add) {
               float ad[8];
-              Raw8h raw;
-              raw.v = add2[mt][qq];
-              cvt_raw(raw, ad);
+              Raw8h rw;
+              rw.v = add2[mt][qq];
+              cvt_raw(rw, ad);
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] += ad[e];
             }
