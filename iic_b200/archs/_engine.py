@@ -140,13 +140,15 @@ class _ViewStats(list):
 #   bn_merged    one launch per BatchNorm pass for all views (0: one launch chain per view, the first implementation)
 #   stem_stats   BatchNorm statistics of the stem accumulated inside the stem conv kernel (0: separate pass over y)
 #   pack_batched all tensor-core weight layouts of a trunk repacked by one launch (0: one launch per conv and layout)
-#   stem_bwd_fused  backward of the 5g stem (conv3x3 -> BN -> ReLU -> MaxPool) in two passes over (y, dpool)
-#                (0: max-pool backward, BatchNorm backward and stem wgrad as separate passes)
+#   stem_bwd_fused  backward of the 5g stem (conv3x3 -> BN -> ReLU -> MaxPool) in two passes over (y, dpool) instead of
+#                max-pool backward, BatchNorm backward and stem wgrad as separate passes.  Correct (tests) but OFF by
+#                default: its first version is latency bound (7.6 ms against 4.4 ms for the chain at the bench shape,
+#                profiles/r01_bench_v10_variants.md)
 OPTIONS = {
   "bn_merged": os.environ.get("IIC_BN_MERGED", "1") != "0",
   "stem_stats": os.environ.get("IIC_STEM_STATS", "1") != "0",
   "pack_batched": os.environ.get("IIC_PACK_BATCHED", "1") != "0",
-  "stem_bwd_fused": os.environ.get("IIC_STEM_BWD_FUSED", "1") != "0",
+  "stem_bwd_fused": os.environ.get("IIC_STEM_BWD_FUSED", "0") != "0",
 }
 
 
