@@ -258,7 +258,12 @@ def run_ours(args):
     nl = sum(v[0] for v in summ.values())
     ach = flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
     roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM fprop/dgrad/wgrad)",
-            "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
+            "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
+            # DRAM bytes per launch of the family's most frequent member from the committed `ncu --set full` capture
+            # (not measured in this run): conv_halo_kernel fprop, 352 images of 49x49x64 -> 108.5 MB read + 65.4 MB
+            # written against 216.4 MB algorithmic (input once + output once; part of the output was still in L2)
+            "traffic": 173.9e6, "traffic_unit": "B per launch (ncu, profiles/r01_ncu_halo.md: conv_halo_kernel fprop at 352 images; "
+                                                "algorithmic 216.4e6 B)",
             "peak_source": pk["src"], "launches_timed": nl,
             "flop_per_launch_avg": flops / max(nl, 1), "ms_per_launch_avg": ms / max(nl, 1),
             "by_kind": {k: {"launches": v[0], "tflops": v[1] / (v[2] * 1e-3) / 1e12 if v[2] > 0 else 0.0,
