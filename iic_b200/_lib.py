@@ -63,6 +63,8 @@ _SIGS = {
   "iic_bn_bwd_apply": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_longlong, c_int, _P]),
   "iic_bn_bwd_fused": (c_int, [_P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_longlong, c_int, _P]),
   "iic_bn_apply_views": (c_int, [_P, _P, _P, _P, _P, c_int, c_longlong, c_int, c_int, c_int, _P]),
+  "iic_bn_apply_views_mask": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_longlong, c_int, c_int, _P]),
+  "iic_bn_bwd_fused_bits": (c_int, [_P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_longlong, c_int, _P]),
   "iic_bn_stats_from_partials_views": (c_int, [_P, c_int, c_int, c_int, c_longlong, c_int, _P, _P, c_float, c_float, _P, _P, _P, _P, _P]),
   "iic_pack_weights_batched": (c_int, [_P, c_int, c_int, _P]),
   "iic_stem_bwd_fused_workspace": (c_longlong, [POINTER(ConvGeom), c_int, c_int, c_int]),

@@ -111,6 +111,7 @@ class _Ctx(object):
     self.groups = groups
     self.saved = []
     self.wcache = {}
+    self.mbits = {}  # id(block output) -> its ReLU mask as bits (option bn_bitmask)
 
   def split(self, t):
     if t is None:
@@ -144,11 +145,15 @@ class _ViewStats(list):
 #                max-pool backward, BatchNorm backward and stem wgrad as separate passes.  Correct (tests) but OFF by
 #                default: its first version is latency bound (7.6 ms against 4.4 ms for the chain at the bench shape,
 #                profiles/r01_bench_v10_variants.md)
+#   bn_bitmask   the ReLU of a residual block's output is kept as a 1-bit mask by the forward apply and read by the bn2
+#                backward instead of the block output (16 -> 12.25 B per element).  Written after the last GPU session
+#                of round 1: OFF until it has run on hardware (its tests carry the `unvalidated` marker)
 OPTIONS = {
   "bn_merged": os.environ.get("IIC_BN_MERGED", "1") != "0",
   "stem_stats": os.environ.get("IIC_STEM_STATS", "1") != "0",
   "pack_batched": os.environ.get("IIC_PACK_BATCHED", "1") != "0",
   "stem_bwd_fused": os.environ.get("IIC_STEM_BWD_FUSED", "0") != "0",
+  "bn_bitmask": os.environ.get("IIC_BN_BITMASK", "0") != "0",
 }
 
 
@@ -204,6 +209,16 @@ def _stats_from_partials(ctx, bn, y, partial, nblk):
     sss.append(ss)
     mis.append(mi)
   return sss, mis
+
+
+def _bn_apply_block_out(ctx, y, ss, res, rss=None):
+  """relu(bn2(y) + residual) of a BasicBlock; with `bn_bitmask` the ReLU mask is also kept as bits for the backward."""
+  if (OPTIONS["bn_bitmask"] and OPTIONS["bn_merged"] and ctx.need_grad and ctx.groups <= 2 and hasattr(ss, "stacked")
+      and (rss is None or hasattr(rss, "stacked"))):
+    out, mbits = K.bn_apply_views_mask(y, ss.stacked, ctx.groups, res=res, rss=None if rss is None else rss.stacked)
+    ctx.mbits[id(out)] = mbits
+    return out
+  return _bn_apply(ctx, y, ss, True, res=res, rss=rss)
 
 
 def _bn_apply(ctx, y, ss, relu, res=None, rss=None):
@@ -346,10 +361,10 @@ def block_forward(ctx, blk, x):
     dconv, dbn = blk.downsample[0], blk.downsample[1]
     gd = dconv.geom(n, h, w)
     yd, ssd, mid = _conv_bn(ctx, dconv, dbn, x, gd)
-    out = _bn_apply(ctx, y2, ss2, True, res=yd, rss=ssd)
+    out = _bn_apply_block_out(ctx, y2, ss2, yd, ssd)
   else:
     gd = yd = mid = None
-    out = _bn_apply(ctx, y2, ss2, True, res=x)
+    out = _bn_apply_block_out(ctx, y2, ss2, x)
   if ctx.need_grad:
     ctx.saved.append(("block", blk, x, g1, y1, mi1, a1, g2, y2, mi2, gd, yd, mid, out, ss1))
   return out
@@ -358,7 +373,14 @@ def block_forward(ctx, blk, x):
 def block_backward(ctx, sink, rec, d_out):
   _, blk, x, g1, y1, mi1, a1, g2, y2, mi2, gd, yd, mid, out, ss1 = rec
   # out = relu(bn2(y2) + r): g = d_out * (out > 0) goes both into bn2 and the residual branch
-  dy2, gres = _bn_backward(ctx, sink, blk.bn2, d_out, out, y2, mi2, True)
+  mbits = ctx.mbits.get(id(out))
+  if mbits is not None:
+    dg, acc1 = sink.buf(blk.bn2.weight)
+    db, acc2 = sink.buf(blk.bn2.bias)
+    assert acc1 == acc2
+    dy2, gres = K.bn_bwd_fused_bits(d_out, mbits, y2, mi2, blk.bn2.weight.detach(), dg, db, acc1, True)
+  else:
+    dy2, gres = _bn_backward(ctx, sink, blk.bn2, d_out, out, y2, mi2, True)
   _conv_wgrad(ctx, sink, blk.conv2, a1, dy2, g2)
   da1 = K.conv_dgrad(dy2, ctx.packed(blk.conv2, 1), g2, ctx.dt)
   dy1, _ = _bn_backward(ctx, sink, blk.bn1, da1, None, y1, mi1, False, mask_ss=ss1)  # a1 = relu(bn1(y1))

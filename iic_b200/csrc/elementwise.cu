@@ -252,10 +252,14 @@ __global__ void bn_fold_finalize_kernel(const float* __restrict__ partial, int n
 }
 
 // out = relu?( y*scale+shift [+ res | + res*rscale + rshift] )   (residual.py:27-43)
-template <typename T>
+// MASKOUT: additionally writes the ReLU mask of the result as one byte per 8 channels (bit j = out[8*c8 + j] > 0),
+// [views * M][C / 8] bytes; the BatchNorm backward of a residual block then reads 1 bit instead of the 16-bit block
+// output to decide where the gradient passes (iic_bn_bwd_fused_bits).
+template <typename T, bool MASKOUT = false>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, const float* __restrict__ ss,
                                                        const T* __restrict__ res, const float* __restrict__ rss,
-                                                       T* __restrict__ out, long long M, int C, int relu, int views) {
+                                                       T* __restrict__ out, long long M, int C, int relu, int views,
+                                                       unsigned char* __restrict__ mask_out = nullptr) {
   // views > 1: the tensor is `views` stacked batches of M rows with their own coefficients ([views][2C]);
   // the grid is split evenly between them
   const int cg = C >> 3;
@@ -266,6 +270,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, 
   ss += (long long)v * 2 * C;
   if (res != nullptr) res += (long long)v * M * C;
   if (rss != nullptr) rss += (long long)v * 2 * C;
+  if (MASKOUT) mask_out += (long long)v * total;
   // a thread's channel group is loop invariant (blockDim.x is a multiple of C/8): keep the coefficients in registers
   const int c8 = (int)((lb * (long long)blockDim.x + threadIdx.x) % cg);
   float sc[8], sh[8], rsc[8], rsh[8];
@@ -289,6 +294,12 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, 
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    if (MASKOUT) {
+      unsigned int bits = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
+      mask_out[i] = (unsigned char)bits;
     }
     if (relu) {
 #pragma unroll
@@ -464,9 +475,10 @@ struct BnBwdFusedArgs {
   long long Mv;         // rows per view
   float* partial;       // [gridDim.x][2C]
   double* sums;         // [views][2C]
+  const unsigned char* mbits;  // MASK == 3: [views * Mv][C / 8] ReLU-mask bytes written by bn_apply_kernel<., true>
 };
 
-// MASK: 0 none, 1 activation sign (three input streams), 2 recomputed from y*scale+shift.
+// MASK: 0 none, 1 activation sign (three input streams), 2 recomputed from y*scale+shift, 3 one bit per element.
 template <typename T, int MASK>
 __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnBwdFusedArgs p) {
   cg::grid_group grid = cg::this_grid();
@@ -486,7 +498,8 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnBwdFusedArgs p) 
   // rows in flight per thread: 2 CTAs / SM (<= 128 registers) leave 48-64 registers for raw loads, and ~100 KB
   // per SM must be in flight to cover the HBM latency (two input streams need more rows than three); the
   // values below are the largest that do not spill
-  constexpr int U = sizeof(T) == 2 ? (MASK == 1 ? 5 : (MASK == 2 ? 6 : 8)) : 2;
+  constexpr int U = sizeof(T) == 2 ? (MASK == 1 ? 5 : ((MASK == 2 || MASK == 3) ? 6 : 8)) : 2;
+  const unsigned char* mbits = MASK == 3 ? p.mbits + (voff >> 3) : nullptr;  // (byte index = element offset / 8)
   float msc[8], msh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -502,6 +515,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnBwdFusedArgs p) 
     }
     for (long long k = 0; k < nk; k += U) {
       Raw rv[U], rg[U], ra[U];
+      unsigned int rb[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (k + u < nk) {
@@ -509,6 +523,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnBwdFusedArgs p) 
           load_raw(y + off, rv[u]);
           load_raw(gin + off, rg[u]);
           if (MASK == 1) load_raw(act + off, ra[u]);
+          if (MASK == 3) rb[u] = mbits[off >> 3];
         }
       }
 #pragma unroll
@@ -523,6 +538,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnBwdFusedArgs p) 
           float gj = g[j];
           if (MASK == 1) gj = a[j] > 0.f ? gj : 0.f;
           else if (MASK == 2) gj = fmaf(vv[j], msc[j], msh[j]) > 0.f ? gj : 0.f;
+          else if (MASK == 3) gj = ((rb[u] >> j) & 1u) ? gj : 0.f;
           a0[j] += gj;
           a1[j] = fmaf(gj, vv[j] - mean[j], a1[j]);
         }
@@ -583,6 +599,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnBwdFusedArgs p) 
   constexpr int U2 = U;
   for (long long k = nk - 1; k >= 0; k -= U2) {
     Raw rv[U2], rg[U2], ra[U2];
+    unsigned int rb[U2];
 #pragma unroll
     for (int u = 0; u < U2; ++u) {
       if (k - u >= 0) {
@@ -590,6 +607,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnBwdFusedArgs p) 
         load_raw(y + off, rv[u]);
         load_raw(gin + off, rg[u]);
         if (MASK == 1) load_raw(act + off, ra[u]);
+        if (MASK == 3) rb[u] = mbits[off >> 3];
       }
     }
 #pragma unroll
@@ -606,6 +624,9 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(BnBwdFusedArgs p) 
       } else if (MASK == 2) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) g[j] = fmaf(vv[j], msc[j], msh[j]) > 0.f ? g[j] : 0.f;
+      } else if (MASK == 3) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = ((rb[u] >> j) & 1u) ? g[j] : 0.f;
       }
       if (gout != nullptr) store8(gout + off, g);
 #pragma unroll
@@ -964,6 +985,7 @@ static int bn_bwd_fused_launch(BnBwdFusedArgs& a, size_t smem, cudaStream_t st) 
 
 template <typename T>
 static int bn_bwd_fused_dispatch(BnBwdFusedArgs& a, size_t smem, cudaStream_t st) {
+  if (a.mbits != nullptr) return bn_bwd_fused_launch<T, 3>(a, smem, st);
   if (a.act != nullptr) return bn_bwd_fused_launch<T, 1>(a, smem, st);
   if (a.mss[0] != nullptr) return bn_bwd_fused_launch<T, 2>(a, smem, st);
   return bn_bwd_fused_launch<T, 0>(a, smem, st);
@@ -981,6 +1003,7 @@ extern "C" int iic_bn_bwd_fused(const void* g_in, const void* act, const void* y
   IIC_REQUIRE(!(act && mask_ss0), IIC_ERR_BAD_ARG, "iic_bn_bwd_fused: one ReLU mask source at most");
   IIC_REQUIRE(dtype == IIC_BF16 || dtype == IIC_F32, IIC_ERR_BAD_ARG, "iic_bn_bwd_fused: bad dtype %d", dtype);
   BnBwdFusedArgs a;
+  a.mbits = nullptr;
   a.gin = g_in; a.act = act; a.y = y; a.dy = dy; a.gout = g_out;
   a.mi[0] = mean_invstd0; a.mi[1] = mean_invstd1; a.mss[0] = mask_ss0; a.mss[1] = mask_ss1;
   a.gamma = gamma; a.dgamma = dgamma; a.dbeta = dbeta; a.accumulate = accumulate; a.views = views; a.C = C;
@@ -988,6 +1011,46 @@ extern "C" int iic_bn_bwd_fused(const void* g_in, const void* act, const void* y
   a.partial = bn_partial_scratch((size_t)device_sm_count() * 8 * 2 * 2048 * sizeof(float));
   a.sums = bn_sums_scratch();
   IIC_REQUIRE(a.partial && a.sums, IIC_ERR_CUDA, "iic_bn_bwd_fused: scratch allocation failed");
+  const size_t smem = sizeof(float) * (size_t)(5 * C > 256 * 17 ? 5 * C : 256 * 17);
+  if (dtype == IIC_BF16) return bn_bwd_fused_dispatch<__nv_bfloat16>(a, smem, (cudaStream_t)stream);
+  return bn_bwd_fused_dispatch<float>(a, smem, (cudaStream_t)stream);
+}
+
+// The residual block's output ReLU as a 1-bit mask: iic_bn_apply_views_mask = iic_bn_apply_views(relu = 1) that also
+// writes one mask byte per 8 channels; iic_bn_bwd_fused_bits = iic_bn_bwd_fused with that mask instead of `act`.
+extern "C" int iic_bn_apply_views_mask(const void* y, const float* scale_shift, const void* res,
+                                       const float* res_scale_shift, void* out, unsigned char* mask_out, int dtype,
+                                       long long M_per_view, int C, int views, void* stream) {
+  IIC_REQUIRE(y && scale_shift && out && mask_out && M_per_view > 0 && C % 8 == 0 && views >= 1 && views <= 8, IIC_ERR_BAD_ARG,
+              "iic_bn_apply_views_mask: bad arguments");
+  IIC_REQUIRE(256 % (C / 8) == 0, IIC_ERR_UNSUPPORTED, "iic_bn_apply_views_mask: C=%d must be 8 * (a divisor of 256)", C);
+  const long long total = M_per_view * (C / 8);
+  const int grid = ew_grid(total, 256) * views;
+  DISPATCH_T(dtype, (bn_apply_kernel<T, true><<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (const T*)y, scale_shift, (const T*)res, res_scale_shift, (T*)out, M_per_view, C, 1, views, mask_out));)
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
+extern "C" int iic_bn_bwd_fused_bits(const void* g_in, const unsigned char* mask_bits, const void* y, int views,
+                                     const float* mean_invstd0, const float* mean_invstd1, const float* gamma, void* dy,
+                                     void* g_out, float* dgamma, float* dbeta, int accumulate, int dtype,
+                                     long long M_per_view, int C, void* stream) {
+  IIC_REQUIRE(g_in && mask_bits && y && mean_invstd0 && gamma && dy && M_per_view > 0 &&
+                  (views == 1 || (views == 2 && mean_invstd1)),
+              IIC_ERR_BAD_ARG, "iic_bn_bwd_fused_bits: bad arguments");
+  IIC_REQUIRE(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, IIC_ERR_UNSUPPORTED, "iic_bn_bwd_fused_bits: C=%d unsupported", C);
+  IIC_REQUIRE(dtype == IIC_BF16 || dtype == IIC_F32, IIC_ERR_BAD_ARG, "iic_bn_bwd_fused_bits: bad dtype %d", dtype);
+  BnBwdFusedArgs a;
+  a.mbits = mask_bits;
+  a.gin = g_in; a.act = nullptr; a.y = y; a.dy = dy; a.gout = g_out;
+  a.mi[0] = mean_invstd0; a.mi[1] = mean_invstd1; a.mss[0] = nullptr; a.mss[1] = nullptr;
+  a.gamma = gamma; a.dgamma = dgamma; a.dbeta = dbeta; a.accumulate = accumulate; a.views = views; a.C = C;
+  a.Mv = M_per_view;
+  a.partial = bn_partial_scratch((size_t)device_sm_count() * 8 * 2 * 2048 * sizeof(float));
+  a.sums = bn_sums_scratch();
+  IIC_REQUIRE(a.partial && a.sums, IIC_ERR_CUDA, "iic_bn_bwd_fused_bits: scratch allocation failed");
   const size_t smem = sizeof(float) * (size_t)(5 * C > 256 * 17 ? 5 * C : 256 * 17);
   if (dtype == IIC_BF16) return bn_bwd_fused_dispatch<__nv_bfloat16>(a, smem, (cudaStream_t)stream);
   return bn_bwd_fused_dispatch<float>(a, smem, (cudaStream_t)stream);

@@ -431,6 +431,37 @@ def bn_apply_views(y, ss, relu, views, res=None, rss=None, out=None):
   return out
 
 
+@_cat("bn_apply")
+def bn_apply_views_mask(y, ss, views, res=None, rss=None):
+  """relu(bn(y) + residual term) for `views` stacked batches plus its ReLU mask, one byte per 8 channels.
+  Returns (out, mask_bits [rows, C / 8] uint8)."""
+  C = y.shape[-1]
+  M = y.numel() // C
+  assert M % views == 0 and ss.is_contiguous() and (rss is None or rss.is_contiguous())
+  out = torch.empty_like(y)
+  mbits = torch.empty((M, C // 8), device=y.device, dtype=torch.uint8)
+  check(_lib.lib().iic_bn_apply_views_mask(_p(y), _p(ss), _p(res), _p(rss), _p(out), _p(mbits), iic_dtype(y), M // views, C,
+                                           views, _stream()), "iic_bn_apply_views_mask")
+  return out, mbits
+
+
+@_cat("bn_bwd")
+def bn_bwd_fused_bits(g_in, mbits, y, mis, gamma, dgamma, dbeta, accumulate, want_g_out):
+  """bn_bwd_fused with the ReLU mask given as bits (bn_apply_views_mask) instead of the activation."""
+  views = len(mis)
+  assert views in (1, 2)
+  C = y.shape[-1]
+  M = y.numel() // C
+  assert M % views == 0 and mbits.dtype == torch.uint8 and mbits.numel() == M * (C // 8) and mbits.is_contiguous()
+  dy = torch.empty_like(y)
+  g_out = torch.empty_like(y) if want_g_out else None
+  mi1 = mis[1] if views == 2 else None
+  check(_lib.lib().iic_bn_bwd_fused_bits(_p(g_in), _p(mbits), _p(y), views, _p(mis[0]), _p(mi1), _p(gamma), _p(dy), _p(g_out),
+                                         _p(dgamma), _p(dbeta), int(bool(accumulate)), iic_dtype(y), M // views, C,
+                                         _stream()), "iic_bn_bwd_fused_bits")
+  return dy, g_out
+
+
 @_cat("bn_bwd")
 def bn_bwd_fused(g_in, act, y, mis, gamma, dgamma, dbeta, accumulate, want_g_out, mask_sss=None):
   """BatchNorm backward of 1 or 2 stacked views in one cooperative launch.  mis / mask_sss: per-view tensors."""

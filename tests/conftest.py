@@ -13,6 +13,19 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
   config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+  config.addinivalue_line("markers", "unvalidated: exercises a kernel variant written after the last GPU session of the "
+                                     "round (default OFF in the product); skipped unless IIC_RUN_UNVALIDATED=1")
+
+
+def pytest_collection_modifyitems(config, items):
+  """Kernel variants that have not yet run on hardware ship switched off, and so do their tests: a GPU suite that is
+  green must mean "everything the product executes by default has been checked on a B200"."""
+  if os.environ.get("IIC_RUN_UNVALIDATED", "0") == "1":
+    return
+  skip = pytest.mark.skip(reason="variant not yet validated on hardware (default off); set IIC_RUN_UNVALIDATED=1")
+  for item in items:
+    if item.get_closest_marker("unvalidated") is not None:
+      item.add_marker(skip)
 
 
 class Golden(dict):

@@ -720,3 +720,38 @@ def test_tc2_two_tile_work_items_forced_exact_small_integers(n, h, cin, cout, k,
   for v in range(views):
     sl = yr[v * (n // views):(v + 1) * (n // views)]
     assert torch.equal(tot[v, 0], sl.sum(dim=(0, 2, 3))) and torch.equal(tot[v, 1], (sl * sl).sum(dim=(0, 2, 3)))
+
+
+@pytest.mark.unvalidated
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape,views", [((6, 13, 13, 64), 2), ((4, 7, 7, 512), 1), ((2, 5, 5, 2048), 2), ((64, 25, 25, 128), 2)])
+def test_bn_relu_bitmask_variant_equals_activation_mask(mode, shape, views):
+  """1-bit ReLU mask (iic_bn_apply_views_mask / iic_bn_bwd_fused_bits, engine switch bn_bitmask): same output as the plain
+  apply, bits == (out > 0), and a backward bit-identical to the one that re-reads the activation."""
+  K = _K()
+  tdt = torch.float32 if mode == "fp32" else torch.bfloat16
+  n, h, w, C = shape
+  g = torch.Generator().manual_seed(55)
+  y = torch.randn(shape, generator=g).cuda().to(tdt)
+  res = torch.randn(shape, generator=g).cuda().to(tdt)
+  gin = torch.randn(shape, generator=g).cuda().to(tdt)
+  gamma = (torch.rand(C, generator=g) + 0.5).cuda()
+  beta = (torch.randn(C, generator=g) * 0.3).cuda()
+  nv = n // views
+  ss = torch.empty(views, 2 * C, device="cuda")
+  mi = torch.empty(views, 2 * C, device="cuda")
+  for v in range(views):
+    K.bn_stats(y[v * nv:(v + 1) * nv], gamma, beta, 1e-5, 0.1, None, None, False, ss=ss[v], mi=mi[v])
+  out_ref = K.bn_apply_views(y, ss, True, views, res=res)
+  out, mbits = K.bn_apply_views_mask(y, ss, views, res=res)
+  assert torch.equal(out, out_ref)
+  M = n * h * w
+  want = (out.view(M, C // 8, 8) > 0).to(torch.int32)
+  weights_ = (2 ** torch.arange(8, device="cuda", dtype=torch.int32)).view(1, 1, 8)
+  assert torch.equal(mbits.to(torch.int32), (want * weights_).sum(-1))
+  mis = [mi[v] for v in range(views)]
+  dg1, db1 = torch.zeros(C).cuda(), torch.zeros(C).cuda()
+  dg2, db2 = torch.full((C,), 3.0).cuda(), torch.full((C,), 3.0).cuda()
+  dy1, go1 = K.bn_bwd_fused(gin, out, y, mis, gamma, dg1, db1, False, True)
+  dy2, go2 = K.bn_bwd_fused_bits(gin, mbits, y, mis, gamma, dg2, db2, False, True)
+  assert torch.equal(dy1, dy2) and torch.equal(go1, go2) and torch.equal(dg1, dg2) and torch.equal(db1, db2)

@@ -267,3 +267,39 @@ def test_pair_batched_pass_equals_two_forward_calls(arch, cfg):
   for key in sd1:
     if "running" in key or "num_batches" in key:
       assert torch.allclose(sd1[key].float(), sd2[key].float(), rtol=1e-5, atol=1e-6), key
+
+
+@pytest.mark.unvalidated
+@pytest.mark.parametrize("cin,cout,stride,hw,n", [(64, 64, 1, 17, 5), (64, 128, 2, 17, 6), (256, 512, 2, 13, 4)])
+def test_bf16_block_with_relu_bitmask(cin, cout, stride, hw, n):
+  """Engine switch bn_bitmask: the residual block forward / backward must give what it gives with the switch off."""
+  import torch.nn as nn
+  from iic_b200.archs import _engine as E
+  from iic_b200.archs.cluster.residual import BasicBlock
+  from iic_b200._lib import BF16
+  ds = None
+  if stride != 1 or cin != cout:
+    ds = nn.Sequential(E.ConvParams(cin, cout, 1, stride, 0), E.BNParams(cout, False))
+  blk = BasicBlock(cin, cout, stride, ds, track_running_stats=False)
+  weights.fill_state_dict(blk, salt=13)
+  blk.cuda()
+  x = torch.relu(weights.normal("bits.x", (2 * n, cin, hw, hw))).permute(0, 2, 3, 1).contiguous().cuda().bfloat16()
+  oh = (hw + 2 - 3) // stride + 1
+  dout = weights.normal("bits.d", (2 * n, oh, oh, cout)).cuda().bfloat16()
+  results = []
+  for flag in (False, True):
+    prev = E.OPTIONS["bn_bitmask"]
+    E.OPTIONS["bn_bitmask"] = flag
+    try:
+      ctx = E._Ctx(BF16, True, True, groups=2)
+      out = E.block_forward(ctx, blk, x)
+      assert (len(ctx.mbits) == 1) == flag
+      sink = E.GradSink()
+      dx = E.block_backward(ctx, sink, ctx.saved[-1], dout)
+      results.append((out, dx, [sink.get(p).clone() for p in blk.parameters()]))
+    finally:
+      E.OPTIONS["bn_bitmask"] = prev
+  (o0, d0, g0), (o1, d1, g1) = results
+  assert torch.equal(o0, o1) and torch.equal(d0, d1)
+  for a, b in zip(g0, g1):
+    assert torch.equal(a, b)
