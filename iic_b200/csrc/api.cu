@@ -47,6 +47,9 @@ static Option g_opts[OPT_COUNT] = {
     // conv_halo_store: halo fprop/dgrad write their output tile with one TMA store out of a shared-memory staging
     // buffer (0 = 16-byte stores from the epilogue threads, one accumulator row per lane)
     {"conv_halo_store", "IIC_CONV_HALO_STORE", 1, 0, false},
+    // stem_bwd_v2: second version of the fused stem backward's wgrad pass (cooperative neighbourhood fetch + shuffles);
+    // written after the last GPU session of round 1, off until it has run on hardware
+    {"stem_bwd_v2", "IIC_STEM_BWD_V2", 0, 0, false},
 };
 
 int option(int id) {

@@ -248,6 +248,123 @@ __global__ void __launch_bounds__(256) stem_bwd_wgrad_kernel(StemBwdArgs p) {
   }
 }
 
+// Second version of pass B (option stem_bwd_v2): the input neighbourhood is fetched cooperatively by the half-warp and
+// broadcast with shuffles (v1 issued 16 * CIN dependent broadcast loads per thread and window and was latency bound).
+template <typename T, int CIN>
+__global__ void __launch_bounds__(256) stem_bwd_wgrad2_kernel(StemBwdArgs p) {
+  constexpr int K = CIN * 9;
+  __shared__ float red[8][16][4 * K];
+  const int Gv = gridDim.x / p.views, v = blockIdx.x / Gv, lb = blockIdx.x % Gv;
+  const int cg = threadIdx.x & 15, wslot = threadIdx.x >> 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long Wv = (long long)(p.n / p.views) * p.oh * p.ow;
+  const T* y = (const T*)p.y;
+  const T* dpool = (const T*)p.dpool;
+  const double invM = 1.0 / (double)((long long)(p.n / p.views) * p.H * p.W);  // BatchNorm rows per view
+  float sc[4], sh[4], cA[4], cB[4], cC[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = cg * 4 + j;
+    sc[j] = p.ss[v * 128 + c];
+    sh[j] = p.ss[v * 128 + 64 + c];
+    const float mean = p.mi[v * 128 + c], istd = p.mi[v * 128 + 64 + c];
+    const float m1 = (float)(p.sums[v * 128 + c] * invM), m2 = (float)(p.sums[v * 128 + 64 + c] * invM);
+    const float A = p.gamma[c] * istd;
+    cA[j] = A;
+    cB[j] = -A * m2 * istd;
+    cC[j] = -A * m1 + A * m2 * istd * mean;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 64) {  // d gamma = sum g*yhat, d beta = sum g, over all views
+    const int c = threadIdx.x;
+    double db = 0.0, dg = 0.0;
+    for (int q = 0; q < p.views; ++q) {
+      db += p.sums[q * 128 + c];
+      dg += p.sums[q * 128 + 64 + c];
+    }
+    if (p.dgamma) p.dgamma[c] = p.bn_accumulate ? p.dgamma[c] + (float)dg : (float)dg;
+    if (p.dbeta) p.dbeta[c] = p.bn_accumulate ? p.dbeta[c] + (float)db : (float)db;
+  }
+  float acc[4][K];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[j][k] = 0.f;
+  // Both half-warps of a warp iterate together (the shuffles below need all 32 lanes); a half-warp past the end mirrors
+  // its neighbour's window and contributes zeros.
+  const int hl = lane & 15;
+  for (long long wl0 = (long long)lb * 16 + (wslot & ~1); wl0 < Wv; wl0 += (long long)Gv * 16) {
+    const long long wl = wl0 + (wslot & 1);
+    const bool active = wl < Wv;
+    const long long wi = (long long)v * Wv + (active ? wl : wl0);
+    const int ox = (int)(wi % p.ow);
+    const long long t = wi / p.ow;
+    const int oy = (int)(t % p.oh);
+    const int img = (int)(t / p.oh);
+    // the window's pixels (iy0+1+qy, ix0+1+qx) share the 4 x 4 input neighbourhood starting at (iy0, ix0); lane hl of
+    // the half-warp fetches its element hl = r*4 + c (of each input channel): ONE load per lane instead of 16 * CIN
+    // dependent broadcast loads per thread, all in flight together with the activation loads below
+    const int iy0 = oy * 2 - p.pad - 1, ix0 = ox * 2 - p.pad - 1;
+    float xown[CIN];
+    {
+      const int iy = iy0 + (hl >> 2), ix = ix0 + (hl & 3);
+      const bool ok = (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci)
+        xown[ci] = ok ? __ldg(p.x + (((long long)img * CIN + ci) * p.H + iy) * p.W + ix) : 0.f;
+    }
+    float yv[4][4], g[4][4], dy[4][4];
+    bool valid[4];
+    window_grad<T>(y, dpool, img, oy, ox, p.H, p.W, p.oh, p.ow, p.pad, cg, sc, sh, yv, valid, g);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        dy[q][j] = (active && valid[q]) ? fmaf(cA[j], g[q][j], fmaf(cB[j], yv[q][j], cC[j])) : 0.f;
+    // element (r, c) meets pixel (qy, qx) under filter tap (a, b) = (r - qy, c - qx)
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float xv = __shfl_sync(0xffffffffu, xown[ci], (lane & 16) | (r * 4 + c));
+#pragma unroll
+          for (int qy = 0; qy < 2; ++qy) {
+            const int a = r - qy;
+            if (a < 0 || a > 2) continue;
+#pragma unroll
+            for (int qx = 0; qx < 2; ++qx) {
+              const int b = c - qx;
+              if (b < 0 || b > 2) continue;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[j][ci * 9 + a * 3 + b] = fmaf(dy[qy * 2 + qx][j], xv, acc[j][ci * 9 + a * 3 + b]);
+            }
+          }
+        }
+      }
+    }
+  }
+  // the two window slots of a warp (lanes l and l ^ 16), then the 8 warps, in fixed order
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[j][k] += __shfl_xor_sync(0xffffffffu, acc[j][k], 16);
+  if (lane < 16) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < K; ++k) red[warp][cg][j * K + k] = acc[j][k];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 64 * K; e += 256) {  // e = co * K + k  (== the OIHW index of the weight gradient)
+    const int co = e / K, k = e % K;
+    float t = 0.f;
+#pragma unroll
+    for (int wp = 0; wp < 8; ++wp) t += red[wp][co >> 2][(co & 3) * K + k];
+    p.partialB[(long long)blockIdx.x * 64 * K + e] = t;
+  }
+}
+
 // grad[i] (+)= sum over blocks of partial[b][i], fixed order
 __global__ void stem_bwd_dw_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad, int count, int nblk,
                                           int accumulate) {
@@ -299,10 +416,18 @@ static int stem_bwd_launch(const StemBwdPlan& pl, StemBwdArgs& a, int cin, float
   stem_bwd_fold_kernel<<<cdiv(a.views * 128, 8), 256, 0, st>>>(a.partialA, a.sums, pl.gridA / a.views, a.views);
   IIC_LAUNCH_CHECK();
   count_launch();
-  if (cin == 1)
-    stem_bwd_wgrad_kernel<T, 1><<<pl.gridB, 256, 0, st>>>(a);
-  else
-    stem_bwd_wgrad_kernel<T, 2><<<pl.gridB, 256, 0, st>>>(a);
+  const bool v2 = option(OPT_STEM_BWD_V2) != 0;
+  if (cin == 1) {
+    if (v2)
+      stem_bwd_wgrad2_kernel<T, 1><<<pl.gridB, 256, 0, st>>>(a);
+    else
+      stem_bwd_wgrad_kernel<T, 1><<<pl.gridB, 256, 0, st>>>(a);
+  } else {
+    if (v2)
+      stem_bwd_wgrad2_kernel<T, 2><<<pl.gridB, 256, 0, st>>>(a);
+    else
+      stem_bwd_wgrad_kernel<T, 2><<<pl.gridB, 256, 0, st>>>(a);
+  }
   IIC_LAUNCH_CHECK();
   count_launch();
   const int count = 64 * cin * 9;

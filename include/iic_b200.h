@@ -61,7 +61,9 @@ long long iic_launch_count(int reset);
  *   "dgrad_prefetch"  [IIC_DGRAD_PREFETCH=1]   dgrad epilogues fetch the residual-gradient addend ahead of its use
  *   "tc2_mt2"         [IIC_TC2_MT2=1]          128-channel fprop/dgrad: two 128-row tiles per weight k-block (0 = one)
  *   "conv_halo_store" [IIC_CONV_HALO_STORE=1]  halo fprop/dgrad: output tile staged in shared memory, one TMA store per
- *                                              work item (0 = per-thread 16-byte global stores)                      */
+ *                                              work item (0 = per-thread 16-byte global stores)
+ *   "stem_bwd_v2"     [IIC_STEM_BWD_V2=0]      iic_stem_bwd_fused: second version of the wgrad pass (not yet run on
+ *                                              hardware)                                                            */
 int iic_get_option(const char* name);
 int iic_set_option(const char* name, int value);
 

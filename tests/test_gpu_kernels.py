@@ -579,7 +579,7 @@ def test_halo_kernels_forced_exact_small_integers(n, h, variant):
 
 def test_runtime_options_roundtrip():
   K = _K()
-  for name in ("conv_halo", "conv_halo_wgrad", "tc_cpasync", "stem_quad", "dgrad_prefetch", "tc2_mt2", "conv_halo_store"):
+  for name in ("conv_halo", "conv_halo_wgrad", "tc_cpasync", "stem_quad", "dgrad_prefetch", "tc2_mt2", "conv_halo_store", "stem_bwd_v2"):
     v = K.get_option(name)
     with K.options(**{name: 0}):
       assert K.get_option(name) == 0
@@ -755,3 +755,15 @@ def test_bn_relu_bitmask_variant_equals_activation_mask(mode, shape, views):
   dy1, go1 = K.bn_bwd_fused(gin, out, y, mis, gamma, dg1, db1, False, True)
   dy2, go2 = K.bn_bwd_fused_bits(gin, mbits, y, mis, gamma, dg2, db2, False, True)
   assert torch.equal(dy1, dy2) and torch.equal(go1, go2) and torch.equal(dg1, dg2) and torch.equal(db1, db2)
+
+
+@pytest.mark.unvalidated
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("cin,hw,pool_pad,views,n", [(2, 32, 1, 2, 6), (2, 96, 1, 2, 4), (1, 24, 0, 1, 3), (2, 6, 0, 1, 3),
+                                                     (2, 18, 1, 1, 5)])
+def test_stem_backward_fused_v2(mode, cin, hw, pool_pad, views, n):
+  """Second version of the fused stem backward's wgrad pass (option stem_bwd_v2: half-warp cooperative fetch of the
+  input neighbourhood + shuffles); (2, 6, 0, 1, 3) has an odd number of windows, i.e. an idle half-warp at the tail."""
+  K = _K()
+  with K.options(stem_bwd_v2=1):
+    test_stem_backward_fused_matches_chain_and_autograd(mode, cin, hw, pool_pad, views, n)
