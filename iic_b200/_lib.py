@@ -72,6 +72,9 @@ _SIGS = {
                                  c_longlong, _P]),
   "iic_stem_fprop_stats_blocks": (c_int, [POINTER(ConvGeom), c_int, c_int]),
   "iic_stem_fprop_stats": (c_int, [_P, _P, _P, POINTER(ConvGeom), c_int, c_int, _P, _P]),
+  "iic_argmax_rows": (c_int, [_P, c_longlong, c_int, _P, _P]),
+  "iic_argmax_channels": (c_int, [_P, c_int, c_int, c_longlong, _P, _P]),
+  "iic_confusion_counts": (c_int, [_P, _P, _P, c_int, c_longlong, c_int, c_int, _P, c_int, _P]),
   "iic_avgpool": (c_int, [_P, c_int, _P, c_int, c_int, c_int, _P]),
   "iic_avgpool_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
   "iic_heads_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),

@@ -622,3 +622,40 @@ def adam_step(params, grads, exp_avgs, exp_avg_sqs, lr, beta1, beta2, eps, weigh
     sizes[i] = p.numel()
   check(_lib.lib().iic_adam_step(ptrs, sizes, T, float(lr), float(beta1), float(beta2), float(eps),
                                  float(weight_decay), int(step), _stream()), "iic_adam_step")
+
+
+# ---- evaluation ---------------------------------------------------------------------
+def argmax_rows(z):
+  """z [..., k] fp32 -> int32 [...]: torch.argmax(dim=-1) semantics (first maximum)."""
+  assert z.dtype == torch.float32
+  k = z.shape[-1]
+  rows = z.numel() // k
+  out = torch.empty(z.shape[:-1], device=z.device, dtype=torch.int32)
+  check(_lib.lib().iic_argmax_rows(_p(z.contiguous()), rows, k, _p(out), _stream()), "iic_argmax_rows")
+  return out
+
+
+def argmax_channels(x):
+  """x [n, k, h, w] fp32 -> int32 [n, h, w]: torch.argmax(dim=1) semantics."""
+  assert x.dtype == torch.float32 and x.dim() == 4
+  n, k, h, w = x.shape
+  out = torch.empty((n, h, w), device=x.device, dtype=torch.int32)
+  check(_lib.lib().iic_argmax_channels(_p(x.contiguous()), n, k, h * w, _p(out), _stream()), "iic_argmax_channels")
+  return out
+
+
+def confusion_counts(preds, targets, preds_k, targets_k, mask=None, counts=None):
+  """preds [S, n] (or [n]) int32, targets [n] int32, mask [n] uint8 | None -> counts [S, preds_k, targets_k] int64
+  (accumulated into `counts` if given)."""
+  if preds.dim() == 1:
+    preds = preds.unsqueeze(0)
+  S, n = preds.shape
+  assert preds.dtype == torch.int32 and targets.dtype == torch.int32 and targets.shape == (n,)
+  assert mask is None or (mask.dtype == torch.uint8 and mask.shape == (n,))
+  acc = counts is not None
+  if counts is None:
+    counts = torch.empty((S, preds_k, targets_k), device=preds.device, dtype=torch.int64)
+  assert counts.shape == (S, preds_k, targets_k) and counts.dtype == torch.int64
+  check(_lib.lib().iic_confusion_counts(_p(preds.contiguous()), _p(targets.contiguous()), _p(mask), S, n, preds_k,
+                                        targets_k, _p(counts), int(acc), _stream()), "iic_confusion_counts")
+  return counts

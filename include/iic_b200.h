@@ -272,6 +272,19 @@ int iic_bn_bwd_fused_bits(const void* g_in, const unsigned char* mask_bits, cons
                           float* dgamma, float* dbeta, int accumulate, int dtype, long long M_per_view, int C,
                           void* stream);
 
+/* ---- evaluation -- code/utils/cluster/cluster_eval.py:46-63 (torch.argmax per sub-head),
+ *      code/utils/segmentation/segmentation_eval.py:100-110 (per-pixel argmax over channels) and the
+ *      `int(((flat_preds == c1) * (flat_targets == c2)).sum())` double loops of code/utils/cluster/eval_metrics.py:9-53.
+ * iic_argmax_rows      z [rows][k] fp32 -> out[rows] int32 (ties: lowest index; NaN counts as the maximum, like torch)
+ * iic_argmax_channels  x [n][k][hw] fp32 (NCHW) -> out[n*hw] int32
+ * iic_confusion_counts counts[s][p][t] (+)= #{i < n : preds[s][i] == p, targets[i] == t, mask[i] != 0}; preds [S][n],
+ *                      targets [n] int32, mask [n] bytes or NULL, counts [S][preds_k][targets_k] int64; labels outside
+ *                      the ranges are ignored (the reference's loops never see them either). */
+int iic_argmax_rows(const float* z, long long rows, int k, int* out, void* stream);
+int iic_argmax_channels(const float* x_nchw, int n, int k, long long hw, int* out, void* stream);
+int iic_confusion_counts(const int* preds, const int* targets, const unsigned char* mask, int S, long long n, int preds_k,
+                         int targets_k, long long* counts, int accumulate, void* stream);
+
 /* AvgPool2d(full extent) + flatten (net5g.py:31-39,:56): x (n,hw,C) -> feat fp32 (n,C) */
 int iic_avgpool(const void* x, int dtype, float* feat, int n, int hw, int C, void* stream);
 int iic_avgpool_bwd(const float* dfeat, void* dx, int dtype, int n, int hw, int C, void* stream);
