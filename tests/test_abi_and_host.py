@@ -78,3 +78,22 @@ def test_missing_library_fails_loudly(monkeypatch):
   monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libiic_b200.so")
   with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
     _lib.lib()
+
+
+def test_default_kernel_variants_are_the_validated_set():
+  """The defaults that ship are the set measured fastest on a B200 with the whole GPU suite green
+  (profiles/r01_bench_v10_variants.md); variants written after the last GPU session must stay off until they have run
+  on hardware."""
+  import os
+  import subprocess
+  import sys
+  code = ("import json, iic_b200.kernels as K, iic_b200.archs._engine as E;"
+          "print(json.dumps([{n: K.get_option(n) for n in ('conv_halo','conv_halo_wgrad','conv_halo_store','tc2_mt2',"
+          "'dgrad_prefetch','stem_quad','tc_cpasync','stem_bwd_v2')}, E.OPTIONS]))")
+  env = {k: v for k, v in os.environ.items() if not k.startswith("IIC_")}
+  out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, check=True).stdout
+  import json
+  lib_opts, host_opts = json.loads(out.strip().splitlines()[-1])
+  assert lib_opts == {"conv_halo": 1, "conv_halo_wgrad": 1, "conv_halo_store": 1, "tc2_mt2": 1, "dgrad_prefetch": 1,
+                      "stem_quad": 2, "tc_cpasync": 0, "stem_bwd_v2": 0}
+  assert host_opts == {"bn_merged": True, "stem_stats": True, "pack_batched": True, "stem_bwd_fused": False, "bn_bitmask": False}
