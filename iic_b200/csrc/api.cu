@@ -50,6 +50,9 @@ static Option g_opts[OPT_COUNT] = {
     // stem_bwd_v2: second version of the fused stem backward's wgrad pass (cooperative neighbourhood fetch + shuffles);
     // written after the last GPU session of round 1, off until it has run on hardware
     {"stem_bwd_v2", "IIC_STEM_BWD_V2", 0, 0, false},
+    // conv_halo_stats: halo fprop accumulates the BatchNorm statistics per lane over all its work items and reduces
+    // across the warp once per CTA (0 = two transpose-reduces per 32-column chunk); not yet run on hardware
+    {"conv_halo_stats", "IIC_CONV_HALO_STATS", 0, 0, false},
 };
 
 int option(int id) {

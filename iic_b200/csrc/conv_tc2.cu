@@ -708,6 +708,222 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 
+// conv_halo_kernel specialised for fprop WITH BatchNorm statistics (option conv_halo_stats; not yet run on hardware, kept
+// as a separate copy so that the validated kernel above stays byte-identical): every epilogue lane keeps running sums of
+// its own accumulator rows (32 columns: sum, sum of squares) over all the work items of the CTA and the transpose-reduce
+// across the warp runs once per CTA and view instead of twice per 32-column chunk -- those shuffles paced the fprop
+// launches (36 % of the issue slots against 19 % for the dgrad, profiles/r01_ncu_halo.md).  No addend path.
+__global__ void __launch_bounds__(HALO_THREADS, 1)
+conv_halo_fstats_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, HaloParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t resb = (raw + 1023u) & ~1023u;           // [9][64 x 128 B] resident weights
+  const uint32_t staging = resb + 9u * 8192u;             // [256][128 B] bf16 output tile (tma_store only)
+  const uint32_t base = staging + (P.tma_store ? HALO_STAGING_BYTES : 0u);  // stages
+  const uint32_t bars = base + (uint32_t)P.stages * (uint32_t)P.stage_bytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };          // s < 4
+  auto empty_bar = [&](int s) { return bars + 8u * (4 + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (8 + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (10 + a); };
+  const uint32_t bres_bar = bars + 8u * 12;
+  uint8_t* bars_ptr = smem_raw + (bars - raw);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_ptr + 8 * 13);
+  float* stat = reinterpret_cast<float*>(bars_ptr + 128);  // [8 warps][2 views][2][32]
+  const bool do_stats = P.stat_partial != nullptr;
+  if (do_stats)
+    for (int i = threadIdx.x; i < 8 * 2 * 2 * 32; i += HALO_THREADS) stat[i] = 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 256);
+    }
+    mbar_init(bres_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (P.tma_store) tma_prefetch_desc(&tmO);
+  }
+  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 9) {
+    // =============================== TMA producer ============================================
+    if (blockIdx.x < P.total_tiles) {
+      if (lane == 0) mbar_expect_tx(bres_bar, 9u * 8192u);
+      __syncwarp();
+      if (lane < 9) tma_load_2d(resb + lane * 8192u, &tmB, bres_bar, (int)P.wtap[lane] * 64, 0);
+    }
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int w = blockIdx.x; w < P.total_tiles; w += gridDim.x, ++it) {
+        const int img = w / P.tiles_per_img;
+        const int y0 = (w - img * P.tiles_per_img) * P.R;
+        const int s = it % P.stages;
+        mbar_wait(empty_bar(s), ((it / P.stages) & 1u) ^ 1u);
+        mbar_expect_tx(full_bar(s), (uint32_t)P.box_bytes);
+        tma_load_4d(base + (uint32_t)s * (uint32_t)P.stage_bytes, &tmA, full_bar(s), 0, -1, y0 - 1, img);
+      }
+    }
+  } else if (warp == 8) {
+    // =============================== MMA issuer ==============================================
+    // Everything that feeds a descriptor stays warp-uniform (wrapping stage counter instead of a modulo, the
+    // nine tap shifts read from the kernel parameters by a fully unrolled loop): ptxas then keeps the
+    // descriptors in uniform registers and issues UTCHMMA back to back; a descriptor that passes through a
+    // vector register costs an ELECT / R2UR round trip per MMA, which at N = 64 (32 MMA cycles) is the bound.
+    constexpr uint32_t idesc = make_idesc(64, 0, 0);
+    uint32_t it = 0, s = 0, sphase = 0;
+    if (blockIdx.x < P.total_tiles) mbar_wait(bres_bar, 0);
+    const uint64_t bdesc_res = make_desc(resb, 16, 1024);
+    for (int w = blockIdx.x; w < P.total_tiles; w += gridDim.x, ++it) {
+      const uint32_t as = it & 1u;
+      mbar_wait(tempty_bar(as), ((it >> 1) & 1u) ^ 1u);
+      mbar_wait(full_bar(s), sphase);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint64_t adesc0 = make_desc(base + s * (uint32_t)P.stage_bytes, 16, 1024);
+        const uint32_t tmem_acc = tmem_base + as * 128u;
+        uint64_t bdesc0 = bdesc_res;
+        asm volatile("" : "+l"(bdesc0));  // opaque per tile: the 36 weight descriptors are rebuilt from one uniform
+                                          // base by immediate adds instead of living in 72 hoisted vector registers
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const uint64_t a_t = adesc0 + (uint64_t)((uint32_t)P.shift[t] * 8u);  // descriptor address unit = 16 B
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t ad = a_t + (uint64_t)((mt * (TC_BM * 128) + kk * 32) >> 4);
+              const uint64_t bd = bdesc0 + (uint64_t)((t * 8192 + kk * 32) >> 4);
+              umma_bf16(tmem_acc + mt * 64, ad, bd, idesc, (t > 0 || kk > 0) ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(empty_bar(s));
+        umma_commit(tfull_bar(as));
+      }
+      __syncwarp();
+      if (++s == (uint32_t)P.stages) {
+        s = 0;
+        sphase ^= 1u;
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 0-7) ======================================
+    const int quad = warp & 3, hsel = warp >> 2;
+    const bool ts = P.tma_store != 0;
+    uint8_t* staging_ptr = smem_raw + (staging - raw);
+    // running per-lane column sums (this lane's rows, 32 columns) of the current view
+    float rs1[32], rs2[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) rs1[e] = rs2[e] = 0.f;
+    int cur_view = -1;
+    auto flush_stats = [&](int vw) {
+      float t[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) t[e] = rs1[e];
+      warp_col_reduce(t, lane);
+      const float s1 = t[0];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) t[e] = rs2[e];
+      warp_col_reduce(t, lane);
+      float* sp = stat + ((warp * 2 + vw) * 2) * 32 + lane;
+      sp[0] += s1;
+      sp[32] += t[0];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) rs1[e] = rs2[e] = 0.f;
+    };
+    uint32_t it = 0;
+    for (int w = blockIdx.x; w < P.total_tiles; w += gridDim.x, ++it) {
+      const int img = w / P.tiles_per_img;
+      const int y0 = (w - img * P.tiles_per_img) * P.R;
+      const int view = img >= P.img_half ? 1 : 0;
+      const uint32_t as = it & 1u;
+      if (cur_view >= 0 && view != cur_view) flush_stats(cur_view);  // (the work items of a CTA change view at most once)
+      cur_view = view;
+      if (ts) {  // the previous work item's TMA store must have read the staging buffer before it is rewritten
+        if (threadIdx.x == 0) bulk_wait_read0();
+        named_bar_sync(1, 256);
+      }
+      // this thread's two accumulator rows (TMEM lane, +128 for the second MMA tile) -> output pixels
+      bool valid2[2];
+      long long pix2[2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int m = mt * TC_BM + quad * 32 + lane;
+        const int r = m / P.Wp, x = m - r * P.Wp;
+        valid2[mt] = r < P.R && x < P.W && y0 + r < P.H;
+        pix2[mt] = ((long long)img * P.H + y0 + r) * P.W + x;
+      }
+      mbar_wait(tfull_bar(as), (it >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const bool valid = valid2[mt];
+        uint32_t v[32];
+        tmem_ld32(tmem_base + as * 128u + mt * 64 + hsel * 32 + ((uint32_t)(quad * 32) << 16), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float f = valid ? __uint_as_float(v[e]) : 0.f;
+          rs1[e] += f;
+          rs2[e] = fmaf(f, f, rs2[e]);
+        }
+        if (valid || ts) {
+          const long long pix = pix2[mt];
+          const int m = mt * TC_BM + quad * 32 + lane;
+          __nv_bfloat16* o = P.out + pix * 64 + hsel * 32;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[qq * 8 + e]);
+            if (ts)  // staging row m, 16-byte chunk (hsel * 4 + qq) at its SWIZZLE_128B position
+              store8(reinterpret_cast<__nv_bfloat16*>(staging_ptr + m * 128 + (((hsel * 4 + qq) ^ (m & 7)) << 4)), f);
+            else
+              store8(o + qq * 8, f);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(as));
+      if (ts) {
+        fence_proxy_async();  // the generic-proxy writes above -> visible to the TMA unit
+        named_bar_sync(1, 256);
+        if (threadIdx.x == 0) {
+          tma_store_4d(&tmO, staging, 0, 0, y0, img);
+          bulk_commit();
+        }
+      }
+    }
+    if (cur_view >= 0) flush_stats(cur_view);
+    if (ts && threadIdx.x == 0) bulk_wait0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 256);
+  if (do_stats)
+    for (int i = threadIdx.x; i < 4 * 64; i += HALO_THREADS) {  // i = (view, q, col); fixed warp order
+      const int col = i & 63, q = (i >> 6) & 1, view = i >> 7;
+      const int h = col >> 5, l = col & 31;
+      float t = 0.f;
+      for (int qd = 0; qd < 4; ++qd) t += stat[(((h * 4 + qd) * 2 + view) * 2 + q) * 32 + l];
+      P.stat_partial[(long long)blockIdx.x * 4 * 64 + i] = t;
+    }
+}
+
+
+
 // ---- halo wgrad: dW[tap][ci][co] = sum_p x[p + tap shift][ci] * dy[p][co] on the padded grid ----------------
 // One work item = R output rows of one image: the x box (R+2 rows x Wp, zero-filled borders) and the dy box
 // (R rows x Wp; its two padding columns are zero-filled, so padding positions contribute nothing) are loaded
@@ -1013,8 +1229,13 @@ static int launch_halo(const HaloPlan& hp, const __nv_bfloat16* src, int H, int 
   Q.addend_prefetch = P.addend_prefetch;
   Q.tma_store = hp.tma_store;
   Q.img_half = (P.stat_half < P.rows) ? nimg / 2 : nimg;
-  IIC_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hp.smem));
-  conv_halo_kernel<<<tc2_grid(hp.total_tiles), HALO_THREADS, hp.smem, st>>>(tmA, tmB, tmO, Q);
+  if (option(OPT_HALO_STATS) != 0 && Q.stat_partial != nullptr && Q.addend == nullptr) {
+    IIC_CUDA(cudaFuncSetAttribute(conv_halo_fstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hp.smem));
+    conv_halo_fstats_kernel<<<tc2_grid(hp.total_tiles), HALO_THREADS, hp.smem, st>>>(tmA, tmB, tmO, Q);
+  } else {
+    IIC_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hp.smem));
+    conv_halo_kernel<<<tc2_grid(hp.total_tiles), HALO_THREADS, hp.smem, st>>>(tmA, tmB, tmO, Q);
+  }
   IIC_LAUNCH_CHECK();
   count_launch();
   return IIC_OK;

@@ -579,7 +579,7 @@ def test_halo_kernels_forced_exact_small_integers(n, h, variant):
 
 def test_runtime_options_roundtrip():
   K = _K()
-  for name in ("conv_halo", "conv_halo_wgrad", "tc_cpasync", "stem_quad", "dgrad_prefetch", "tc2_mt2", "conv_halo_store", "stem_bwd_v2"):
+  for name in ("conv_halo", "conv_halo_wgrad", "tc_cpasync", "stem_quad", "dgrad_prefetch", "tc2_mt2", "conv_halo_store", "stem_bwd_v2", "conv_halo_stats"):
     v = K.get_option(name)
     with K.options(**{name: 0}):
       assert K.get_option(name) == 0
@@ -767,3 +767,14 @@ def test_stem_backward_fused_v2(mode, cin, hw, pool_pad, views, n):
   K = _K()
   with K.options(stem_bwd_v2=1):
     test_stem_backward_fused_matches_chain_and_autograd(mode, cin, hw, pool_pad, views, n)
+
+
+@pytest.mark.unvalidated
+@pytest.mark.parametrize("n,h", [(2, 13), (4, 49), (2, 96), (6, 5), (3, 30)])
+@pytest.mark.parametrize("variant", ["tma-store", "direct-store"])
+def test_halo_fprop_with_per_lane_running_statistics(n, h, variant):
+  """conv_halo_stats = 1: the halo fprop keeps per-lane running BatchNorm sums over a CTA's work items (one warp
+  reduction per CTA and view); statistics and output must equal the per-chunk variant exactly on small integers."""
+  K = _K()
+  with K.options(conv_halo_stats=1):
+    test_halo_kernels_forced_exact_small_integers(n, h, variant)

@@ -27,7 +27,7 @@ stamp "1 suite, serial, as the driver runs it rc=$?"; tail -3 $O/r2_tests_serial
 IIC_RUN_UNVALIDATED=1 timeout 600 python -m pytest tests -m "gpu and unvalidated" -q --tb=short -p no:cacheprovider -n 4 --timeout 200 > $O/r2_tests_unvalidated.log 2>&1
 stamp "2 unvalidated variants rc=$?"; grep -E "^(FAILED|ERROR)|passed|failed" $O/r2_tests_unvalidated.log | tail -30
 timeout 300 python bench.py > $O/r2_bench.json 2> $O/r2_bench.err; stamp "3 bench default rc=$?"; tail -2 $O/r2_bench.err; summ $O/r2_bench.json
-for v in IIC_BN_BITMASK=1 IIC_STEM_BWD_FUSED=1 "IIC_STEM_BWD_FUSED=1 IIC_STEM_BWD_V2=1"; do
+for v in IIC_BN_BITMASK=1 IIC_CONV_HALO_STATS=1 IIC_STEM_BWD_FUSED=1 "IIC_STEM_BWD_FUSED=1 IIC_STEM_BWD_V2=1"; do
   f=$(echo "$v" | tr ' =' '__')
   env $v timeout 200 python bench.py --steps 5 --no-cpu-baseline > $O/r2_bench_$f.json 2> $O/r2_bench_$f.err; stamp "4 bench $v rc=$?"; summ $O/r2_bench_$f.json
 done
