@@ -1,0 +1,29 @@
+"""Checkpoint wire format of xu-ji/IIC.
+
+The reference saves ``net.module.state_dict()`` / ``optimiser.state_dict()`` with ``torch.save``
+(code/scripts/cluster/cluster_sobel_twohead.py:425-438) and restores them with
+``net.load_state_dict(torch.load(path, map_location=lambda storage, loc: storage))`` (:176-178) before ``net.cuda()``.
+The iic_b200 networks are ``nn.Module``s holding parameters under the reference's names, shapes and (torch) layouts, and
+``FusedAdam`` keeps torch's Adam state layout, so those two calls work unchanged.  This module only deals with what differs
+between the files found in the wild: pickles written by Python 2 (the published models) and state dicts saved from a
+``DataParallel`` wrapper (keys prefixed with ``module.``)."""
+import torch
+
+
+def load_reference_state_dict(path):
+  """torch.load for a reference checkpoint: CPU tensors, Python-2 pickles accepted, ``module.`` prefixes removed."""
+  try:
+    sd = torch.load(path, map_location="cpu", weights_only=False)
+  except UnicodeDecodeError:  # written by Python 2
+    sd = torch.load(path, map_location="cpu", weights_only=False, encoding="latin1")
+  if not isinstance(sd, dict):
+    raise AssertionError("%s does not hold a state dict" % path)
+  if sd and all(isinstance(k, str) and k.startswith("module.") for k in sd):
+    sd = type(sd)((k[len("module."):], v) for k, v in sd.items())
+  return sd
+
+
+def load_into(net, path, strict=True):
+  """``net.load_state_dict`` of a reference checkpoint; raises on missing / unexpected keys or shape mismatches (strict),
+  exactly like the reference's own call."""
+  return net.load_state_dict(load_reference_state_dict(path), strict=strict)
