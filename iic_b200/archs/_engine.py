@@ -246,19 +246,38 @@ def _bn_relu_maxpool_bwd(ctx, y, ss, dpool, pad):
 
 
 class GradSink(object):
-  """Collects parameter gradients produced by a trunk backward, keyed by parameter object."""
+  """Collects parameter gradients produced by a trunk backward, keyed by parameter object.
+
+  A parameter whose ``.grad`` is a view of a ``GradArena`` (iic_b200/arena.py) is accumulated in place -- the kernels
+  add into the arena, autograd gets ``None`` for it -- and reported to the arena once the kernels of the current
+  backward record are enqueued (``commit``), which is what lets the arena all-reduce a bucket while the backward of
+  the earlier layers is still running."""
 
   def __init__(self):
     self.g = {}
+    self.direct = {}
+    self._touched = []
 
   def buf(self, p):
+    if id(p) in self.direct:
+      return p.grad, True
     if id(p) not in self.g:
+      arena = getattr(p, "_iic_arena", None)
+      if arena is not None and arena.holds(p):
+        self.direct[id(p)] = arena
+        self._touched.append(p)
+        return p.grad, True
       self.g[id(p)] = torch.empty_like(p, dtype=torch.float32)
       return self.g[id(p)], False
     return self.g[id(p)], True
 
+  def commit(self):
+    for p in self._touched:
+      self.direct[id(p)].mark(p)
+    self._touched = []
+
   def get(self, p):
-    return self.g.get(id(p))
+    return None if id(p) in self.direct else self.g.get(id(p))
 
 
 def _bn_backward(ctx, sink, bn, g_in, act, y, mi, want_g_out, mask_ss=None):
@@ -426,6 +445,8 @@ class TrunkFunction(torch.autograd.Function):
   @staticmethod
   def forward(ctx, trunk, run, need_grad, groups, x, *params):
     ectx = _Ctx(_PRECISIONS[trunk.precision], trunk.training, need_grad, groups)
+    # the packed dgrad weights live in per-module buffers that the next forward overwrites: remember the versions
+    ectx.wversions = [(p, p._version) for p in params if p.dim() == 4] if need_grad else []
     _prepack(trunk, ectx)
     feat, finisher = run(ectx, x)
     ctx.ectx, ctx.finisher, ctx.params = ectx, finisher, params
@@ -434,11 +455,20 @@ class TrunkFunction(torch.autograd.Function):
   @staticmethod
   def backward(ctx, dfeat):
     ectx = ctx.ectx
+    if ectx.saved is None:
+      raise RuntimeError("iic_b200: this trunk forward has already been differentiated once; its saved activations "
+                         "were released (retain_graph / double backward are not supported -- run the forward again)")
+    for p, v in ectx.wversions:
+      if p._version != v:
+        raise RuntimeError("iic_b200: a convolution weight was modified in place between this forward and its backward; "
+                           "the packed tensor-core copies of the weights belong to the old values (run forward -> "
+                           "backward -> optimiser.step() in that order)")
     sink = GradSink()
     d = ctx.finisher(dfeat)
     for rec in reversed(ectx.saved):
       d = _BACKWARD[rec[0]](ectx, sink, rec, d)
-    ectx.saved = []
+      sink.commit()
+    ectx.saved = None
     ectx.wcache = {}
     grads = tuple(sink.get(p) for p in ctx.params)
     return (None, None, None, None, None) + grads

@@ -631,7 +631,8 @@ def argmax_rows(z):
   k = z.shape[-1]
   rows = z.numel() // k
   out = torch.empty(z.shape[:-1], device=z.device, dtype=torch.int32)
-  check(_lib.lib().iic_argmax_rows(_p(z.contiguous()), rows, k, _p(out), _stream()), "iic_argmax_rows")
+  z = z.contiguous()  # bound to a local: the pointer must outlive the enqueue
+  check(_lib.lib().iic_argmax_rows(_p(z), rows, k, _p(out), _stream()), "iic_argmax_rows")
   return out
 
 
@@ -640,7 +641,8 @@ def argmax_channels(x):
   assert x.dtype == torch.float32 and x.dim() == 4
   n, k, h, w = x.shape
   out = torch.empty((n, h, w), device=x.device, dtype=torch.int32)
-  check(_lib.lib().iic_argmax_channels(_p(x.contiguous()), n, k, h * w, _p(out), _stream()), "iic_argmax_channels")
+  x = x.contiguous()
+  check(_lib.lib().iic_argmax_channels(_p(x), n, k, h * w, _p(out), _stream()), "iic_argmax_channels")
   return out
 
 
@@ -656,6 +658,7 @@ def confusion_counts(preds, targets, preds_k, targets_k, mask=None, counts=None)
   if counts is None:
     counts = torch.empty((S, preds_k, targets_k), device=preds.device, dtype=torch.int64)
   assert counts.shape == (S, preds_k, targets_k) and counts.dtype == torch.int64
-  check(_lib.lib().iic_confusion_counts(_p(preds.contiguous()), _p(targets.contiguous()), _p(mask), S, n, preds_k,
+  preds, targets = preds.contiguous(), targets.contiguous()
+  check(_lib.lib().iic_confusion_counts(_p(preds), _p(targets), _p(mask), S, n, preds_k,
                                         targets_k, _p(counts), int(acc), _stream()), "iic_confusion_counts")
   return counts

@@ -10,12 +10,23 @@ between the files found in the wild: pickles written by Python 2 (the published 
 import torch
 
 
-def load_reference_state_dict(path):
-  """torch.load for a reference checkpoint: CPU tensors, Python-2 pickles accepted, ``module.`` prefixes removed."""
+def _load(path, weights_only):
   try:
-    sd = torch.load(path, map_location="cpu", weights_only=False)
+    return torch.load(path, map_location="cpu", weights_only=weights_only)
   except UnicodeDecodeError:  # written by Python 2
-    sd = torch.load(path, map_location="cpu", weights_only=False, encoding="latin1")
+    return torch.load(path, map_location="cpu", weights_only=weights_only, encoding="latin1")
+
+
+def load_reference_state_dict(path, trusted=False):
+  """torch.load for a reference checkpoint: CPU tensors, Python-2 pickles accepted, ``module.`` prefixes removed.
+  A state dict is tensors in an (Ordered)dict, so the restricted unpickler (``weights_only=True``) is enough; the full
+  pickle machinery -- which executes code from the file -- is only used when the caller says the file is ``trusted``."""
+  try:
+    sd = _load(path, True)
+  except Exception:  # noqa: BLE001 -- pickle.UnpicklingError and friends; the message of the retry is the useful one
+    if not trusted:
+      raise
+    sd = _load(path, False)
   if not isinstance(sd, dict):
     raise AssertionError("%s does not hold a state dict" % path)
   if sd and all(isinstance(k, str) and k.startswith("module.") for k in sd):

@@ -69,3 +69,24 @@ def test_adam_state_interchanges_with_torch():
     assert float(out["state"][i]["step"]) == 1.0
   back = torch.optim.Adam(ps, lr=1e-4)
   back.load_state_dict(out)
+
+
+def test_adam_state_written_by_torch_0_4_1_loads():
+  """the reference's optimiser checkpoints (torch 0.4.1) keep `step` as a Python int and an `amsgrad`
+  key in the param groups; FusedAdam.load_state_dict must accept them (resume path, cluster_sobel_twohead.py:187)."""
+  from iic_b200.optim import FusedAdam
+  ps = [torch.nn.Parameter(torch.randn(4, 3)), torch.nn.Parameter(torch.randn(5))]
+  legacy = {"state": {i: {"step": 7, "exp_avg": torch.randn_like(p), "exp_avg_sq": torch.rand_like(p)}
+                      for i, p in enumerate(ps)},
+            "param_groups": [{"lr": 1e-4, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False,
+                              "params": [0, 1]}]}
+  ours = FusedAdam(ps, lr=1e-3)
+  ours.load_state_dict(legacy)
+  for p in ps:
+    st = ours.state[p]
+    assert torch.is_tensor(st["step"]) and float(st["step"]) == 7.0
+  assert ours.param_groups[0]["lr"] == 1e-4
+  # a pickled optimiser (torch.save(optimiser)) goes through __setstate__ as well
+  import pickle
+  again = pickle.loads(pickle.dumps(ours))
+  assert all(torch.is_tensor(again.state[p]["step"]) for p in again.param_groups[0]["params"])
