@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libiic_b200.so")
 
 F32, BF16 = 0, 1
+TF32, TF32X3 = 2, 3  # conv compute modes on F32 storage (include/iic_b200.h)
 PHASE_FUSED, PHASE_PARTIAL, PHASE_FINISH = 0, 1, 2
 
 

@@ -9,7 +9,10 @@ head group runs the hand-written backward.
 Precision modes (``net.precision``):
   "bf16" (default): NHWC bf16 activations, tcgen05 bf16 MMA with fp32 TMEM accumulation;
                     BN statistics, parameters, heads and losses stay fp32.
-  "fp32":           NHWC fp32 activations, fp32 SIMT convolutions (reference precision).
+  "tf32":           NHWC fp32 activations, tcgen05 kind::tf32 convolutions (conv_tf32.cu).
+  "tf32x3":         the same kernel with the 3xTF32 error-compensated operand split: fp32-grade results from the
+                    tensor cores -- the mode that meets the fp32 tolerance of the reference.
+  "fp32":           NHWC fp32 activations, fp32 SIMT convolutions (reference precision; slow, the on-device checker).
 """
 import math
 
@@ -19,9 +22,10 @@ import torch
 import torch.nn as nn
 
 from .. import kernels as K
-from .._lib import BF16, F32
+from .._lib import BF16, F32, TF32, TF32X3
 
-_PRECISIONS = {"bf16": BF16, "fp32": F32}
+# precision -> (storage dtype of the activations, compute mode of the convolutions)
+_PRECISIONS = {"bf16": (BF16, BF16), "fp32": (F32, F32), "tf32": (F32, TF32), "tf32x3": (F32, TF32X3)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -103,8 +107,9 @@ def initialize_weights(net, mode):
 class _Ctx(object):
   """Per-forward record of what backward needs."""
 
-  def __init__(self, dt, training, need_grad, groups=1):
+  def __init__(self, dt, training, need_grad, groups=1, cdt=None):
     self.dt, self.training, self.need_grad = dt, training, need_grad
+    self.cdt = dt if cdt is None else cdt  # compute mode of the convolutions (TF32 / TF32X3 on F32 storage)
     # groups > 1: the batch is the concatenation of `groups` views (x, x_tf) pushed through the trunk in
     # ONE pass; BatchNorm statistics stay per view, exactly as in the reference's two separate forward
     # calls (cluster_sobel_twohead.py:320-321), everything else sees one batch of groups*n images.
@@ -180,7 +185,7 @@ def _conv_bn(ctx, conv, bn, x, g):
   if ctx.dt == BF16 and (ctx.training or not bn.track_running_stats):
     fused = K.conv_fprop_stats(x, ctx.packed(conv, 0), g, ctx.dt, ctx.groups)
   if fused is None:
-    y = K.conv_fprop(x, ctx.packed(conv, 0), g, ctx.dt)
+    y = K.conv_fprop(x, ctx.packed(conv, 0), g, ctx.cdt)
     ss, mi = _bn_stats(ctx, bn, y)
     return y, ss, mi
   y, partial, nblk = fused
@@ -301,7 +306,7 @@ def _bn_backward(ctx, sink, bn, g_in, act, y, mi, want_g_out, mask_ss=None):
 
 def _conv_wgrad(ctx, sink, conv, x, dy, g):
   gw, acc = sink.buf(conv.weight)
-  K.conv_wgrad(x, dy, g, ctx.dt, gw, acc)
+  K.conv_wgrad(x, dy, g, ctx.cdt, gw, acc)
 
 
 # ---- stem: conv(NCHW input) + BN + ReLU [+ MaxPool(2,2,pad)] -----------------------------------
@@ -365,7 +370,7 @@ def convbn_backward(ctx, sink, rec, d_out):
   else:
     dy, _ = _bn_backward(ctx, sink, bn, d_out, None, y, mi, False, mask_ss=ss)
   _conv_wgrad(ctx, sink, conv, x, dy, g)
-  return K.conv_dgrad(dy, ctx.packed(conv, 1), g, ctx.dt)
+  return K.conv_dgrad(dy, ctx.packed(conv, 1), g, ctx.cdt)
 
 
 # ---- residual BasicBlock (residual.py:10-43) -----------------------------------------------------
@@ -401,16 +406,16 @@ def block_backward(ctx, sink, rec, d_out):
   else:
     dy2, gres = _bn_backward(ctx, sink, blk.bn2, d_out, out, y2, mi2, True)
   _conv_wgrad(ctx, sink, blk.conv2, a1, dy2, g2)
-  da1 = K.conv_dgrad(dy2, ctx.packed(blk.conv2, 1), g2, ctx.dt)
+  da1 = K.conv_dgrad(dy2, ctx.packed(blk.conv2, 1), g2, ctx.cdt)
   dy1, _ = _bn_backward(ctx, sink, blk.bn1, da1, None, y1, mi1, False, mask_ss=ss1)  # a1 = relu(bn1(y1))
   _conv_wgrad(ctx, sink, blk.conv1, x, dy1, g1)
   if blk.downsample is not None:
     dconv, dbn = blk.downsample[0], blk.downsample[1]
     dyd, _ = _bn_backward(ctx, sink, dbn, gres, None, yd, mid, False)
     _conv_wgrad(ctx, sink, dconv, x, dyd, gd)
-    dxd = K.conv_dgrad(dyd, ctx.packed(dconv, 1), gd, ctx.dt)
-    return K.conv_dgrad(dy1, ctx.packed(blk.conv1, 1), g1, ctx.dt, addend=dxd)
-  return K.conv_dgrad(dy1, ctx.packed(blk.conv1, 1), g1, ctx.dt, addend=gres)
+    dxd = K.conv_dgrad(dyd, ctx.packed(dconv, 1), gd, ctx.cdt)
+    return K.conv_dgrad(dy1, ctx.packed(blk.conv1, 1), g1, ctx.cdt, addend=dxd)
+  return K.conv_dgrad(dy1, ctx.packed(blk.conv1, 1), g1, ctx.cdt, addend=gres)
 
 
 def _prepack(trunk, ectx):
@@ -444,7 +449,7 @@ class TrunkFunction(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, trunk, run, need_grad, groups, x, *params):
-    ectx = _Ctx(_PRECISIONS[trunk.precision], trunk.training, need_grad, groups)
+    ectx = _Ctx(_PRECISIONS[trunk.precision][0], trunk.training, need_grad, groups, cdt=_PRECISIONS[trunk.precision][1])
     # the packed dgrad weights live in per-module buffers that the next forward overwrites: remember the versions
     ectx.wversions = [(p, p._version) for p in params if p.dim() == 4] if need_grad else []
     _prepack(trunk, ectx)
@@ -478,7 +483,7 @@ def run_trunk(trunk, run, x, groups=1):
   if not x.is_cuda:
     raise RuntimeError("iic_b200 networks run on CUDA tensors only (no CPU fallback; the CPU restatement in "
                        "oracle/ is a test checker)")
-  assert trunk.precision in _PRECISIONS, "precision must be 'bf16' or 'fp32'"
+  assert trunk.precision in _PRECISIONS, "precision must be one of %s" % sorted(_PRECISIONS)
   params = [p for p in trunk.parameters()]
   # (inside Function.forward grad mode is off and needs_input_grad ignores torch.no_grad())
   need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)

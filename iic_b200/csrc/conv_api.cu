@@ -1,5 +1,6 @@
-// Dispatch of the conv entry points onto the two kernels: IIC_F32 -> fp32 SIMT implicit GEMM
-// (conv_simt.cu), IIC_BF16 -> tcgen05 implicit GEMM (conv_tc.cu).  This is a precision mode of
+// Dispatch of the conv entry points onto the kernels: IIC_F32 -> fp32 SIMT implicit GEMM (conv_simt.cu),
+// IIC_BF16 -> tcgen05 kind::f16 implicit GEMM on bf16 activations (conv_tc2.cu), IIC_TF32 / IIC_TF32X3 -> tcgen05
+// kind::tf32 on fp32 activations, plain or 3xTF32 error-compensated (conv_tf32.cu).  These are precision modes of
 // one sm_100a code base, not a backend switch: there is no CPU or library fallback.
 #include <stdlib.h>
 
@@ -27,9 +28,20 @@ int tc2_conv_gather_gemm_stats(const __nv_bfloat16* src, int srcH, int srcW, int
                                cudaStream_t st);
 int tc2_conv_dgrad_s2(const __nv_bfloat16* dy, const __nv_bfloat16* wpacked_t, const __nv_bfloat16* addend,
                       __nv_bfloat16* dx, const iic_conv_geom* g, cudaStream_t st);
+int tf32_conv_gather_gemm(const float* src, int srcH, int srcW, int srcC, int rowH, int rowW, int nimg, const iic_conv_geom* g,
+                          int transposed, const float* wpacked, int N, const float* addend, float* out, int split,
+                          cudaStream_t st);
+int tf32_conv_dgrad_s2(const float* dy, const float* wpacked_t, const float* addend, float* dx, const iic_conv_geom* g, int split,
+                       cudaStream_t st);
+long long tf32_conv_wgrad_workspace(const iic_conv_geom* g);
+int tf32_conv_wgrad(const float* x, const float* dy, float* dw, float* ws, const iic_conv_geom* g, int split, cudaStream_t st);
 }  // namespace iic
 
 using namespace iic;
+
+// IIC_TF32 / IIC_TF32X3: fp32 storage, tcgen05 kind::tf32 (conv_tf32.cu), plain or 3xTF32 error-compensated
+static bool is_tf32(int dtype) { return dtype == IIC_TF32 || dtype == IIC_TF32X3; }
+static int tf32_split(int dtype) { return dtype == IIC_TF32X3 ? 3 : 1; }
 
 // The TMA-fed persistent kernel (conv_tc2.cu) is the default tensor-core path; IIC_TC_CPASYNC=1 selects the
 // cp.async-fed kernel (conv_tc.cu) everywhere (kept for stride-2 dgrad and for A/B measurements).
@@ -54,6 +66,9 @@ extern "C" int iic_conv_fprop(const void* x, const void* w_packed, void* y, cons
   IIC_REQUIRE(x && w_packed && y, IIC_ERR_BAD_ARG, "iic_conv_fprop: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == IIC_F32) return simt_conv_fprop((const float*)x, (const float*)w_packed, (float*)y, g, st);
+  if (is_tf32(dtype))
+    return tf32_conv_gather_gemm((const float*)x, g->h, g->w, g->cin, g->oh, g->ow, g->n, g, 0, (const float*)w_packed, g->cout,
+                                 nullptr, (float*)y, tf32_split(dtype), st);
   if (dtype == IIC_BF16)
     return (use_tma() ? tc2_conv_gather_gemm : tc_conv_gather_gemm)(
         (const __nv_bfloat16*)x, g->h, g->w, g->cin, g->oh, g->ow, g->n, g, 0, (const __nv_bfloat16*)w_packed, g->cout,
@@ -70,6 +85,12 @@ extern "C" int iic_conv_dgrad(const void* dy, const void* w_packed_t, const void
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == IIC_F32)
     return simt_conv_dgrad((const float*)dy, (const float*)w_packed_t, (const float*)addend, (float*)dx, g, st);
+  if (is_tf32(dtype) && g->stride == 2 && g->dil == 1 && g->kh == g->kw)
+    return tf32_conv_dgrad_s2((const float*)dy, (const float*)w_packed_t, (const float*)addend, (float*)dx, g, tf32_split(dtype),
+                              st);
+  if (is_tf32(dtype))
+    return tf32_conv_gather_gemm((const float*)dy, g->oh, g->ow, g->cout, g->h, g->w, g->n, g, 1, (const float*)w_packed_t,
+                                 g->cin, (const float*)addend, (float*)dx, tf32_split(dtype), st);
   if (dtype == IIC_BF16 && use_tma() && g->stride == 2 && g->dil == 1 && g->kh == g->kw)
     return tc2_conv_dgrad_s2((const __nv_bfloat16*)dy, (const __nv_bfloat16*)w_packed_t, (const __nv_bfloat16*)addend,
                              (__nv_bfloat16*)dx, g, st);
@@ -84,6 +105,7 @@ extern "C" int iic_conv_dgrad(const void* dy, const void* w_packed_t, const void
 extern "C" long long iic_conv_wgrad_workspace(const iic_conv_geom* g, int dtype) {
   if (g == nullptr) return -1;
   if (dtype == IIC_BF16) return use_tma() ? tc2_conv_wgrad_workspace(g) : tc_conv_wgrad_workspace(g);
+  if (is_tf32(dtype)) return tf32_conv_wgrad_workspace(g);
   return simt_conv_wgrad_workspace(g);
 }
 
@@ -94,6 +116,8 @@ extern "C" int iic_conv_wgrad(const void* x, const void* dy, float* dw_packed, v
   IIC_REQUIRE(x && dy && dw_packed && workspace, IIC_ERR_BAD_ARG, "iic_conv_wgrad: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == IIC_F32) return simt_conv_wgrad((const float*)x, (const float*)dy, dw_packed, (float*)workspace, g, st);
+  if (is_tf32(dtype))
+    return tf32_conv_wgrad((const float*)x, (const float*)dy, dw_packed, (float*)workspace, g, tf32_split(dtype), st);
   if (dtype == IIC_BF16)
     return (use_tma() ? tc2_conv_wgrad : tc_conv_wgrad)((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw_packed,
                                                         (float*)workspace, g, st);

@@ -9,9 +9,10 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import BF16, F32, ConvGeom, check
+from ._lib import BF16, F32, TF32, TF32X3, ConvGeom, check
 
-_TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16}
+# storage dtype per mode (TF32 / TF32X3 are compute modes of the convolutions on fp32 storage)
+_TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, TF32: torch.float32, TF32X3: torch.float32}
 
 
 def torch_dtype(dt):

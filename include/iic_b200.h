@@ -18,7 +18,13 @@
  *     row-major [M = n*h*w][C]) in one of two storage dtypes:
  *       IIC_F32  (fp32 storage, fp32 SIMT convolutions  -- reference-precision mode)
  *       IIC_BF16 (bf16 storage, tcgen05 bf16 MMA with fp32 TMEM accumulation)
- *     Parameters, BN statistics, the heads and every loss are fp32 in both modes.
+ *     The convolution entry points (iic_conv_fprop / _dgrad / _wgrad / _wgrad_workspace) additionally accept two
+ *     COMPUTE modes on IIC_F32 storage (every tensor is fp32, weights packed with dst_dtype IIC_F32):
+ *       IIC_TF32   tcgen05 kind::tf32 (10-bit mantissa operands, fp32 TMEM accumulation)
+ *       IIC_TF32X3 the same tensor-core kernel with each operand split hi + lo in shared memory and three MMAs
+ *                  per product (3xTF32): fp32-grade results (what `north_star` calls "a stated fp32 tolerance":
+ *                  1e-5 relative per convolution) at ~10x the SIMT kernel's rate.
+ *     Parameters, BN statistics, the heads and every loss are fp32 in all modes.
  *   - entry points are re-entrant; the only global state is a per-device cache of
  *     device properties.
  */
@@ -38,6 +44,8 @@ extern "C" {
 
 #define IIC_F32 0
 #define IIC_BF16 1
+#define IIC_TF32 2   /* conv entry points only: fp32 storage, tcgen05 kind::tf32               */
+#define IIC_TF32X3 3 /* conv entry points only: fp32 storage, error-compensated 3xTF32 split   */
 
 /* phases of the joint/MI kernels (multi-GPU splits at the all-reduce of the joint) */
 #define IIC_PHASE_FUSED 0    /* partial joint -> reduce -> MI -> gradients, one launch      */
@@ -155,8 +163,9 @@ int iic_pack_weights_batched(const iic_pack_job* jobs_device, int njobs, int dst
 int iic_unpack_wgrad(const float* dw_packed, float* grad_oihw, int accumulate, int cout, int cin, int kh,
                      int kw, void* stream);
 
-/* fprop: y[M][cout] = conv(x, w).  dtype IIC_F32 -> SIMT fp32 kernel; IIC_BF16 -> tcgen05.
- * w is the kind-0 packed weight in the same dtype.  y has dtype `dtype`. */
+/* fprop: y[M][cout] = conv(x, w).  dtype IIC_F32 -> SIMT fp32 kernel; IIC_BF16 -> tcgen05 kind::f16;
+ * IIC_TF32 / IIC_TF32X3 -> tcgen05 kind::tf32 on fp32 tensors (cin % 32 == 0, cout % 64 == 0).
+ * w is the kind-0 packed weight in the storage dtype.  y has the storage dtype. */
 int iic_conv_fprop(const void* x, const void* w_packed, void* y, const iic_conv_geom* g, int dtype,
                    void* stream);
 /* fprop with the BatchNorm batch statistics of y fused into the epilogue (IIC_BF16 only; otherwise
