@@ -41,6 +41,7 @@ _SIGS = {
   "iic_seg_corr_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
   "iic_box_filter": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
   "iic_sobel": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+  "iic_grey_sobel": (c_int, [_P, c_int, _P, c_int, c_int, c_int, _P]),
   "iic_nchw_to_nhwc": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
   "iic_nhwc_to_nchw": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P]),
   "iic_cast": (c_int, [_P, c_int, _P, c_int, c_longlong, _P]),

@@ -781,6 +781,60 @@ extern "C" int iic_sobel(const float* imgs, float* out, int n, int c_in, int h, 
   return IIC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dataloader tail fused with sobel_process: RGB image -> grey -> [dx, dy].
+// The reference converts to grey on the CPU inside the dataloader (custom_greyscale_to_tensor,
+// code/utils/cluster/transforms.py:12-16: PIL "L" = (19595 R + 38470 G + 7471 B + 0x8000) >> 16 on uint8, then / 255),
+// uploads the grey batch and runs sobel_process on it.  Here the RGB batch (uint8 as the dataloader holds it, or fp32
+// in [0,1]) is uploaded once and grey + both Sobel filters are evaluated per output pixel.
+// ---------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float grey_of(const T* r, const T* g, const T* b, long long i);
+template <> __device__ __forceinline__ float grey_of<float>(const float* r, const float* g, const float* b, long long i) {
+  return 0.299f * r[i] + 0.587f * g[i] + 0.114f * b[i];
+}
+template <> __device__ __forceinline__ float grey_of<unsigned char>(const unsigned char* r, const unsigned char* g,
+                                                                    const unsigned char* b, long long i) {
+  const unsigned int l = (19595u * r[i] + 38470u * g[i] + 7471u * b[i] + 0x8000u) >> 16;
+  return (float)l / 255.f;  // tf.to_tensor
+}
+
+template <typename T>
+__global__ void grey_sobel_kernel(const T* __restrict__ in, float* __restrict__ out, int n, int h, int w) {
+  const long long total = (long long)n * h * w, plane = (long long)h * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    const int y = (int)((i / w) % h);
+    const long long ni = i / plane;
+    const T* r = in + ni * 3 * plane;
+    float v[3][3];
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int yy = y + dy, xx = x + dx;
+        v[dy + 1][dx + 1] =
+            (yy >= 0 && yy < h && xx >= 0 && xx < w) ? grey_of<T>(r, r + plane, r + 2 * plane, (long long)yy * w + xx) : 0.f;
+      }
+    const float sx = v[0][0] - v[0][2] + 2.f * v[1][0] - 2.f * v[1][2] + v[2][0] - v[2][2];
+    const float sy = v[0][0] + 2.f * v[0][1] + v[0][2] - v[2][0] - 2.f * v[2][1] - v[2][2];
+    float* o = out + ni * 2 * plane + (long long)y * w + x;
+    o[0] = sx;
+    o[plane] = sy;
+  }
+}
+
+extern "C" int iic_grey_sobel(const void* rgb, int src_is_u8, float* out, int n, int h, int w, void* stream) {
+  IIC_REQUIRE(rgb && out && n > 0 && h > 0 && w > 0, IIC_ERR_BAD_ARG, "iic_grey_sobel: bad arguments");
+  const int grid = ew_grid((long long)n * h * w, 256);
+  if (src_is_u8)
+    grey_sobel_kernel<unsigned char><<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)rgb, out, n, h, w);
+  else
+    grey_sobel_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)rgb, out, n, h, w);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
 static int bn_reduce_blocks(long long M, int C) {
   const int rpi = 256 / (C / 8);
   long long blocks = (M + 4 * rpi - 1) / (4 * rpi);

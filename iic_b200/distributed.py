@@ -66,3 +66,39 @@ def allreduce_gradients(params, bucket_bytes=64 << 20):
       flush()
       bucket, size = [], 0
   flush()
+
+
+def emulate_sharded_backward(net, xs, xts, head="B", lamb=1.0, sobel=False):
+  """One-device emulation of the W-rank sharded step (SURVEY.md S8e "Equivalence check"): the chunks ``xs[r]`` /
+  ``xts[r]`` are pushed through ``net`` one after the other (so BatchNorm statistics are per chunk, as they are per
+  rank), the PARTIAL joints are summed, every chunk is FINISHed against the global joint and backpropagated -- the
+  parameter gradients accumulate to what the SUM all-reduce produces.  Returns the (global) mean loss.
+  Used by tests/test_gpu_multi.py and ``bench.py --verify``."""
+  import sys
+
+  from . import _lib, kernels
+  from .step import _to_net_input
+  assert not active(), "emulation runs on one device without a process group"
+  zs, zts = [], []
+  for x, xt in zip(xs, xts):
+    x, xt = _to_net_input(x, sobel, False), _to_net_input(xt, sobel, False)
+    if hasattr(net, "forward_stacked_pair"):
+      z, zt = net.forward_stacked_pair(x, xt, head=head)
+    else:
+      z, zt = net.forward_stacked(x, head=head), net.forward_stacked(xt, head=head)
+    zs.append(z)
+    zts.append(zt)
+  S, _, k = zs[0].shape
+  eps = sys.float_info.epsilon
+  joint = torch.zeros(S, k, k, device=zs[0].device)
+  for z, zt in zip(zs, zts):
+    j = torch.empty_like(joint)
+    kernels.iid_loss(z.detach().contiguous(), zt.detach().contiguous(), lamb, eps, False, phase=_lib.PHASE_PARTIAL,
+                     joint_ws=j)
+    joint += j
+  loss = None
+  for z, zt in zip(zs, zts):
+    loss, dz, dzt, _ = kernels.iid_loss(z.detach().contiguous(), zt.detach().contiguous(), lamb, eps, True,
+                                        phase=_lib.PHASE_FINISH, joint_ws=joint)
+    torch.autograd.backward([z, zt], [dz / S, dzt / S])
+  return loss[:, 0].mean()

@@ -223,6 +223,16 @@ def sobel(imgs, include_rgb, using_ir):
   return out
 
 
+@_cat("sobel")
+def grey_sobel(rgb):
+  """rgb [n,3,h,w] uint8 or fp32 -> [n,2,h,w] sobel of the grey image (dataloader tail + sobel_process fused)."""
+  n, c, h, w = rgb.shape
+  assert c == 3 and rgb.dtype in (torch.uint8, torch.float32)
+  out = torch.empty((n, 2, h, w), device=rgb.device, dtype=torch.float32)
+  check(_lib.lib().iic_grey_sobel(_p(rgb), int(rgb.dtype == torch.uint8), _p(out), n, h, w, _stream()), "iic_grey_sobel")
+  return out
+
+
 # ---- layout ---------------------------------------------------------------------------------
 def nchw_to_nhwc(x, dt):
   n, c, h, w = x.shape

@@ -130,6 +130,10 @@ int iic_box_filter(const float* in, float* tmp, float* out, int n, int k, int h,
  * :50-66,:84-94 selected by include_rgb / using_ir. */
 int iic_sobel(const float* imgs, float* out, int n, int c_in, int h, int w, int include_rgb,
               int using_ir, void* stream);
+/* Dataloader tail + sobel_process in one pass: rgb [n,3,h,w] (uint8 when src_is_u8, else fp32 in
+ * [0,1]) -> grey as custom_greyscale_to_tensor computes it (code/utils/cluster/transforms.py:12-16; PIL's integer "L"
+ * formula for uint8, 0.299/0.587/0.114 for fp32) -> out [n,2,h,w] = [dx, dy] (transforms.py:69,75). */
+int iic_grey_sobel(const void* rgb, int src_is_u8, float* out, int n, int h, int w, void* stream);
 
 /* ---- layout / dtype plumbing between the reference's NCHW fp32 tensors and the internal
  *      NHWC activations (no reference counterpart: torch does this implicitly). */

@@ -44,3 +44,15 @@ def sobel_process(imgs, include_rgb, using_IR=False):
   dy = F.conv2d(grey, wy, padding=1)
   parts = ([rgb] if rgb is not None else []) + [dx, dy] + ([ir] if ir is not None else [])
   return torch.cat(parts, dim=1).detach()
+
+
+def grey_from_rgb(imgs):
+  """``custom_greyscale_to_tensor(include_rgb=False)`` of the reference (code/utils/cluster/transforms.py:12-16) on a
+  batch: uint8 RGB -> PIL "L" (ImagingConvert rgb2l: (19595 R + 38470 G + 7471 B + 0x8000) >> 16) -> to_tensor (/255);
+  fp32 RGB in [0,1] -> the same weights without the uint8 rounding (0.299, 0.587, 0.114)."""
+  assert imgs.dim() == 4 and imgs.shape[1] == 3
+  if imgs.dtype == torch.uint8:
+    v = imgs.to(torch.int64)
+    l = (19595 * v[:, 0:1] + 38470 * v[:, 1:2] + 7471 * v[:, 2:3] + 0x8000) >> 16
+    return l.float() / 255.0
+  return 0.299 * imgs[:, 0:1] + 0.587 * imgs[:, 1:2] + 0.114 * imgs[:, 2:3]

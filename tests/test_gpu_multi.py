@@ -38,7 +38,7 @@ def _data():
   return x, x + 0.3 * weights.normal("multi.xt", (12, 2, 32, 32))
 
 
-def _worker(rank, world, port, outdir):
+def _worker(rank, world, port, outdir, use_arena):
   import torch.distributed as dist
   os.environ["MASTER_ADDR"] = "127.0.0.1"
   os.environ["MASTER_PORT"] = str(port)
@@ -52,23 +52,32 @@ def _worker(rank, world, port, outdir):
   x, xt = _data()
   per = x.shape[0] // world
   xs, xts = x[rank * per:(rank + 1) * per].to(dev), xt[rank * per:(rank + 1) * per].to(dev)
-  o, ot = net(xs, head="A"), net(xts, head="A")
-  loss = sum(IID_loss(a, b, lamb=1.2)[0] for a, b in zip(o, ot)) / len(o)
-  loss.backward()
-  iicd.allreduce_gradients(net.parameters())
+  if use_arena:
+    # the path bench.py times: flat in-place gradients, buckets all-reduced on a side stream during the backward
+    from iic_b200.arena import GradArena
+    from iic_b200.step import iic_cluster_step
+    arena = GradArena(net, bucket_bytes=4 << 20)
+    loss, _ = iic_cluster_step(net, None, xs, xts, head="A", lamb=1.2, sobel=False, arena=arena)
+    assert len(arena.reduce_log) == len(arena.buckets) > 3 and arena.reduce_log[-1] == len(arena.buckets) - 1
+  else:
+    o, ot = net(xs, head="A"), net(xts, head="A")
+    loss = sum(IID_loss(a, b, lamb=1.2)[0] for a, b in zip(o, ot)) / len(o)
+    loss.backward()
+    iicd.allreduce_gradients(net.parameters())
   torch.cuda.synchronize()
   torch.save({"loss": loss.item(), "grads": {n: p.grad.cpu() for n, p in net.named_parameters() if p.grad is not None}},
-             os.path.join(outdir, "rank%d.pt" % rank))
+             os.path.join(outdir, "rank%d.pt" % rank))  # (the idle head's arena gradients are exact zeros)
   dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_ranks_match_single_device_emulation():
+@pytest.mark.parametrize("use_arena", [False, True], ids=["cat-allreduce", "arena-overlapped"])
+def test_two_ranks_match_single_device_emulation(use_arena):
   import torch.multiprocessing as mp
   from iic_b200 import _lib, kernels
   world = 2
   with tempfile.TemporaryDirectory() as d:
-    mp.spawn(_worker, args=(world, _free_port(), d), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), d, use_arena), nprocs=world, join=True)
     res = [torch.load(os.path.join(d, "rank%d.pt" % r)) for r in range(world)]
   # all ranks hold the same loss and, after the all-reduce, the same gradients
   assert abs(res[0]["loss"] - res[1]["loss"]) < 1e-6
@@ -95,6 +104,7 @@ def test_two_ranks_match_single_device_emulation():
   assert abs(loss[:, 0].mean().item() - res[0]["loss"]) < 2e-6
   for n, p in net.named_parameters():
     if p.grad is None:
+      assert n not in res[0]["grads"] or float(res[0]["grads"][n].abs().max()) == 0.0, n
       continue
     want, got = p.grad.cpu(), res[0]["grads"][n]
     assert ((got - want).norm() / (want.norm() + 1e-30)).item() < 2e-3, n

@@ -142,3 +142,20 @@ def test_net_oracle_matches_reference_goldens(name, golden_nets):
   sd = net.state_dict()
   for key in c.sub("buf"):
     np.testing.assert_allclose(sd[key].numpy(), c["buf/" + key], rtol=1e-5, atol=1e-6)
+
+
+def test_grey_from_rgb_is_pil_L():
+  """oracle.transforms.grey_from_rgb restates custom_greyscale_to_tensor (code/utils/cluster/transforms.py:12-16);
+  pinned against PIL itself (what tf.to_grayscale calls) and against the documented luma weights."""
+  import numpy as np
+  import torch
+  from oracle.transforms import grey_from_rgb
+  PIL = pytest.importorskip("PIL.Image")
+  rng = np.random.default_rng(0)
+  a = rng.integers(0, 256, (3, 17, 23, 3), dtype=np.uint8)
+  for img in a:
+    want = np.asarray(PIL.fromarray(img).convert("L")).astype(np.float32) / 255.0
+    got = grey_from_rgb(torch.from_numpy(img).permute(2, 0, 1)[None])[0, 0].numpy()
+    assert np.array_equal(got, want)
+  f = torch.rand(2, 3, 5, 5)
+  assert torch.allclose(grey_from_rgb(f), (0.299 * f[:, 0] + 0.587 * f[:, 1] + 0.114 * f[:, 2])[:, None])
