@@ -36,6 +36,8 @@ _SIGS = {
   "iic_seg_kp": (c_int, [c_int]),
   "iic_seg_prepare": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
   "iic_seg_unprepare": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+  "iic_seg_prepare_shift": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+  "iic_seg_unprepare_shift": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
   "iic_seg_joint_workspace": (c_longlong, [c_int, c_int, c_int]),
   "iic_seg_joint": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
   "iic_seg_corr_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P]),

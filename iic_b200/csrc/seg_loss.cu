@@ -32,15 +32,20 @@ __device__ __forceinline__ void affine_src(const float* th, int x, int y, int w,
 
 __global__ void seg_prepare_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
                                    const float* __restrict__ theta, const float* __restrict__ mask,
-                                   float* __restrict__ x1m, float* __restrict__ x2m, int n, int k, int h, int w, int KP) {
+                                   float* __restrict__ x1m, float* __restrict__ x2m, int n, int k, int h, int w, int KP,
+                                   int tx, int ty) {
+  // (tx, ty): the sparse random displacement of the reference (random_translation_multiple, seg transforms.py:146-166):
+  // the resampled x2 is read at (x + tx, y + ty) and is zero where that falls outside the frame
   const long long total = (long long)n * h * w;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % w);
     const int y = (int)((i / w) % h);
     const int ni = (int)(i / ((long long)w * h));
-    const float m = mask[i];
+    const int xs = x + tx, ys = y + ty;
+    const float m = (xs >= 0 && xs < w && ys >= 0 && ys < h) ? mask[i] : 0.f;
+    const float m1 = mask[i];
     float ix, iy;
-    affine_src(theta + ni * 6, x, y, w, h, ix, iy);
+    affine_src(theta + ni * 6, xs, ys, w, h, ix, iy);
     const float fx = floorf(ix), fy = floorf(iy);
     const int x0 = (int)fx, y0 = (int)fy;
     const float lx = ix - fx, ly = iy - fy;
@@ -49,7 +54,7 @@ __global__ void seg_prepare_kernel(const float* __restrict__ x1, const float* __
     for (int c = 0; c < KP; ++c) {
       float a = 0.f, b = 0.f;
       if (c < k) {
-        a = x1[((long long)ni * k + c) * h * w + (long long)y * w + x] * m;
+        a = x1[((long long)ni * k + c) * h * w + (long long)y * w + x] * m1;
         const float* pl = x2 + ((long long)ni * k + c) * h * w;
         float v = 0.f;
         if (vy0 && vx0) v += w00 * pl[(long long)y0 * w + x0];
@@ -67,22 +72,25 @@ __global__ void seg_prepare_kernel(const float* __restrict__ x1, const float* __
 // adjoint: dx1 = d x1m * mask (gather) ; dx2 += bilinear^T (d x2m * mask) (atomics; dx2 pre-zeroed)
 __global__ void seg_unprepare_kernel(const float* __restrict__ dx1m, const float* __restrict__ dx2m,
                                      const float* __restrict__ theta, const float* __restrict__ mask,
-                                     float* __restrict__ dx1, float* __restrict__ dx2, int n, int k, int h, int w, int KP) {
+                                     float* __restrict__ dx1, float* __restrict__ dx2, int n, int k, int h, int w, int KP,
+                                     int tx, int ty) {
   const long long total = (long long)n * h * w;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % w);
     const int y = (int)((i / w) % h);
     const int ni = (int)(i / ((long long)w * h));
-    const float m = mask[i];
+    const int xs = x + tx, ys = y + ty;
+    const float m = (xs >= 0 && xs < w && ys >= 0 && ys < h) ? mask[i] : 0.f;
+    const float m1 = mask[i];
     float ix, iy;
-    affine_src(theta + ni * 6, x, y, w, h, ix, iy);
+    affine_src(theta + ni * 6, xs, ys, w, h, ix, iy);
     const float fx = floorf(ix), fy = floorf(iy);
     const int x0 = (int)fx, y0 = (int)fy;
     const float lx = ix - fx, ly = iy - fy;
     const float w00 = (1.f - lx) * (1.f - ly), w01 = lx * (1.f - ly), w10 = (1.f - lx) * ly, w11 = lx * ly;
     const bool vx0 = x0 >= 0 && x0 < w, vx1 = x0 + 1 >= 0 && x0 + 1 < w, vy0 = y0 >= 0 && y0 < h, vy1 = y0 + 1 >= 0 && y0 + 1 < h;
     for (int c = 0; c < k; ++c) {
-      dx1[((long long)ni * k + c) * h * w + (long long)y * w + x] = dx1m[i * KP + c] * m;
+      dx1[((long long)ni * k + c) * h * w + (long long)y * w + x] = dx1m[i * KP + c] * m1;
       const float g = dx2m[i * KP + c] * m;
       float* pl = dx2 + ((long long)ni * k + c) * h * w;
       if (g != 0.f) {
@@ -276,6 +284,11 @@ extern "C" int iic_seg_kp(int k) { return seg_kp(k); }
 
 extern "C" int iic_seg_prepare(const float* x1, const float* x2, const float* theta, const float* mask, float* x1m,
                                float* x2m, int n, int k, int h, int w, void* stream) {
+  return iic_seg_prepare_shift(x1, x2, theta, mask, x1m, x2m, n, k, h, w, 0, 0, stream);
+}
+
+extern "C" int iic_seg_prepare_shift(const float* x1, const float* x2, const float* theta, const float* mask, float* x1m,
+                                     float* x2m, int n, int k, int h, int w, int tx, int ty, void* stream) {
   IIC_REQUIRE(x1 && x2 && theta && mask && x1m && x2m && n > 0 && k > 0 && h > 0 && w > 0, IIC_ERR_BAD_ARG,
               "iic_seg_prepare: bad arguments");
   const int KP = seg_kp(k);
@@ -283,7 +296,7 @@ extern "C" int iic_seg_prepare(const float* x1, const float* x2, const float* th
   const long long total = (long long)n * h * w;
   int blocks = cdiv(total, 256);
   if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
-  seg_prepare_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x1, x2, theta, mask, x1m, x2m, n, k, h, w, KP);
+  seg_prepare_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x1, x2, theta, mask, x1m, x2m, n, k, h, w, KP, tx, ty);
   IIC_LAUNCH_CHECK();
   count_launch();
   return IIC_OK;
@@ -291,6 +304,11 @@ extern "C" int iic_seg_prepare(const float* x1, const float* x2, const float* th
 
 extern "C" int iic_seg_unprepare(const float* dx1m, const float* dx2m, const float* theta, const float* mask, float* dx1,
                                  float* dx2, int n, int k, int h, int w, void* stream) {
+  return iic_seg_unprepare_shift(dx1m, dx2m, theta, mask, dx1, dx2, n, k, h, w, 0, 0, stream);
+}
+
+extern "C" int iic_seg_unprepare_shift(const float* dx1m, const float* dx2m, const float* theta, const float* mask,
+                                       float* dx1, float* dx2, int n, int k, int h, int w, int tx, int ty, void* stream) {
   IIC_REQUIRE(dx1m && dx2m && theta && mask && dx1 && dx2 && n > 0 && k > 0, IIC_ERR_BAD_ARG,
               "iic_seg_unprepare: bad arguments");
   const int KP = seg_kp(k);
@@ -300,7 +318,7 @@ extern "C" int iic_seg_unprepare(const float* dx1m, const float* dx2m, const flo
   const long long total = (long long)n * h * w;
   int blocks = cdiv(total, 256);
   if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
-  seg_unprepare_kernel<<<blocks, 256, 0, st>>>(dx1m, dx2m, theta, mask, dx1, dx2, n, k, h, w, KP);
+  seg_unprepare_kernel<<<blocks, 256, 0, st>>>(dx1m, dx2m, theta, mask, dx1, dx2, n, k, h, w, KP, tx, ty);
   IIC_LAUNCH_CHECK();
   count_launch();
   return IIC_OK;

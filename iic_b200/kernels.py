@@ -169,22 +169,22 @@ def seg_kp(k):
   return kp
 
 
-def seg_prepare(x1, x2, theta, mask):
+def seg_prepare(x1, x2, theta, mask, shift=(0, 0)):
   n, k, h, w = x1.shape
   kp = seg_kp(k)
   x1m = torch.empty((n, h, w, kp), device=x1.device, dtype=torch.float32)
   x2m = torch.empty_like(x1m)
-  check(_lib.lib().iic_seg_prepare(_p(x1), _p(x2), _p(theta), _p(mask), _p(x1m), _p(x2m), n, k, h, w, _stream()),
-        "iic_seg_prepare")
+  check(_lib.lib().iic_seg_prepare_shift(_p(x1), _p(x2), _p(theta), _p(mask), _p(x1m), _p(x2m), n, k, h, w, int(shift[0]),
+                                         int(shift[1]), _stream()), "iic_seg_prepare")
   return x1m, x2m
 
 
-def seg_unprepare(dx1m, dx2m, theta, mask, k):
+def seg_unprepare(dx1m, dx2m, theta, mask, k, shift=(0, 0)):
   n, h, w, _ = dx1m.shape
   dx1 = torch.empty((n, k, h, w), device=dx1m.device, dtype=torch.float32)
   dx2 = torch.empty_like(dx1)
-  check(_lib.lib().iic_seg_unprepare(_p(dx1m), _p(dx2m), _p(theta), _p(mask), _p(dx1), _p(dx2), n, k, h, w, _stream()),
-        "iic_seg_unprepare")
+  check(_lib.lib().iic_seg_unprepare_shift(_p(dx1m), _p(dx2m), _p(theta), _p(mask), _p(dx1), _p(dx2), n, k, h, w,
+                                           int(shift[0]), int(shift[1]), _stream()), "iic_seg_unprepare")
   return dx1, dx2
 
 

@@ -23,9 +23,9 @@ RENDER = False
 
 class _SegLoss(torch.autograd.Function):
   @staticmethod
-  def forward(ctx, x1, x2, theta, mask, lamb, T, collapsed, want_grad):
+  def forward(ctx, x1, x2, theta, mask, lamb, T, collapsed, want_grad, shift):
     n, k, h, w = x1.shape
-    x1m, x2m = kernels.seg_prepare(x1, x2, theta, mask)
+    x1m, x2m = kernels.seg_prepare(x1, x2, theta, mask, shift)
     if collapsed:
       b1 = kernels.box_filter(x1m, k, T)
       joint = kernels.seg_joint(b1, x2m, k, 0)  # [1, k, k]
@@ -44,7 +44,7 @@ class _SegLoss(torch.autograd.Function):
       else:
         dx1m = kernels.seg_corr_bwd(x2m, H, k, T, 1, 1.0 / V2)
         dx2m = kernels.seg_corr_bwd(x1m, H, k, T, -1, 1.0 / V2)
-      dx1, dx2 = kernels.seg_unprepare(dx1m, dx2m, theta, mask, k)
+      dx1, dx2 = kernels.seg_unprepare(dx1m, dx2m, theta, mask, k, shift)
       ctx.save_for_backward(dx1, dx2)
     ctx.set_materialize_grads(False)
     return out[0], out[1]
@@ -54,7 +54,20 @@ class _SegLoss(torch.autograd.Function):
     if g_nolamb is not None:
       raise NotImplementedError("loss_no_lamb is for analysis only (reference :78-81); backpropagate through `loss`")
     dx1, dx2 = ctx.saved_tensors
-    return dx1 * g_loss, dx2 * g_loss, None, None, None, None, None, None
+    return dx1 * g_loss, dx2 * g_loss, None, None, None, None, None, None, None
+
+
+def random_translation_multiple_draw(half_side_min, half_side_max):
+  """The random part of the reference's ``random_translation_multiple`` (code/utils/segmentation/transforms.py:146-166,
+  called at IID_losses.py:29-32 / :101-104): one (x, y) displacement for the whole batch, drawn from numpy's GLOBAL
+  generator with the reference's own calls in the reference's order (so ``np.random.seed`` reproduces its runs).  The
+  shift itself -- x2_inv read at (x + tx, y + ty), zero outside the frame, which is what the pad-and-crop at :150-163
+  does -- is applied inside the resampling kernel (iic_seg_prepare_shift)."""
+  import numpy as np
+  t = np.random.randint(half_side_min, half_side_max + 1, size=(2,))
+  polarities = np.random.choice([-1, 1], size=(2,), replace=True)
+  t *= polarities
+  return int(t[0]), int(t[1])
 
 
 def _seg_loss(collapsed, x1_outs, x2_outs, all_affine2_to_1, all_mask_img1, lamb, half_T_side_dense,
@@ -64,16 +77,16 @@ def _seg_loss(collapsed, x1_outs, x2_outs, all_affine2_to_1, all_mask_img1, lamb
   assert (not all_affine2_to_1.requires_grad)
   assert (not all_mask_img1.requires_grad)
   assert (x1_outs.shape == x2_outs.shape)
+  shift = (0, 0)
   if (half_T_side_sparse_min != 0) or (half_T_side_sparse_max != 0):
-    raise NotImplementedError("sparse random displacement is unused by every published IIC command "
-                              "(examples/commands.txt:74-103 set min=max=0) and is not implemented")
+    shift = random_translation_multiple_draw(half_T_side_sparse_min, half_T_side_sparse_max)
   if not x1_outs.is_cuda:
     raise RuntimeError("iic_b200 segmentation losses: CUDA tensors only (no CPU fallback)")
   bn, k, h, w = x1_outs.shape
   want_grad = torch.is_grad_enabled()
   return _SegLoss.apply(x1_outs.float().contiguous(), x2_outs.float().contiguous(),
                         all_affine2_to_1.float().contiguous(), all_mask_img1.reshape(bn, h, w).float().contiguous(),
-                        float(lamb), int(half_T_side_dense), collapsed, want_grad)
+                        float(lamb), int(half_T_side_dense), collapsed, want_grad, shift)
 
 
 def IID_segmentation_loss(x1_outs, x2_outs, all_affine2_to_1=None, all_mask_img1=None, lamb=1.0,

@@ -118,6 +118,13 @@ int iic_seg_prepare(const float* x1, const float* x2, const float* theta, const 
                     int n, int k, int h, int w, void* stream);
 int iic_seg_unprepare(const float* dx1m, const float* dx2m, const float* theta, const float* mask, float* dx1,
                       float* dx2, int n, int k, int h, int w, void* stream);
+/* The same with the reference's sparse random displacement (random_translation_multiple, seg transforms.py:146-166,
+ * called at seg IID_losses.py:29-32 / :101-104): the resampled x2 is read at (x + tx, y + ty), zero outside the frame
+ * (the caller draws (tx, ty) from numpy's global RNG exactly as the reference does). */
+int iic_seg_prepare_shift(const float* x1, const float* x2, const float* theta, const float* mask, float* x1m, float* x2m,
+                          int n, int k, int h, int w, int tx, int ty, void* stream);
+int iic_seg_unprepare_shift(const float* dx1m, const float* dx2m, const float* theta, const float* mask, float* dx1,
+                            float* dx2, int n, int k, int h, int w, int tx, int ty, void* stream);
 long long iic_seg_joint_workspace(int n, int k, int T);
 int iic_seg_joint(const float* x1m, const float* x2m, float* joint, void* workspace, int n, int k, int h, int w,
                   int T, void* stream);

@@ -70,6 +70,7 @@ def load():
                  IID_segmentation_loss=sg.IID_segmentation_loss,
                  IID_segmentation_loss_uncollapsed=sg.IID_segmentation_loss_uncollapsed,
                  perform_affine_tf=tf.perform_affine_tf,
+                 random_translation_multiple=tf.random_translation_multiple,
                  ClusterNet5g=n5.ClusterNet5g, ClusterNet5gTwoHead=n5t.ClusterNet5gTwoHead,
                  ClusterNet6c=n6.ClusterNet6c, ClusterNet6cTwoHead=n6t.ClusterNet6cTwoHead,
                  SegmentationNet10a=n10.SegmentationNet10a,

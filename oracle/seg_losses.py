@@ -13,9 +13,10 @@ Version drift: torch 0.4.1's ``affine_grid``/``grid_sample`` behaved like
 reference generates) both conventions agree to ~4e-6.  The
 oracle pins ``align_corners=True`` -- the reference's era semantics.
 
-Sparse random displacement (``half_T_side_sparse_*``) is unused by every
-published command (examples/commands.txt:74-103 set min=max=0) and is asserted
-off here.
+Sparse random displacement (``half_T_side_sparse_*``, unused by the published
+commands: examples/commands.txt:74-103 set min=max=0) is restated as
+``random_translation_multiple`` (code/utils/segmentation/transforms.py:146-166)
+and pinned against the unmodified reference function under ``np.random.seed``.
 
 Parity pinning: tests/golden/seg_loss_*.npz, generated from the reference.
 """
@@ -35,10 +36,25 @@ def perform_affine_tf(data, tf_matrices, align_corners=True):
                        align_corners=align_corners)
 
 
-def _masked_pair(x1, x2, affine2_to_1, mask, align_corners):
+def random_translation_multiple(data, half_side_min, half_side_max):
+  """code/utils/segmentation/transforms.py:146-166: zero-pad by half_side_max, draw one (x, y) displacement with
+  magnitude in [min, max] and random sign from numpy's global generator, crop back to (h, w)."""
+  import numpy as np
+  n, c, h, w = data.shape
+  data = F.pad(data, (half_side_max, half_side_max, half_side_max, half_side_max), "constant", 0)
+  t = np.random.randint(half_side_min, half_side_max + 1, size=(2,))
+  polarities = np.random.choice([-1, 1], size=(2,), replace=True)
+  t *= polarities
+  t += half_side_max
+  return data[:, :, t[1]:(t[1] + h), t[0]:(t[0] + w)]
+
+
+def _masked_pair(x1, x2, affine2_to_1, mask, align_corners, sparse=(0, 0)):
   assert x1.shape == x2.shape
   n, k, h, w = x1.shape
   x2_inv = perform_affine_tf(x2, affine2_to_1, align_corners)  # reference :27 / :99
+  if sparse[0] or sparse[1]:  # reference :29-32 / :101-104
+    x2_inv = random_translation_multiple(x2_inv, sparse[0], sparse[1])
   m = mask.view(n, 1, h, w)
   return x1 * m, x2_inv * m  # reference :42-45 / :114-117
 
@@ -66,8 +82,8 @@ def IID_segmentation_loss(x1_outs, x2_outs, all_affine2_to_1=None, all_mask_img1
                           half_T_side_sparse_min=None, half_T_side_sparse_max=None,
                           align_corners=True):
   """Collapsed form; reference :14-83.  The normaliser is detached (:60)."""
-  assert not (half_T_side_sparse_min or half_T_side_sparse_max)
-  x1m, x2m = _masked_pair(x1_outs, x2_outs, all_affine2_to_1, all_mask_img1, align_corners)
+  x1m, x2m = _masked_pair(x1_outs, x2_outs, all_affine2_to_1, all_mask_img1, align_corners,
+                          (half_T_side_sparse_min or 0, half_T_side_sparse_max or 0))
   P = seg_joint_displacements(x1m, x2m, half_T_side_dense).sum(dim=(2, 3))  # :53-55
   P = P / float(P.detach().sum())  # :60-61 (python float => no gradient through the norm)
   P = (P + P.t()) / 2.  # :64
@@ -83,9 +99,9 @@ def IID_segmentation_loss_uncollapsed(x1_outs, x2_outs, all_affine2_to_1=None,
                                       half_T_side_sparse_min=None,
                                       half_T_side_sparse_max=None, align_corners=True):
   """One MI per displacement, averaged; reference :86-159."""
-  assert not (half_T_side_sparse_min or half_T_side_sparse_max)
   k = x1_outs.shape[1]
-  x1m, x2m = _masked_pair(x1_outs, x2_outs, all_affine2_to_1, all_mask_img1, align_corners)
+  x1m, x2m = _masked_pair(x1_outs, x2_outs, all_affine2_to_1, all_mask_img1, align_corners,
+                          (half_T_side_sparse_min or 0, half_T_side_sparse_max or 0))
   A = seg_joint_displacements(x1m, x2m, half_T_side_dense)
   side = 2 * half_T_side_dense + 1
   P = A.permute(2, 3, 0, 1)  # (T,T,k,k) :133

@@ -236,11 +236,45 @@ def gen_seg_nets(ref, out):
   out["net/%s/mask" % name] = mask.numpy()
 
 
+def gen_precision(ref, out):
+  """The well-conditioned end-to-end fixture (tests/precision_fixture.py) evaluated by the UNMODIFIED reference
+  network: ClusterNet5gTwoHead 32x32, 64 pairs, centred sub-head biases, head gain 200.  It pins the oracle at the
+  operating point where the tensor-core modes are given their stated tolerances (tests/test_gpu_precision.py)."""
+  sys.path.insert(0, os.path.dirname(HERE))
+  import precision_fixture as fx
+  for sz, pairs, head in [(32, 64, "B")]:
+    net = ref.ClusterNet5gTwoHead(Namespace(**fx.config(sz)))
+    trunk_mean = fx.prepare(net, sz, pairs, head)
+    net.train()
+    x, xt = fx.inputs(sz, pairs)
+    o, ot = net(x, head=head), net(xt, head=head)
+    loss = sum(iid_losses.IID_loss(a, b)[0] for a, b in zip(o, ot)) / len(o)
+    loss.backward()
+    p = "wc/%d_%d_%s/" % (sz, pairs, head)
+    out[p + "trunk_mean"] = trunk_mean.numpy()
+    out[p + "ref_out"] = torch.stack(o).detach().numpy()
+    out[p + "ref_out_tf"] = torch.stack(ot).detach().numpy()
+    out[p + "loss"] = np.float64(loss.item())
+    names, norms = [], []
+    for pn, pp in net.named_parameters():
+      g = pp.grad
+      names.append(pn)
+      norms.append(0.0 if g is None else float(g.double().norm()))
+      if g is not None and (g.numel() <= 4096 or pn in ("trunk.layer1.0.conv1.weight", "trunk.layer2.0.downsample.0.weight")):
+        out[p + "grad/" + pn] = g.numpy().copy()
+    out[p + "grad_names"] = np.array(names)
+    out[p + "grad_norms"] = np.array(norms)
+    print("precision fixture", sz, pairs, head, loss.item())
+
+
 def main():
   assert refshim.available(), "needs /root/reference"
   ref = refshim.load()
+  only = sys.argv[1:]
   for fname, gens in [("iid_loss.npz", [gen_iid]), ("seg_loss.npz", [gen_seg]),
-                      ("nets.npz", [gen_nets, gen_seg_nets])]:
+                      ("nets.npz", [gen_nets, gen_seg_nets]), ("precision.npz", [gen_precision])]:
+    if only and fname not in only:
+      continue
     out = {}
     for g in gens:
       g(ref, out)

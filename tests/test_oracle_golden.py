@@ -159,3 +159,30 @@ def test_grey_from_rgb_is_pil_L():
     assert np.array_equal(got, want)
   f = torch.rand(2, 3, 5, 5)
   assert torch.allclose(grey_from_rgb(f), (0.299 * f[:, 0] + 0.587 * f[:, 1] + 0.114 * f[:, 2])[:, None])
+
+
+@pytest.mark.skipif(not refshim.available(), reason="needs /root/reference (build container only)")
+def test_sparse_displacement_oracle_matches_reference_under_seed():
+  """random_translation_multiple (seg transforms.py:146-166) and the losses that call it (seg IID_losses.py:29-32,
+  :101-104): the oracle draws from numpy's global generator with the reference's calls, so the same seed gives the
+  same displacement, loss and gradients."""
+  ref = refshim.load()
+  x = weights.normal("sparse.x", (2, 3, 12, 12))
+  for seed in range(6):
+    np.random.seed(seed)
+    a = ref.random_translation_multiple(x, 2, 4)
+    np.random.seed(seed)
+    b = seg_losses.random_translation_multiple(x, 2, 4)
+    assert torch.equal(a, b)
+  x1, x2, theta, mask = make_golden.seg_inputs("seg.sparse", 3, 4, 16, flips=True)
+  for fn_name in ("IID_segmentation_loss", "IID_segmentation_loss_uncollapsed"):
+    res = []
+    for mod in (ref, seg_losses):
+      np.random.seed(11)
+      a, b = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)
+      l, l1 = getattr(mod, fn_name)(a, b, all_affine2_to_1=theta, all_mask_img1=mask, lamb=1.2, half_T_side_dense=2,
+                                    half_T_side_sparse_min=1, half_T_side_sparse_max=3)
+      ga, gb = torch.autograd.grad(l, [a, b])
+      res.append((l.item(), l1.item(), ga, gb))
+    assert abs(res[0][0] - res[1][0]) < 1e-6 and abs(res[0][1] - res[1][1]) < 1e-6
+    assert torch.allclose(res[0][2], res[1][2], rtol=1e-4, atol=1e-8) and torch.allclose(res[0][3], res[1][3], rtol=1e-4, atol=1e-8)
