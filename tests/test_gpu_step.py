@@ -13,7 +13,8 @@ from argparse import Namespace
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+# `unvalidated` until the file has passed once on a B200 (tools/gpu_r2_a.sh runs it with IIC_RUN_UNVALIDATED=1)
+pytestmark = [pytest.mark.gpu, pytest.mark.unvalidated]
 
 from oracle import iid_losses as oracle_iid  # noqa: E402
 from oracle import nets as oracle_nets  # noqa: E402

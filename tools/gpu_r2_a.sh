@@ -25,6 +25,7 @@ PY
 }
 IIC_RUN_UNVALIDATED=1 timeout 400 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -n 4 --timeout 300 > $O/a_tests.log 2>&1
 stamp "1 suite (incl. unvalidated + new) rc=$?"; grep -E "^(FAILED|ERROR)|passed|failed|crashed" $O/a_tests.log | tail -40
+timeout 60 tools/umma_sw64_probe > $O/a_sw64_probe.txt 2>&1; stamp "1b SWIZZLE_64B overlapped-operand probe rc=$?"; cat $O/a_sw64_probe.txt
 timeout 200 python tools/precision_probe.py --sz 32 --pairs 64 --steps 40 --modes bf16,tf32,tf32x3,fp32 --fp64 > $O/a_prec32.json 2> $O/a_prec32.err
 stamp "2a precision 32x32 rc=$?"; tail -2 $O/a_prec32.err; python - <<'PY'
 import json
