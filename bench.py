@@ -186,7 +186,7 @@ def pairs_for(args, world):
   return c["batch"] // world
 
 
-def make_host_batch(args, B, seed):
+def make_host_batch(args, B, seed, pin=True):
   """Synthetic dataloader output for one rank: the tensors the reference's loop receives (pinned host memory)."""
   import torch
   c = CONFIGS[args.config]
@@ -203,7 +203,7 @@ def make_host_batch(args, B, seed):
   else:
     ch = 3 if (c["sobel"] and c["rgb"] and not args.grey_input) else 1
     batch = [torch.rand(B, ch, sz, sz, generator=g) for _ in range(2)]
-  return [t.pin_memory() for t in batch]
+  return [t.pin_memory() for t in batch] if pin else batch
 
 
 # ---------------------------------------------------------------------------------------------
@@ -222,7 +222,7 @@ def cpu_reference_step_fn(args, pairs):
   net = getattr(oracle_nets, c["net"])(net_config(args.config))
   net.train()
   opt = torch.optim.Adam(net.parameters(), lr=1e-4)
-  batch = [t.clone() for t in make_host_batch(args, pairs, 7)]
+  batch = make_host_batch(args, pairs, 7, pin=False)
   head = args.head
 
   def grey(x):  # custom_greyscale_to_tensor (code/utils/cluster/transforms.py:12-16) without the uint8 rounding

@@ -208,3 +208,50 @@ def test_seg_step_matches_oracle_with_torch_adam():
       continue
     upd, want = sd[k].cpu() - start[k], osd[k] - start[k]
     assert _rel(upd, want) < 3e-2, (k, _rel(upd, want))
+
+
+def test_legacy_format_checkpoint_loads_and_reproduces_the_oracle(tmp_path):
+  """SURVEY S8f row 3 on the GPU: a checkpoint in torch 0.4.1's on-disk format (legacy non-zip serialisation, pickle
+  protocol 2, saved from a DataParallel wrapper -> `module.` prefixes, the layout of the published models.tar.gz)
+  loads through iic_b200.utils.checkpoint into the CUDA network, whose eval-mode forward (running statistics) then
+  equals the oracle's; the optimiser state of the same file resumes training."""
+  import collections
+
+  import iic_b200.archs as archs
+  from iic_b200.optim import FusedAdam
+  from iic_b200.step import iic_cluster_step
+  from iic_b200.utils.checkpoint import load_into
+  ora = oracle_nets.ClusterNet5gTwoHead(Namespace(**CFG))
+  weights.fill_state_dict(ora, salt=21)
+  ora.train()
+  oopt = torch.optim.Adam(ora.parameters(), lr=LR)
+  x = weights.uniform("ckpt.x", (8, 1, 32, 32))
+  for head in ("A", "B"):  # two steps so that running statistics and Adam moments are non-trivial
+    _oracle_cluster_step(ora, oopt, x, x.flip(3), head, 1.0)
+  path = str(tmp_path / "latest.pytorch")
+  osd = oopt.state_dict()
+  for st in osd["state"].values():
+    st["step"] = int(st["step"])  # torch 0.4.1 kept a Python int
+  torch.save({"net": collections.OrderedDict(("module." + k, v) for k, v in ora.state_dict().items()), "optimiser": osd},
+             path, _use_new_zipfile_serialization=False, pickle_protocol=2)
+  blob = torch.load(path, map_location="cpu", weights_only=False)
+  net_path = str(tmp_path / "net.pytorch")
+  torch.save(blob["net"], net_path, _use_new_zipfile_serialization=False, pickle_protocol=2)
+  net = archs.ClusterNet5gTwoHead(Namespace(precision="fp32", **CFG))
+  load_into(net, net_path)
+  net.cuda().eval()
+  ora.eval()
+  xs = oracle_tf.sobel_process(x, False)
+  with torch.no_grad():
+    for head in ("A", "B"):
+      for a, b in zip(net(xs.cuda(), head=head), ora(xs, head=head)):
+        assert torch.allclose(a.cpu(), b, rtol=0, atol=2e-4)
+  # resume: the reference's `optimiser.load_state_dict(...)` call (cluster_sobel_twohead.py:187), then one more step
+  opt = FusedAdam(net.parameters(), lr=LR)
+  opt.load_state_dict(blob["optimiser"])
+  net.train(), ora.train()
+  loss, _ = iic_cluster_step(net, opt, x.cuda(), x.flip(3).cuda(), head="B")
+  want = _oracle_cluster_step(ora, oopt, x, x.flip(3), "B", 1.0)
+  assert abs(loss.item() - want) < 2e-5
+  for (k, p), (_, q) in zip(net.named_parameters(), ora.named_parameters()):
+    assert torch.allclose(p.detach().cpu(), q.detach(), rtol=1e-3, atol=3 * LR), k

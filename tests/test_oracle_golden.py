@@ -186,3 +186,23 @@ def test_sparse_displacement_oracle_matches_reference_under_seed():
       res.append((l.item(), l1.item(), ga, gb))
     assert abs(res[0][0] - res[1][0]) < 1e-6 and abs(res[0][1] - res[1][1]) < 1e-6
     assert torch.allclose(res[0][2], res[1][2], rtol=1e-4, atol=1e-8) and torch.allclose(res[0][3], res[1][3], rtol=1e-4, atol=1e-8)
+
+
+def test_precision_fixture_oracle_matches_reference_golden():
+  """The oracle at the well-conditioned operating point (tests/precision_fixture.py) against the golden produced by
+  the unmodified reference network: same loss to fp32 rounding, same outputs, same gradients."""
+  sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+  from tests import precision_fixture as fx
+  from tests.conftest import load_golden
+  g = load_golden("precision.npz").sub("wc/32_64_B")
+  f = fx.Fixture(32, 64, "B")
+  r = f.oracle(torch.float32)
+  assert np.allclose(f.trunk_mean.numpy(), g["trunk_mean"], rtol=1e-5, atol=1e-6)
+  assert abs(r["loss"] - float(g["loss"])) < 1e-6
+  assert np.abs(r["out"].numpy() - g["ref_out"]).max() < 1e-5
+  for pn, norm in zip(g["grad_names"], g["grad_norms"]):
+    if str(pn) in r["grads"]:
+      assert abs(float(r["grads"][str(pn)].norm()) - norm) <= 1e-3 * norm + 1e-9, pn
+  for key in g.sub("grad"):
+    want = torch.from_numpy(g["grad/" + key]).double()
+    assert float((r["grads"][key] - want).norm() / want.norm()) < 5e-3, key
