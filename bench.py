@@ -498,7 +498,7 @@ def run_ours(args):
   if rank == 0:
     from iic_b200.archs import _engine
     variants = {k: kernels.get_option(k) for k in ("conv_halo", "conv_halo_wgrad", "conv_halo_store", "stem_quad",
-                                                   "dgrad_prefetch", "tc2_mt2", "tc_cpasync")}
+                                                   "dgrad_prefetch", "tc2_mt2")}
     variants.update({k: int(v) for k, v in _engine.OPTIONS.items()})
     h2d = sum(t.numel() * t.element_size() for t in host) * world
     line = {"metric": METRIC, "value": value, "unit": "img-pairs/s", "n_gpus": world, "steps": args.steps,

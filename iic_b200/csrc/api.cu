@@ -35,8 +35,6 @@ static Option g_opts[OPT_COUNT] = {
     {"conv_halo", "IIC_CONV_HALO", 1, 0, false},
     // conv_halo_wgrad: same switch for the halo wgrad kernel (needs conv_halo's geometry test to pass as well)
     {"conv_halo_wgrad", "IIC_CONV_HALO_WGRAD", 1, 0, false},
-    // tc_cpasync: 1 = cp.async-fed tcgen05 kernel (conv_tc.cu) instead of the TMA-fed one
-    {"tc_cpasync", "IIC_TC_CPASYNC", 0, 0, false},
     // stem_quad: 4-pixels-per-thread stem conv kernel (with optional fused BN statistics): 2 = channel-interleaved thread
     // layout (whole-sector stores), 1 = 16 consecutive channels per thread, 0 = the one-pixel-per-thread kernel
     {"stem_quad", "IIC_STEM_QUAD", 2, 0, false},

@@ -11,11 +11,6 @@ int simt_conv_fprop(const float* x, const float* w, float* y, const iic_conv_geo
 int simt_conv_dgrad(const float* dy, const float* wt, const float* addend, float* dx, const iic_conv_geom* g, cudaStream_t st);
 long long simt_conv_wgrad_workspace(const iic_conv_geom* g);
 int simt_conv_wgrad(const float* x, const float* dy, float* dw, float* ws, const iic_conv_geom* g, cudaStream_t st);
-int tc_conv_gather_gemm(const __nv_bfloat16* src, int srcH, int srcW, int srcC, int rowH, int rowW, int nimg,
-                        const iic_conv_geom* g, int transposed, const __nv_bfloat16* wpacked, int N,
-                        const __nv_bfloat16* addend, __nv_bfloat16* out, cudaStream_t st);
-long long tc_conv_wgrad_workspace(const iic_conv_geom* g);
-int tc_conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* ws, const iic_conv_geom* g, cudaStream_t st);
 int tc2_conv_gather_gemm(const __nv_bfloat16* src, int srcH, int srcW, int srcC, int rowH, int rowW, int nimg,
                          const iic_conv_geom* g, int transposed, const __nv_bfloat16* wpacked, int N,
                          const __nv_bfloat16* addend, __nv_bfloat16* out, cudaStream_t st);
@@ -43,9 +38,8 @@ using namespace iic;
 static bool is_tf32(int dtype) { return dtype == IIC_TF32 || dtype == IIC_TF32X3; }
 static int tf32_split(int dtype) { return dtype == IIC_TF32X3 ? 3 : 1; }
 
-// The TMA-fed persistent kernel (conv_tc2.cu) is the default tensor-core path; IIC_TC_CPASYNC=1 selects the
-// cp.async-fed kernel (conv_tc.cu) everywhere (kept for stride-2 dgrad and for A/B measurements).
-static bool use_tma() { return option(OPT_TC_CPASYNC) != 1; }
+// (Round 1's cp.async-fed tcgen05 kernel, conv_tc.cu, was removed in round 2: the TMA-fed persistent kernels cover
+// fprop of any stride, stride-1 dgrad, stride-2 dgrad by parity classes and wgrad; other dgrad strides are unsupported.)
 
 static int geom_check(const iic_conv_geom* g, const char* who) {
   IIC_REQUIRE(g != nullptr, IIC_ERR_BAD_ARG, "%s: null geometry", who);
@@ -70,9 +64,8 @@ extern "C" int iic_conv_fprop(const void* x, const void* w_packed, void* y, cons
     return tf32_conv_gather_gemm((const float*)x, g->h, g->w, g->cin, g->oh, g->ow, g->n, g, 0, (const float*)w_packed, g->cout,
                                  nullptr, (float*)y, tf32_split(dtype), st);
   if (dtype == IIC_BF16)
-    return (use_tma() ? tc2_conv_gather_gemm : tc_conv_gather_gemm)(
-        (const __nv_bfloat16*)x, g->h, g->w, g->cin, g->oh, g->ow, g->n, g, 0, (const __nv_bfloat16*)w_packed, g->cout,
-        nullptr, (__nv_bfloat16*)y, st);
+    return tc2_conv_gather_gemm((const __nv_bfloat16*)x, g->h, g->w, g->cin, g->oh, g->ow, g->n, g, 0,
+                                (const __nv_bfloat16*)w_packed, g->cout, nullptr, (__nv_bfloat16*)y, st);
   set_error("iic_conv_fprop: bad dtype %d", dtype);
   return IIC_ERR_BAD_ARG;
 }
@@ -85,26 +78,28 @@ extern "C" int iic_conv_dgrad(const void* dy, const void* w_packed_t, const void
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == IIC_F32)
     return simt_conv_dgrad((const float*)dy, (const float*)w_packed_t, (const float*)addend, (float*)dx, g, st);
-  if (is_tf32(dtype) && g->stride == 2 && g->dil == 1 && g->kh == g->kw)
+  if (is_tf32(dtype) && g->stride == 2)
     return tf32_conv_dgrad_s2((const float*)dy, (const float*)w_packed_t, (const float*)addend, (float*)dx, g, tf32_split(dtype),
                               st);
   if (is_tf32(dtype))
     return tf32_conv_gather_gemm((const float*)dy, g->oh, g->ow, g->cout, g->h, g->w, g->n, g, 1, (const float*)w_packed_t,
                                  g->cin, (const float*)addend, (float*)dx, tf32_split(dtype), st);
-  if (dtype == IIC_BF16 && use_tma() && g->stride == 2 && g->dil == 1 && g->kh == g->kw)
+  if ((dtype == IIC_BF16 || is_tf32(dtype)) && g->stride != 1)
+    IIC_REQUIRE(g->stride == 2 && g->dil == 1 && g->kh == g->kw, IIC_ERR_UNSUPPORTED,
+                "iic_conv_dgrad (tensor-core modes): stride 1, or stride 2 with dilation 1 and a square filter");
+  if (dtype == IIC_BF16 && g->stride == 2)
     return tc2_conv_dgrad_s2((const __nv_bfloat16*)dy, (const __nv_bfloat16*)w_packed_t, (const __nv_bfloat16*)addend,
                              (__nv_bfloat16*)dx, g, st);
   if (dtype == IIC_BF16)
-    return ((use_tma() && g->stride == 1) ? tc2_conv_gather_gemm : tc_conv_gather_gemm)(
-        (const __nv_bfloat16*)dy, g->oh, g->ow, g->cout, g->h, g->w, g->n, g, 1, (const __nv_bfloat16*)w_packed_t, g->cin,
-        (const __nv_bfloat16*)addend, (__nv_bfloat16*)dx, st);
+    return tc2_conv_gather_gemm((const __nv_bfloat16*)dy, g->oh, g->ow, g->cout, g->h, g->w, g->n, g, 1,
+                                (const __nv_bfloat16*)w_packed_t, g->cin, (const __nv_bfloat16*)addend, (__nv_bfloat16*)dx, st);
   set_error("iic_conv_dgrad: bad dtype %d", dtype);
   return IIC_ERR_BAD_ARG;
 }
 
 extern "C" long long iic_conv_wgrad_workspace(const iic_conv_geom* g, int dtype) {
   if (g == nullptr) return -1;
-  if (dtype == IIC_BF16) return use_tma() ? tc2_conv_wgrad_workspace(g) : tc_conv_wgrad_workspace(g);
+  if (dtype == IIC_BF16) return tc2_conv_wgrad_workspace(g);
   if (is_tf32(dtype)) return tf32_conv_wgrad_workspace(g);
   return simt_conv_wgrad_workspace(g);
 }
@@ -119,8 +114,7 @@ extern "C" int iic_conv_wgrad(const void* x, const void* dy, float* dw_packed, v
   if (is_tf32(dtype))
     return tf32_conv_wgrad((const float*)x, (const float*)dy, dw_packed, (float*)workspace, g, tf32_split(dtype), st);
   if (dtype == IIC_BF16)
-    return (use_tma() ? tc2_conv_wgrad : tc_conv_wgrad)((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw_packed,
-                                                        (float*)workspace, g, st);
+    return tc2_conv_wgrad((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw_packed, (float*)workspace, g, st);
   set_error("iic_conv_wgrad: bad dtype %d", dtype);
   return IIC_ERR_BAD_ARG;
 }
@@ -128,7 +122,7 @@ extern "C" int iic_conv_wgrad(const void* x, const void* dy, float* dw_packed, v
 // fprop with the BatchNorm statistics of the output fused into the epilogue (tensor-core path only): the
 // separate statistics pass (one full read of y) disappears.  Returns the number of partial rows written.
 extern "C" int iic_conv_fprop_stats_blocks(const iic_conv_geom* g, int dtype) {
-  if (g == nullptr || dtype != IIC_BF16 || !use_tma()) return 0;
+  if (g == nullptr || dtype != IIC_BF16) return 0;
   return tc2_conv_fprop_blocks(g);
 }
 
@@ -137,7 +131,7 @@ extern "C" int iic_conv_fprop_stats(const void* x, const void* w_packed, void* y
   int rc = geom_check(g, "iic_conv_fprop_stats");
   if (rc != IIC_OK) return rc;
   IIC_REQUIRE(x && w_packed && y && stat_partial, IIC_ERR_BAD_ARG, "iic_conv_fprop_stats: null pointer");
-  IIC_REQUIRE(dtype == IIC_BF16 && use_tma(), IIC_ERR_UNSUPPORTED, "iic_conv_fprop_stats: tensor-core (bf16) path only");
+  IIC_REQUIRE(dtype == IIC_BF16, IIC_ERR_UNSUPPORTED, "iic_conv_fprop_stats: tensor-core (bf16) path only");
   return tc2_conv_gather_gemm_stats((const __nv_bfloat16*)x, g->h, g->w, g->cin, g->oh, g->ow, g->n, g, 0,
                                     (const __nv_bfloat16*)w_packed, g->cout, nullptr, (__nv_bfloat16*)y, stat_partial, views,
                                     (cudaStream_t)stream);

@@ -2,7 +2,7 @@
 //
 // This is the IIC_F32 mode of the conv entry points: every multiply-add is an fp32 FFMA, so the
 // trunk matches the reference (fp32 cuDNN/MKL) to rounding.  It doubles as the on-device
-// cross-check for the tcgen05 path (conv_tc.cu) and runs the tiny head GEMMs in both modes.
+// cross-check for the tcgen05 path (conv_tc2.cu, conv_tf32.cu) and runs the tiny head GEMMs in both modes.
 //
 //   C[M][N] = sum_k A(m,k) * B(k,n), 64x64 tiles, BK=16, 256 threads x (4x4) register tiles,
 //   operands fetched through loader functors (dense strided / im2col gather / transposed-conv

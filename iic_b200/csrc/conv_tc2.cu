@@ -1,8 +1,7 @@
 // tcgen05 implicit-GEMM convolution, TMA-fed persistent version (sm_100a).
 //
-// Same math and tile shapes as conv_tc.cu, but the operands are staged by the Tensor Memory
-// Accelerator instead of 16-byte cp.async gathers (which saturate the LSU at ~1/3-2/3 of the
-// tensor rate, profiles/r01_conv_sweep_v1.md):
+// The operands are staged by the Tensor Memory Accelerator (round 1's first version gathered them with 16-byte
+// cp.async copies, which saturated the LSU at ~1/3-2/3 of the tensor rate: profiles/r01_conv_sweep.md):
 //   * activation operand: ONE `cp.async.bulk.tensor.4d...im2col` per 128x64 tile -- the TMA unit
 //     walks the output pixels of the tile (n, oh, ow order), applies the conv stride, the filter-tap
 //     offset and zero-fills the padding, writing 128-byte rows with the SWIZZLE_128B pattern the
@@ -13,8 +12,7 @@
 //   warps 0-3    : epilogue; TMEM accumulators are double-buffered (2 x BN columns) so the
 //                  epilogue of tile i overlaps the main loop of tile i+1.
 // Used for fprop (stride 1/2), dgrad of stride-1 convs (im2col of dy with reversed taps) and wgrad
-// (both operands MN-major).  Stride-2 dgrad keeps the cp.async kernel (fractional stride is not an
-// im2col access pattern).
+// (both operands MN-major).  Stride-2 dgrad is decomposed into four stride-1 parity-class problems (tc2_conv_dgrad_s2).
 #include <cuda.h>
 
 #include <cstdlib>
@@ -1358,7 +1356,7 @@ static int tc2_wgrad_splits(const iic_conv_geom* g) {
 // dgrad of a stride-2 convolution, decomposed by output parity: dx[2i+py, 2j+px] only receives the taps a
 // with (py + pad - a) even, read at dy[i + (py + pad - a)/2]; each of the four classes is a stride-1 im2col
 // problem over dy with its own tap subset (1+2+2+4 = 9 taps for 3x3: no wasted MMAs, unlike the zero-filled
-// fractional-stride gather of conv_tc.cu).  w = kind-1 packed weight [cin][kh][kw][cout].
+// fractional-stride gather of round 1's first kernel).  w = kind-1 packed weight [cin][kh][kw][cout].
 int tc2_conv_dgrad_s2(const __nv_bfloat16* dy, const __nv_bfloat16* wpacked_t, const __nv_bfloat16* addend,
                       __nv_bfloat16* dx, const iic_conv_geom* g, cudaStream_t st) {
   int rc = tma_init();

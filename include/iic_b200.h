@@ -62,7 +62,6 @@ long long iic_launch_count(int reset);
  *   "conv_halo"       [IIC_CONV_HALO=1]        halo kernel for 3x3/s1/p1 64->64 fprop+dgrad: 0 never, 1 when it pays,
  *                                              2 whenever the geometry fits
  *   "conv_halo_wgrad" [IIC_CONV_HALO_WGRAD=1]  halo kernel for the wgrad of the same layers (0 = im2col split-K kernel)
- *   "tc_cpasync"      [IIC_TC_CPASYNC=0]       1 = cp.async-fed tcgen05 kernel instead of the TMA-fed one
  *   "stem_quad"       [IIC_STEM_QUAD=2]        stem conv: 4 pixels x 16 channels per thread (and the fused-statistics
  *                                              entry point): 2 = channel-interleaved lanes (whole-sector stores),
  *                                              1 = 16 consecutive channels per thread; 0 = one pixel per thread
