@@ -1,0 +1,376 @@
+// Uncollapsed segmentation joint on the tensor cores (tcgen05 kind::tf32, 3xTF32 split) -- SURVEY S8 a11:
+//
+//   A[u][v][c][c'] = sum_{n,y,x} x1m[n, y+u-T, x+v-T, c] * x2m[n, y, x, c']          (k <= 16 channels, V = 2T+1 <= 24)
+//
+// the reference's F.conv2d(x1^T, weight=x2^T, padding=T) (code/utils/segmentation/IID_losses.py:125), 390 GFLOP per
+// sub-head at the COCO-Stuff-3 shape.  The fp32 SIMT kernel (seg_loss.cu::seg_joint_kernel) runs it at ~23 TFLOP/s.
+//
+// Formulation.  Both views are pixel-major, 16 channels = 64 bytes per pixel.  For one image row y of x2 and one
+// displacement row u, with x1row = row y+u-T of x1 zero-padded by T pixels on the left and 24-T... on the right:
+//
+//     D[m = (v, c)][c'] += sum_x  x1row[x + v][c] * x2row[x][c']            M = 8 displacements x 16 channels = 128
+//
+// i.e. a GEMM whose A operand is the Toeplitz "displaced copies" matrix of x1row.  In pixel-major memory that operand
+// needs no copies at all: element (m = v*16 + c, k = x) lives at byte (x + v)*64 + c*4, which is exactly an MN-major
+// SWIZZLE_64B UMMA layout with K rows 64 B apart and M atoms (16 channels) ALSO 64 B apart (LBO = 64: atom v+1 of pixel x
+// is atom v of pixel x+1 -- the atoms overlap the K rows; tools/umma_sw64_probe.cu checks this on hardware).  So one TMA
+// box per x1 row feeds all 24 displacements, and the row is reused for the 7 values of u a CTA owns as y advances
+// (ring of 8 row slots): x1 and x2 cross L2 -> SM once per CTA instead of (2T+1) times.
+// B (x2row) is MN-major too: [pixel][16 channels].  N = 16, K = 8 pixels per MMA, fp32 accumulators in TMEM
+// (7 u x 3 M tiles x 16 columns = 336 columns).  The MMA is operand-fetch bound (4.5 KB of shared memory per 16 K MACs).
+// Precision: probabilities span many orders of magnitude and the loss tolerance is 2e-5, so each operand is split
+// x = hi + lo (tf32 each, seg_split_kernel) and three MMAs per product are issued (lo*hi + hi*lo + hi*hi): fp32-grade.
+//
+// Work item = (image n, chunk of rows y, group of 7 displacement rows u); partial results per CTA, fixed-order reduce.
+#include <cuda.h>
+
+#include "tc_ptx.cuh"
+
+namespace iic {
+
+constexpr int SJ_U = 7;        // displacement rows per CTA
+constexpr int SJ_MT = 3;       // M tiles of 8 displacements: v < 24
+constexpr int SJ_SLOTS = 8;    // x1 row ring (U + 1)
+constexpr int SJ_ST2 = 2;      // x2 row stages
+constexpr int SJ_THREADS = 192;
+
+struct SjParams {
+  int n, h, w, wp, T, V;
+  int ychunk, nychunks, ugroups;
+  int row1_bytes, row2_bytes;  // one precision part of an x1 / x2 row buffer in shared memory (1024-byte multiples)
+  int box1_bytes, box2_bytes;  // bytes one TMA box delivers ((wp + 24) * 64 and wp * 64)
+  float* part;                 // [cta][SJ_U][24][16][16]
+};
+
+__device__ __forceinline__ uint64_t sj_desc(uint32_t saddr) {
+  // MN-major, SWIZZLE_64B, LBO = 64 B (next 16-channel atom = next pixel), SBO = 512 B (8 K rows)
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(64 >> 4) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+__device__ __forceinline__ void sj_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void seg_split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    float4 h, l;
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x - h.x)); l.x = __uint_as_float(t);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y - h.y)); l.y = __uint_as_float(t);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z - h.z)); l.z = __uint_as_float(t);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w - h.w)); l.w = __uint_as_float(t);
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = l;
+  }
+}
+
+// tensor maps: x1 hi / lo (box 16 x (wp+24) x 1, start x = -T), x2 hi / lo (box 16 x wp x 1); all views [n*h][w][16]
+__global__ void __launch_bounds__(SJ_THREADS, 1)
+seg_joint_tc_kernel(const __grid_constant__ CUtensorMap tm1h, const __grid_constant__ CUtensorMap tm1l,
+                    const __grid_constant__ CUtensorMap tm2h, const __grid_constant__ CUtensorMap tm2l, SjParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t slot_bytes = 2u * (uint32_t)P.row1_bytes;   // [hi | lo]
+  const uint32_t st2_bytes = 2u * (uint32_t)P.row2_bytes;
+  const uint32_t x2base = base + SJ_SLOTS * slot_bytes;
+  const uint32_t bars = x2base + SJ_ST2 * st2_bytes;
+  auto full1 = [&](int s) { return bars + 8u * s; };
+  auto empty1 = [&](int s) { return bars + 8u * (SJ_SLOTS + s); };
+  auto full2 = [&](int s) { return bars + 8u * (2 * SJ_SLOTS + s); };
+  auto empty2 = [&](int s) { return bars + 8u * (2 * SJ_SLOTS + SJ_ST2 + s); };
+  const uint32_t done_bar = bars + 8u * (2 * SJ_SLOTS + 2 * SJ_ST2);
+  uint8_t* bars_ptr = smem_raw + (bars - raw);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_ptr + 8 * (2 * SJ_SLOTS + 2 * SJ_ST2 + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SJ_SLOTS; ++s) {
+      mbar_init(full1(s), 1);
+      mbar_init(empty1(s), 1);
+    }
+    for (int s = 0; s < SJ_ST2; ++s) {
+      mbar_init(full2(s), 1);
+      mbar_init(empty2(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm1h);
+    tma_prefetch_desc(&tm1l);
+    tma_prefetch_desc(&tm2h);
+    tma_prefetch_desc(&tm2l);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item
+  const int g = blockIdx.x % P.ugroups;
+  const int yc = (blockIdx.x / P.ugroups) % P.nychunks;
+  const int img = blockIdx.x / (P.ugroups * P.nychunks);
+  const int ya = yc * P.ychunk, yb = min(P.h, ya + P.ychunk);
+  const int u0 = g * SJ_U;
+  const int nu = min(SJ_U, P.V - u0);           // displacement rows this CTA really owns
+  const int r_lo = max(0, ya + u0 - P.T);        // first / last valid x1 row this CTA ever touches
+  const int r_hi = min(P.h - 1, (yb - 1) + (u0 + nu - 1) - P.T);
+
+  if (warp == 0) {
+    // =============================== TMA producer ============================================
+    if (lane == 0) {
+      int r_next = r_lo;
+      for (int y = ya; y < yb; ++y) {
+        const int need = min(r_hi, y + (u0 + nu - 1) - P.T);
+        for (; r_next <= need; ++r_next) {
+          const int idx = r_next - r_lo, s = idx % SJ_SLOTS;
+          mbar_wait(empty1(s), ((idx / SJ_SLOTS) & 1u) ^ 1u);
+          mbar_expect_tx(full1(s), 2u * (uint32_t)P.box1_bytes);
+          const uint32_t dst = base + s * slot_bytes;
+          tma_load_3d(dst, &tm1h, full1(s), 0, -P.T, img * P.h + r_next);
+          tma_load_3d(dst + P.row1_bytes, &tm1l, full1(s), 0, -P.T, img * P.h + r_next);
+        }
+        const int it = y - ya, s2 = it % SJ_ST2;
+        mbar_wait(empty2(s2), ((it / SJ_ST2) & 1u) ^ 1u);
+        mbar_expect_tx(full2(s2), 2u * (uint32_t)P.box2_bytes);
+        const uint32_t dst2 = x2base + s2 * st2_bytes;
+        tma_load_3d(dst2, &tm2h, full2(s2), 0, 0, img * P.h + y);
+        tma_load_3d(dst2 + P.row2_bytes, &tm2l, full2(s2), 0, 0, img * P.h + y);
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ==============================================
+    // instruction descriptor: kind::tf32, D = f32, M = 128, N = 16, A and B MN-major
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(16 >> 3) << 17) |
+                               ((uint32_t)(128 >> 4) << 24);
+    uint32_t touched = 0u;
+    const int nkk = P.wp / 8;
+    for (int y = ya; y < yb; ++y) {
+      const int it = y - ya, s2 = it % SJ_ST2;
+      mbar_wait(full2(s2), (it / SJ_ST2) & 1u);
+      const uint32_t b_hi = x2base + s2 * st2_bytes, b_lo = b_hi + P.row2_bytes;
+      for (int ul = 0; ul < nu; ++ul) {
+        const int r = y + u0 + ul - P.T;
+        if (r < 0 || r >= P.h) continue;  // x1 row outside the image: contributes zeros
+        const int idx = r - r_lo, s = idx % SJ_SLOTS;
+        mbar_wait(full1(s), (idx / SJ_SLOTS) & 1u);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t a_hi = base + s * slot_bytes, a_lo = a_hi + P.row1_bytes;
+#pragma unroll 1
+          for (int mt = 0; mt < SJ_MT; ++mt) {
+            const uint32_t acc = tmem_base + (uint32_t)((ul * SJ_MT + mt) * 16);
+            const uint32_t bit = 1u << (ul * SJ_MT + mt);
+            uint32_t first = (touched & bit) ? 1u : 0u;  // accumulate flag of the first MMA into this block
+            for (int kk = 0; kk < nkk; ++kk) {
+              const uint32_t aoff = (uint32_t)(kk * 8 + mt * 8) * 64u, boff = (uint32_t)(kk * 8) * 64u;
+              sj_mma(acc, sj_desc(a_lo + aoff), sj_desc(b_hi + boff), idesc, first);  // lo_a * hi_b
+              sj_mma(acc, sj_desc(a_hi + aoff), sj_desc(b_lo + boff), idesc, 1u);     // hi_a * lo_b
+              sj_mma(acc, sj_desc(a_hi + aoff), sj_desc(b_hi + boff), idesc, 1u);     // hi_a * hi_b
+              first = 1u;
+            }
+          }
+          if (ul == 0) umma_commit(empty1(s));  // u = u0 is the last use of row r (larger y pairs it with smaller u)
+        }
+        __syncwarp();
+        for (int mt = 0; mt < SJ_MT; ++mt) touched |= 1u << (ul * SJ_MT + mt);
+      }
+      // rows whose last use is this step but which were skipped above cannot exist (a valid row r is last used at
+      // y = r - u0 + T, where it is paired with ul = 0 and is in range by construction of r_lo / r_hi) -- except when that
+      // step lies beyond this CTA's chunk; those slots are never reused because the producer stops at r_hi.
+      if (elect_one_sync()) umma_commit(empty2(s2));
+      __syncwarp();
+    }
+    if (elect_one_sync()) umma_commit(done_bar);
+    __syncwarp();
+  } else {
+    // =============================== epilogue (warps 2-5) ======================================
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    // accumulator blocks that received at least one MMA: displacement row ul met a valid x1 row inside this chunk
+    uint32_t touched = 0u;
+    for (int ul = 0; ul < nu; ++ul) {
+      const int lo = max(ya, P.T - u0 - ul), hi = min(yb, P.h + P.T - u0 - ul);  // y with 0 <= y + u0 + ul - T < h
+      if (lo < hi) touched |= 7u << (ul * SJ_MT);
+    }
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;  // accumulator row = (v within the tile, c)
+    const int vl = m >> 4, c = m & 15;
+    float* out = P.part + (long long)blockIdx.x * SJ_U * 24 * 256;
+    const int nblk = SJ_U * SJ_MT;
+    for (int b0 = 0; b0 < nblk; b0 += 2) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b0 * 16), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {
+        const int blk = b0 + hb;
+        if (blk >= nblk) break;
+        const int ul = blk / SJ_MT, mt = blk % SJ_MT;
+        const bool live = (touched >> blk) & 1u;
+        float* o = out + ((long long)(ul * 24 + mt * 8 + vl) * 16 + c) * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(o + q * 4) =
+              live ? make_float4(__uint_as_float(v[hb * 16 + q * 4]), __uint_as_float(v[hb * 16 + q * 4 + 1]),
+                                 __uint_as_float(v[hb * 16 + q * 4 + 2]), __uint_as_float(v[hb * 16 + q * 4 + 3]))
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// joint[(u*V + v)][c][c'] = sum over (image, row chunk) of the partial of group u / 7      (fixed order: deterministic)
+__global__ void seg_joint_tc_reduce_kernel(const float* __restrict__ part, float* __restrict__ joint, int items, int ugroups,
+                                           int V, int k) {
+  const long long total = (long long)V * V * k * k;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cp = (int)(i % k);
+    const int c = (int)((i / k) % k);
+    const int v = (int)((i / ((long long)k * k)) % V);
+    const int u = (int)(i / ((long long)k * k * V));
+    const int g = u / SJ_U, ul = u % SJ_U;
+    double t = 0.0;
+    for (int it = 0; it < items; ++it)
+      t += (double)part[(((long long)(it * ugroups + g) * SJ_U + ul) * 24 + v) * 256 + c * 16 + cp];
+    joint[i] = (float)t;
+  }
+}
+
+// ---- host ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_sjEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_sjEncodeTiled sj_encodeTiled = nullptr;
+
+static int sj_init() {
+  if (sj_encodeTiled) return IIC_OK;
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  IIC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  IIC_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, IIC_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  sj_encodeTiled = (PFN_sjEncodeTiled)fn;
+  return IIC_OK;
+}
+
+static int sj_map(CUtensorMap* tm, const float* ptr, int rows, int w, int box_w) {
+  cuuint64_t gdim[3] = {16, (cuuint64_t)w, (cuuint64_t)rows};
+  cuuint64_t gstr[2] = {64, (cuuint64_t)w * 64};
+  cuuint32_t box[3] = {16, (cuuint32_t)box_w, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = sj_encodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IIC_REQUIRE(r == CUDA_SUCCESS, IIC_ERR_CUDA, "cuTensorMapEncodeTiled(seg joint) failed (%d) rows=%d w=%d box_w=%d", (int)r, rows,
+              w, box_w);
+  return IIC_OK;
+}
+
+struct SjPlan {
+  bool ok;
+  int wp, ychunk, nychunks, ugroups, items, ctas, row1_bytes, row2_bytes, smem;
+};
+
+static SjPlan sj_plan(int n, int k, int h, int w, int T) {
+  SjPlan p = {};
+  const int V = 2 * T + 1;
+  if (k > 16 || k < 5 || V > 24 || T < 1 || n < 1) return p;   // (k <= 4 / 8 stay on the SIMT kernel: 1/16 of the work)
+  p.wp = (w + 7) / 8 * 8;
+  if (p.wp + 24 > 256) return p;                                // TMA box extent
+  p.row1_bytes = ((p.wp + 24) * 64 + 1023) / 1024 * 1024;
+  p.row2_bytes = (p.wp * 64 + 1023) / 1024 * 1024;
+  p.smem = 1024 + SJ_SLOTS * 2 * p.row1_bytes + SJ_ST2 * 2 * p.row2_bytes + 256;
+  if (p.smem > 232448) return p;
+  p.ugroups = (V + SJ_U - 1) / SJ_U;
+  // row chunks: ~3 waves of CTAs over the SMs, at least T + 1 rows per chunk
+  int want = (3 * device_sm_count() + n * p.ugroups - 1) / (n * p.ugroups);
+  if (want < 1) want = 1;
+  p.ychunk = (h + want - 1) / want;
+  if (p.ychunk < T + 1) p.ychunk = T + 1;
+  if (p.ychunk > h) p.ychunk = h;
+  p.nychunks = (h + p.ychunk - 1) / p.ychunk;
+  p.items = n * p.nychunks;
+  p.ctas = p.items * p.ugroups;
+  p.ok = true;
+  return p;
+}
+
+// workspace: hi/lo copies of both views + per-CTA partials; 0 = geometry not supported by the tensor-core kernel
+long long seg_joint_tc_workspace(int n, int k, int h, int w, int T) {
+  const SjPlan p = sj_plan(n, k, h, w, T);
+  if (!p.ok) return 0;
+  return 4ll * n * h * w * 16 * (long long)sizeof(float) + (long long)p.ctas * SJ_U * 24 * 256 * (long long)sizeof(float);
+}
+
+int seg_joint_tc(const float* x1m, const float* x2m, float* joint, void* workspace, int n, int k, int h, int w, int T,
+                 cudaStream_t st) {
+  int rc = sj_init();
+  if (rc != IIC_OK) return rc;
+  const SjPlan p = sj_plan(n, k, h, w, T);
+  IIC_REQUIRE(p.ok, IIC_ERR_UNSUPPORTED, "seg_joint_tc: unsupported geometry (k=%d, T=%d, w=%d)", k, T, w);
+  const long long elems = (long long)n * h * w * 16;
+  float* x1h = (float*)workspace;
+  float* x1l = x1h + elems;
+  float* x2h = x1l + elems;
+  float* x2l = x2h + elems;
+  float* part = x2l + elems;
+  int blocks = cdiv(elems / 4, 256);
+  if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
+  seg_split_kernel<<<blocks, 256, 0, st>>>(x1m, x1h, x1l, elems / 4);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  seg_split_kernel<<<blocks, 256, 0, st>>>(x2m, x2h, x2l, elems / 4);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  alignas(64) CUtensorMap tm1h, tm1l, tm2h, tm2l;
+  if ((rc = sj_map(&tm1h, x1h, n * h, w, p.wp + 24)) != IIC_OK) return rc;
+  if ((rc = sj_map(&tm1l, x1l, n * h, w, p.wp + 24)) != IIC_OK) return rc;
+  if ((rc = sj_map(&tm2h, x2h, n * h, w, p.wp)) != IIC_OK) return rc;
+  if ((rc = sj_map(&tm2l, x2l, n * h, w, p.wp)) != IIC_OK) return rc;
+  SjParams P = {};
+  P.n = n; P.h = h; P.w = w; P.wp = p.wp; P.T = T; P.V = 2 * T + 1;
+  P.ychunk = p.ychunk; P.nychunks = p.nychunks; P.ugroups = p.ugroups;
+  P.row1_bytes = p.row1_bytes; P.row2_bytes = p.row2_bytes;
+  P.box1_bytes = (p.wp + 24) * 64; P.box2_bytes = p.wp * 64;
+  P.part = part;
+  IIC_CUDA(cudaFuncSetAttribute(seg_joint_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem));
+  seg_joint_tc_kernel<<<p.ctas, SJ_THREADS, p.smem, st>>>(tm1h, tm1l, tm2h, tm2l, P);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  const long long total = (long long)P.V * P.V * k * k;
+  seg_joint_tc_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(part, joint, p.items, p.ugroups, P.V, k);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
+}  // namespace iic
+
+extern "C" long long iic_seg_joint_tc_workspace(int n, int k, int h, int w, int T) {
+  return iic::seg_joint_tc_workspace(n, k, h, w, T);
+}
+
+extern "C" int iic_seg_joint_tc(const float* x1m, const float* x2m, float* joint, void* workspace, int n, int k, int h, int w,
+                                int T, void* stream) {
+  IIC_REQUIRE(x1m && x2m && joint && workspace && n > 0 && k > 0 && T >= 0, IIC_ERR_BAD_ARG, "iic_seg_joint_tc: bad arguments");
+  return iic::seg_joint_tc(x1m, x2m, joint, workspace, n, k, h, w, T, (cudaStream_t)stream);
+}

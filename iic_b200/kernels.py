@@ -188,7 +188,31 @@ def seg_unprepare(dx1m, dx2m, theta, mask, k, shift=(0, 0)):
   return dx1, dx2
 
 
+# host-side switch: uncollapsed segmentation joint on the tensor cores (csrc/seg_joint_tc.cu).  OFF until the kernel has
+# passed tests/test_gpu_parity_seg.py::test_seg_joint_tensor_core_* on a B200.
+SEG_JOINT_TC = {"on": __import__("os").environ.get("IIC_SEG_JOINT_TC", "0") != "0"}
+
+
+def seg_joint_tc(x1m, x2m, k, T):
+  """Tensor-core joint; returns None when the geometry is not supported."""
+  n, h, w, kp = x1m.shape
+  if kp != 16:
+    return None
+  nbytes = int(_lib.lib().iic_seg_joint_tc_workspace(n, k, h, w, T))
+  if nbytes <= 0:
+    return None
+  V = 2 * T + 1
+  ws = torch.empty(nbytes // 4, device=x1m.device, dtype=torch.float32)
+  joint = torch.empty((V * V, k, k), device=x1m.device, dtype=torch.float32)
+  check(_lib.lib().iic_seg_joint_tc(_p(x1m), _p(x2m), _p(joint), _p(ws), n, k, h, w, T, _stream()), "iic_seg_joint_tc")
+  return joint
+
+
 def seg_joint(x1m, x2m, k, T):
+  if SEG_JOINT_TC["on"] and T > 0:
+    j = seg_joint_tc(x1m, x2m, k, T)
+    if j is not None:
+      return j
   n, h, w, _ = x1m.shape
   V = 2 * T + 1
   nbytes = int(_lib.lib().iic_seg_joint_workspace(n, k, T))

@@ -127,6 +127,13 @@ int iic_seg_unprepare_shift(const float* dx1m, const float* dx2m, const float* t
 long long iic_seg_joint_workspace(int n, int k, int T);
 int iic_seg_joint(const float* x1m, const float* x2m, float* joint, void* workspace, int n, int k, int h, int w,
                   int T, void* stream);
+/* The same joint on the tensor cores (tcgen05 kind::tf32, 3xTF32 operand split -> fp32-grade sums), for pixel-major inputs
+ * with KP = 16 (5 <= k <= 16) and 2T+1 <= 24: the Toeplitz operand of F.conv2d(x1^T, weight=x2^T, padding=T) (:125) is read
+ * straight out of one shared-memory row per displacement row.  iic_seg_joint_tc_workspace returns 0 when the geometry is
+ * not supported (the caller then uses iic_seg_joint), otherwise the bytes of `workspace`. */
+long long iic_seg_joint_tc_workspace(int n, int k, int h, int w, int T);
+int iic_seg_joint_tc(const float* x1m, const float* x2m, float* joint, void* workspace, int n, int k, int h, int w, int T,
+                     void* stream);
 int iic_seg_corr_bwd(const float* in, const float* H, float* out, int n, int k, int h, int w, int T, int sgn,
                      float scale, void* stream);
 int iic_box_filter(const float* in, float* tmp, float* out, int n, int k, int h, int w, int T, void* stream);
