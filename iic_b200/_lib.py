@@ -42,6 +42,8 @@ _SIGS = {
   "iic_seg_joint": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
   "iic_seg_joint_tc_workspace": (c_longlong, [c_int, c_int, c_int, c_int, c_int]),
   "iic_seg_joint_tc": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+  "iic_seg_corr_tc_workspace": (c_longlong, [c_int, c_int, c_int, c_int, c_int]),
+  "iic_seg_corr_tc": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
   "iic_seg_corr_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
   "iic_box_filter": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
   "iic_sobel": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),

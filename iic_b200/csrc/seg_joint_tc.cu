@@ -363,7 +363,311 @@ int seg_joint_tc(const float* x1m, const float* x2m, float* joint, void* workspa
   return IIC_OK;
 }
 
+// =================================================================================================
+// Backward contractions on the tensor cores:
+//     out[n,Y,X,c] = scale * sum_{u,v,c'} H[u][v][c][c'] * in[n, Y - s(u-T), X - s(v-T), c']        s = +1 | -1
+// (s = +1, in = x2m -> d x1m ; s = -1, in = x1m -> d x2m ; what seg_corr_bwd_kernel evaluates in fp32 SIMT).
+// Per output row Y and displacement row u this is D[X][c] += A[X][(j, c')] * B[c][(j, c')] with the input row
+// inb[b] (b = x + T, zero halo) and  A[X][(j, c')] = inb[X + j][c']  -- a K-major operand whose rows are 64 B apart and
+// OVERLAP along K (SWIZZLE_64B, the K offset j is applied by moving the descriptor start by j pixels; probe mode 1) --
+// and B[c][(j, c')] = H[u][v(j)][c][c'] (v = 2T - j for s = +1, v = j for s = -1), prepared once in global memory and
+// kept resident in shared memory for the CTA's group of 6 displacement rows.  M = 128 pixels (w <= 128), N = 16, K = 8
+// (half a pixel's channels) per MMA; 16 accumulator columns per output row, double buffered.  Single-pass tf32 with
+// round-to-nearest operands: the gradient tolerance is 2e-3 of max|g| (tests/test_gpu_parity_seg.py), the rounding
+// noise of a 7056-term signed sum is ~3e-4 of it.
+constexpr int SC_U = 6;
+constexpr int SC_SLOTS = 7;
+constexpr int SC_THREADS = 192;
+
+struct ScParams {
+  int n, h, w, T, V, sgn;
+  int ychunk, nychunks, ugroups;
+  int row_bytes, box_bytes;
+  float* part;  // [ugroups][n*h*w][16]
+};
+
+__global__ void seg_round_tf32_kernel(const float* __restrict__ x, float* __restrict__ out, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    float4 h;
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t);
+    reinterpret_cast<float4*>(out)[i] = h;
+  }
+}
+
+// H [V*V][k][k] -> Bg[u][j][c (16)][c' (16)], tf32-rounded, scaled, zero padded; v = (sgn > 0) ? 2T - j : j
+__global__ void seg_hprep_kernel(const float* __restrict__ H, float* __restrict__ Bg, int V, int k, int T, int sgn, float scale) {
+  const int total = V * V * 256;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int cp = i & 15, c = (i >> 4) & 15, j = (i >> 8) % V, u = (i >> 8) / V;
+    const int v = sgn > 0 ? 2 * T - j : j;
+    float val = (c < k && cp < k) ? H[(((long long)u * V + v) * k + c) * k + cp] * scale : 0.f;
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(val));
+    Bg[i] = __uint_as_float(t);
+  }
+}
+
+__device__ __forceinline__ uint64_t sc_desc(uint32_t saddr) {
+  // K-major, SWIZZLE_64B: rows 64 B apart, 8-row groups 512 B apart (LBO unused)
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(SC_THREADS, 1)
+seg_corr_tc_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmB, ScParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                    // SC_SLOTS input-row slots
+  const uint32_t bbase = base + SC_SLOTS * (uint32_t)P.row_bytes;   // [SC_U][V][16 rows][64 B] resident coefficients
+  const uint32_t bars = bbase + (uint32_t)(SC_U * P.V) * 1024u;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (SC_SLOTS + s); };
+  auto tfull = [&](int a) { return bars + 8u * (2 * SC_SLOTS + a); };
+  auto tempty = [&](int a) { return bars + 8u * (2 * SC_SLOTS + 2 + a); };
+  const uint32_t bres = bars + 8u * (2 * SC_SLOTS + 4);
+  uint8_t* bars_ptr = smem_raw + (bars - raw);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_ptr + 8 * (2 * SC_SLOTS + 5));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SC_SLOTS; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull(a), 1);
+      mbar_init(tempty(a), 128);
+    }
+    mbar_init(bres, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmIn);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 32);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int g = blockIdx.x % P.ugroups;
+  const int yc = (blockIdx.x / P.ugroups) % P.nychunks;
+  const int img = blockIdx.x / (P.ugroups * P.nychunks);
+  const int Ya = yc * P.ychunk, Yb = min(P.h, Ya + P.ychunk);
+  const int u0 = g * SC_U;
+  const int nu = min(SC_U, P.V - u0);
+  // input row of (Y, ul): r = Y + d(ul), d(ul) = -sgn * (u0 + ul - T); d is monotone in ul
+  const int d_first = -P.sgn * (u0 - P.T), d_last = -P.sgn * (u0 + nu - 1 - P.T);
+  const int dmin = min(d_first, d_last), dmax = max(d_first, d_last);
+  const int r_lo = max(0, Ya + dmin), r_hi = min(P.h - 1, Yb - 1 + dmax);
+
+  if (warp == 0) {
+    // =============================== TMA producer ============================================
+    if (lane == 0) {
+      // resident coefficients of this displacement-row group: rows (u, j, c) are contiguous in Bg; boxes of 7 j's
+      mbar_expect_tx(bres, (uint32_t)(nu * P.V) * 1024u);
+      for (int ul = 0; ul < nu; ++ul)
+        for (int j0 = 0; j0 < P.V; j0 += 7) {
+          const int nj = min(7, P.V - j0);
+          (void)nj;  // (V is a multiple of 7 for T = 3, 10; other T take the 1-j box map: see sc_plan)
+          tma_load_2d(bbase + (uint32_t)((ul * P.V + j0) * 1024), &tmB, bres, 0, ((u0 + ul) * P.V + j0) * 16);
+        }
+      int r_next = r_lo;
+      for (int Y = Ya; Y < Yb; ++Y) {
+        const int need = min(r_hi, Y + dmax);
+        for (; r_next <= need; ++r_next) {
+          const int idx = r_next - r_lo, s = idx % SC_SLOTS;
+          mbar_wait(empty(s), ((idx / SC_SLOTS) & 1u) ^ 1u);
+          mbar_expect_tx(full(s), (uint32_t)P.box_bytes);
+          tma_load_3d(base + s * (uint32_t)P.row_bytes, &tmIn, full(s), 0, -P.T, img * P.h + r_next);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ==============================================
+    // kind::tf32, D = f32, M = 128, N = 16, A and B K-major
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    mbar_wait(bres, 0);
+    for (int Y = Ya; Y < Yb; ++Y) {
+      const uint32_t it = (uint32_t)(Y - Ya), as = it & 1u;
+      mbar_wait(tempty(as), ((it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + as * 16u;
+      uint32_t started = 0u;
+      for (int ul = 0; ul < nu; ++ul) {
+        const int d = -P.sgn * (u0 + ul - P.T);
+        const int r = Y + d;
+        if (r < 0 || r >= P.h) continue;
+        const int idx = r - r_lo, s = idx % SC_SLOTS;
+        mbar_wait(full(s), (idx / SC_SLOTS) & 1u);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t a0 = base + s * (uint32_t)P.row_bytes, b0 = bbase + (uint32_t)(ul * P.V) * 1024u;
+          for (int j = 0; j < P.V; ++j) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              sj_mma(acc, sc_desc(a0 + (uint32_t)j * 64u + half * 32u), sc_desc(b0 + (uint32_t)j * 1024u + half * 32u), idesc,
+                     (started | (uint32_t)j | (uint32_t)half) ? 1u : 0u);
+            }
+          }
+          if (d == dmin) umma_commit(empty(s));  // last use of input row r (later rows Y pair it with smaller offsets only)
+        }
+        __syncwarp();
+        started = 1u;
+      }
+      if (elect_one_sync()) umma_commit(tfull(as));
+      __syncwarp();
+    }
+  } else {
+    // =============================== epilogue (warps 2-5) ======================================
+    const int quad = warp & 3;
+    const int X = quad * 32 + lane;
+    float* out = P.part + (long long)g * P.n * P.h * P.w * 16;
+    for (int Y = Ya; Y < Yb; ++Y) {
+      const uint32_t it = (uint32_t)(Y - Ya), as = it & 1u;
+      bool any = false;
+      for (int ul = 0; ul < nu; ++ul) {
+        const int r = Y - P.sgn * (u0 + ul - P.T);
+        any |= (r >= 0 && r < P.h);
+      }
+      mbar_wait(tfull(as), (it >> 1) & 1u);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16), v);  // both 16-column accumulators
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(tempty(as));
+      if (X < P.w) {
+        float* o = out + (((long long)img * P.h + Y) * P.w + X) * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (any) {
+            if (as == 0)
+              t = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
+                              __uint_as_float(v[q * 4 + 3]));
+            else
+              t = make_float4(__uint_as_float(v[16 + q * 4]), __uint_as_float(v[16 + q * 4 + 1]),
+                              __uint_as_float(v[16 + q * 4 + 2]), __uint_as_float(v[16 + q * 4 + 3]));
+          }
+          *reinterpret_cast<float4*>(o + q * 4) = t;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 32);
+}
+
+__global__ void seg_corr_tc_sum_kernel(const float* __restrict__ part, float* __restrict__ out, long long n4, int groups) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 t = reinterpret_cast<const float4*>(part)[i];
+    for (int gi = 1; gi < groups; ++gi) {
+      const float4 a = reinterpret_cast<const float4*>(part)[(long long)gi * n4 + i];
+      t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = t;
+  }
+}
+
+struct ScPlan {
+  bool ok;
+  int ychunk, nychunks, ugroups, ctas, row_bytes, box_bytes, smem;
+};
+
+static ScPlan sc_plan(int n, int k, int h, int w, int T) {
+  ScPlan p = {};
+  const int V = 2 * T + 1;
+  if (k > 16 || k < 5 || V > 24 || V % 7 != 0 || n < 1 || w > 128) return p;  // coefficient boxes hold 7 j's: T = 3, 10
+  p.box_bytes = (128 + V - 1) * 64;
+  p.row_bytes = (p.box_bytes + 1023) / 1024 * 1024;
+  p.smem = 1024 + SC_SLOTS * p.row_bytes + SC_U * V * 1024 + 256;
+  if (p.smem > 232448) return p;
+  p.ugroups = (V + SC_U - 1) / SC_U;
+  int want = (3 * device_sm_count() + n * p.ugroups - 1) / (n * p.ugroups);
+  if (want < 1) want = 1;
+  p.ychunk = (h + want - 1) / want;
+  if (p.ychunk < 4) p.ychunk = 4;
+  if (p.ychunk > h) p.ychunk = h;
+  p.nychunks = (h + p.ychunk - 1) / p.ychunk;
+  p.ctas = n * p.nychunks * p.ugroups;
+  p.ok = true;
+  return p;
+}
+
+long long seg_corr_tc_workspace(int n, int k, int h, int w, int T) {
+  const ScPlan p = sc_plan(n, k, h, w, T);
+  if (!p.ok) return 0;
+  const int V = 2 * T + 1;
+  return ((long long)n * h * w * 16 * (1 + p.ugroups) + (long long)V * V * 256) * (long long)sizeof(float);
+}
+
+int seg_corr_tc(const float* in, const float* H, float* out, void* workspace, int n, int k, int h, int w, int T, int sgn, float scale,
+                cudaStream_t st) {
+  int rc = sj_init();
+  if (rc != IIC_OK) return rc;
+  const ScPlan p = sc_plan(n, k, h, w, T);
+  IIC_REQUIRE(p.ok, IIC_ERR_UNSUPPORTED, "seg_corr_tc: unsupported geometry (k=%d, T=%d, w=%d)", k, T, w);
+  const int V = 2 * T + 1;
+  const long long elems = (long long)n * h * w * 16;
+  float* inr = (float*)workspace;
+  float* part = inr + elems;
+  float* Bg = part + elems * p.ugroups;
+  int blocks = cdiv(elems / 4, 256);
+  if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
+  seg_round_tf32_kernel<<<blocks, 256, 0, st>>>(in, inr, elems / 4);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  seg_hprep_kernel<<<cdiv((long long)V * V * 256, 256), 256, 0, st>>>(H, Bg, V, k, T, sgn, scale);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  alignas(64) CUtensorMap tmIn, tmB;
+  if ((rc = sj_map(&tmIn, inr, n * h, w, 128 + V - 1)) != IIC_OK) return rc;
+  {
+    cuuint64_t gdim[2] = {16, (cuuint64_t)V * V * 16};
+    cuuint64_t gstr[1] = {64};
+    cuuint32_t box[2] = {16, 7 * 16};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = sj_encodeTiled(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, Bg, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IIC_REQUIRE(r == CUDA_SUCCESS, IIC_ERR_CUDA, "cuTensorMapEncodeTiled(seg corr coefficients) failed (%d)", (int)r);
+  }
+  ScParams P = {};
+  P.n = n; P.h = h; P.w = w; P.T = T; P.V = V; P.sgn = sgn;
+  P.ychunk = p.ychunk; P.nychunks = p.nychunks; P.ugroups = p.ugroups;
+  P.row_bytes = p.row_bytes; P.box_bytes = p.box_bytes;
+  P.part = part;
+  IIC_CUDA(cudaFuncSetAttribute(seg_corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem));
+  seg_corr_tc_kernel<<<p.ctas, SC_THREADS, p.smem, st>>>(tmIn, tmB, P);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  seg_corr_tc_sum_kernel<<<blocks, 256, 0, st>>>(part, out, elems / 4, p.ugroups);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
 }  // namespace iic
+
+extern "C" long long iic_seg_corr_tc_workspace(int n, int k, int h, int w, int T) { return iic::seg_corr_tc_workspace(n, k, h, w, T); }
+
+extern "C" int iic_seg_corr_tc(const float* in, const float* H, float* out, void* workspace, int n, int k, int h, int w, int T,
+                               int sgn, float scale, void* stream) {
+  IIC_REQUIRE(in && H && out && workspace && n > 0 && k > 0 && T >= 0 && (sgn == 1 || sgn == -1), IIC_ERR_BAD_ARG,
+              "iic_seg_corr_tc: bad arguments");
+  return iic::seg_corr_tc(in, H, out, workspace, n, k, h, w, T, sgn, scale, (cudaStream_t)stream);
+}
 
 extern "C" long long iic_seg_joint_tc_workspace(int n, int k, int h, int w, int T) {
   return iic::seg_joint_tc_workspace(n, k, h, w, T);

@@ -222,7 +222,26 @@ def seg_joint(x1m, x2m, k, T):
   return joint
 
 
+def seg_corr_tc(inp, H, k, T, sgn, scale):
+  """Tensor-core version of seg_corr_bwd; None when the geometry is not supported."""
+  n, h, w, kp = inp.shape
+  if kp != 16:
+    return None
+  nbytes = int(_lib.lib().iic_seg_corr_tc_workspace(n, k, h, w, T))
+  if nbytes <= 0:
+    return None
+  ws = torch.empty(nbytes // 4, device=inp.device, dtype=torch.float32)
+  out = torch.empty_like(inp)
+  check(_lib.lib().iic_seg_corr_tc(_p(inp), _p(H), _p(out), _p(ws), n, k, h, w, T, sgn, float(scale), _stream()),
+        "iic_seg_corr_tc")
+  return out
+
+
 def seg_corr_bwd(inp, H, k, T, sgn, scale):
+  if SEG_JOINT_TC["on"] and T > 0:
+    o = seg_corr_tc(inp, H, k, T, sgn, scale)
+    if o is not None:
+      return o
   n, h, w, _ = inp.shape
   out = torch.empty_like(inp)
   check(_lib.lib().iic_seg_corr_bwd(_p(inp), _p(H), _p(out), n, k, h, w, T, sgn, float(scale), _stream()),

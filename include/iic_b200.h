@@ -134,6 +134,11 @@ int iic_seg_joint(const float* x1m, const float* x2m, float* joint, void* worksp
 long long iic_seg_joint_tc_workspace(int n, int k, int h, int w, int T);
 int iic_seg_joint_tc(const float* x1m, const float* x2m, float* joint, void* workspace, int n, int k, int h, int w, int T,
                      void* stream);
+/* iic_seg_corr_bwd on the tensor cores (kind::tf32, round-to-nearest operands, single pass: relative error ~3e-4 of the
+ * gradient scale), KP = 16, w <= 128, 2T+1 a multiple of 7 (T = 3, 10).  _workspace returns 0 if unsupported. */
+long long iic_seg_corr_tc_workspace(int n, int k, int h, int w, int T);
+int iic_seg_corr_tc(const float* in, const float* H, float* out, void* workspace, int n, int k, int h, int w, int T, int sgn,
+                    float scale, void* stream);
 int iic_seg_corr_bwd(const float* in, const float* H, float* out, int n, int k, int h, int w, int T, int sgn,
                      float scale, void* stream);
 int iic_box_filter(const float* in, float* tmp, float* out, int n, int k, int h, int w, int T, void* stream);
