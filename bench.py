@@ -53,6 +53,12 @@ CONFIGS = {
 }
 
 
+# Defaults that depend on code having run on a B200 (flipped by hand after tools/gpu_r2_a.sh passes): until then the
+# default command line takes round 1's validated path, so that the driver's round-end run cannot be broken by a kernel
+# that has never executed.  Every item stays selectable from the command line.
+VALIDATED = {"arena": False, "rgb_input": False, "also": ""}
+
+
 def parse():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
@@ -62,16 +68,20 @@ def parse():
   ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
   ap.add_argument("--pairs-per-gpu", type=int, default=0, help="override the configuration's batch (per GPU)")
   ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "tf32x3", "fp32"])
-  ap.add_argument("--also", default="tf32x3", help="comma list of further precision modes measured briefly at N=1 "
+  ap.add_argument("--also", default=VALIDATED["also"], help="comma list of further precision modes measured briefly at N=1 "
                                                    "(reported under precision_modes); '' for none")
   ap.add_argument("--head", default=None, help="A | B (default: B for clustering, A for segmentation)")
   ap.add_argument("--seg-collapsed", action="store_true", help="c5: IID_segmentation_loss instead of _uncollapsed")
-  ap.add_argument("--grey-input", action="store_true", help="clustering: feed 1-channel grey batches (round-1 bench input) "
-                                                            "instead of RGB -> grey -> sobel")
+  ap.add_argument("--grey-input", dest="grey_input", action="store_true", default=not VALIDATED["rgb_input"],
+                  help="clustering: feed 1-channel grey batches (round-1 bench input) instead of RGB -> grey -> sobel")
+  ap.add_argument("--rgb-input", dest="grey_input", action="store_false", help="clustering: RGB batches, fused grey + sobel")
   ap.add_argument("--cpu-pairs", type=int, default=0, help="bounded CPU sample: image pairs per reference step")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-roofline", action="store_true")
-  ap.add_argument("--no-arena", action="store_true", help="round-1 gradient path (autograd accumulation, cat + all-reduce)")
+  ap.add_argument("--no-arena", dest="no_arena", action="store_true", default=not VALIDATED["arena"],
+                  help="round-1 gradient path (autograd accumulation, cat + all-reduce)")
+  ap.add_argument("--arena", dest="no_arena", action="store_false",
+                  help="flat in-place gradients, bucketed all-reduce overlapped with the backward")
   ap.add_argument("--verify", action="store_true", help="check the N-rank loss / gradient checksum against the one-device "
                                                         "emulation of the sharded algorithm; adds parity_ok to the line")
   a = ap.parse_args()
