@@ -93,6 +93,8 @@ _SIGS = {
                                c_int, c_int, _P]),
   "iic_adam_step": (c_int, [POINTER(c_void_p), POINTER(c_longlong), c_int, c_float, c_float, c_float, c_float,
                             c_float, c_int, _P]),
+  "iic_adam_step_dev": (c_int, [POINTER(c_void_p), POINTER(c_longlong), c_int, c_float, c_float, c_float, c_float,
+                                c_float, _P, _P]),
 }
 
 _lib = None

@@ -21,8 +21,17 @@ struct AdamTable {
   int count;
 };
 
+// step_dev != nullptr: the step count lives in device memory (a float scalar the caller increments before each launch)
+// and the bias corrections are evaluated here -- the launch arguments then never change, so the step can be replayed from
+// a CUDA graph (iic_b200/graph.py).
 __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamTable tb, float lr, float b1, float b2,
-                                                   float eps, float wd, float bc1, float bc2_sqrt) {
+                                                   float eps, float wd, float bc1, float bc2_sqrt,
+                                                   const float* __restrict__ step_dev) {
+  if (step_dev != nullptr) {
+    const float step = *step_dev;
+    bc1 = 1.f - powf(b1, step);
+    bc2_sqrt = sqrtf(1.f - powf(b2, step));
+  }
   const int total_chunks = tb.chunk_begin[tb.count];
   for (int ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
     int t = 0;
@@ -55,9 +64,23 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamT
 
 using namespace iic;
 
+static int adam_launch(const void* const* ptrs_host, const long long* sizes_host, int T, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, int step, const float* step_dev, void* stream);
+
 extern "C" int iic_adam_step(const void* const* ptrs_host, const long long* sizes_host, int T, float lr, float beta1,
                              float beta2, float eps, float weight_decay, int step, void* stream) {
   IIC_REQUIRE(ptrs_host && sizes_host && T > 0 && step > 0, IIC_ERR_BAD_ARG, "iic_adam_step: bad arguments");
+  return adam_launch(ptrs_host, sizes_host, T, lr, beta1, beta2, eps, weight_decay, step, nullptr, stream);
+}
+
+extern "C" int iic_adam_step_dev(const void* const* ptrs_host, const long long* sizes_host, int T, float lr, float beta1,
+                                 float beta2, float eps, float weight_decay, const float* step_dev, void* stream) {
+  IIC_REQUIRE(ptrs_host && sizes_host && T > 0 && step_dev, IIC_ERR_BAD_ARG, "iic_adam_step_dev: bad arguments");
+  return adam_launch(ptrs_host, sizes_host, T, lr, beta1, beta2, eps, weight_decay, 1, step_dev, stream);
+}
+
+static int adam_launch(const void* const* ptrs_host, const long long* sizes_host, int T, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, int step, const float* step_dev, void* stream) {
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
   for (int t0 = 0; t0 < T; t0 += ADAM_MAX_T) {
@@ -80,7 +103,7 @@ extern "C" int iic_adam_step(const void* const* ptrs_host, const long long* size
     int blocks = chunks;
     const int cap = device_sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(tb, lr, beta1, beta2, eps, weight_decay, bc1, bc2s);
+    adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(tb, lr, beta1, beta2, eps, weight_decay, bc1, bc2s, step_dev);
     IIC_LAUNCH_CHECK();
     count_launch();
   }

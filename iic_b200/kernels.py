@@ -665,7 +665,8 @@ def seg_head_bwd(feat, w, zlow, dout, dfeat, accumulate):
 
 # ---- optimiser ------------------------------------------------------------------------------
 @_cat("adam")
-def adam_step(params, grads, exp_avgs, exp_avg_sqs, lr, beta1, beta2, eps, weight_decay, step):
+def adam_step(params, grads, exp_avgs, exp_avg_sqs, lr, beta1, beta2, eps, weight_decay, step, step_dev=None):
+  """step_dev: float32 device scalar holding the step count (graph-replayable form, iic_adam_step_dev)."""
   T = len(params)
   ptrs = (ctypes.c_void_p * (4 * T))()
   sizes = (ctypes.c_longlong * T)()
@@ -674,6 +675,11 @@ def adam_step(params, grads, exp_avgs, exp_avg_sqs, lr, beta1, beta2, eps, weigh
       assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float32
     ptrs[4 * i], ptrs[4 * i + 1], ptrs[4 * i + 2], ptrs[4 * i + 3] = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()
     sizes[i] = p.numel()
+  if step_dev is not None:
+    assert step_dev.is_cuda and step_dev.dtype == torch.float32 and step_dev.numel() == 1
+    check(_lib.lib().iic_adam_step_dev(ptrs, sizes, T, float(lr), float(beta1), float(beta2), float(eps),
+                                       float(weight_decay), _p(step_dev), _stream()), "iic_adam_step_dev")
+    return
   check(_lib.lib().iic_adam_step(ptrs, sizes, T, float(lr), float(beta1), float(beta2), float(eps),
                                  float(weight_decay), int(step), _stream()), "iic_adam_step")
 

@@ -36,10 +36,16 @@ class FusedAdam(torch.optim.Optimizer):
 
   @torch.no_grad()
   def step(self, closure=None):
+    """``self.graph_safe = True``: the step count of every launch group also lives in a device scalar that is incremented
+    on the stream, and the kernel computes the bias corrections from it -- the enqueued work is then identical from step
+    to step and can be captured into a CUDA graph (iic_b200/graph.py).  While a capture is in progress the host-side
+    ``state['step']`` counters are NOT advanced (nothing executes); ``note_replay()`` advances them per replay."""
     assert closure is None
+    graph = getattr(self, "graph_safe", False)
+    capturing = graph and torch.cuda.is_current_stream_capturing()
+    self._last_states = []
     for group in self.param_groups:
-      ps, gs, ms, vs = [], [], [], []
-      step = None
+      buckets = {}  # step value -> (params, grads, exp_avgs, exp_avg_sqs); parameters that joined later step separately
       for p in group["params"]:
         if p.grad is None or (self.grad_filter is not None and not self.grad_filter(p)):
           continue
@@ -50,21 +56,32 @@ class FusedAdam(torch.optim.Optimizer):
           st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
         if not torch.is_tensor(st["step"]):  # state assigned by hand after load_state_dict
           st["step"] = torch.tensor(float(st["step"]))
-        st["step"] += 1
-        s = int(st["step"].item())
-        if step is None:
-          step = s
-        if s != step:  # parameters that joined later: separate launch group
-          kernels.adam_step(ps, gs, ms, vs, group["lr"], group["betas"][0], group["betas"][1], group["eps"],
-                            group["weight_decay"], step)
-          ps, gs, ms, vs, step = [], [], [], [], s
-        ps.append(p)
-        gs.append(p.grad.contiguous())
-        ms.append(st["exp_avg"])
-        vs.append(st["exp_avg_sq"])
-      if ps:
+        s = int(st["step"].item()) + 1
+        if not capturing:
+          st["step"] += 1
+        self._last_states.append(st)
+        b = buckets.setdefault(s, ([], [], [], []))
+        b[0].append(p)
+        b[1].append(p.grad.contiguous())
+        b[2].append(st["exp_avg"])
+        b[3].append(st["exp_avg_sq"])
+      for s, (ps, gs, ms, vs) in buckets.items():
+        step_dev = None
+        if graph:
+          key = tuple(id(p) for p in ps)
+          store = self.__dict__.setdefault("_dev_steps", {})
+          step_dev = store.get(key)
+          if step_dev is None:
+            step_dev = store[key] = torch.full((1,), float(s - 1), device=ps[0].device, dtype=torch.float32)
+          step_dev.add_(1.0)  # on the stream: executed eagerly, recorded under capture
         kernels.adam_step(ps, gs, ms, vs, group["lr"], group["betas"][0], group["betas"][1], group["eps"],
-                          group["weight_decay"], step)
+                          group["weight_decay"], s, step_dev=step_dev)
+
+  def note_replay(self):
+    """Host-side bookkeeping for one replay of a captured step: advance the ``state['step']`` counters of the
+    parameters the captured step updates (the device-side counters advance inside the graph)."""
+    for st in self._last_states:
+      st["step"] += 1
 
 
 def zero_grad_like_reference(net):

@@ -353,6 +353,11 @@ int iic_seg_head_bwd(const void* feat, int dtype, const float* w, const float* z
  *  ptrs_host: 4*T device pointers [param, grad, exp_avg, exp_avg_sq] per tensor, sizes_host: T counts. */
 int iic_adam_step(const void* const* ptrs_host, const long long* sizes_host, int T, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int step, void* stream);
+/* The same with the step count read from device memory (a float scalar the caller increments on the stream before the
+ * call) and the bias corrections computed on the device: the launch arguments never change, so a training step that
+ * contains it can be captured once into a CUDA graph and replayed. */
+int iic_adam_step_dev(const void* const* ptrs_host, const long long* sizes_host, int n_tensors, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, const float* step_dev, void* stream);
 
 #ifdef __cplusplus
 }

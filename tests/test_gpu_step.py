@@ -255,3 +255,40 @@ def test_legacy_format_checkpoint_loads_and_reproduces_the_oracle(tmp_path):
   assert abs(loss.item() - want) < 2e-5
   for (k, p), (_, q) in zip(net.named_parameters(), ora.named_parameters()):
     assert torch.allclose(p.detach().cpu(), q.detach(), rtol=1e-3, atol=3 * LR), k
+
+
+def test_graphed_step_equals_eager_steps():
+  """iic_b200.graph.GraphedStep (one cudaGraphLaunch per step) against the eager step: same losses and parameters over
+  several steps (fp32 mode, identical kernels -> tight), Adam step counters advance, the idle head is untouched."""
+  import iic_b200.archs as archs
+  from iic_b200.arena import GradArena
+  from iic_b200.graph import GraphedStep
+  from iic_b200.optim import FusedAdam
+  from iic_b200.step import iic_cluster_step
+  nets, opts, arenas = [], [], []
+  for _ in range(2):
+    net = archs.ClusterNet5gTwoHead(Namespace(precision="fp32", **CFG))
+    weights.fill_state_dict(net, salt=31)
+    net.cuda().train()
+    nets.append(net)
+    opts.append(FusedAdam(net.parameters(), lr=LR))
+    arenas.append(GradArena(net))
+  batches = []
+  for i in range(6):
+    g = weights.uniform("graph.g%d" % i, (8, 1, 32, 32))
+    batches.append((g.cuda(), (g + 0.05 * weights.normal("graph.t%d" % i, (8, 1, 32, 32))).clamp(0, 1).cuda()))
+  # eager net: 3 warm-up steps on batch 0 (what GraphedStep does while it builds), then batches 1..5
+  eager_losses = []
+  for _ in range(3):
+    iic_cluster_step(nets[0], opts[0], *batches[0], head="B", arena=arenas[0])
+  for b in batches[1:]:
+    eager_losses.append(iic_cluster_step(nets[0], opts[0], *b, head="B", arena=arenas[0])[0].item())
+  gs = GraphedStep(nets[1], opts[1], arenas[1], batches[0], head="B", warmup=3)
+  graph_losses = [gs(*b)[0].item() for b in batches[1:]]
+  for a, b in zip(eager_losses, graph_losses):
+    assert abs(a - b) < 1e-6, (eager_losses, graph_losses)
+  for (k, p), (_, q) in zip(nets[0].named_parameters(), nets[1].named_parameters()):
+    assert torch.allclose(p, q, rtol=1e-5, atol=1e-7), k
+  pa, pb = dict(nets[1].named_parameters()), opts[1]
+  assert int(pb.state[pa["trunk.conv1.weight"]]["step"]) == 8
+  assert len(pb.state[pa["head_A.heads.0.0.weight"]]) == 0  # never trained: no state, untouched

@@ -47,6 +47,10 @@ for v in IIC_BN_BITMASK=1 IIC_CONV_HALO_STATS=1 "IIC_STEM_BWD_FUSED=1 IIC_STEM_B
   f=$(echo "$v" | tr ' =' '__')
   env $v timeout 120 python bench.py --arena --rgb-input --steps 5 --no-cpu-baseline --also '' > $O/a_bench_$f.json 2> $O/a_bench_$f.err; stamp "4 bench $v rc=$?"; summ $O/a_bench_$f.json
 done
+timeout 150 python bench.py --arena --rgb-input --graph --steps 10 --no-cpu-baseline --no-roofline --also '' > $O/a_bench_graph.json 2> $O/a_bench_graph.err; stamp "4a bench c4, CUDA graph rc=$?"; tail -2 $O/a_bench_graph.err; summ $O/a_bench_graph.json
+timeout 150 python bench.py --arena --rgb-input --graph --config c2 --steps 10 --no-cpu-baseline --no-roofline --also '' > $O/a_bench_graph_c2.json 2> $O/a_bench_graph_c2.err; stamp "4a bench c2, CUDA graph rc=$?"; tail -2 $O/a_bench_graph_c2.err; summ $O/a_bench_graph_c2.json
+timeout 150 python bench.py --arena --rgb-input --graph --pairs-per-gpu 88 --steps 10 --no-cpu-baseline --no-roofline --also '' > $O/a_bench_graph_88.json 2> $O/a_bench_graph_88.err; stamp "4a bench c4 88 pairs, CUDA graph rc=$?"; summ $O/a_bench_graph_88.json
+timeout 150 python bench.py --arena --rgb-input --pairs-per-gpu 88 --steps 10 --no-cpu-baseline --no-roofline --also '' > $O/a_bench_eager_88.json 2> $O/a_bench_eager_88.err; stamp "4a bench c4 88 pairs, eager rc=$?"; summ $O/a_bench_eager_88.json
 timeout 150 python bench.py --steps 5 --no-cpu-baseline > $O/a_bench_r1path.json 2> $O/a_bench_r1path.err; stamp "4b bench, round-1 path (no arena, grey input) rc=$?"; summ $O/a_bench_r1path.json
 for c in c2 c3 c4-strong c5; do
   timeout 150 python bench.py --arena --rgb-input --config $c --steps 5 --no-cpu-baseline --also '' > $O/a_bench_$c.json 2> $O/a_bench_$c.err; stamp "5 bench $c rc=$?"; tail -1 $O/a_bench_$c.err; summ $O/a_bench_$c.json
