@@ -61,4 +61,8 @@ stamp "6a ncu launch list rc=$?"; python tools/ncu_launch_table.py $O/a_launches
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:"conv_tc2_kernel|conv_halo" -s 40 -c 12 -o $O/a_prof_conv \
    python bench.py --arena --rgb-input --steps 1 --warmup 0 --no-cpu-baseline --no-roofline --also '' > $O/a_ncu_conv.log 2>&1
 stamp "6b ncu conv kernels rc=$?"
-timeout 100 python tools/conv_sweep.py 1408 > $O/a_conv_sweep.txt 2>&1; stamp "7 sweep rc=$?"; tail -45 $O/a_conv_sweep.txt
+timeout 100 python tools/conv_sweep.py 1408 > $O/a_conv_sweep.txt 2>&1; stamp "7 sweep rc=$?"; tail -12 $O/a_conv_sweep.txt
+timeout 100 python tools/conv_sweep.py 352 tf32x3 > $O/a_conv_sweep_tf32x3.txt 2>&1; stamp "7b sweep tf32x3 rc=$?"; tail -12 $O/a_conv_sweep_tf32x3.txt
+timeout 100 python tools/conv_sweep.py 352 tf32 > $O/a_conv_sweep_tf32.txt 2>&1; stamp "7c sweep tf32 rc=$?"; tail -12 $O/a_conv_sweep_tf32.txt
+IIC_SEG_JOINT_TC=1 timeout 100 python tools/seg_step.py 15 A > $O/a_seg_tc.json 2>&1; stamp "8 seg step, tensor-core joint rc=$?"; tail -1 $O/a_seg_tc.json
+timeout 100 python tools/seg_step.py 15 A > $O/a_seg_simt.json 2>&1; stamp "8b seg step, SIMT joint rc=$?"; tail -1 $O/a_seg_simt.json
