@@ -40,20 +40,21 @@ try:
 except Exception as e:
   print("no precision json", e)
 PY
-timeout 200 python tools/precision_probe.py --sz 96 --pairs 32 --steps 0 --modes bf16,tf32,tf32x3 > $O/a_prec96.json 2> $O/a_prec96.err
-stamp "2b precision 96x96 rc=$?"; tail -2 $O/a_prec96.err; grep -E "grad_rel_l2_total|grad_cos_min|loss_rel|out_max" $O/a_prec96.json | head -20
 timeout 300 python bench.py --arena --rgb-input --also tf32x3 > $O/a_bench.json 2> $O/a_bench.err; stamp "3 bench default rc=$?"; tail -2 $O/a_bench.err; summ $O/a_bench.json
-for v in IIC_BN_BITMASK=1 IIC_CONV_HALO_STATS=1 "IIC_STEM_BWD_FUSED=1 IIC_STEM_BWD_V2=1" ; do
-  f=$(echo "$v" | tr ' =' '__')
-  env $v timeout 120 python bench.py --arena --rgb-input --steps 5 --no-cpu-baseline --also '' > $O/a_bench_$f.json 2> $O/a_bench_$f.err; stamp "4 bench $v rc=$?"; summ $O/a_bench_$f.json
+timeout 150 python bench.py --steps 5 --no-cpu-baseline > $O/a_bench_r1path.json 2> $O/a_bench_r1path.err; stamp "4b bench, round-1 path (no arena, grey input) rc=$?"; summ $O/a_bench_r1path.json
+for c in c2 c3 c4-strong c5; do
+  timeout 150 python bench.py --arena --rgb-input --config $c --steps 5 --no-cpu-baseline --also '' > $O/a_bench_$c.json 2> $O/a_bench_$c.err; stamp "5 bench $c rc=$?"; tail -1 $O/a_bench_$c.err; summ $O/a_bench_$c.json
 done
 timeout 150 python bench.py --arena --rgb-input --graph --steps 10 --no-cpu-baseline --no-roofline --also '' > $O/a_bench_graph.json 2> $O/a_bench_graph.err; stamp "4a bench c4, CUDA graph rc=$?"; tail -2 $O/a_bench_graph.err; summ $O/a_bench_graph.json
 timeout 150 python bench.py --arena --rgb-input --graph --config c2 --steps 10 --no-cpu-baseline --no-roofline --also '' > $O/a_bench_graph_c2.json 2> $O/a_bench_graph_c2.err; stamp "4a bench c2, CUDA graph rc=$?"; tail -2 $O/a_bench_graph_c2.err; summ $O/a_bench_graph_c2.json
 timeout 150 python bench.py --arena --rgb-input --graph --pairs-per-gpu 88 --steps 10 --no-cpu-baseline --no-roofline --also '' > $O/a_bench_graph_88.json 2> $O/a_bench_graph_88.err; stamp "4a bench c4 88 pairs, CUDA graph rc=$?"; summ $O/a_bench_graph_88.json
 timeout 150 python bench.py --arena --rgb-input --pairs-per-gpu 88 --steps 10 --no-cpu-baseline --no-roofline --also '' > $O/a_bench_eager_88.json 2> $O/a_bench_eager_88.err; stamp "4a bench c4 88 pairs, eager rc=$?"; summ $O/a_bench_eager_88.json
-timeout 150 python bench.py --steps 5 --no-cpu-baseline > $O/a_bench_r1path.json 2> $O/a_bench_r1path.err; stamp "4b bench, round-1 path (no arena, grey input) rc=$?"; summ $O/a_bench_r1path.json
-for c in c2 c3 c4-strong c5; do
-  timeout 150 python bench.py --arena --rgb-input --config $c --steps 5 --no-cpu-baseline --also '' > $O/a_bench_$c.json 2> $O/a_bench_$c.err; stamp "5 bench $c rc=$?"; tail -1 $O/a_bench_$c.err; summ $O/a_bench_$c.json
+timeout 100 python tools/conv_sweep.py 352 tf32x3 > $O/a_conv_sweep_tf32x3.txt 2>&1; stamp "7b sweep tf32x3 rc=$?"; tail -12 $O/a_conv_sweep_tf32x3.txt
+IIC_SEG_JOINT_TC=1 timeout 100 python tools/seg_step.py 15 A > $O/a_seg_tc.json 2>&1; stamp "8 seg step, tensor-core joint rc=$?"; tail -1 $O/a_seg_tc.json
+timeout 100 python tools/seg_step.py 15 A > $O/a_seg_simt.json 2>&1; stamp "8b seg step, SIMT joint rc=$?"; tail -1 $O/a_seg_simt.json
+for v in IIC_BN_BITMASK=1 IIC_CONV_HALO_STATS=1 "IIC_STEM_BWD_FUSED=1 IIC_STEM_BWD_V2=1" ; do
+  f=$(echo "$v" | tr ' =' '__')
+  env $v timeout 120 python bench.py --arena --rgb-input --steps 5 --no-cpu-baseline --also '' > $O/a_bench_$f.json 2> $O/a_bench_$f.err; stamp "4 bench $v rc=$?"; summ $O/a_bench_$f.json
 done
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/a_launches.csv \
    python bench.py --arena --rgb-input --steps 1 --warmup 1 --no-cpu-baseline --no-roofline --also '' > $O/a_ncu_list.log 2>&1
@@ -61,8 +62,7 @@ stamp "6a ncu launch list rc=$?"; python tools/ncu_launch_table.py $O/a_launches
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:"conv_tc2_kernel|conv_halo" -s 40 -c 12 -o $O/a_prof_conv \
    python bench.py --arena --rgb-input --steps 1 --warmup 0 --no-cpu-baseline --no-roofline --also '' > $O/a_ncu_conv.log 2>&1
 stamp "6b ncu conv kernels rc=$?"
+timeout 200 python tools/precision_probe.py --sz 96 --pairs 32 --steps 0 --modes bf16,tf32,tf32x3 > $O/a_prec96.json 2> $O/a_prec96.err
+stamp "2b precision 96x96 rc=$?"; tail -2 $O/a_prec96.err; grep -E "grad_rel_l2_total|grad_cos_min|loss_rel|out_max" $O/a_prec96.json | head -20
 timeout 100 python tools/conv_sweep.py 1408 > $O/a_conv_sweep.txt 2>&1; stamp "7 sweep rc=$?"; tail -12 $O/a_conv_sweep.txt
-timeout 100 python tools/conv_sweep.py 352 tf32x3 > $O/a_conv_sweep_tf32x3.txt 2>&1; stamp "7b sweep tf32x3 rc=$?"; tail -12 $O/a_conv_sweep_tf32x3.txt
 timeout 100 python tools/conv_sweep.py 352 tf32 > $O/a_conv_sweep_tf32.txt 2>&1; stamp "7c sweep tf32 rc=$?"; tail -12 $O/a_conv_sweep_tf32.txt
-IIC_SEG_JOINT_TC=1 timeout 100 python tools/seg_step.py 15 A > $O/a_seg_tc.json 2>&1; stamp "8 seg step, tensor-core joint rc=$?"; tail -1 $O/a_seg_tc.json
-timeout 100 python tools/seg_step.py 15 A > $O/a_seg_simt.json 2>&1; stamp "8b seg step, SIMT joint rc=$?"; tail -1 $O/a_seg_simt.json
