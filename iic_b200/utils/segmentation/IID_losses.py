@@ -21,40 +21,56 @@ EPS = float_info.epsilon
 RENDER = False
 
 
+def _seg_forward(x1, x2, theta, mask, lamb, T, collapsed, want_grad, shift):
+  """-> (out [2] = (loss, loss_no_lamb), dx1, dx2) with dx* = d loss / d x* (None unless want_grad)."""
+  n, k, h, w = x1.shape
+  x1m, x2m = kernels.seg_prepare(x1, x2, theta, mask, shift)
+  if collapsed:
+    b1 = kernels.box_filter(x1m, k, T)
+    joint = kernels.seg_joint(b1, x2m, k, 0)  # [1, k, k]
+  else:
+    joint = kernels.seg_joint(x1m, x2m, k, T)  # [(2T+1)^2, k, k]
+  if distributed.active():
+    distributed.allreduce_sum_(joint)
+  loss, H = kernels.joint_mi(joint, lamb, EPS, collapsed, want_grad)
+  V2 = 1 if collapsed else (2 * T + 1) ** 2
+  out = loss.sum(dim=0) / float(V2)  # (:150-157): mean over displacements
+  dx1 = dx2 = None
+  if want_grad:
+    if collapsed:
+      d_b1 = kernels.seg_corr_bwd(x2m, H, k, 0, 1, 1.0)
+      dx1m = kernels.box_filter(d_b1, k, T)  # the zero-padded box filter is self-adjoint
+      dx2m = kernels.seg_corr_bwd(b1, H, k, 0, -1, 1.0)
+    else:
+      dx1m = kernels.seg_corr_bwd(x2m, H, k, T, 1, 1.0 / V2)
+      dx2m = kernels.seg_corr_bwd(x1m, H, k, T, -1, 1.0 / V2)
+    dx1, dx2 = kernels.seg_unprepare(dx1m, dx2m, theta, mask, k, shift)
+  return out, dx1, dx2
+
+
 class _SegLoss(torch.autograd.Function):
   @staticmethod
   def forward(ctx, x1, x2, theta, mask, lamb, T, collapsed, want_grad, shift):
-    n, k, h, w = x1.shape
-    x1m, x2m = kernels.seg_prepare(x1, x2, theta, mask, shift)
-    if collapsed:
-      b1 = kernels.box_filter(x1m, k, T)
-      joint = kernels.seg_joint(b1, x2m, k, 0)  # [1, k, k]
-    else:
-      joint = kernels.seg_joint(x1m, x2m, k, T)  # [(2T+1)^2, k, k]
-    if distributed.active():
-      distributed.allreduce_sum_(joint)
-    loss, H = kernels.joint_mi(joint, lamb, EPS, collapsed, want_grad)
-    V2 = 1 if collapsed else (2 * T + 1) ** 2
-    out = loss.sum(dim=0) / float(V2)  # (:150-157): mean over displacements
+    out, dx1, dx2 = _seg_forward(x1, x2, theta, mask, lamb, T, collapsed, want_grad, shift)
     if want_grad:
-      if collapsed:
-        d_b1 = kernels.seg_corr_bwd(x2m, H, k, 0, 1, 1.0)
-        dx1m = kernels.box_filter(d_b1, k, T)  # the zero-padded box filter is self-adjoint
-        dx2m = kernels.seg_corr_bwd(b1, H, k, 0, -1, 1.0)
-      else:
-        dx1m = kernels.seg_corr_bwd(x2m, H, k, T, 1, 1.0 / V2)
-        dx2m = kernels.seg_corr_bwd(x1m, H, k, T, -1, 1.0 / V2)
-      dx1, dx2 = kernels.seg_unprepare(dx1m, dx2m, theta, mask, k, shift)
-      ctx.save_for_backward(dx1, dx2)
+      ctx.save_for_backward(dx1, dx2, x1, x2, theta, mask)
+      ctx.args = (T, collapsed, shift)
     ctx.set_materialize_grads(False)
     return out[0], out[1]
 
   @staticmethod
   def backward(ctx, g_loss, g_nolamb):
+    dx1, dx2, x1, x2, theta, mask = ctx.saved_tensors
+    g1 = g2 = None
+    if g_loss is not None:
+      g1, g2 = dx1 * g_loss, dx2 * g_loss
     if g_nolamb is not None:
-      raise NotImplementedError("loss_no_lamb is for analysis only (reference :78-81); backpropagate through `loss`")
-    dx1, dx2 = ctx.saved_tensors
-    return dx1 * g_loss, dx2 * g_loss, None, None, None, None, None, None, None
+      # rarely used (the reference only logs loss_no_lamb, :78-81): re-evaluate the analytic gradient with lamb = 1
+      T, collapsed, shift = ctx.args
+      _, e1, e2 = _seg_forward(x1, x2, theta, mask, 1.0, T, collapsed, True, shift)
+      g1 = e1 * g_nolamb if g1 is None else g1 + e1 * g_nolamb
+      g2 = e2 * g_nolamb if g2 is None else g2 + e2 * g_nolamb
+    return g1, g2, None, None, None, None, None, None, None
 
 
 def random_translation_multiple_draw(half_side_min, half_side_max):
