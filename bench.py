@@ -372,6 +372,8 @@ def measure(job, resident, host, steps, warmup, world, dev, sampler=None):
   kernels.launch_count(reset=True)
   sec, wall, last = timed(resident, False)
   launches = kernels.launch_count()
+  if getattr(job, "gstep", None) is not None:  # replays do not pass through the host-side counter
+    launches += steps * job.gstep.launches_per_replay
   clocks = sampler.stop() if sampler is not None else None
   job.step(host)
   sec_e, _, _ = timed(host, True)
@@ -516,6 +518,14 @@ def run_ours(args):
 
   ver = verify(args, world, rank, dev) if args.verify else None
 
+  overlap = None
+  if world > 1 and job.arena is not None and not args.graph:
+    job.arena.profile = True
+    job.step(resident)
+    torch.cuda.synchronize()
+    overlap = job.arena.timeline()
+    job.arena.profile = False
+
   cpu = None
   if rank == 0 and not args.no_cpu_baseline and world == 1:
     cpu, _ = time_cpu_reference(args, args.cpu_pairs or c["cpu_pairs"], 3, 1)
@@ -538,6 +548,8 @@ def run_ours(args):
       line["roofline"] = roof
     if modes:
       line["precision_modes"] = modes
+    if overlap is not None:
+      line["allreduce_timeline"] = overlap
     if ver is not None:
       line["verify"] = ver
       line["parity_ok"] = ver.get("parity_ok")

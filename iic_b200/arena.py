@@ -63,6 +63,8 @@ class GradArena(object):
     self.live = [False] * len(order)
     self._side = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
     self._overlap = False
+    self.profile = False  # record CUDA events around every bucket reduction (timeline(), bench.py --overlap-report)
+    self._events = None
     self._reset_step()
 
   # ---- per-step protocol ------------------------------------------------------------------------
@@ -81,6 +83,11 @@ class GradArena(object):
     self.flat.zero_()
     self._overlap = bool(overlap) and distributed.active()
     self._reset_step()
+    if self.profile and self._side is not None:
+      self._events = {"t0": torch.cuda.Event(enable_timing=True), "buckets": [], "bwd_end": None, "all_end": None}
+      self._events["t0"].record()
+    else:
+      self._events = None
 
   def holds(self, p):
     i = self._index.get(id(p))
@@ -120,17 +127,43 @@ class GradArena(object):
     cur = torch.cuda.current_stream(self.flat.device)
     self._side.wait_stream(cur)
     with torch.cuda.stream(self._side):
+      if self._events is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
       distributed.allreduce_sum_(self.flat[a:e])
+      if self._events is not None:
+        e1.record()
+        self._events["buckets"].append((b, (e - a) * 4, e0, e1))
 
   def flush(self):
     """After backward(): reduce whatever has not been reduced yet (same order on every rank) and make the compute
     stream wait for all reductions."""
     if not distributed.active():
       return
+    if self._events is not None:  # the backward has been enqueued up to here on the compute stream
+      self._events["bwd_end"] = torch.cuda.Event(enable_timing=True)
+      self._events["bwd_end"].record()
     for b in range(len(self.buckets)):
       self._reduce(b)
     if self._side is not None:
       torch.cuda.current_stream(self.flat.device).wait_stream(self._side)
+    if self._events is not None:
+      self._events["all_end"] = torch.cuda.Event(enable_timing=True)
+      self._events["all_end"].record()
+
+  def timeline(self):
+    """After a profiled step (``profile = True``) and a device synchronise: milliseconds since begin_step of every bucket
+    reduction on the side stream, of the end of the backward on the compute stream, and of the point where the compute
+    stream has the reduced gradients.  ``exposed_ms`` = all-reduce time the backward did not hide."""
+    ev = self._events
+    if ev is None or ev["bwd_end"] is None:
+      return None
+    t0 = ev["t0"]
+    rows = [{"bucket": b, "bytes": nbytes, "start_ms": t0.elapsed_time(e0), "end_ms": t0.elapsed_time(e1)}
+            for b, nbytes, e0, e1 in ev["buckets"]]
+    bwd_end, all_end = t0.elapsed_time(ev["bwd_end"]), t0.elapsed_time(ev["all_end"])
+    return {"buckets": rows, "backward_end_ms": bwd_end, "gradients_ready_ms": all_end, "exposed_ms": max(0.0, all_end - bwd_end),
+            "allreduce_busy_ms": sum(r["end_ms"] - r["start_ms"] for r in rows)}
 
   def grad_checksum(self):
     """fp64 sum and sum of squares of the whole arena (bench.py --verify)."""

@@ -34,9 +34,13 @@ class GraphedStep(object):
         self.fn(net, optimiser, *self.static, arena=arena, **self.kw)
     torch.cuda.current_stream(dev).wait_stream(side)
     torch.cuda.synchronize(dev)
+    from . import kernels
     self.graph = torch.cuda.CUDAGraph()
+    c0 = kernels.launch_count()
     with torch.cuda.graph(self.graph):
       self.out = self.fn(net, optimiser, *self.static, arena=arena, **self.kw)
+    # kernels of this library inside the graph (the host-side launch counter does not see replays)
+    self.launches_per_replay = kernels.launch_count() - c0
     self.warmup_steps = warmup  # these were real optimiser steps
 
   def __call__(self, *batch):
