@@ -159,12 +159,22 @@ class ClockSampler(object):
 
 
 def host_threads():
-  """All the cores this process may run on -- torch.distributed.run exports OMP_NUM_THREADS=1, which would otherwise pin
-  the CPU arm to one thread (4.3 pairs/s 'reference' numbers at N >= 2)."""
+  """One thread per PHYSICAL core this process may run on.  torch.distributed.run exports OMP_NUM_THREADS=1, which would
+  otherwise pin the CPU arm to one thread (4.3 pairs/s 'reference' numbers at N >= 2); one thread per logical
+  CPU (128 on the B200 hosts) oversubscribes the 64 cores and is 5x slower than 64 threads (measured: 3.2 vs 16 pairs/s)."""
   try:
-    return max(1, len(os.sched_getaffinity(0)))
+    logical = len(os.sched_getaffinity(0))
   except AttributeError:
-    return max(1, os.cpu_count() or 1)
+    logical = os.cpu_count() or 1
+  physical = None
+  try:
+    import psutil
+    physical = psutil.cpu_count(logical=False)
+  except Exception:
+    pass
+  if not physical:
+    physical = max(1, logical // 2)
+  return max(1, min(logical, physical))
 
 
 def workload_config(args, pairs_per_gpu, n):
@@ -179,7 +189,7 @@ def workload_config(args, pairs_per_gpu, n):
     elif args.grey_input:
       inp = "%dx%dx1 grey pair -> sobel" % (sz, sz)
     else:
-      inp = "%dx%dx3 rgb pair -> grey (0.299/0.587/0.114) -> sobel, fused on device" % (sz, sz)
+      inp = "%dx%dx3 uint8 rgb pair -> grey (PIL 'L' formula) -> sobel, fused on device" % (sz, sz)
     loss = "IID_loss lamb=1"
   return {"workload": "%s: %s head %s, %s, Adam" % (args.config, c["desc"], args.head, loss), "name": args.config,
           "pairs_per_gpu": pairs_per_gpu, "global_batch": pairs_per_gpu * n, "input": inp,
@@ -214,8 +224,11 @@ def make_host_batch(args, B, seed, pin=True):
     mask = (torch.rand(B, sz, sz, generator=g) < 0.7).float()
     batch = imgs + [theta, mask]
   else:
-    ch = 3 if (c["sobel"] and c["rgb"] and not args.grey_input) else 1
-    batch = [torch.rand(B, ch, sz, sz, generator=g) for _ in range(2)]
+    if c["sobel"] and c["rgb"] and not args.grey_input:
+      # RGB as the dataloader holds it (PIL images are uint8); the grey conversion + sobel run fused on the device
+      batch = [torch.randint(0, 256, (B, 3, sz, sz), generator=g, dtype=torch.uint8) for _ in range(2)]
+    else:
+      batch = [torch.rand(B, 1, sz, sz, generator=g) for _ in range(2)]
   return [t.pin_memory() for t in batch] if pin else batch
 
 
@@ -238,8 +251,8 @@ def cpu_reference_step_fn(args, pairs):
   batch = make_host_batch(args, pairs, 7, pin=False)
   head = args.head
 
-  def grey(x):  # custom_greyscale_to_tensor (code/utils/cluster/transforms.py:12-16) without the uint8 rounding
-    return x if x.shape[1] == 1 else (0.299 * x[:, 0:1] + 0.587 * x[:, 1:2] + 0.114 * x[:, 2:3])
+  def grey(x):  # custom_greyscale_to_tensor (code/utils/cluster/transforms.py:12-16)
+    return x if x.shape[1] == 1 else oracle_tf.grey_from_rgb(x)
 
   def step():
     opt.zero_grad(set_to_none=False)
