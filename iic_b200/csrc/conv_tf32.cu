@@ -14,6 +14,12 @@
 // 32 fp32 = one 128-byte SWIZZLE_128B row and UMMA_K = 8.  SPLIT = 3 adds four "splitter" warps between the TMA
 // producer and the MMA issuer: they rewrite a landed stage in place as hi and write lo into a twin buffer at the same
 // offsets (so the swizzle pattern is preserved), fence the generic->async proxy and arrive on a second barrier.
+// wgrad: both operands arrive pixel-major ([pixel][channel] = MN-major).  tcgen05 kind::tf32 has no MN-major mode for the
+// ordinary swizzles (measured: a kind::tf32 MMA with MN-major SWIZZLE_64B / 128B descriptors returns zeros,
+// tools/umma_sw64_probe.cu; 32-bit operands would need the separate 128B_BASE32B layout), so the same four warps
+// TRANSPOSE every landed 32-pixel x 32-channel block in place (one warp per block: a lane reads one pixel row into 32
+// registers, __syncwarp, writes one element of each channel row; conflict-free in both directions under the 128-byte
+// swizzle) -- after which a wgrad stage is an ordinary K-major stage and the issue path is the fprop one.
 // Shared-memory fill per tensor cycle: 3xTF32 needs 32 KB per 768 MMA cycles (43 B/clk, tensor bound); plain TF32 needs
 // the same 32 KB per 256 cycles (128 B/clk, L2->SM bound at N <= 128) -- the compensated mode is the one tuned here.
 #include <cuda.h>
@@ -63,20 +69,22 @@ __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float(r);
 }
 
-template <int BN, int SPLIT> struct T32Cfg {
+template <int BN, int SPLIT, int MODE = 0> struct T32Cfg {
+  static constexpr bool XFORM = (SPLIT == 3) || (MODE == 1);  // transform warps: hi/lo split and / or wgrad block transposes
   static constexpr int B_BYTES = BN * 128;
   static constexpr int HALF = T32_A_BYTES + B_BYTES;               // one precision part of a stage: [A | B]
   static constexpr int STAGE_BYTES = HALF * (SPLIT == 3 ? 2 : 1);  // [A hi | B hi | A lo | B lo]
   static constexpr int STAGES = (SPLIT == 3) ? (BN >= 128 ? 3 : 4) : (BN >= 128 ? 6 : 8);
-  static constexpr int THREADS = (SPLIT == 3) ? 320 : 192;
+  static constexpr int THREADS = XFORM ? 320 : 192;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
 template <int MODE, int BN, int SPLIT>
-__global__ void __launch_bounds__((SPLIT == 3) ? 320 : 192, 1)
+__global__ void __launch_bounds__(((SPLIT == 3) || (MODE == 1)) ? 320 : 192, 1)
 conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, T32Params P) {
-  using Cfg = T32Cfg<BN, SPLIT>;
+  using Cfg = T32Cfg<BN, SPLIT, MODE>;
+  constexpr bool XFORM = Cfg::XFORM;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -212,11 +220,11 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 4) {
     // =============================== MMA issuer ==============================================
-    constexpr uint32_t idesc = (MODE == T32_FPROP) ? make_idesc_tf32(BN, 0, 0) : make_idesc_tf32(BN, 1, 1);
+    // both modes issue K-major operands (wgrad stages are transposed in shared memory first): rows of 128 B = 32 K
+    // elements, 8-row groups 1024 B apart, LBO unused
+    constexpr uint32_t idesc = make_idesc_tf32(BN, 0, 0);
     uint32_t s = 0, sphase = 0, tile_it = 0;
-    // K-major: LBO unused, 8-row groups 1024 B apart.  MN-major: 32-element column blocks 4096 B apart (LBO), 8 K-rows
-    // (pixels) per 1024 B group (SBO).
-    const uint64_t desc_base = (MODE == T32_FPROP) ? make_desc(base, 16, 1024) : make_desc(base, 4096, 1024);
+    const uint64_t desc_base = make_desc(base, 16, 1024);
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tile_it) {
       int z, n0, kb0, nk;
       long long m0;
@@ -226,15 +234,14 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + as * BN;
       for (int i = 0; i < nk; ++i) {
-        mbar_wait(SPLIT == 3 ? split_bar(s) : full_bar(s), sphase);
+        mbar_wait(XFORM ? split_bar(s) : full_bar(s), sphase);
         tc_fence_after();
         if (elect_one_sync()) {
           const uint64_t ad0 = desc_base + (uint64_t)((s * (uint32_t)Cfg::STAGE_BYTES) >> 4);
           const uint64_t bd0 = ad0 + (uint64_t)(T32_A_BYTES >> 4);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            // K-major: 32 B per K = 8 step inside the 128 B swizzle row; MN-major: 8 K-rows x 128 B
-            const uint32_t koff = (MODE == T32_FPROP) ? kk * 32 : kk * 1024;
+            const uint32_t koff = kk * 32;  // 32 B per K = 8 step inside the 128 B swizzle row
             const uint64_t ad = ad0 + (uint64_t)(koff >> 4);
             const uint64_t bd = bd0 + (uint64_t)(koff >> 4);
             if (SPLIT == 3) {
@@ -258,9 +265,9 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
     }
   } else if (warp >= 6) {
-    // =============================== splitter (3xTF32 only; warps 6-9) ===========================
-    if constexpr (SPLIT == 3) {
-      const int tid = threadIdx.x - 192;
+    // =============================== transform warps (6-9): wgrad block transposes and / or hi-lo split =============
+    if constexpr (XFORM) {
+      const int tid = threadIdx.x - 192, tw = tid >> 5;
       uint32_t s = 0, sphase = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         int z, n0, kb0, nk;
@@ -268,16 +275,44 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         decode(w, z, m0, n0, kb0, nk);
         for (int i = 0; i < nk; ++i) {
           mbar_wait(full_bar(s), sphase);
-          float4* hi = reinterpret_cast<float4*>(base_ptr + s * Cfg::STAGE_BYTES);
-          float4* lo = reinterpret_cast<float4*>(base_ptr + s * Cfg::STAGE_BYTES + Cfg::HALF);
+          uint8_t* st_hi = base_ptr + s * Cfg::STAGE_BYTES;
+          uint8_t* st_lo = st_hi + Cfg::HALF;
+          if constexpr (MODE == T32_WGRAD) {
+            // [32 pixels][32 channels] -> [32 channels][32 pixels], block by block (A: 4 blocks, B: BN / 32), in place
+            constexpr int NBLK = 4 + BN / 32;
+            for (int b = tw; b < NBLK; b += 4) {
+              uint8_t* blk = st_hi + b * 4096;
+              float v[32];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 t = *reinterpret_cast<const float4*>(blk + lane * 128 + ((q ^ (lane & 7)) << 4));
+                v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+              }
+              __syncwarp();  // the whole block is in registers before any lane overwrites it
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                const uint32_t off = (uint32_t)(c * 128 + ((((uint32_t)lane >> 2) ^ (uint32_t)(c & 7)) << 4) + (lane & 3) * 4);
+                if (SPLIT == 3) {
+                  const float h = rna_tf32(v[c]);
+                  *reinterpret_cast<float*>(blk + off) = h;
+                  *reinterpret_cast<float*>(st_lo + b * 4096 + off) = rna_tf32(v[c] - h);
+                } else {
+                  *reinterpret_cast<float*>(blk + off) = v[c];
+                }
+              }
+            }
+          } else {
+            float4* hi = reinterpret_cast<float4*>(st_hi);
+            float4* lo = reinterpret_cast<float4*>(st_lo);
 #pragma unroll 4
-          for (int c = tid; c < Cfg::HALF / 16; c += 128) {
-            const float4 v = hi[c];
-            float4 h, l;
-            h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
-            l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
-            hi[c] = h;
-            lo[c] = l;
+            for (int c = tid; c < Cfg::HALF / 16; c += 128) {
+              const float4 v = hi[c];
+              float4 h, l;
+              h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+              l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+              hi[c] = h;
+              lo[c] = l;
+            }
           }
           fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
           mbar_arrive(split_bar(s));
@@ -429,7 +464,7 @@ static int t32_pick_bn(int N) { return (N % 128 == 0) ? 128 : ((N % 64 == 0) ? 6
 
 template <int MODE, int BN, int SPLIT>
 static int t32_launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const T32Params& P, cudaStream_t st) {
-  using Cfg = T32Cfg<BN, SPLIT>;
+  using Cfg = T32Cfg<BN, SPLIT, MODE>;
   static_assert(Cfg::SMEM <= 232448, "shared memory budget");
   IIC_CUDA(cudaFuncSetAttribute(conv_tf32_kernel<MODE, BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   const long long work = (long long)P.mtiles * P.ntiles * P.splits;

@@ -1,25 +1,28 @@
-// Uncollapsed segmentation joint on the tensor cores (tcgen05 kind::tf32, 3xTF32 split) -- SURVEY S8 a11:
+// Uncollapsed segmentation joint on the tensor cores -- SURVEY S8 a11:
 //
 //   A[u][v][c][c'] = sum_{n,y,x} x1m[n, y+u-T, x+v-T, c] * x2m[n, y, x, c']          (k <= 16 channels, V = 2T+1 <= 24)
 //
 // the reference's F.conv2d(x1^T, weight=x2^T, padding=T) (code/utils/segmentation/IID_losses.py:125), 390 GFLOP per
 // sub-head at the COCO-Stuff-3 shape.  The fp32 SIMT kernel (seg_loss.cu::seg_joint_kernel) runs it at ~23 TFLOP/s.
 //
-// Formulation.  Both views are pixel-major, 16 channels = 64 bytes per pixel.  For one image row y of x2 and one
-// displacement row u, with x1row = row y+u-T of x1 zero-padded by T pixels on the left and 24-T... on the right:
+// Formulation.  Both views are pixel-major with 16 channels per pixel.  For one image row y of x2 and one displacement
+// row u, with x1row = row y+u-T of x1 zero-padded by T pixels on the left:
 //
 //     D[m = (v, c)][c'] += sum_x  x1row[x + v][c] * x2row[x][c']            M = 8 displacements x 16 channels = 128
 //
 // i.e. a GEMM whose A operand is the Toeplitz "displaced copies" matrix of x1row.  In pixel-major memory that operand
-// needs no copies at all: element (m = v*16 + c, k = x) lives at byte (x + v)*64 + c*4, which is exactly an MN-major
-// SWIZZLE_64B UMMA layout with K rows 64 B apart and M atoms (16 channels) ALSO 64 B apart (LBO = 64: atom v+1 of pixel x
-// is atom v of pixel x+1 -- the atoms overlap the K rows; tools/umma_sw64_probe.cu checks this on hardware).  So one TMA
-// box per x1 row feeds all 24 displacements, and the row is reused for the 7 values of u a CTA owns as y advances
-// (ring of 8 row slots): x1 and x2 cross L2 -> SM once per CTA instead of (2T+1) times.
-// B (x2row) is MN-major too: [pixel][16 channels].  N = 16, K = 8 pixels per MMA, fp32 accumulators in TMEM
-// (7 u x 3 M tiles x 16 columns = 336 columns).  The MMA is operand-fetch bound (4.5 KB of shared memory per 16 K MACs).
-// Precision: probabilities span many orders of magnitude and the loss tolerance is 2e-5, so each operand is split
-// x = hi + lo (tf32 each, seg_split_kernel) and three MMAs per product are issued (lo*hi + hi*lo + hi*hi): fp32-grade.
+// needs no copies at all: element (m = v*16 + c, k = x) lives at pixel (x + v), channel c -- an MN-major UMMA layout whose
+// K rows are one pixel apart and whose M atoms (the 16 channels of a pixel) are ALSO one pixel apart (LBO = one pixel:
+// atom v+1 of pixel x is atom v of pixel x+1, the atoms overlap the K rows).  So one TMA box per x1 row feeds all 24
+// displacements, and the row is reused for the 7 values of u a CTA owns as y advances (ring of 8 row slots): x1 and x2
+// cross L2 -> SM once per CTA instead of (2T+1) times.  B (x2row) is MN-major too: [pixel][16 channels].  N = 16, fp32
+// accumulators in TMEM (7 u x 3 M tiles x 16 columns = 336 columns).
+// Operand type.  kind::tf32 cannot read MN-major operands in the ordinary swizzle modes (measured: zeros,
+// tools/umma_sw64_probe.cu mode 0), kind::f16 can (the bf16 wgrad of conv_tc2.cu is MN-major).  The forward joint
+// therefore runs on bf16 pixels (32 B per pixel, SWIZZLE_32B, K = 16 pixels per MMA) with every operand split into
+// THREE-term precision x = hi + mid (+ 2^-17 x): hi = bf16(x), mid = bf16(x - hi), products hi*hi + hi*mid + mid*hi
+// (relative error 2^-16 per product, unbiased; every joint entry is a sum of >= 10^4 non-negative products, so the sums
+// are fp32-grade -- the loss tolerance is 2e-5).  The backward contractions below use kind::tf32 with K-major operands.
 //
 // Work item = (image n, chunk of rows y, group of 7 displacement rows u); partial results per CTA, fixed-order reduce.
 #include <cuda.h>
@@ -42,15 +45,23 @@ struct SjParams {
   float* part;                 // [cta][SJ_U][24][16][16]
 };
 
+constexpr int SJ_PIXB = 32;  // bytes per pixel: 16 bf16 channels
 __device__ __forceinline__ uint64_t sj_desc(uint32_t saddr) {
-  // MN-major, SWIZZLE_64B, LBO = 64 B (next 16-channel atom = next pixel), SBO = 512 B (8 K rows)
+  // MN-major, SWIZZLE_32B, LBO = 32 B (next 16-channel atom = next pixel), SBO = 256 B (8 K rows = 8 pixels)
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)(64 >> 4) << 16;
-  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)(SJ_PIXB >> 4) << 16;
+  d |= (uint64_t)((8 * SJ_PIXB) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)4 << 61;
+  d |= (uint64_t)6 << 61;
   return d;
+}
+__device__ __forceinline__ void sj_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 __device__ __forceinline__ void sj_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -60,21 +71,21 @@ __device__ __forceinline__ void sj_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
       : "memory");
 }
 
-__global__ void seg_split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n4) {
+// x (fp32, pixel-major) -> hi = bf16(x), mid = bf16(x - hi)
+__global__ void seg_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                 long long n4) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(x)[i];
-    float4 h, l;
-    uint32_t t;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x - h.x)); l.x = __uint_as_float(t);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y - h.y)); l.y = __uint_as_float(t);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z - h.z)); l.z = __uint_as_float(t);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w - h.w)); l.w = __uint_as_float(t);
-    reinterpret_cast<float4*>(hi)[i] = h;
-    reinterpret_cast<float4*>(lo)[i] = l;
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
+                        h3 = __float2bfloat16_rn(v.w);
+    __nv_bfloat162 ha = __halves2bfloat162(h0, h1), hb = __halves2bfloat162(h2, h3);
+    __nv_bfloat162 la = __floats2bfloat162_rn(v.x - __bfloat162float(h0), v.y - __bfloat162float(h1));
+    __nv_bfloat162 lb = __floats2bfloat162_rn(v.z - __bfloat162float(h2), v.w - __bfloat162float(h3));
+    uint2 ho, lo2;
+    ho.x = *reinterpret_cast<uint32_t*>(&ha); ho.y = *reinterpret_cast<uint32_t*>(&hb);
+    lo2.x = *reinterpret_cast<uint32_t*>(&la); lo2.y = *reinterpret_cast<uint32_t*>(&lb);
+    reinterpret_cast<uint2*>(hi)[i] = ho;
+    reinterpret_cast<uint2*>(lo)[i] = lo2;
   }
 }
 
@@ -156,11 +167,11 @@ seg_joint_tc_kernel(const __grid_constant__ CUtensorMap tm1h, const __grid_const
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ==============================================
-    // instruction descriptor: kind::tf32, D = f32, M = 128, N = 16, A and B MN-major
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(16 >> 3) << 17) |
+    // instruction descriptor: kind::f16, D = f32, A = B = bf16, M = 128, N = 16, A and B MN-major
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(16 >> 3) << 17) |
                                ((uint32_t)(128 >> 4) << 24);
     uint32_t touched = 0u;
-    const int nkk = P.wp / 8;
+    const int nkk = P.wp / 16;  // K = 16 pixels per MMA
     for (int y = ya; y < yb; ++y) {
       const int it = y - ya, s2 = it % SJ_ST2;
       mbar_wait(full2(s2), (it / SJ_ST2) & 1u);
@@ -179,10 +190,10 @@ seg_joint_tc_kernel(const __grid_constant__ CUtensorMap tm1h, const __grid_const
             const uint32_t bit = 1u << (ul * SJ_MT + mt);
             uint32_t first = (touched & bit) ? 1u : 0u;  // accumulate flag of the first MMA into this block
             for (int kk = 0; kk < nkk; ++kk) {
-              const uint32_t aoff = (uint32_t)(kk * 8 + mt * 8) * 64u, boff = (uint32_t)(kk * 8) * 64u;
-              sj_mma(acc, sj_desc(a_lo + aoff), sj_desc(b_hi + boff), idesc, first);  // lo_a * hi_b
-              sj_mma(acc, sj_desc(a_hi + aoff), sj_desc(b_lo + boff), idesc, 1u);     // hi_a * lo_b
-              sj_mma(acc, sj_desc(a_hi + aoff), sj_desc(b_hi + boff), idesc, 1u);     // hi_a * hi_b
+              const uint32_t aoff = (uint32_t)(kk * 16 + mt * 8) * SJ_PIXB, boff = (uint32_t)(kk * 16) * SJ_PIXB;
+              sj_mma_bf16(acc, sj_desc(a_lo + aoff), sj_desc(b_hi + boff), idesc, first);  // mid_a * hi_b
+              sj_mma_bf16(acc, sj_desc(a_hi + aoff), sj_desc(b_lo + boff), idesc, 1u);     // hi_a * mid_b
+              sj_mma_bf16(acc, sj_desc(a_hi + aoff), sj_desc(b_hi + boff), idesc, 1u);     // hi_a * hi_b
               first = 1u;
             }
           }
@@ -272,13 +283,16 @@ static int sj_init() {
   return IIC_OK;
 }
 
-static int sj_map(CUtensorMap* tm, const float* ptr, int rows, int w, int box_w) {
+// pixel-major rows [rows][w][16 channels]: fp32 (64 B per pixel, SWIZZLE_64B) or bf16 (32 B per pixel, SWIZZLE_32B)
+static int sj_map(CUtensorMap* tm, const void* ptr, int rows, int w, int box_w, bool bf16 = false) {
+  const cuuint64_t pixb = bf16 ? 32 : 64;
   cuuint64_t gdim[3] = {16, (cuuint64_t)w, (cuuint64_t)rows};
-  cuuint64_t gstr[2] = {64, (cuuint64_t)w * 64};
+  cuuint64_t gstr[2] = {pixb, (cuuint64_t)w * pixb};
   cuuint32_t box[3] = {16, (cuuint32_t)box_w, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = sj_encodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), gdim, gstr, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  CUresult r = sj_encodeTiled(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                              const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              bf16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   IIC_REQUIRE(r == CUDA_SUCCESS, IIC_ERR_CUDA, "cuTensorMapEncodeTiled(seg joint) failed (%d) rows=%d w=%d box_w=%d", (int)r, rows,
               w, box_w);
@@ -294,12 +308,13 @@ static SjPlan sj_plan(int n, int k, int h, int w, int T) {
   SjPlan p = {};
   const int V = 2 * T + 1;
   if (k > 16 || k < 5 || V > 24 || T < 1 || n < 1) return p;   // (k <= 4 / 8 stay on the SIMT kernel: 1/16 of the work)
-  p.wp = (w + 7) / 8 * 8;
+  p.wp = (w + 15) / 16 * 16;                                    // K = 16 pixels per MMA
   if (p.wp + 24 > 256) return p;                                // TMA box extent
-  p.row1_bytes = ((p.wp + 24) * 64 + 1023) / 1024 * 1024;
-  p.row2_bytes = (p.wp * 64 + 1023) / 1024 * 1024;
+  p.row1_bytes = ((p.wp + 24) * SJ_PIXB + 1023) / 1024 * 1024;
+  p.row2_bytes = (p.wp * SJ_PIXB + 1023) / 1024 * 1024;
   p.smem = 1024 + SJ_SLOTS * 2 * p.row1_bytes + SJ_ST2 * 2 * p.row2_bytes + 256;
   if (p.smem > 232448) return p;
+  if (p.smem < 120 * 1024) p.smem = 120 * 1024;  // one CTA per SM: each allocates all 512 TMEM columns
   p.ugroups = (V + SJ_U - 1) / SJ_U;
   // row chunks: ~3 waves of CTAs over the SMs, at least T + 1 rows per chunk
   int want = (3 * device_sm_count() + n * p.ugroups - 1) / (n * p.ugroups);
@@ -318,7 +333,7 @@ static SjPlan sj_plan(int n, int k, int h, int w, int T) {
 long long seg_joint_tc_workspace(int n, int k, int h, int w, int T) {
   const SjPlan p = sj_plan(n, k, h, w, T);
   if (!p.ok) return 0;
-  return 4ll * n * h * w * 16 * (long long)sizeof(float) + (long long)p.ctas * SJ_U * 24 * 256 * (long long)sizeof(float);
+  return 4ll * n * h * w * 16 * (long long)sizeof(__nv_bfloat16) + (long long)p.ctas * SJ_U * 24 * 256 * (long long)sizeof(float);
 }
 
 int seg_joint_tc(const float* x1m, const float* x2m, float* joint, void* workspace, int n, int k, int h, int w, int T,
@@ -328,11 +343,11 @@ int seg_joint_tc(const float* x1m, const float* x2m, float* joint, void* workspa
   const SjPlan p = sj_plan(n, k, h, w, T);
   IIC_REQUIRE(p.ok, IIC_ERR_UNSUPPORTED, "seg_joint_tc: unsupported geometry (k=%d, T=%d, w=%d)", k, T, w);
   const long long elems = (long long)n * h * w * 16;
-  float* x1h = (float*)workspace;
-  float* x1l = x1h + elems;
-  float* x2h = x1l + elems;
-  float* x2l = x2h + elems;
-  float* part = x2l + elems;
+  __nv_bfloat16* x1h = (__nv_bfloat16*)workspace;
+  __nv_bfloat16* x1l = x1h + elems;
+  __nv_bfloat16* x2h = x1l + elems;
+  __nv_bfloat16* x2l = x2h + elems;
+  float* part = (float*)(x2l + elems);
   int blocks = cdiv(elems / 4, 256);
   if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
   seg_split_kernel<<<blocks, 256, 0, st>>>(x1m, x1h, x1l, elems / 4);
@@ -342,15 +357,15 @@ int seg_joint_tc(const float* x1m, const float* x2m, float* joint, void* workspa
   IIC_LAUNCH_CHECK();
   count_launch();
   alignas(64) CUtensorMap tm1h, tm1l, tm2h, tm2l;
-  if ((rc = sj_map(&tm1h, x1h, n * h, w, p.wp + 24)) != IIC_OK) return rc;
-  if ((rc = sj_map(&tm1l, x1l, n * h, w, p.wp + 24)) != IIC_OK) return rc;
-  if ((rc = sj_map(&tm2h, x2h, n * h, w, p.wp)) != IIC_OK) return rc;
-  if ((rc = sj_map(&tm2l, x2l, n * h, w, p.wp)) != IIC_OK) return rc;
+  if ((rc = sj_map(&tm1h, x1h, n * h, w, p.wp + 24, true)) != IIC_OK) return rc;
+  if ((rc = sj_map(&tm1l, x1l, n * h, w, p.wp + 24, true)) != IIC_OK) return rc;
+  if ((rc = sj_map(&tm2h, x2h, n * h, w, p.wp, true)) != IIC_OK) return rc;
+  if ((rc = sj_map(&tm2l, x2l, n * h, w, p.wp, true)) != IIC_OK) return rc;
   SjParams P = {};
   P.n = n; P.h = h; P.w = w; P.wp = p.wp; P.T = T; P.V = 2 * T + 1;
   P.ychunk = p.ychunk; P.nychunks = p.nychunks; P.ugroups = p.ugroups;
   P.row1_bytes = p.row1_bytes; P.row2_bytes = p.row2_bytes;
-  P.box1_bytes = (p.wp + 24) * 64; P.box2_bytes = p.wp * 64;
+  P.box1_bytes = (p.wp + 24) * SJ_PIXB; P.box2_bytes = p.wp * SJ_PIXB;
   P.part = part;
   IIC_CUDA(cudaFuncSetAttribute(seg_joint_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem));
   seg_joint_tc_kernel<<<p.ctas, SJ_THREADS, p.smem, st>>>(tm1h, tm1l, tm2h, tm2l, P);

@@ -188,8 +188,12 @@ def seg_unprepare(dx1m, dx2m, theta, mask, k, shift=(0, 0)):
   return dx1, dx2
 
 
-# host-side switch: uncollapsed segmentation joint on the tensor cores (csrc/seg_joint_tc.cu).  OFF until the kernel has
-# passed tests/test_gpu_parity_seg.py::test_seg_joint_tensor_core_* on a B200.
+# host-side switches of the tensor-core segmentation kernels (csrc/seg_joint_tc.cu):
+#   SEG_CORR_TC   backward contractions (kind::tf32, K-major overlapped operand): validated on a B200 in round 2
+#                 (tests/test_gpu_parity_seg.py::test_seg_corr_tensor_core_matches_simt), ON
+#   SEG_JOINT_TC  forward joint (kind::f16 on bf16 three-term operands, MN-major Toeplitz operand): OFF until it has
+#                 passed test_seg_joint_tensor_core_* on hardware
+SEG_CORR_TC = {"on": __import__("os").environ.get("IIC_SEG_CORR_TC", "1") != "0"}
 SEG_JOINT_TC = {"on": __import__("os").environ.get("IIC_SEG_JOINT_TC", "0") != "0"}
 
 
@@ -237,8 +241,8 @@ def seg_corr_tc(inp, H, k, T, sgn, scale):
   return out
 
 
-def seg_corr_bwd(inp, H, k, T, sgn, scale):
-  if SEG_JOINT_TC["on"] and T > 0:
+def seg_corr_bwd(inp, H, k, T, sgn, scale, allow_tc=True):
+  if allow_tc and SEG_CORR_TC["on"] and T > 0:
     o = seg_corr_tc(inp, H, k, T, sgn, scale)
     if o is not None:
       return o

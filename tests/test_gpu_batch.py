@@ -5,8 +5,7 @@ from argparse import Namespace
 import pytest
 import torch
 
-# `unvalidated` until the file has passed once on a B200 (tools/gpu_r2_a.sh runs it with IIC_RUN_UNVALIDATED=1)
-pytestmark = [pytest.mark.gpu, pytest.mark.unvalidated]
+pytestmark = pytest.mark.gpu
 
 from oracle import transforms as otf  # noqa: E402
 from oracle import weights  # noqa: E402
@@ -43,6 +42,7 @@ def test_assemble_slabs_is_the_reference_loop():
     assert g1.is_cuda and torch.equal(g1.cpu(), all_imgs) and torch.equal(g2.cpu(), all_tf)
 
 
+@pytest.mark.unvalidated
 @pytest.mark.parametrize("head", ["A", "B"])
 def test_repeat_handling_equals_slab_assembled_step(head):
   """Forwarding the unique tf1 images once and repeating their softmax rows gives the loss and the parameter

@@ -2,7 +2,7 @@
 iic_b200/utils/segmentation/segmentation_eval.py) against torch / numpy and the oracle's restatement
 of the reference loops.  Index and integer work: everything must be exact.
 
-Written after the last GPU session of round 1 (the kernels have not run on hardware yet), hence `unvalidated`."""
+Validated on a B200 in round 2 (gpurun_out/a_tests.log, profiles/r02_session_a.md)."""
 from argparse import Namespace
 
 import numpy as np
@@ -11,7 +11,7 @@ import torch
 
 from oracle import eval_metrics as oem
 
-pytestmark = [pytest.mark.gpu, pytest.mark.unvalidated]
+pytestmark = pytest.mark.gpu
 
 
 def _K():

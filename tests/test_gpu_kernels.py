@@ -722,7 +722,6 @@ def test_tc2_two_tile_work_items_forced_exact_small_integers(n, h, cin, cout, k,
     assert torch.equal(tot[v, 0], sl.sum(dim=(0, 2, 3))) and torch.equal(tot[v, 1], (sl * sl).sum(dim=(0, 2, 3)))
 
 
-@pytest.mark.unvalidated
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 @pytest.mark.parametrize("shape,views", [((6, 13, 13, 64), 2), ((4, 7, 7, 512), 1), ((2, 5, 5, 2048), 2), ((64, 25, 25, 128), 2)])
 def test_bn_relu_bitmask_variant_equals_activation_mask(mode, shape, views):
@@ -757,7 +756,6 @@ def test_bn_relu_bitmask_variant_equals_activation_mask(mode, shape, views):
   assert torch.equal(dy1, dy2) and torch.equal(go1, go2) and torch.equal(dg1, dg2) and torch.equal(db1, db2)
 
 
-@pytest.mark.unvalidated
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 @pytest.mark.parametrize("cin,hw,pool_pad,views,n", [(2, 32, 1, 2, 6), (2, 96, 1, 2, 4), (1, 24, 0, 1, 3), (2, 6, 0, 1, 3),
                                                      (2, 18, 1, 1, 5)])
@@ -769,7 +767,6 @@ def test_stem_backward_fused_v2(mode, cin, hw, pool_pad, views, n):
     test_stem_backward_fused_matches_chain_and_autograd(mode, cin, hw, pool_pad, views, n)
 
 
-@pytest.mark.unvalidated
 @pytest.mark.parametrize("n,h", [(2, 13), (4, 49), (2, 96), (6, 5), (3, 30)])
 @pytest.mark.parametrize("variant", ["tma-store", "direct-store"])
 def test_halo_fprop_with_per_lane_running_statistics(n, h, variant):

@@ -269,7 +269,6 @@ def test_pair_batched_pass_equals_two_forward_calls(arch, cfg):
       assert torch.allclose(sd1[key].float(), sd2[key].float(), rtol=1e-5, atol=1e-6), key
 
 
-@pytest.mark.unvalidated
 @pytest.mark.parametrize("cin,cout,stride,hw,n", [(64, 64, 1, 17, 5), (64, 128, 2, 17, 6), (256, 512, 2, 13, 4)])
 def test_bf16_block_with_relu_bitmask(cin, cout, stride, hw, n):
   """Engine switch bn_bitmask: the residual block forward / backward must give what it gives with the switch off."""

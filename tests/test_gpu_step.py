@@ -13,8 +13,9 @@ from argparse import Namespace
 import pytest
 import torch
 
-# `unvalidated` until the file has passed once on a B200 (tools/gpu_r2_a.sh runs it with IIC_RUN_UNVALIDATED=1)
-pytestmark = [pytest.mark.gpu, pytest.mark.unvalidated]
+pytestmark = pytest.mark.gpu
+
+# tests whose tolerances were re-set after their first hardware run keep the `unvalidated` marker until they have passed
 
 from oracle import iid_losses as oracle_iid  # noqa: E402
 from oracle import nets as oracle_nets  # noqa: E402
@@ -40,6 +41,7 @@ def _oracle_cluster_step(ora, opt, g, gt, head, lamb):
   return loss.item()
 
 
+@pytest.mark.unvalidated
 @pytest.mark.parametrize("pair_batched,use_arena", [(True, False), (False, False), (True, True), (False, True)])
 def test_cluster_step_matches_oracle_with_torch_adam(pair_batched, use_arena):
   import iic_b200.archs as archs
@@ -171,6 +173,7 @@ def test_backward_guards():
     loss.backward()
 
 
+@pytest.mark.unvalidated
 def test_seg_step_matches_oracle_with_torch_adam():
   import iic_b200.archs as archs
   from iic_b200.optim import FusedAdam
@@ -212,6 +215,7 @@ def test_seg_step_matches_oracle_with_torch_adam():
     assert _rel(upd, want) < 0.15, (k, _rel(upd, want))  # three Adam steps at lr 1e-3: +-lr sign flips (measured 0.08)
 
 
+@pytest.mark.unvalidated
 def test_legacy_format_checkpoint_loads_and_reproduces_the_oracle(tmp_path):
   """SURVEY S8f row 3 on the GPU: a checkpoint in torch 0.4.1's on-disk format (legacy non-zip serialisation, pickle
   protocol 2, saved from a DataParallel wrapper -> `module.` prefixes, the layout of the published models.tar.gz)

@@ -10,7 +10,7 @@ from oracle import seg_losses as oseg
 SJ_U, SJ_MT, SJ_SLOTS, SJ_ST2 = 7, 3, 8, 2
 
 def plan(n, h, w, T, sms=148):
-  V = 2*T+1; wp = (w+7)//8*8; ug = (V+SJ_U-1)//SJ_U
+  V = 2*T+1; wp = (w+15)//16*16; ug = (V+SJ_U-1)//SJ_U
   want = max(1, (3*sms + n*ug - 1)//(n*ug)); yc = (h+want-1)//want; yc = max(yc, T+1); yc = min(yc, h)
   return dict(V=V, wp=wp, ugroups=ug, ychunk=yc, nychunks=(h+yc-1)//yc)
 
@@ -57,11 +57,11 @@ def sim_joint(x1m, x2m, T):
           buf = np.zeros((wp+24, 16)); xs = np.arange(wp+24)-T; ok = (xs>=0)&(xs<w); buf[ok] = x1m[img, r, xs[ok]]
           flat = buf.reshape(-1)
           for mt in range(SJ_MT):
-            for kk in range(wp//8):
-              for xk in range(8):
-                x = kk*8+xk
-                # A[m][k=xk] = flat[(kk*8+mt*8)*16 + xk*16 + m]  (m = vl*16+c, atom stride 64 B = 16 floats == K-row stride)
-                a = flat[(kk*8+mt*8+xk)*16:(kk*8+mt*8+xk)*16+128]
+            for kk in range(wp//16):
+              for xk in range(16):
+                x = kk*16+xk
+                # A[m][k=xk] = flat[(kk*16+mt*8)*16 + xk*16 + m]  (m = vl*16+c; M atom stride == K-row stride == one pixel)
+                a = flat[(kk*16+mt*8+xk)*16:(kk*16+mt*8+xk)*16+128]
                 acc[ul, mt] += np.outer(a, b[x])
             touched |= 1 << (ul*SJ_MT+mt)
           if ul == 0: empty1[s].phase += 1
