@@ -71,7 +71,7 @@ long long iic_launch_count(int reset);
  *                                              work item (0 = per-thread 16-byte global stores)
  *   "stem_bwd_v2"     [IIC_STEM_BWD_V2=0]      iic_stem_bwd_fused: second version of the wgrad pass (not yet run on
  *                                              hardware)
- *   "conv_halo_stats" [IIC_CONV_HALO_STATS=0]  halo fprop: per-lane running BatchNorm sums, one warp reduction per CTA
+ *   "conv_halo_stats" [IIC_CONV_HALO_STATS=1]  halo fprop: per-lane running BatchNorm sums, one warp reduction per CTA
  *                                              (not yet run on hardware)                                            */
 int iic_get_option(const char* name);
 int iic_set_option(const char* name, int value);
