@@ -49,6 +49,7 @@ timeout 150 python bench.py --config c5 --steps 5 --no-cpu-baseline > $O/c_bench
 IIC_SEG_JOINT_TC=1 timeout 150 python bench.py --config c5 --steps 5 --no-cpu-baseline > $O/c_bench_c5_tc.json 2> $O/c_bench_c5_tc.err; stamp "6b bench c5 + tensor-core joint rc=$?"; summ $O/c_bench_c5_tc.json
 timeout 100 python tools/conv_sweep.py 352 tf32x3 > $O/c_conv_sweep_tf32x3.txt 2>&1; stamp "7 sweep tf32x3 rc=$?"; tail -12 $O/c_conv_sweep_tf32x3.txt
 timeout 100 python tools/conv_sweep.py 352 tf32 > $O/c_conv_sweep_tf32.txt 2>&1; stamp "7b sweep tf32 rc=$?"; tail -3 $O/c_conv_sweep_tf32.txt
+timeout 100 python bench.py --pairs-per-gpu 88 --steps 10 --no-cpu-baseline > $O/c_bench_88.json 2> $O/c_bench_88.err; stamp "7c bench 88 pairs (breakdown) rc=$?"; summ $O/c_bench_88.json
 timeout 250 ncu --set full --clock-control none --import-source on -k regex:"conv_tf32_kernel" -s 30 -c 9 -o $O/c_prof_tf32 \
    python bench.py --precision tf32x3 --pairs-per-gpu 176 --steps 1 --warmup 0 --no-cpu-baseline --no-roofline > $O/c_ncu_tf32.log 2>&1
 stamp "8 ncu conv_tf32 rc=$?"
