@@ -5,9 +5,9 @@
 // ~35-50 % gradient error (ReLU sign flips: gradient error ~ sqrt(forward error)).  This file keeps the
 // activations in fp32 in HBM and offers two tensor-core modes of the same kernel:
 //   SPLIT = 1 (IIC_TF32)   : operands read as tf32 (10-bit mantissa), fp32 accumulation in TMEM.
-//   SPLIT = 3 (IIC_TF32X3) : each operand x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi); the product is
-//                            accumulated as lo_a*hi_b + hi_a*lo_b + hi_a*hi_b (the dropped lo*lo term is 2^-22
-//                            relative): fp32-grade results from the tensor pipe at 1/3 of the tf32 rate, ~10x the fp32
+//   SPLIT = 3 (IIC_TF32X3) : each operand x = hi + lo with hi = x truncated to tf32, lo = x - hi (exact); the product is
+//                            accumulated as lo_a*hi_b + hi_a*lo_b + hi_a*hi_b (dropped: lo*lo and the truncation of lo, both
+//                            ~2^-20 relative): fp32-grade results from the tensor pipe at 1/3 of the tf32 rate, ~10x the fp32
 //                            SIMT kernel (conv_simt.cu).
 // Same design as conv_tc2.cu (TMA im2col A operand, tiled TMA dense operand, persistent CTAs, double-buffered TMEM
 // accumulators, split-K wgrad with both operands MN-major, stride-2 dgrad by output-parity classes), with a k-block of
@@ -68,6 +68,10 @@ __device__ __forceinline__ float rna_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// hi part of the 3xTF32 split by truncation (one LOP3; cvt.rna.tf32 is a slow-path conversion and the four transform warps
+// have ~16 K elements to split per stage): hi = x with the 13 low mantissa bits cleared, so lo = x - hi is EXACT in fp32
+// and is itself read by the tensor core as tf32 (truncated to 10 bits: |x - hi - tf32(lo)| <= 2^-20 |x|).
+__device__ __forceinline__ float hi_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 template <int BN, int SPLIT, int MODE = 0> struct T32Cfg {
   static constexpr bool XFORM = (SPLIT == 3) || (MODE == 1);  // transform warps: hi/lo split and / or wgrad block transposes
@@ -293,9 +297,9 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int c = 0; c < 32; ++c) {
                 const uint32_t off = (uint32_t)(c * 128 + ((((uint32_t)lane >> 2) ^ (uint32_t)(c & 7)) << 4) + (lane & 3) * 4);
                 if (SPLIT == 3) {
-                  const float h = rna_tf32(v[c]);
+                  const float h = hi_tf32(v[c]);
                   *reinterpret_cast<float*>(blk + off) = h;
-                  *reinterpret_cast<float*>(st_lo + b * 4096 + off) = rna_tf32(v[c] - h);
+                  *reinterpret_cast<float*>(st_lo + b * 4096 + off) = v[c] - h;
                 } else {
                   *reinterpret_cast<float*>(blk + off) = v[c];
                 }
@@ -308,8 +312,8 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int c = tid; c < Cfg::HALF / 16; c += 128) {
               const float4 v = hi[c];
               float4 h, l;
-              h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
-              l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+              h.x = hi_tf32(v.x); h.y = hi_tf32(v.y); h.z = hi_tf32(v.z); h.w = hi_tf32(v.w);
+              l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
               hi[c] = h;
               lo[c] = l;
             }
