@@ -117,6 +117,21 @@ class _Ctx(object):
     self.saved = []
     self.wcache = {}
     self.mbits = {}  # id(block output) -> its ReLU mask as bits (option bn_bitmask)
+    self.nbt = {}    # num_batches_tracked buffers to advance, by increment: one multi-tensor add per forward
+
+  def count_batch(self, bn, k):
+    """nn.BatchNorm2d's `num_batches_tracked += 1` per forward call, deferred: 72 one-element add kernels per step of
+    ClusterNet5g become one `torch._foreach_add_`."""
+    inc = self.nbt.setdefault(id(bn), [bn.num_batches_tracked, 0])
+    inc[1] += k
+
+  def flush_batch_counts(self):
+    by_k = {}
+    for t, k in self.nbt.values():
+      by_k.setdefault(k, []).append(t)
+    for k, ts in by_k.items():
+      torch._foreach_add_(ts, k)
+    self.nbt = {}
 
   def split(self, t):
     if t is None:
@@ -173,7 +188,7 @@ def _bn_stats(ctx, bn, y):
   mis = _ViewStats(torch.empty((ctx.groups, 2 * C), device=y.device, dtype=torch.float32))
   for yg, ss, mi in zip(ctx.split(y), sss, mis):  # running statistics are updated view by view, in call order
     if update:
-      bn.num_batches_tracked += 1
+      ctx.count_batch(bn, 1)
     K.bn_stats(yg, bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum, rm, rv, use_running, ss=ss, mi=mi)
   return sss, mis
 
@@ -201,14 +216,14 @@ def _stats_from_partials(ctx, bn, y, partial, nblk):
   M = (y.numel() // y.shape[-1]) // ctx.groups
   if OPTIONS["bn_merged"]:
     if update:
-      bn.num_batches_tracked += ctx.groups
+      ctx.count_batch(bn, ctx.groups)
     ss, mi = K.bn_stats_from_partials_views(partial, nblk, 2, ctx.groups, M, bn.weight.detach(), bn.bias.detach(),
                                             bn.eps, bn.momentum, rm, rv)
     return _ViewStats(ss), _ViewStats(mi)
   sss, mis = [], []
   for v in range(ctx.groups):
     if update:
-      bn.num_batches_tracked += 1
+      ctx.count_batch(bn, 1)
     ss, mi = K.bn_stats_from_partials(partial, nblk, 2, v, M, bn.weight.detach(), bn.bias.detach(), bn.eps,
                                       bn.momentum, rm, rv)
     sss.append(ss)
@@ -454,6 +469,7 @@ class TrunkFunction(torch.autograd.Function):
     ectx.wversions = [(p, p._version) for p in params if p.dim() == 4] if need_grad else []
     _prepack(trunk, ectx)
     feat, finisher = run(ectx, x)
+    ectx.flush_batch_counts()
     ctx.ectx, ctx.finisher, ctx.params = ectx, finisher, params
     return feat
 
