@@ -16,6 +16,8 @@ int tc2_conv_gather_gemm(const __nv_bfloat16* src, int srcH, int srcW, int srcC,
                          const __nv_bfloat16* addend, __nv_bfloat16* out, cudaStream_t st);
 long long tc2_conv_wgrad_workspace(const iic_conv_geom* g);
 int tc2_conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* ws, const iic_conv_geom* g, cudaStream_t st);
+int tc2_conv_wgrad_oihw(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* grad_oihw, int accumulate, float* ws,
+                        const iic_conv_geom* g, cudaStream_t st);
 int tc2_conv_fprop_blocks(const iic_conv_geom* g);
 int tc2_conv_gather_gemm_stats(const __nv_bfloat16* src, int srcH, int srcW, int srcC, int rowH, int rowW, int nimg,
                                const iic_conv_geom* g, int transposed, const __nv_bfloat16* wpacked, int N,
@@ -135,4 +137,27 @@ extern "C" int iic_conv_fprop_stats(const void* x, const void* w_packed, void* y
   return tc2_conv_gather_gemm_stats((const __nv_bfloat16*)x, g->h, g->w, g->cin, g->oh, g->ow, g->n, g, 0,
                                     (const __nv_bfloat16*)w_packed, g->cout, nullptr, (__nv_bfloat16*)y, stat_partial, views,
                                     (cudaStream_t)stream);
+}
+
+// wgrad straight into the torch-layout gradient (optionally accumulating): on the bf16 tensor-core path the split-K fold
+// writes [cout][cin][kh][kw] itself; the other modes run iic_conv_wgrad into the tail of the workspace + iic_unpack_wgrad.
+extern "C" long long iic_conv_wgrad_oihw_workspace(const iic_conv_geom* g, int dtype) {
+  const long long base = iic_conv_wgrad_workspace(g, dtype);
+  if (base < 0 || dtype == IIC_BF16) return base;
+  return base + (long long)g->cout * g->cin * g->kh * g->kw * (long long)sizeof(float) + 256;
+}
+
+extern "C" int iic_conv_wgrad_oihw(const void* x, const void* dy, float* grad_oihw, int accumulate, void* workspace,
+                                   const iic_conv_geom* g, int dtype, void* stream) {
+  int rc = geom_check(g, "iic_conv_wgrad_oihw");
+  if (rc != IIC_OK) return rc;
+  IIC_REQUIRE(x && dy && grad_oihw && workspace, IIC_ERR_BAD_ARG, "iic_conv_wgrad_oihw: null pointer");
+  if (dtype == IIC_BF16)
+    return tc2_conv_wgrad_oihw((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, grad_oihw, accumulate, (float*)workspace, g,
+                               (cudaStream_t)stream);
+  const long long base = (iic_conv_wgrad_workspace(g, dtype) + 255) / 256 * 256;
+  float* packed = (float*)((char*)workspace + base);
+  rc = iic_conv_wgrad(x, dy, packed, workspace, g, dtype, stream);
+  if (rc != IIC_OK) return rc;
+  return iic_unpack_wgrad(packed, grad_oihw, accumulate, g->cout, g->cin, g->kh, g->kw, stream);
 }

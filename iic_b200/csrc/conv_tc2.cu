@@ -1460,7 +1460,36 @@ __global__ void wgrad2_reduce_kernel(const float* __restrict__ partial, float* _
   }
 }
 
+// Split-K fold that writes the torch layout [cout][cin][kh][kw] directly (optionally accumulating): the separate
+// iic_unpack_wgrad pass (one more launch and one more read + write of every gradient) disappears.
+__global__ void wgrad2_reduce_unpack_kernel(const float* __restrict__ partial, float* __restrict__ grad, int Ktot, int N,
+                                            int splits, int cin, int taps, int accumulate) {
+  const long long total = (long long)Ktot * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % N);
+    const int j = (int)(i / N);  // (tap, ci)
+    float t = 0.f;
+    for (int z = 0; z < splits; ++z) t += partial[(long long)z * total + i];
+    const int tap = j / cin, ci = j - tap * cin;
+    const long long o = ((long long)co * cin + ci) * taps + tap;
+    grad[o] = accumulate ? grad[o] + t : t;
+  }
+}
+
+int tc2_conv_wgrad_impl(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* ws, const iic_conv_geom* g,
+                        cudaStream_t st, float* grad_oihw, int accumulate);
+
 int tc2_conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* ws, const iic_conv_geom* g, cudaStream_t st) {
+  return tc2_conv_wgrad_impl(x, dy, dw, ws, g, st, nullptr, 0);
+}
+
+int tc2_conv_wgrad_oihw(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* grad_oihw, int accumulate, float* ws,
+                        const iic_conv_geom* g, cudaStream_t st) {
+  return tc2_conv_wgrad_impl(x, dy, nullptr, ws, g, st, grad_oihw, accumulate);
+}
+
+int tc2_conv_wgrad_impl(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, float* ws, const iic_conv_geom* g,
+                        cudaStream_t st, float* grad_oihw, int accumulate) {
   int rc = tma_init();
   if (rc != IIC_OK) return rc;
   const int bn = pick_bn2(g->cout);
@@ -1484,7 +1513,10 @@ int tc2_conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, f
     IIC_LAUNCH_CHECK();
     count_launch();
     const long long total = 576ll * 64;
-    wgrad2_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(ws, dw, 576, 64, grid);
+    if (grad_oihw != nullptr)
+      wgrad2_reduce_unpack_kernel<<<cdiv(total, 256), 256, 0, st>>>(ws, grad_oihw, 576, 64, grid, 64, 9, accumulate);
+    else
+      wgrad2_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(ws, dw, 576, 64, grid);
     IIC_LAUNCH_CHECK();
     count_launch();
     return IIC_OK;
@@ -1523,7 +1555,10 @@ int tc2_conv_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, f
   const long long total = (long long)P.Ktot * g->cout;
   int blocks = cdiv(total, 256);
   if (blocks > device_sm_count() * 8) blocks = device_sm_count() * 8;
-  wgrad2_reduce_kernel<<<blocks, 256, 0, st>>>(ws, dw, P.Ktot, g->cout, P.splits);
+  if (grad_oihw != nullptr)
+    wgrad2_reduce_unpack_kernel<<<blocks, 256, 0, st>>>(ws, grad_oihw, P.Ktot, g->cout, P.splits, g->cin, g->kh * g->kw, accumulate);
+  else
+    wgrad2_reduce_kernel<<<blocks, 256, 0, st>>>(ws, dw, P.Ktot, g->cout, P.splits);
   IIC_LAUNCH_CHECK();
   count_launch();
   return IIC_OK;

@@ -387,8 +387,19 @@ def conv_dgrad(dy, wpt, g, dt, addend=None):
   return dx
 
 
+# host-side switch: wgrad writes the torch-layout gradient itself (iic_conv_wgrad_oihw) instead of wgrad + unpack
+WGRAD_FUSED_UNPACK = {"on": __import__("os").environ.get("IIC_WGRAD_FUSED", "0") != "0"}
+
+
 def conv_wgrad(x, dy, g, dt, grad_out, accumulate):
   """Accumulates (or writes) the torch-layout [cout][cin][kh][kw] fp32 gradient into grad_out."""
+  if WGRAD_FUSED_UNPACK["on"]:
+    nbytes = int(_lib.lib().iic_conv_wgrad_oihw_workspace(ctypes.byref(g), dt))
+    ws = torch.empty((max(nbytes, 4) + 3) // 4, device=x.device, dtype=torch.float32)
+    with _timed("wgrad", g):
+      check(_lib.lib().iic_conv_wgrad_oihw(_p(x), _p(dy), _p(grad_out), int(bool(accumulate)), _p(ws), ctypes.byref(g), dt,
+                                           _stream()), "iic_conv_wgrad_oihw")
+    return grad_out
   nbytes = int(_lib.lib().iic_conv_wgrad_workspace(ctypes.byref(g), dt))
   ws = torch.empty((max(nbytes, 4) + 3) // 4, device=x.device, dtype=torch.float32)
   dwp = torch.empty((g.cout, g.kh, g.kw, g.cin), device=x.device, dtype=torch.float32)

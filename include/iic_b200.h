@@ -219,6 +219,12 @@ int iic_conv_dgrad(const void* dy, const void* w_packed_t, const void* addend, v
 long long iic_conv_wgrad_workspace(const iic_conv_geom* g, int dtype);
 int iic_conv_wgrad(const void* x, const void* dy, float* dw_packed, void* workspace, const iic_conv_geom* g,
                    int dtype, void* stream);
+/* wgrad written straight into the torch-layout gradient [cout][cin][kh][kw] (accumulate ? += : =), i.e. iic_conv_wgrad +
+ * iic_unpack_wgrad in one call; on the IIC_BF16 path the split-K fold itself writes that layout (one launch and one pass
+ * over the gradient less).  workspace: iic_conv_wgrad_oihw_workspace(g, dtype) bytes. */
+long long iic_conv_wgrad_oihw_workspace(const iic_conv_geom* g, int dtype);
+int iic_conv_wgrad_oihw(const void* x, const void* dy, float* grad_oihw, int accumulate, void* workspace,
+                        const iic_conv_geom* g, int dtype, void* stream);
 
 /* ---- stem: first conv of ClusterNet5g (net5g.py:21-23) / 6c (vgg.py) / 10a: tiny cin
  *      (1..5), read straight from the reference's NCHW fp32 input. Direct SIMT conv.

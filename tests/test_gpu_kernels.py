@@ -775,3 +775,34 @@ def test_halo_fprop_with_per_lane_running_statistics(n, h, variant):
   K = _K()
   with K.options(conv_halo_stats=1):
     test_halo_kernels_forced_exact_small_integers(n, h, variant)
+
+
+@pytest.mark.unvalidated
+@pytest.mark.parametrize("case", [(3, 13, 64, 64, 3, 1, 1, 1), (32, 49, 64, 64, 3, 1, 1, 1), (3, 25, 64, 128, 3, 2, 1, 1),
+                                  (3, 25, 64, 128, 1, 2, 0, 1), (4, 7, 256, 512, 3, 1, 1, 1), (2, 12, 64, 128, 5, 1, 2, 1)])
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_wgrad_written_in_torch_layout_equals_wgrad_plus_unpack(case, mode):
+  """iic_conv_wgrad_oihw (the split-K fold writes [cout][cin][kh][kw] itself on the bf16 path) == iic_conv_wgrad +
+  iic_unpack_wgrad, bit for bit (same partial sums, same fold order), with and without accumulation."""
+  K = _K()
+  from iic_b200._lib import BF16, F32
+  n, h, cin, cout, k, s, p, d = case
+  dt, tdt = (F32, torch.float32) if mode == "fp32" else (BF16, torch.bfloat16)
+  x, w, dy, _ = _conv_inputs(case)
+  g = K.conv_geom(n, h, h, cin, cout, k, k, s, p, d)
+  xh, dyh = to_nhwc(x, tdt), to_nhwc(dy, tdt)
+  base = torch.randn_like(w)
+  outs = {}
+  for fused in (False, True):
+    old = K.WGRAD_FUSED_UNPACK["on"]
+    K.WGRAD_FUSED_UNPACK["on"] = fused
+    try:
+      a = torch.zeros_like(w)
+      K.conv_wgrad(xh, dyh, g, dt, a, False)
+      b = base.clone()
+      K.conv_wgrad(xh, dyh, g, dt, b, True)
+      outs[fused] = (a, b)
+    finally:
+      K.WGRAD_FUSED_UNPACK["on"] = old
+  assert torch.equal(outs[False][0], outs[True][0])
+  assert torch.equal(outs[False][1], outs[True][1])

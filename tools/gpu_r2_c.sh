@@ -40,6 +40,7 @@ except Exception as e:
   print("no precision json", e)
 PY
 timeout 400 python bench.py --also tf32x3,tf32 > $O/c_bench.json 2> $O/c_bench.err; stamp "3 bench default (+ tf32x3, tf32 modes) rc=$?"; tail -2 $O/c_bench.err; summ $O/c_bench.json
+IIC_WGRAD_FUSED=1 timeout 150 python bench.py --steps 10 --no-cpu-baseline > $O/c_bench_wgrad_fused.json 2> $O/c_bench_wgrad_fused.err; stamp "3b bench, wgrad writes the torch layout rc=$?"; summ $O/c_bench_wgrad_fused.json
 timeout 200 python __graft_entry__.py smoke > $O/c_smoke.log 2>&1; stamp "4 smoke rc=$?"; tail -6 $O/c_smoke.log
 IIC_SMOKE_MODES=fp32,tf32x3,bf16 timeout 200 python __graft_entry__.py smoke > $O/c_smoke_all.log 2>&1; stamp "4b smoke incl. tf32x3 rc=$?"; tail -6 $O/c_smoke_all.log
 timeout 100 python tools/seg_step.py 15 A > $O/c_seg_default.json 2>&1; stamp "5 seg step, default (tensor-core backward, SIMT joint) rc=$?"; tail -1 $O/c_seg_default.json
