@@ -56,7 +56,7 @@ CONFIGS = {
 # Defaults that depend on code having run on a B200 (flipped by hand after tools/gpu_r2_a.sh passes): until then the
 # default command line takes round 1's validated path, so that the driver's round-end run cannot be broken by a kernel
 # that has never executed.  Every item stays selectable from the command line.
-VALIDATED = {"arena": True, "rgb_input": True, "also": ""}  # arena / rgb: gpurun_out/a_tests.log, a_bench.json (round 2, session A)
+VALIDATED = {"arena": True, "rgb_input": True, "also": "tf32x3"}  # arena / rgb: gpurun_out/a_tests.log, a_bench.json (round 2, session A)
 
 
 def parse():

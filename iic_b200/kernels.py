@@ -191,10 +191,10 @@ def seg_unprepare(dx1m, dx2m, theta, mask, k, shift=(0, 0)):
 # host-side switches of the tensor-core segmentation kernels (csrc/seg_joint_tc.cu):
 #   SEG_CORR_TC   backward contractions (kind::tf32, K-major overlapped operand): validated on a B200 in round 2
 #                 (tests/test_gpu_parity_seg.py::test_seg_corr_tensor_core_matches_simt), ON
-#   SEG_JOINT_TC  forward joint (kind::f16 on bf16 three-term operands, MN-major Toeplitz operand): OFF until it has
-#                 passed test_seg_joint_tensor_core_* on hardware
+#   SEG_JOINT_TC  forward joint (kind::f16 on bf16 three-term operands, MN-major Toeplitz operand): validated on a B200 in
+#                 round 2 (test_seg_joint_tensor_core_matches_simt_and_oracle, the reference golden of the loss), ON
 SEG_CORR_TC = {"on": __import__("os").environ.get("IIC_SEG_CORR_TC", "1") != "0"}
-SEG_JOINT_TC = {"on": __import__("os").environ.get("IIC_SEG_JOINT_TC", "0") != "0"}
+SEG_JOINT_TC = {"on": __import__("os").environ.get("IIC_SEG_JOINT_TC", "1") != "0"}
 
 
 def seg_joint_tc(x1m, x2m, k, T):
@@ -212,8 +212,8 @@ def seg_joint_tc(x1m, x2m, k, T):
   return joint
 
 
-def seg_joint(x1m, x2m, k, T):
-  if SEG_JOINT_TC["on"] and T > 0:
+def seg_joint(x1m, x2m, k, T, allow_tc=True):
+  if allow_tc and SEG_JOINT_TC["on"] and T > 0:
     j = seg_joint_tc(x1m, x2m, k, T)
     if j is not None:
       return j

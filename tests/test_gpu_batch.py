@@ -42,7 +42,6 @@ def test_assemble_slabs_is_the_reference_loop():
     assert g1.is_cuda and torch.equal(g1.cpu(), all_imgs) and torch.equal(g2.cpu(), all_tf)
 
 
-@pytest.mark.unvalidated
 @pytest.mark.parametrize("head", ["A", "B"])
 def test_repeat_handling_equals_slab_assembled_step(head):
   """Forwarding the unique tf1 images once and repeating their softmax rows gives the loss and the parameter

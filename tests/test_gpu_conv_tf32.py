@@ -12,8 +12,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-# `unvalidated` until the file has passed once on a B200 (tools/gpu_r2_a.sh runs it with IIC_RUN_UNVALIDATED=1)
-pytestmark = [pytest.mark.gpu, pytest.mark.unvalidated]
+pytestmark = pytest.mark.gpu
 
 CASES = [
   # n, h, cin, cout, k, stride, pad, dil

@@ -198,7 +198,6 @@ def test_backward_guards():
     loss.backward()
 
 
-@pytest.mark.unvalidated
 def test_seg_step_matches_oracle_with_torch_adam():
   import iic_b200.archs as archs
   from iic_b200.optim import FusedAdam
@@ -240,7 +239,6 @@ def test_seg_step_matches_oracle_with_torch_adam():
     assert _rel(upd, want) < 0.15, (k, _rel(upd, want))  # three Adam steps at lr 1e-3: +-lr sign flips (measured 0.08)
 
 
-@pytest.mark.unvalidated
 def test_legacy_format_checkpoint_loads_and_reproduces_the_oracle(tmp_path):
   """SURVEY S8f row 3 on the GPU: a checkpoint in torch 0.4.1's on-disk format (legacy non-zip serialisation, pickle
   protocol 2, saved from a DataParallel wrapper -> `module.` prefixes, the layout of the published models.tar.gz)
