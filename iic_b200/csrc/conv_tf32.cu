@@ -308,14 +308,25 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           } else {
             float4* hi = reinterpret_cast<float4*>(st_hi);
             float4* lo = reinterpret_cast<float4*>(st_lo);
-#pragma unroll 4
-            for (int c = tid; c < Cfg::HALF / 16; c += 128) {
-              const float4 v = hi[c];
-              float4 h, l;
-              h.x = hi_tf32(v.x); h.y = hi_tf32(v.y); h.z = hi_tf32(v.z); h.w = hi_tf32(v.w);
-              l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-              hi[c] = h;
-              lo[c] = l;
+            // all of a thread's 16-byte chunks are loaded before the first is used (the loop was bound by the
+            // shared-memory load latency: 23 % of the kernel's stall samples sat on its first LOP3, profiles/r02_ncu_conv_tf32.md)
+            constexpr int ITER = Cfg::HALF / 16 / 128;
+            static_assert(ITER * 128 * 16 == Cfg::HALF, "stage size must be a multiple of 128 x 16 bytes");
+            constexpr int HALF_IT = ITER / 2;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              float4 v[HALF_IT];
+#pragma unroll
+              for (int it = 0; it < HALF_IT; ++it) v[it] = hi[tid + (half * HALF_IT + it) * 128];
+#pragma unroll
+              for (int it = 0; it < HALF_IT; ++it) {
+                const int c = tid + (half * HALF_IT + it) * 128;
+                float4 h, l;
+                h.x = hi_tf32(v[it].x); h.y = hi_tf32(v[it].y); h.z = hi_tf32(v[it].z); h.w = hi_tf32(v[it].w);
+                l.x = v[it].x - h.x; l.y = v[it].y - h.y; l.z = v[it].z - h.z; l.w = v[it].w - h.w;
+                hi[c] = h;
+                lo[c] = l;
+              }
             }
           }
           fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads

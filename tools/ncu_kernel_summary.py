@@ -52,8 +52,11 @@ def main():
     e = agg.setdefault(name, {"n": 0})
     e["n"] += 1
     for m in METRICS:
-      if m in col and d[col[m]] not in ("", "n/a"):
-        v = float(d[col[m]].replace(",", "")) * SCALE.get(units[col[m]], 1.0)
+      if m in col and d[col[m]] not in ("", "n/a", "no data"):
+        try:
+          v = float(d[col[m]].replace(",", "")) * SCALE.get(units[col[m]], 1.0)
+        except ValueError:
+          continue
         e[m] = e.get(m, 0.0) + v
   print("| kernel | launches | avg us | DRAM read MB | DRAM write MB | DRAM GB/s | tensor pipe % | DRAM % | warps active % |")
   print("|---|---:|---:|---:|---:|---:|---:|---:|---:|")
