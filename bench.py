@@ -570,6 +570,12 @@ def run_ours(args):
       line["cpu_baseline"] = cpu
     print(json.dumps(line))
   if world > 1:
+    # captured graphs hold NCCL work: destroy them (and everything else that references the communicator's streams) before
+    # the process group, or the teardown hangs (seen at N = 2 with --graph)
+    job.gstep = None
+    del job
+    torch.cuda.synchronize()
+    dist.barrier()
     dist.destroy_process_group()
 
 
