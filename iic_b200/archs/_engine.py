@@ -174,7 +174,21 @@ OPTIONS = {
   "pack_batched": os.environ.get("IIC_PACK_BATCHED", "1") != "0",
   "stem_bwd_fused": os.environ.get("IIC_STEM_BWD_FUSED", "0") != "0",
   "bn_bitmask": os.environ.get("IIC_BN_BITMASK", "0") != "0",
+  # wgrad_stream: weight-gradient convolutions run on a second stream.  A wgrad depends on (x, dy) only and nothing in
+  # the backward depends on it, while the critical chain alternates tensor-bound dgrads with HBM-bound BatchNorm passes:
+  # with the dgrad enqueued first, the (persistent, one CTA per SM) wgrad starts when the dgrad drains and then shares the
+  # SMs with the BatchNorm backward of the next stage (tensor pipe + HBM busy at the same time).  Needs BatchNorm kernels
+  # that fit beside a resident conv CTA: library option bn_bwd_ctas = 1.
+  "wgrad_stream": os.environ.get("IIC_WGRAD_STREAM", "0") != "0",
 }
+_WSTREAMS = {}
+
+
+def _wgrad_stream(device):
+  s = _WSTREAMS.get(device)
+  if s is None:
+    s = _WSTREAMS[device] = torch.cuda.Stream(device=device)
+  return s
 
 
 def _bn_stats(ctx, bn, y):
@@ -277,6 +291,7 @@ class GradSink(object):
     self.g = {}
     self.direct = {}
     self._touched = []
+    self.wstream = None  # side stream that produced some of the gradients (OPTIONS["wgrad_stream"])
 
   def buf(self, p):
     if id(p) in self.direct:
@@ -293,7 +308,7 @@ class GradSink(object):
 
   def commit(self):
     for p in self._touched:
-      self.direct[id(p)].mark(p)
+      self.direct[id(p)].mark(p, producer=self.wstream)
     self._touched = []
 
   def get(self, p):
@@ -321,7 +336,17 @@ def _bn_backward(ctx, sink, bn, g_in, act, y, mi, want_g_out, mask_ss=None):
 
 def _conv_wgrad(ctx, sink, conv, x, dy, g):
   gw, acc = sink.buf(conv.weight)
-  K.conv_wgrad(x, dy, g, ctx.cdt, gw, acc)
+  if not (OPTIONS["wgrad_stream"] and x.is_cuda):
+    K.conv_wgrad(x, dy, g, ctx.cdt, gw, acc)
+    return
+  cur = torch.cuda.current_stream(x.device)
+  ws = _wgrad_stream(x.device)
+  ws.wait_stream(cur)  # x, dy (and the gradient buffer's previous contents) are ready on the compute stream
+  with torch.cuda.stream(ws):
+    K.conv_wgrad(x, dy, g, ctx.cdt, gw, acc)
+  for t in (x, dy, gw):
+    t.record_stream(ws)  # the allocator must not hand this memory out again before the side stream is done with it
+  sink.wstream = ws
 
 
 # ---- stem: conv(NCHW input) + BN + ReLU [+ MaxPool(2,2,pad)] -----------------------------------
@@ -384,8 +409,9 @@ def convbn_backward(ctx, sink, rec, d_out):
     dy, _ = _bn_backward(ctx, sink, bn, gmask, None, y, mi, False)
   else:
     dy, _ = _bn_backward(ctx, sink, bn, d_out, None, y, mi, False, mask_ss=ss)
+  dx = K.conv_dgrad(dy, ctx.packed(conv, 1), g, ctx.cdt)
   _conv_wgrad(ctx, sink, conv, x, dy, g)
-  return K.conv_dgrad(dy, ctx.packed(conv, 1), g, ctx.cdt)
+  return dx
 
 
 # ---- residual BasicBlock (residual.py:10-43) -----------------------------------------------------
@@ -420,17 +446,22 @@ def block_backward(ctx, sink, rec, d_out):
     dy2, gres = K.bn_bwd_fused_bits(d_out, mbits, y2, mi2, blk.bn2.weight.detach(), dg, db, acc1, True)
   else:
     dy2, gres = _bn_backward(ctx, sink, blk.bn2, d_out, out, y2, mi2, True)
-  _conv_wgrad(ctx, sink, blk.conv2, a1, dy2, g2)
+  # (the dgrad -- critical path -- is enqueued before the wgrad of the same layer: with OPTIONS["wgrad_stream"] the wgrad
+  # then starts when the dgrad drains and overlaps the BatchNorm backward that follows)
   da1 = K.conv_dgrad(dy2, ctx.packed(blk.conv2, 1), g2, ctx.cdt)
+  _conv_wgrad(ctx, sink, blk.conv2, a1, dy2, g2)
   dy1, _ = _bn_backward(ctx, sink, blk.bn1, da1, None, y1, mi1, False, mask_ss=ss1)  # a1 = relu(bn1(y1))
-  _conv_wgrad(ctx, sink, blk.conv1, x, dy1, g1)
   if blk.downsample is not None:
     dconv, dbn = blk.downsample[0], blk.downsample[1]
     dyd, _ = _bn_backward(ctx, sink, dbn, gres, None, yd, mid, False)
-    _conv_wgrad(ctx, sink, dconv, x, dyd, gd)
     dxd = K.conv_dgrad(dyd, ctx.packed(dconv, 1), gd, ctx.cdt)
-    return K.conv_dgrad(dy1, ctx.packed(blk.conv1, 1), g1, ctx.cdt, addend=dxd)
-  return K.conv_dgrad(dy1, ctx.packed(blk.conv1, 1), g1, ctx.cdt, addend=gres)
+    dx = K.conv_dgrad(dy1, ctx.packed(blk.conv1, 1), g1, ctx.cdt, addend=dxd)
+    _conv_wgrad(ctx, sink, dconv, x, dyd, gd)
+    _conv_wgrad(ctx, sink, blk.conv1, x, dy1, g1)
+    return dx
+  dx = K.conv_dgrad(dy1, ctx.packed(blk.conv1, 1), g1, ctx.cdt, addend=gres)
+  _conv_wgrad(ctx, sink, blk.conv1, x, dy1, g1)
+  return dx
 
 
 def _prepack(trunk, ectx):
@@ -489,6 +520,8 @@ class TrunkFunction(torch.autograd.Function):
     for rec in reversed(ectx.saved):
       d = _BACKWARD[rec[0]](ectx, sink, rec, d)
       sink.commit()
+    if sink.wstream is not None:  # every weight gradient is complete before autograd / the optimiser sees it
+      torch.cuda.current_stream(dfeat.device).wait_stream(sink.wstream)
     ectx.saved = None
     ectx.wcache = {}
     grads = tuple(sink.get(p) for p in ctx.params)

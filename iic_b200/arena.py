@@ -72,6 +72,7 @@ class GradArena(object):
     self._pending = [hi - lo for lo, hi in self.buckets]
     self._marked = [False] * len(self.params)
     self._launched = [False] * len(self.buckets)
+    self._producers = set()  # streams other than the compute stream that wrote gradients in this step
     self.reduce_log = []  # bucket ids in launch order (tests)
 
   def begin_step(self, overlap=True):
@@ -100,11 +101,13 @@ class GradArena(object):
   def _autograd_hook(self, p):
     self.mark(p)
 
-  def mark(self, p):
-    """The gradient of ``p`` for this step has been enqueued on the current stream."""
+  def mark(self, p, producer=None):
+    """The gradient of ``p`` for this step has been enqueued on the current stream (or on the stream ``producer``)."""
     i = self._index.get(id(p))
     if i is None:
       return
+    if producer is not None:
+      self._producers.add(producer)
     self.live[i] = True
     if self._marked[i]:
       return
@@ -126,6 +129,8 @@ class GradArena(object):
       return
     cur = torch.cuda.current_stream(self.flat.device)
     self._side.wait_stream(cur)
+    for ps in self._producers:
+      self._side.wait_stream(ps)
     with torch.cuda.stream(self._side):
       if self._events is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -52,6 +52,10 @@ static Option g_opts[OPT_COUNT] = {
     // across the warp once per CTA (0 = two transpose-reduces per 32-column chunk).  Validated on a B200 in round 2:
     // layer1 fprop 1073 -> 1172 TFLOP/s over the net's fprop launches, step 43.00 -> 42.42 ms (profiles/r02_session_a.md)
     {"conv_halo_stats", "IIC_CONV_HALO_STATS", 1, 0, false},
+    // bn_bwd_ctas: CTAs per SM of the cooperative BatchNorm-backward kernel (2 = fastest alone; 1 = fits beside a resident
+    // persistent convolution CTA, 17 KB + 198 KB of shared memory, so that it can overlap a wgrad running on a second
+    // stream: _engine.OPTIONS["wgrad_stream"])
+    {"bn_bwd_ctas", "IIC_BN_BWD_CTAS", 2, 0, false},
 };
 
 int option(int id) {

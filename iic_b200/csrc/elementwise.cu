@@ -1028,7 +1028,10 @@ static int bn_bwd_fused_launch(BnBwdFusedArgs& a, size_t smem, cudaStream_t st) 
     cached[dev] = occ > 2 ? 2 : occ;
     IIC_REQUIRE(cached[dev] > 0, IIC_ERR_CUDA, "iic_bn_bwd_fused: kernel does not fit");
   }
-  int grid = device_sm_count() * cached[dev];
+  int per_sm = option(OPT_BN_BWD_CTAS);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > cached[dev]) per_sm = cached[dev];
+  int grid = device_sm_count() * per_sm;
   grid -= grid % a.views;
   void* args[] = {&a};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)bn_bwd_fused_kernel<T, MASK>, dim3(grid), dim3(256), args, smem, st);

@@ -66,6 +66,7 @@ long long iic_launch_count(int reset);
  *                                              entry point): 2 = channel-interleaved lanes (whole-sector stores),
  *                                              1 = 16 consecutive channels per thread; 0 = one pixel per thread
  *   "dgrad_prefetch"  [IIC_DGRAD_PREFETCH=1]   dgrad epilogues fetch the residual-gradient addend ahead of its use
+ *   "bn_bwd_ctas"     [IIC_BN_BWD_CTAS=2]      CTAs per SM of the cooperative BatchNorm backward (1 = fits beside a resident conv CTA)
  *   "tc2_mt2"         [IIC_TC2_MT2=1]          128-channel fprop/dgrad: two 128-row tiles per weight k-block (0 = one)
  *   "conv_halo_store" [IIC_CONV_HALO_STORE=1]  halo fprop/dgrad: output tile staged in shared memory, one TMA store per
  *                                              work item (0 = per-thread 16-byte global stores)

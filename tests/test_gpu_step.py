@@ -321,3 +321,42 @@ def test_graphed_step_equals_eager_steps():
   pa, pb = dict(nets[1].named_parameters()), opts[1]
   assert int(pb.state[pa["trunk.conv1.weight"]]["step"]) == 8
   assert len(pb.state[pa["head_A.heads.0.0.weight"]]) == 0  # never trained: no state, untouched
+
+
+@pytest.mark.unvalidated
+def test_wgrad_on_second_stream_gives_identical_gradients():
+  """OPTIONS["wgrad_stream"] (weight-gradient convolutions on a second stream, overlapping the BatchNorm backward of
+  the next stage; library option bn_bwd_ctas = 1) only changes the schedule: losses and every gradient are bit-identical
+  to the single-stream step, eager and with the arena, over two steps (stream-ordering bugs show up as garbage)."""
+  import iic_b200.archs as archs
+  from iic_b200 import kernels as K
+  from iic_b200.archs import _engine as E
+  from iic_b200.arena import GradArena
+  from iic_b200.step import iic_cluster_step
+  res = {}
+  for mode in ("single", "second-stream"):
+    for use_arena in (False, True):
+      net = archs.ClusterNet5gTwoHead(Namespace(precision="bf16", **CFG))
+      weights.fill_state_dict(net, salt=41)
+      net.cuda().train()
+      arena = GradArena(net) if use_arena else None
+      old = E.OPTIONS["wgrad_stream"]
+      E.OPTIONS["wgrad_stream"] = mode != "single"
+      try:
+        with K.options(bn_bwd_ctas=1 if mode != "single" else 2):
+          out = []
+          for i in range(2):
+            g = weights.uniform("ws.g%d" % i, (24, 1, 32, 32)).cuda()
+            loss, _ = iic_cluster_step(net, None, g, g.flip(3), head="B", arena=arena)
+            torch.cuda.synchronize()
+            out.append((loss.item(), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}))
+      finally:
+        E.OPTIONS["wgrad_stream"] = old
+      res[(mode, use_arena)] = out
+  for use_arena in (False, True):
+    a, b = res[("single", use_arena)], res[("second-stream", use_arena)]
+    for (la, ga), (lb, gb) in zip(a, b):
+      assert la == lb
+      assert ga.keys() == gb.keys()
+      for k in ga:
+        assert torch.equal(ga[k], gb[k]), k
