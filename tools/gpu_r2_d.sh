@@ -30,5 +30,8 @@ timeout 400 python bench.py > $O/d_bench.json 2> $O/d_bench.err; stamp "4 bench 
 IIC_WGRAD_FUSED=1 timeout 200 python bench.py --steps 10 --no-cpu-baseline --also '' > $O/d_bench_wgrad_fused.json 2> $O/d_bench_wgrad_fused.err; stamp "5 bench, wgrad writes the torch layout rc=$?"; summ $O/d_bench_wgrad_fused.json
 timeout 200 python bench.py --steps 10 --no-cpu-baseline --also '' > $O/d_bench_again.json 2> $O/d_bench_again.err; stamp "5b bench default again (A/B) rc=$?"; summ $O/d_bench_again.json
 timeout 200 python bench.py --graph --steps 10 --no-cpu-baseline --also '' > $O/d_bench_graph.json 2> $O/d_bench_graph.err; stamp "5c bench --graph rc=$?"; summ $O/d_bench_graph.json
+IIC_BN_BWD_CTAS=1 timeout 200 python bench.py --steps 10 --no-cpu-baseline --also '' > $O/d_bench_bnctas1.json 2> $O/d_bench_bnctas1.err; stamp "5d bench, bn_bwd 1 CTA/SM rc=$?"; summ $O/d_bench_bnctas1.json
+IIC_BN_BWD_CTAS=1 IIC_WGRAD_STREAM=1 timeout 200 python bench.py --steps 10 --no-cpu-baseline --also '' > $O/d_bench_wstream.json 2> $O/d_bench_wstream.err; stamp "5e bench, wgrad on a second stream rc=$?"; tail -2 $O/d_bench_wstream.err; summ $O/d_bench_wstream.json
+IIC_WGRAD_STREAM=1 timeout 200 python bench.py --steps 10 --no-cpu-baseline --also '' > $O/d_bench_wstream2.json 2> $O/d_bench_wstream2.err; stamp "5f bench, wgrad on a second stream, bn_bwd 2 CTAs/SM rc=$?"; summ $O/d_bench_wstream2.json
 timeout 200 python bench.py --config c5 --steps 5 --no-cpu-baseline > $O/d_bench_c5.json 2> $O/d_bench_c5.err; stamp "6 bench c5 rc=$?"; summ $O/d_bench_c5.json
 timeout 200 python bench.py --impl reference --steps 3 > $O/d_ref.json 2> $O/d_ref.err; stamp "7 reference arm rc=$?"; tail -c 600 $O/d_ref.json
