@@ -388,7 +388,8 @@ def conv_dgrad(dy, wpt, g, dt, addend=None):
 
 
 # host-side switch: wgrad writes the torch-layout gradient itself (iic_conv_wgrad_oihw) instead of wgrad + unpack
-WGRAD_FUSED_UNPACK = {"on": __import__("os").environ.get("IIC_WGRAD_FUSED", "0") != "0"}
+# (validated on a B200 in round 2: bit-identical in 12 geometries; 350 launches per step less)
+WGRAD_FUSED_UNPACK = {"on": __import__("os").environ.get("IIC_WGRAD_FUSED", "1") != "0"}
 
 
 def conv_wgrad(x, dy, g, dt, grad_out, accumulate):

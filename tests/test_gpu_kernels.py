@@ -777,7 +777,6 @@ def test_halo_fprop_with_per_lane_running_statistics(n, h, variant):
     test_halo_kernels_forced_exact_small_integers(n, h, variant)
 
 
-@pytest.mark.unvalidated
 @pytest.mark.parametrize("case", [(3, 13, 64, 64, 3, 1, 1, 1), (32, 49, 64, 64, 3, 1, 1, 1), (3, 25, 64, 128, 3, 2, 1, 1),
                                   (3, 25, 64, 128, 1, 2, 0, 1), (4, 7, 256, 512, 3, 1, 1, 1), (2, 12, 64, 128, 5, 1, 2, 1)])
 @pytest.mark.parametrize("mode", ["bf16", "fp32"])

@@ -44,7 +44,6 @@ def _vs_golden(got, g, out_atol, loss_rtol, norm_rtol, grad_rel):
     assert rel <= grad_rel, (key, rel)
 
 
-@pytest.mark.unvalidated  # tolerance re-set after session C (measured 1.55e-2 against 1.5e-2): passes on the next hardware run
 @pytest.mark.parametrize("mode", ["fp32", "tf32x3"])
 def test_fp32_grade_modes_meet_the_fp32_tolerance(mode, setup):
   """fp32 SIMT and 3xTF32 tensor-core convolutions: loss 1e-4 relative, outputs 5e-4, every parameter gradient within
@@ -87,7 +86,6 @@ def test_bf16_mode_tolerance_and_agreement_with_bf16_storage_oracle(setup):
   assert c["grad_cos_min"] > 0.5, c
 
 
-@pytest.mark.unvalidated  # tolerance re-set after session C (bf16 2.3 % at step 0 against 2 %)
 def test_training_trajectories_track_fp32(setup):
   """40 Adam steps (lr 1e-4) on the fixture batch: every mode's loss curve stays within 3 % (bf16; measured 2.3 % at the
   first step -- its forward loss error -- and 0.2 % from step 3 on) / 0.5 % (tf32x3; measured 0.12 %) of the fp32-SIMT
