@@ -15,7 +15,6 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-# tests whose tolerances were re-set after their first hardware run keep the `unvalidated` marker until they have passed
 
 from oracle import iid_losses as oracle_iid  # noqa: E402
 from oracle import nets as oracle_nets  # noqa: E402
@@ -197,7 +196,6 @@ def test_backward_guards():
     loss.backward()
 
 
-@pytest.mark.unvalidated  # restructured after session D (one step at a time): passes on the next hardware run
 def test_seg_step_matches_oracle_with_torch_adam():
   """iic_seg_step (segmentation_twohead.py:262-361) against the oracle stepped by torch.optim.Adam, one step at a time
   from re-synchronised states (see _sync_oracle_to): loss 5e-5, Adam moments 2e-2 / 4e-2, updates element-wise."""
@@ -284,7 +282,6 @@ def test_graphed_step_equals_eager_steps():
   assert len(pb.state[pa["head_A.heads.0.0.weight"]]) == 0  # never trained: no state, untouched
 
 
-@pytest.mark.unvalidated
 def test_wgrad_on_second_stream_gives_identical_gradients():
   """OPTIONS["wgrad_stream"] (weight-gradient convolutions on a second stream, overlapping the BatchNorm backward of
   the next stage; library option bn_bwd_ctas = 1) only changes the schedule: losses and every gradient are bit-identical
