@@ -453,8 +453,32 @@ def stem_bwd_fused(x_nchw, y, dpool, ss, mi, gamma, dgamma, dbeta, bn_accumulate
   return True
 
 
+# host-side switch: stem wgrad as im2col + the tcgen05 1x1 wgrad kernel (bf16 mode; OFF until validated on hardware)
+STEM_WGRAD_TC = {"on": __import__("os").environ.get("IIC_STEM_WGRAD_TC", "0") != "0"}
+
+
+def stem_wgrad_tc(x_nchw, dy, g, grad_out, accumulate):
+  """bf16 tensor-core stem wgrad (include/iic_b200.h: iic_stem_im2col); returns False if the geometry is unsupported.
+  (Calls the library directly: the 1x1 product has no share in the algorithmic conv FLOPs of the roofline.)"""
+  K = g.cin * g.kh * g.kw
+  if not (K <= 64 and g.stride == 1 and g.dil == 1 and g.oh == g.h and g.ow == g.w and g.cout % 64 == 0 and dy.dtype == torch.bfloat16):
+    return False
+  col = torch.empty((g.n, g.h, g.w, 64), device=dy.device, dtype=torch.bfloat16)
+  check(_lib.lib().iic_stem_im2col(_p(x_nchw), _p(col), ctypes.byref(g), _stream()), "iic_stem_im2col")
+  g1 = conv_geom(g.n, g.h, g.w, 64, g.cout, 1, 1, 1, 0, 1)
+  gcol = torch.empty((g.cout, 64), device=dy.device, dtype=torch.float32)
+  nbytes = int(_lib.lib().iic_conv_wgrad_oihw_workspace(ctypes.byref(g1), BF16))
+  ws = torch.empty((max(nbytes, 4) + 3) // 4, device=dy.device, dtype=torch.float32)
+  check(_lib.lib().iic_conv_wgrad_oihw(_p(col), _p(dy), _p(gcol), 0, _p(ws), ctypes.byref(g1), BF16, _stream()),
+        "iic_conv_wgrad_oihw")
+  check(_lib.lib().iic_stem_col_unpack(_p(gcol), _p(grad_out), int(bool(accumulate)), g.cout, K, _stream()), "iic_stem_col_unpack")
+  return True
+
+
 @_cat("stem_wgrad")
 def stem_wgrad(x_nchw, dy, g, dt, grad_out, accumulate):
+  if STEM_WGRAD_TC["on"] and dt == BF16 and stem_wgrad_tc(x_nchw, dy, g, grad_out, accumulate):
+    return grad_out
   ws = torch.empty(2 * 1024 * 1024, device=dy.device, dtype=torch.float32)  # 8 MB of per-block partials
   check(_lib.lib().iic_stem_wgrad(_p(x_nchw), _p(dy), _p(grad_out), int(bool(accumulate)), _p(ws), ws.numel() * 4,
                                   ctypes.byref(g), dt, _stream()), "iic_stem_wgrad")

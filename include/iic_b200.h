@@ -242,6 +242,12 @@ int iic_stem_fprop_stats(const float* x_nchw, const float* w_oihw, void* y, cons
                          float* stat_partial, void* stream);
 int iic_stem_wgrad(const float* x_nchw, const void* dy, float* grad_oihw, int accumulate, void* workspace,
                    long long workspace_bytes, const iic_conv_geom* g, int dtype, void* stream);
+/* Stem wgrad on the tensor cores: iic_stem_im2col writes the patches of the NCHW fp32 input as a [pixels][64] bf16 matrix
+ * (columns in OIHW order ci*kh*kw + a*kw + b, zero padded; cin*kh*kw <= 64, stride 1, 'same' padding); the product with
+ * dy is then iic_conv_wgrad(_oihw) of a 1x1 convolution with cin = 64, and iic_stem_col_unpack adds the first K columns
+ * of its [cout][64] result into the torch-layout gradient [cout][cin][kh][kw]. */
+int iic_stem_im2col(const float* x_nchw, void* col_bf16, const iic_conv_geom* g, void* stream);
+int iic_stem_col_unpack(const float* grad_col, float* grad_oihw, int accumulate, int cout, int K, void* stream);
 /* Whole backward of the ClusterNet5g stem, conv3x3(cin 1|2 -> 64, pad 1) -> BatchNorm -> ReLU -> MaxPool(2, 2, pool_pad)
  * (net5g.py:21-26), in two passes over (y, dpool) instead of six over y-sized tensors: the pooled gradient is routed
  * and ReLU-masked on the fly, reduced for the BatchNorm backward, and the BatchNorm input gradient is consumed by the

@@ -805,3 +805,36 @@ def test_wgrad_written_in_torch_layout_equals_wgrad_plus_unpack(case, mode):
       K.WGRAD_FUSED_UNPACK["on"] = old
   assert torch.equal(outs[False][0], outs[True][0])
   assert torch.equal(outs[False][1], outs[True][1])
+
+
+@pytest.mark.unvalidated
+@pytest.mark.parametrize("cin,k,pad,hw,n", [(2, 3, 1, 32, 3), (2, 3, 1, 96, 4), (1, 5, 2, 24, 5), (5, 3, 1, 20, 2)])
+def test_stem_wgrad_on_tensor_cores_matches_the_simt_kernel(cin, k, pad, hw, n):
+  """Stem wgrad as im2col ([pixels][64] bf16 patches) + the tcgen05 1x1 wgrad kernel + column unpack (option
+  STEM_WGRAD_TC) against torch autograd on the same bf16-rounded operands and against the SIMT Gram-product kernel."""
+  K = _K()
+  from iic_b200._lib import BF16
+  cout = 64
+  g = torch.Generator().manual_seed(9)
+  x = torch.randn(n, cin, hw, hw, generator=g).cuda()
+  dy = torch.randn(n, cout, hw, hw, generator=g).cuda().bfloat16().float()
+  geo = K.conv_geom(n, hw, hw, cin, cout, k, k, 1, pad, 1)
+  wr = torch.zeros(cout, cin, k, k, device="cuda", requires_grad=True)
+  F.conv2d(x.bfloat16().float(), wr, None, 1, pad).backward(dy)  # (the patches are rounded to bf16 by the im2col)
+  dyh = to_nhwc(dy, torch.bfloat16)
+  base = torch.randn(cout, cin, k, k, generator=g).cuda()
+  a = torch.zeros_like(base)
+  assert K.stem_wgrad_tc(x, dyh, geo, a, False)
+  scale = wr.grad.abs().max().item()
+  assert (a - wr.grad).abs().max().item() <= 2e-3 * scale
+  b = base.clone()
+  assert K.stem_wgrad_tc(x, dyh, geo, b, True)
+  assert (b - base - wr.grad).abs().max().item() <= 2e-3 * scale
+  c = torch.zeros_like(base)
+  old = K.STEM_WGRAD_TC["on"]
+  K.STEM_WGRAD_TC["on"] = False
+  try:
+    K.stem_wgrad(x, dyh, geo, BF16, c, False)
+  finally:
+    K.STEM_WGRAD_TC["on"] = old
+  assert (a - c).abs().max().item() <= 1e-2 * scale  # (the SIMT kernel reads x in fp32)
