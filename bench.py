@@ -85,7 +85,10 @@ def parse():
   ap.add_argument("--graph", action="store_true", help="capture the step into a CUDA graph and replay it (needs --arena): "
                                                        "removes the ~4 ms of host launch work per step that bounds small per-GPU batches")
   ap.add_argument("--verify", action="store_true", help="check the N-rank loss / gradient checksum against the one-device "
-                                                        "emulation of the sharded algorithm; adds parity_ok to the line")
+                                                        "emulation of the sharded algorithm; adds parity_ok to the line "
+                                                        "(on by default for N > 1; untimed, ~2 s)")
+  ap.add_argument("--no-verify", action="store_true")
+  ap.add_argument("--layer-table", action="store_true", help="add the live per-geometry conv table to roofline.by_layer")
   a = ap.parse_args()
   if a.head is None:
     a.head = "A" if CONFIGS[a.config]["kind"] == "seg" else "B"
@@ -402,6 +405,7 @@ def roofline(job, resident, sec_per_step, pairs, flop_per_pair, precision):
     job.step(resident)
   torch.cuda.synchronize()
   summ = kernels.conv_timing_summary()
+  layers = kernels.conv_timing_by_layer() if getattr(job.args, "layer_table", False) else None
   kernels.conv_timing(False)
   pk = peaks(precision)
   other = {k: {"launches": v[0] // 2, "ms_per_step": v[2] / 2} for k, v in summ.items() if v[1] == 0.0}
@@ -424,13 +428,51 @@ def roofline(job, resident, sec_per_step, pairs, flop_per_pair, precision):
         traffic, tsrc = t["dram_bytes_per_launch"], t["source"]
     except Exception:
       pass
-  return {"bound": "tensor", "kernel": kernel, "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
+  extra = {}
+  if layers:
+    extra["by_layer"] = {k: {"launches": v[0] // 2, "ms_per_step": round(v[2] / 2, 4),
+                             "tflops": round(v[1] / (v[2] * 1e-3) / 1e12, 1)} for k, v in sorted(layers.items())}
+  return {**extra, "bound": "tensor", "kernel": kernel, "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
           "frac": ach / pk["tflops"], "traffic": traffic, "traffic_source": tsrc, "peak_source": pk["src"],
           "launches_timed": nl, "flop_per_launch_avg": flops / max(nl, 1), "ms_per_launch_avg": ms / max(nl, 1),
           "by_kind": {k: {"launches": v[0], "tflops": v[1] / (v[2] * 1e-3) / 1e12 if v[2] > 0 else 0.0,
                           "ms_per_step": v[2] / 2} for k, v in summ.items()},
           "conv_share_of_step": (ms / 2) / (sec_per_step * 1e3), "other_kernels_ms_per_step": other,
           "whole_step_frac": pairs / sec_per_step * flop_per_pair / 1e12 / pk["tflops"]}
+
+
+def _verify_batch(args, B, seed, dev):
+  """A pair of CORRELATED views (view 2 = view 1 + a few grey levels of noise): with the bench's independent random views
+  the mutual information is zero whatever the network does."""
+  import torch
+  x = make_host_batch(args, B, seed, pin=False)[0]
+  g = torch.Generator().manual_seed(seed + 77)
+  if x.dtype == torch.uint8:
+    xt = (x.int() + torch.randint(-6, 7, x.shape, generator=g)).clamp_(0, 255).to(torch.uint8)
+  else:
+    xt = (x + 0.03 * torch.randn(x.shape, generator=g)).clamp_(0, 1)
+  return [x.to(dev), xt.to(dev)]
+
+
+def _condition_for_verify(net, args, x):
+  """The conditioning of tests/precision_fixture.py, applied on the device: head gain 200 and sub-head biases centred on
+  the mean trunk feature of ``x``.  A randomly initialised IIC network has collapsed (all images in one cluster, loss
+  ~ 1e-9): loss and gradients are then rounding noise and no cross-rank comparison means anything.  Deterministic, so
+  every rank and the emulation end up with bit-identical parameters."""
+  import torch
+
+  from iic_b200.step import _to_net_input
+  c = CONFIGS[args.config]
+  heads = (net.head_A if args.head == "A" else net.head_B).heads if hasattr(net, "head_B") else net.head.heads
+  with torch.no_grad():
+    f = net(_to_net_input(x, c["sobel"], False), trunk_features=True).float().mean(0)
+    for h in heads:
+      h[0].weight.mul_(200.0)
+      h[0].bias.copy_(-(h[0].weight.float() @ f).to(h[0].bias.dtype))
+    for m in net.modules():  # undo the probe forward's running-statistics update
+      if getattr(m, "track_running_stats", False) and getattr(m, "running_mean", None) is not None:
+        m.running_mean.zero_()
+        m.running_var.fill_(1.)
 
 
 def verify(args, world, rank, dev):
@@ -445,7 +487,8 @@ def verify(args, world, rank, dev):
     return {"parity_ok": None, "why": "verify covers the clustering workloads"}
   B = min(pairs_for(args, world), 48)
   job = Job(args, args.precision, dev)
-  batches = [[t.to(dev) for t in make_host_batch(args, B, 5000 + r)] for r in range(world)]
+  batches = [_verify_batch(args, B, 5000 + r, dev) for r in range(world)]
+  _condition_for_verify(job.net, args, batches[0][0])
   loss, _ = job.step(batches[rank])  # includes the Adam step: compare the gradients it consumed
   if job.arena is not None:
     gsum, gsq = job.arena.grad_checksum()
@@ -467,6 +510,7 @@ def verify(args, world, rank, dev):
   try:
     emu = Job(args, args.precision, dev)
     emu.arena = None
+    _condition_for_verify(emu.net, args, batches[0][0])
     el = iicd.emulate_sharded_backward(emu.net, [b[0] for b in batches], [b[1] for b in batches], head=args.head, lamb=1.0,
                                        sobel=c["sobel"])
     gs = [p.grad.double() for p in emu.net.parameters() if p.grad is not None]
@@ -510,7 +554,7 @@ def run_ours(args):
   e2e = B * world * args.steps / m["sec_e2e"]
 
   roof = None
-  if not args.no_roofline:
+  if not args.no_roofline and not args.graph:  # (per-launch events do not exist inside a graph replay)
     roof = roofline(job, resident, m["sec"] / args.steps, B, c["flop"], args.precision)
 
   modes = {}
@@ -529,7 +573,14 @@ def run_ours(args):
                                                "conv_share_of_step", "whole_step_frac")}
       modes[mode] = entry
 
-  ver = verify(args, world, rank, dev) if args.verify else None
+  ver = None
+  if args.verify or (world > 1 and not args.no_verify):
+    try:
+      ver = verify(args, world, rank, dev)
+    except Exception as e:  # the check is a collective: every rank raises together or none does
+      if args.verify:
+        raise
+      ver = {"parity_ok": None, "why": "verify failed to run: %r" % (e,)}
 
   overlap = None
   if world > 1 and job.arena is not None and not args.graph:
@@ -546,8 +597,11 @@ def run_ours(args):
   if rank == 0:
     from iic_b200.archs import _engine
     variants = {k: kernels.get_option(k) for k in ("conv_halo", "conv_halo_wgrad", "conv_halo_store", "stem_quad",
-                                                   "dgrad_prefetch", "tc2_mt2")}
+                                                   "dgrad_prefetch", "tc2_mt2", "conv_halo_stats", "bn_bwd_ctas",
+                                                   "tf32x3_raw_hi")}
     variants.update({k: int(v) for k, v in _engine.OPTIONS.items()})
+    variants.update({"stem_wgrad_tc": int(kernels.STEM_WGRAD_TC["on"]), "wgrad_fused_unpack": int(kernels.WGRAD_FUSED_UNPACK["on"]),
+                     "seg_joint_tc": int(kernels.SEG_JOINT_TC["on"]), "seg_corr_tc": int(kernels.SEG_CORR_TC["on"])})
     h2d = sum(t.numel() * t.element_size() for t in host) * world
     line = {"metric": METRIC, "value": value, "unit": "img-pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": m["sec"] / args.steps * 1e3, "higher_is_better": True,

@@ -56,6 +56,11 @@ static Option g_opts[OPT_COUNT] = {
     // persistent convolution CTA, 17 KB + 198 KB of shared memory, so that it can overlap a wgrad running on a second
     // stream: _engine.OPTIONS["wgrad_stream"])
     {"bn_bwd_ctas", "IIC_BN_BWD_CTAS", 2, 0, false},
+    // tf32x3_raw_hi: the 3xTF32 fprop / dgrad splitter leaves the landed fp32 stage untouched and writes only lo = x - trunc(x):
+    // the tensor core ignores the 13 low mantissa bits of a kind::tf32 operand, so x itself IS the hi operand.  A third less
+    // shared-memory traffic for the transform warps that bound this mode.  Off until the truncation has been checked on hardware
+    // (tests/test_gpu_conv_tf32.py runs both settings).
+    {"tf32x3_raw_hi", "IIC_TF32X3_RAW_HI", 0, 0, false},
 };
 
 int option(int id) {

@@ -49,6 +49,7 @@ struct T32Params {
   float* out;
   const float* addend;
   float* partial;
+  int raw_hi;  // 3xTF32 fprop / dgrad: the stage keeps the raw fp32 values as the hi operand (option tf32x3_raw_hi)
 };
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -313,6 +314,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             constexpr int ITER = Cfg::HALF / 16 / 128;
             static_assert(ITER * 128 * 16 == Cfg::HALF, "stage size must be a multiple of 128 x 16 bytes");
             constexpr int HALF_IT = ITER / 2;
+            const bool raw_hi = P.raw_hi != 0;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               float4 v[HALF_IT];
@@ -324,7 +326,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 float4 h, l;
                 h.x = hi_tf32(v[it].x); h.y = hi_tf32(v[it].y); h.z = hi_tf32(v[it].z); h.w = hi_tf32(v[it].w);
                 l.x = v[it].x - h.x; l.y = v[it].y - h.y; l.z = v[it].z - h.z; l.w = v[it].w - h.w;
-                hi[c] = h;
+                if (!raw_hi) hi[c] = h;
                 lo[c] = l;
               }
             }
@@ -507,6 +509,7 @@ int tf32_conv_gather_gemm(const float* src, int srcH, int srcW, int srcC, int ro
   IIC_REQUIRE(g->kh == g->kw, IIC_ERR_UNSUPPORTED, "tf32 conv: square filters only");
   IIC_REQUIRE(!transposed || g->stride == 1, IIC_ERR_UNSUPPORTED, "tf32 dgrad: stride-1 only on this entry");
   T32Params P = {};
+  P.raw_hi = (split == 3) ? option(OPT_TF32X3_RAW_HI) : 0;
   P.rows = (long long)nimg * rowH * rowW;
   P.rowH = rowH; P.rowW = rowW; P.KH = g->kh; P.KW = g->kw; P.d = g->dil;
   const int span = (g->kh - 1) * g->dil;
@@ -573,6 +576,7 @@ int tf32_conv_dgrad_s2(const float* dy, const float* wpacked_t, const float* add
       const int Hc = (g->h - py + 1) / 2, Wc = (g->w - px + 1) / 2;
       if (Hc <= 0 || Wc <= 0) continue;
       T32Params P = {};
+      P.raw_hi = (split == 3) ? option(OPT_TF32X3_RAW_HI) : 0;
       int offs_h[8], taps_h[8], nh = 0, offs_w[8], taps_w[8], nw = 0;
       for (int a = 0; a < g->kh; ++a) {
         const int tnum = py + g->pad - a;

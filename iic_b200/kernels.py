@@ -57,9 +57,22 @@ def conv_timing(enable):
 def conv_timing_summary():
   """-> dict kind -> (launches, algorithmic FLOPs, device ms); call after torch.cuda.synchronize()."""
   out = {}
-  for kind, flops, e0, e1 in _conv_timing["records"]:
+  for kind, flops, e0, e1 in (r[:4] for r in _conv_timing["records"]):
     n, f, ms = out.get(kind, (0, 0.0, 0.0))
     out[kind] = (n + 1, f + flops, ms + e0.elapsed_time(e1))
+  return out
+
+
+def conv_timing_by_layer():
+  """-> dict "kind KxK sS CIN->COUT @H xN" -> (launches, algorithmic FLOPs, device ms): the live per-geometry table."""
+  out = {}
+  for rec in _conv_timing["records"]:
+    if len(rec) < 5 or rec[4] is None:
+      continue
+    kind, flops, e0, e1, g = rec
+    key = "%s %dx%d s%d %d->%d @%d n%d" % (kind, g.kh, g.kw, g.stride, g.cin, g.cout, g.h, g.n)
+    n, f, ms = out.get(key, (0, 0.0, 0.0))
+    out[key] = (n + 1, f + flops, ms + e0.elapsed_time(e1))
   return out
 
 
@@ -78,7 +91,7 @@ class _timed(object):
       self.e1.record()
       g = self.g
       flops = 2.0 * g.n * g.oh * g.ow * g.cout * g.kh * g.kw * g.cin  # 2*MAC, identical for fprop/dgrad/wgrad
-      _conv_timing["records"].append((self.kind, flops, self.e0, self.e1))
+      _conv_timing["records"].append((self.kind, flops, self.e0, self.e1, g))
     return False
 
 

@@ -123,3 +123,27 @@ def test_tf32x3_recovers_bits_that_tf32_drops():
   y1 = K.conv_fprop(x, K.pack_weight(w, F32, 0), g, TF32)
   assert (y3.double() - want).abs().max().item() < 2e-7
   assert (y1.double() - want).abs().max().item() > 5e-5  # plain tf32 sees 1.0 * 1.0
+
+
+@pytest.mark.unvalidated
+@pytest.mark.parametrize("case", CASES[:5])
+def test_tf32x3_raw_hi_operand(case):
+  """Option tf32x3_raw_hi: the splitter writes only lo and the tensor core truncates the raw fp32 stage itself.  Same
+  tolerance as the explicit split -- if the hardware ROUNDED the low 13 bits instead, hi + lo would double count up to
+  2^-11 of every operand (5e-4 relative) and this fails."""
+  from iic_b200 import kernels as K
+  n, h, cin, cout, k, s, p, d = case
+  g = torch.Generator().manual_seed(1)
+  oh = (h + 2 * p - d * (k - 1) - 1) // s + 1
+  x = torch.randn(n, cin, h, h, generator=g).cuda()
+  w = (torch.randn(cout, cin, k, k, generator=g) * math.sqrt(2.0 / (cin * k * k))).cuda()
+  dy = torch.randn(n, cout, oh, oh, generator=g).cuda()
+  add = torch.randn(n, cin, h, h, generator=g).cuda()
+  yr, dxr, dwr = _ref(case, x, w, dy)
+  with K.options(tf32x3_raw_hi=1):
+    y, dx, dx2, gw, gw2 = _run(case, "tf32x3", x, w, dy, add)
+  for name, got, want in (("fprop", y, yr), ("dgrad", dx, dxr), ("dgrad+addend", dx2, dxr + add.double().cpu()),
+                          ("wgrad", gw, dwr)):
+    err = (got.double().cpu() - want).abs().max().item()
+    scale = want.abs().max().item()
+    assert err <= 5e-5 * scale, "%s: max |err| %g, scale %g (rel %g)" % (name, err, scale, err / scale)
