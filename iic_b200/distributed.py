@@ -36,7 +36,22 @@ def group():
   return _group["pg"]
 
 
+_checked_shapes = set()
+
+
 def allreduce_sum_(t):
+  """In-place SUM over the ranks.  The first time a shape is seen, the ranks compare it (one small all-gather): a rank
+  whose (S, k) differs -- a different config, a ragged last batch routed to another head -- would otherwise hang or
+  silently corrupt the NCCL collective."""
+  key = (tuple(t.shape), t.dtype)
+  if key not in _checked_shapes:
+    mine = torch.tensor([t.dim()] + list(t.shape) + [0] * (7 - t.dim()), dtype=torch.int64, device=t.device)
+    every = [torch.empty_like(mine) for _ in range(dist.get_world_size(_group["pg"]))]
+    dist.all_gather(every, mine, group=_group["pg"])
+    shapes = [tuple(int(v) for v in e[1:1 + int(e[0])]) for e in every]
+    if any(sh != shapes[0] for sh in shapes):
+      raise RuntimeError("iic_b200.distributed: ranks disagree on the shape of a summed tensor: %s" % (shapes,))
+    _checked_shapes.add(key)
   dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_group["pg"])
   return t
 

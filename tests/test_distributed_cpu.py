@@ -67,6 +67,13 @@ def _worker(rank, world, port, q):
     dz_local = zt[lo:hi] @ H.T
     assert abs(loss - full["loss"]) < 1e-12
     assert np.abs(dz_local - full["dz"][lo:hi]).max() < 1e-12
+    # ---- ranks that disagree on the shape of a summed tensor get an error instead of a hang ----
+    bad = torch.zeros(1, 3 + rank, 3 + rank)
+    try:
+      iicd.allreduce_sum_(bad)
+      raise AssertionError("shape disagreement went unnoticed")
+    except RuntimeError as e:
+      assert "disagree" in str(e), e
     iicd.disable()
     assert not iicd.active()
     q.put((rank, "ok"))
