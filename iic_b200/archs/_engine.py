@@ -144,7 +144,7 @@ class _Ctx(object):
   def packed(self, conv, kind):
     key = (id(conv), kind)
     if key not in self.wcache:
-      self.wcache[key] = K.pack_weight(conv.weight.detach(), self.dt, kind)
+      self.wcache[key] = K.pack_weight(conv.weight.detach(), K.weight_dtype(self.dt, self.cdt), kind)
     return self.wcache[key]
 
 
@@ -474,11 +474,12 @@ def _prepack(trunk, ectx):
     return
   weights = [c.weight.detach() for c in convs]
   kinds = (0, 1) if ectx.need_grad else (0,)
-  key = K.PackPlan.make_key(weights, kinds, ectx.dt)
+  wdt = K.weight_dtype(ectx.dt, ectx.cdt)
+  key = K.PackPlan.make_key(weights, kinds, wdt)
   plans = trunk.__dict__.setdefault("_iic_pack_plans", {})
-  plan = plans.get((kinds, ectx.dt))
+  plan = plans.get((kinds, wdt))
   if plan is None or plan.key != key:
-    plan = plans[(kinds, ectx.dt)] = K.PackPlan(weights, kinds, ectx.dt)
+    plan = plans[(kinds, wdt)] = K.PackPlan(weights, kinds, wdt)
   out = plan.run()
   for wi, c in enumerate(convs):
     for kind in kinds:

@@ -58,9 +58,9 @@ static Option g_opts[OPT_COUNT] = {
     {"bn_bwd_ctas", "IIC_BN_BWD_CTAS", 2, 0, false},
     // tf32x3_raw_hi: the 3xTF32 fprop / dgrad splitter leaves the landed fp32 stage untouched and writes only lo = x - trunc(x):
     // the tensor core ignores the 13 low mantissa bits of a kind::tf32 operand, so x itself IS the hi operand.  A third less
-    // shared-memory traffic for the transform warps that bound this mode.  Off until the truncation has been checked on hardware
-    // (tests/test_gpu_conv_tf32.py runs both settings).
-    {"tf32x3_raw_hi", "IIC_TF32X3_RAW_HI", 0, 0, false},
+    // shared-memory traffic for the transform warps that bound this mode.  Validated on a B200 in round 2 (precision tests
+    // and smoke green; fprop 58.9 -> 43.6 ms, dgrad 61.3 -> 49.8 ms per c4 step, profiles/r02_session_f.md); 0 = write hi too.
+    {"tf32x3_raw_hi", "IIC_TF32X3_RAW_HI", 1, 0, false},
 };
 
 int option(int id) {

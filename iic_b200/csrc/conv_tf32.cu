@@ -161,12 +161,15 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int s = it % STAGES;
           mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u);
           const uint32_t sa = base + s * Cfg::STAGE_BYTES, sb = sa + T32_A_BYTES;
-          if (lane == 0) mbar_expect_tx(full_bar(s), Cfg::HALF);
+          // 3xTF32: the weights arrive split (second plane of the packed buffer = lo, N rows further down)
+          if (lane == 0) mbar_expect_tx(full_bar(s), Cfg::HALF + (SPLIT == 3 ? Cfg::B_BYTES : 0));
           __syncwarp();
           if (lane == 0)
             tma_load_im2col(sa, &tmA, full_bar(s), c0, cw, ch, img, (uint16_t)P.offw[tap], (uint16_t)P.offh[tap]);
           else if (lane == 1)
             tma_load_2d(sb, &tmB, full_bar(s), (int)P.wtap[tap] * P.srcC + c0, n0);
+          else if (SPLIT == 3 && lane == 2)
+            tma_load_2d(sb + Cfg::HALF, &tmB, full_bar(s), (int)P.wtap[tap] * P.srcC + c0, n0 + P.N);
           c0 += T32_KB;
           if (c0 >= P.srcC) {
             c0 = 0;
@@ -307,28 +310,25 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           } else {
+            // only the activation tile is split here: the weight tile arrives as [raw | lo] from the packed buffer
             float4* hi = reinterpret_cast<float4*>(st_hi);
             float4* lo = reinterpret_cast<float4*>(st_lo);
             // all of a thread's 16-byte chunks are loaded before the first is used (the loop was bound by the
             // shared-memory load latency: 23 % of the kernel's stall samples sat on its first LOP3, profiles/r02_ncu_conv_tf32.md)
-            constexpr int ITER = Cfg::HALF / 16 / 128;
-            static_assert(ITER * 128 * 16 == Cfg::HALF, "stage size must be a multiple of 128 x 16 bytes");
-            constexpr int HALF_IT = ITER / 2;
+            constexpr int ITER = T32_A_BYTES / 16 / 128;
+            static_assert(ITER * 128 * 16 == T32_A_BYTES, "A tile size must be a multiple of 128 x 16 bytes");
             const bool raw_hi = P.raw_hi != 0;
+            float4 v[ITER];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              float4 v[HALF_IT];
+            for (int it = 0; it < ITER; ++it) v[it] = hi[tid + it * 128];
 #pragma unroll
-              for (int it = 0; it < HALF_IT; ++it) v[it] = hi[tid + (half * HALF_IT + it) * 128];
-#pragma unroll
-              for (int it = 0; it < HALF_IT; ++it) {
-                const int c = tid + (half * HALF_IT + it) * 128;
-                float4 h, l;
-                h.x = hi_tf32(v[it].x); h.y = hi_tf32(v[it].y); h.z = hi_tf32(v[it].z); h.w = hi_tf32(v[it].w);
-                l.x = v[it].x - h.x; l.y = v[it].y - h.y; l.z = v[it].z - h.z; l.w = v[it].w - h.w;
-                if (!raw_hi) hi[c] = h;
-                lo[c] = l;
-              }
+            for (int it = 0; it < ITER; ++it) {
+              const int c = tid + it * 128;
+              float4 h, l;
+              h.x = hi_tf32(v[it].x); h.y = hi_tf32(v[it].y); h.z = hi_tf32(v[it].z); h.w = hi_tf32(v[it].w);
+              l.x = v[it].x - h.x; l.y = v[it].y - h.y; l.z = v[it].z - h.z; l.w = v[it].w - h.w;
+              if (!raw_hi) hi[c] = h;
+              lo[c] = l;
             }
           }
           fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
@@ -538,7 +538,7 @@ int tf32_conv_gather_gemm(const float* src, int srcH, int srcW, int srcC, int ro
   alignas(64) CUtensorMap tmA, tmB;
   rc = t32_im2col_map(&tmA, src, nimg, srcH, srcW, srcC, P.lower, P.lower, upper, upper, P.s, TC_BM);
   if (rc != IIC_OK) return rc;
-  rc = t32_tiled_map(&tmB, wpacked, N, P.Ktot, bn);
+  rc = t32_tiled_map(&tmB, wpacked, (split == 3 ? 2 : 1) * (long long)N, P.Ktot, bn);  // split 3: [raw plane | lo plane]
   if (rc != IIC_OK) return rc;
   return t32_launch<T32_FPROP>(tmA, tmB, P, bn, split, st);
 }
@@ -553,7 +553,7 @@ int tf32_conv_dgrad_s2(const float* dy, const float* wpacked_t, const float* add
               IIC_ERR_UNSUPPORTED, "tf32 stride-2 dgrad: unsupported geometry");
   alignas(64) CUtensorMap tmB;
   const int Kw = g->kh * g->kw * g->cout;
-  rc = t32_tiled_map(&tmB, wpacked_t, g->cin, Kw, bn);
+  rc = t32_tiled_map(&tmB, wpacked_t, (split == 3 ? 2 : 1) * (long long)g->cin, Kw, bn);  // split 3: [raw plane | lo plane]
   if (rc != IIC_OK) return rc;
   auto parity_taps = [&](int par, int ksz) {
     int cnt = 0;

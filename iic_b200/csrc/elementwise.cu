@@ -660,9 +660,15 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ dfeat, T* __restric
 }
 
 // weight repacking: torch [cout][cin][kh][kw] -> kind0 [cout][kh][kw][cin] / kind1 [cin][kh][kw][cout]
+// `split` (fp32 destination only, IIC_TF32X3): a second plane of `total` elements follows the packed weights and receives
+// lo = w - trunc_tf32(w); the first plane keeps the raw fp32 value (the tensor core ignores its 13 low mantissa bits)
+__device__ __forceinline__ void store_lo(float* dst, long long i, float v) {
+  dst[i] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+}
+__device__ __forceinline__ void store_lo(__nv_bfloat16*, long long, float) {}
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ dst, int kind, int cout, int cin,
-                                   int kh, int kw) {
+                                   int kh, int kw, int split) {
   const long long total = (long long)cout * cin * kh * kw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long t = i;
@@ -671,18 +677,22 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
       inner = (int)(t % cin); t /= cin;
       b = (int)(t % kw); t /= kw;
       a = (int)(t % kh); outer = (int)(t / kh);
-      dst[i] = from_f<T>(w[(((long long)outer * cin + inner) * kh + a) * kw + b]);
+      const float v = w[(((long long)outer * cin + inner) * kh + a) * kw + b];
+      dst[i] = from_f<T>(v);
+      if (split) store_lo(dst, total + i, v);
     } else {  // i = ((ci*kh + a)*kw + b)*cout + co
       inner = (int)(t % cout); t /= cout;
       b = (int)(t % kw); t /= kw;
       a = (int)(t % kh); outer = (int)(t / kh);
-      dst[i] = from_f<T>(w[(((long long)inner * cin + outer) * kh + a) * kw + b]);
+      const float v = w[(((long long)inner * cin + outer) * kh + a) * kw + b];
+      dst[i] = from_f<T>(v);
+      if (split) store_lo(dst, total + i, v);
     }
   }
 }
 // all convolutions of a trunk in one launch: blockIdx.y = job, blockIdx.x strides over the job's elements
 template <typename T>
-__global__ void pack_weights_batched_kernel(const iic_pack_job* __restrict__ jobs) {
+__global__ void pack_weights_batched_kernel(const iic_pack_job* __restrict__ jobs, int split) {
   const iic_pack_job j = jobs[blockIdx.y];
   const float* __restrict__ w = j.w;
   T* __restrict__ dst = (T*)j.dst;
@@ -696,7 +706,9 @@ __global__ void pack_weights_batched_kernel(const iic_pack_job* __restrict__ job
     const int a = t % kh;
     const int outer = t / kh;
     const int co = j.kind == 0 ? outer : inner, ci = j.kind == 0 ? inner : outer;
-    dst[i] = from_f<T>(w[((co * cin + ci) * kh + a) * kw + b]);
+    const float v = w[((co * cin + ci) * kh + a) * kw + b];
+    dst[i] = from_f<T>(v);
+    if (split) store_lo(dst, (long long)total + i, v);
   }
 }
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ grad, int accumulate, int cout,
@@ -1133,14 +1145,18 @@ extern "C" int iic_pack_weight(const float* w_oihw, void* dst, int dst_dtype, in
   IIC_REQUIRE(w_oihw && dst && (kind == 0 || kind == 1) && cout > 0 && cin > 0 && kh > 0 && kw > 0, IIC_ERR_BAD_ARG,
               "iic_pack_weight: bad arguments");
   const long long total = (long long)cout * cin * kh * kw;
-  DISPATCH_T(dst_dtype, pack_weight_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, (T*)dst, kind, cout, cin, kh, kw);)
+  const int split = dst_dtype == IIC_TF32X3 ? 1 : 0;  // fp32 [2][...]: raw plane + lo plane (include/iic_b200.h)
+  if (dst_dtype == IIC_TF32X3 || dst_dtype == IIC_TF32) dst_dtype = IIC_F32;
+  DISPATCH_T(dst_dtype, pack_weight_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, (T*)dst, kind, cout, cin, kh, kw, split);)
   IIC_LAUNCH_CHECK();
   count_launch();
   return IIC_OK;
 }
 extern "C" int iic_pack_weights_batched(const iic_pack_job* jobs_device, int njobs, int dst_dtype, void* stream) {
   IIC_REQUIRE(jobs_device && njobs > 0 && njobs <= 65535, IIC_ERR_BAD_ARG, "iic_pack_weights_batched: bad arguments");
-  DISPATCH_T(dst_dtype, pack_weights_batched_kernel<T><<<dim3(32, njobs), 256, 0, (cudaStream_t)stream>>>(jobs_device);)
+  const int split = dst_dtype == IIC_TF32X3 ? 1 : 0;
+  if (dst_dtype == IIC_TF32X3 || dst_dtype == IIC_TF32) dst_dtype = IIC_F32;
+  DISPATCH_T(dst_dtype, pack_weights_batched_kernel<T><<<dim3(32, njobs), 256, 0, (cudaStream_t)stream>>>(jobs_device, split);)
   IIC_LAUNCH_CHECK();
   count_launch();
   return IIC_OK;

@@ -492,70 +492,3 @@ extern "C" int iic_stem_wgrad(const float* x_nchw, const void* dy, float* grad_o
   count_launch();
   return IIC_OK;
 }
-
-
-// ---- stem wgrad on the tensor cores (option stem_wgrad_tc) -----------------------------------------------------------
-// dW[cout][cin*kh*kw] = sum over pixels of dy[pixel][cout] * patch(x)[pixel][cin*kh*kw] is a GEMM with K = 13 M pixels and
-// a 18..45-wide operand; the SIMT Gram-product kernel above runs it at ~15 TFLOP/s (2.05 ms at the bench shape, 5 % of the
-// step).  Here the patches are written out once as a [pixels][64] bf16 matrix (columns in torch's OIHW order
-// ci*kh*kw + a*kw + b, zero padded) and the product is handed to the tcgen05 wgrad kernel as a 1x1 convolution with
-// cin = 64; iic_stem_col_unpack adds the first K columns into the torch-layout gradient.
-__global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int n, int cin, int h, int w, int kh,
-                                   int kw, int pad) {
-  const long long total = (long long)n * h * w * 8;  // 8 threads per pixel, 8 columns each
-  const int K = cin * kh * kw;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int part = (int)(i & 7);
-    const long long pix = i >> 3;
-    const int px = (int)(pix % w);
-    const int py = (int)((pix / w) % h);
-    const int ni = (int)(pix / ((long long)w * h));
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = part * 8 + j;
-      float t = 0.f;
-      if (c < K) {
-        const int ci = c / (kh * kw), r = c - ci * kh * kw, a = r / kw, b = r - a * kw;
-        const int yy = py + a - pad, xx = px + b - pad;
-        if (yy >= 0 && yy < h && xx >= 0 && xx < w) t = x[(((long long)ni * cin + ci) * h + yy) * w + xx];
-      }
-      v[j] = t;
-    }
-    store8(col + pix * 64 + part * 8, v);
-  }
-}
-
-__global__ void stem_col_unpack_kernel(const float* __restrict__ gcol, float* __restrict__ grad, int cout, int K, int accumulate) {
-  const int total = cout * K;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int co = i / K, c = i - co * K;
-    const float t = gcol[co * 64 + c];
-    grad[i] = accumulate ? grad[i] + t : t;
-  }
-}
-
-extern "C" int iic_stem_im2col(const float* x_nchw, void* col_bf16, const iic_conv_geom* g, void* stream) {
-  int rc = stem_check(g, "iic_stem_im2col");
-  if (rc != IIC_OK) return rc;
-  IIC_REQUIRE(x_nchw && col_bf16, IIC_ERR_BAD_ARG, "iic_stem_im2col: null pointer");
-  IIC_REQUIRE(g->cin * g->kh * g->kw <= 64 && g->stride == 1 && g->dil == 1 && g->oh == g->h && g->ow == g->w, IIC_ERR_UNSUPPORTED,
-              "iic_stem_im2col: needs cin*kh*kw <= 64, stride 1, 'same' padding");
-  const long long total = (long long)g->n * g->h * g->w * 8;
-  long long blocks = (total + 255) / 256;
-  const long long cap = (long long)device_sm_count() * 16;
-  if (blocks > cap) blocks = cap;
-  stem_im2col_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x_nchw, (__nv_bfloat16*)col_bf16, g->n, g->cin, g->h, g->w,
-                                                                     g->kh, g->kw, g->pad);
-  IIC_LAUNCH_CHECK();
-  count_launch();
-  return IIC_OK;
-}
-
-extern "C" int iic_stem_col_unpack(const float* grad_col, float* grad_oihw, int accumulate, int cout, int K, void* stream) {
-  IIC_REQUIRE(grad_col && grad_oihw && cout > 0 && K > 0 && K <= 64, IIC_ERR_BAD_ARG, "iic_stem_col_unpack: bad arguments");
-  stem_col_unpack_kernel<<<cdiv((long long)cout * K, 256), 256, 0, (cudaStream_t)stream>>>(grad_col, grad_oihw, cout, K, accumulate);
-  IIC_LAUNCH_CHECK();
-  count_launch();
-  return IIC_OK;
-}

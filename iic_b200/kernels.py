@@ -315,11 +315,22 @@ def cast(x, dt):
 
 
 # ---- convolution ----------------------------------------------------------------------------
+def weight_dtype(dt, cdt):
+  """dtype to hand to pack_weight for storage dtype `dt` and compute dtype `cdt`: 3xTF32 convolutions take their
+  weights pre-split ([2][...] fp32: raw plane + lo plane, include/iic_b200.h: iic_pack_weight)."""
+  return TF32X3 if cdt == TF32X3 else dt
+
+
+def _packed_shape(w, dt, kind):
+  cout, cin, kh, kw = w.shape
+  shape = (cout, kh, kw, cin) if kind == 0 else (cin, kh, kw, cout)
+  return (2,) + shape if dt == TF32X3 else shape
+
+
 @_cat("pack_weight")
 def pack_weight(w, dt, kind):
   cout, cin, kh, kw = w.shape
-  shape = (cout, kh, kw, cin) if kind == 0 else (cin, kh, kw, cout)
-  out = torch.empty(shape, device=w.device, dtype=_TORCH_DT[dt])
+  out = torch.empty(_packed_shape(w, dt, kind), device=w.device, dtype=_TORCH_DT[dt])
   check(_lib.lib().iic_pack_weight(_p(w), _p(out), dt, kind, cout, cin, kh, kw, _stream()), "iic_pack_weight")
   return out
 
@@ -340,8 +351,7 @@ class PackPlan(object):
       assert w.is_cuda and w.is_contiguous() and w.dtype == torch.float32
       cout, cin, kh, kw = w.shape
       for kind in kinds:
-        shape = (cout, kh, kw, cin) if kind == 0 else (cin, kh, kw, cout)
-        dst = torch.empty(shape, device=w.device, dtype=_TORCH_DT[dt])
+        dst = torch.empty(_packed_shape(w, dt, kind), device=w.device, dtype=_TORCH_DT[dt])
         self.out[(wi, kind)] = dst
         jobs[i] = _lib.PackJob(w.data_ptr(), dst.data_ptr(), kind, cout, cin, kh, kw, 0)
         i += 1
@@ -359,7 +369,13 @@ class PackPlan(object):
     return self.out
 
 
+def _check_packed(wp, g, dt):
+  want = (2 if dt == TF32X3 else 1) * g.cout * g.cin * g.kh * g.kw
+  assert wp.numel() == want, "weights for dtype %d must be packed with pack_weight(w, weight_dtype(store, %d), kind): %d elements, expected %d" % (dt, dt, wp.numel(), want)
+
+
 def conv_fprop(x, wp, g, dt):
+  _check_packed(wp, g, dt)
   y = torch.empty((g.n, g.oh, g.ow, g.cout), device=x.device, dtype=_TORCH_DT[dt])
   with _timed("fprop", g):
     check(_lib.lib().iic_conv_fprop(_p(x), _p(wp), _p(y), ctypes.byref(g), dt, _stream()), "iic_conv_fprop")
@@ -393,6 +409,7 @@ def bn_stats_from_partials(partial, nblk, views, view, M, gamma, beta, eps, mome
 
 
 def conv_dgrad(dy, wpt, g, dt, addend=None):
+  _check_packed(wpt, g, dt)
   dx = torch.empty((g.n, g.h, g.w, g.cin), device=dy.device, dtype=_TORCH_DT[dt])
   with _timed("dgrad", g):
     check(_lib.lib().iic_conv_dgrad(_p(dy), _p(wpt), _p(addend), _p(dx), ctypes.byref(g), dt, _stream()),
@@ -471,20 +488,14 @@ STEM_WGRAD_TC = {"on": __import__("os").environ.get("IIC_STEM_WGRAD_TC", "0") !=
 
 
 def stem_wgrad_tc(x_nchw, dy, g, grad_out, accumulate):
-  """bf16 tensor-core stem wgrad (include/iic_b200.h: iic_stem_im2col); returns False if the geometry is unsupported.
-  (Calls the library directly: the 1x1 product has no share in the algorithmic conv FLOPs of the roofline.)"""
+  """bf16 tcgen05 stem wgrad (include/iic_b200.h: iic_stem_wgrad_tc); returns False if the geometry is unsupported."""
   K = g.cin * g.kh * g.kw
-  if not (K <= 64 and g.stride == 1 and g.dil == 1 and g.oh == g.h and g.ow == g.w and g.cout % 64 == 0 and dy.dtype == torch.bfloat16):
+  if not (K <= 32 and g.cout == 64 and g.stride == 1 and g.dil == 1 and g.oh == g.h and g.ow == g.w and dy.dtype == torch.bfloat16):
     return False
-  col = torch.empty((g.n, g.h, g.w, 64), device=dy.device, dtype=torch.bfloat16)
-  check(_lib.lib().iic_stem_im2col(_p(x_nchw), _p(col), ctypes.byref(g), _stream()), "iic_stem_im2col")
-  g1 = conv_geom(g.n, g.h, g.w, 64, g.cout, 1, 1, 1, 0, 1)
-  gcol = torch.empty((g.cout, 64), device=dy.device, dtype=torch.float32)
-  nbytes = int(_lib.lib().iic_conv_wgrad_oihw_workspace(ctypes.byref(g1), BF16))
-  ws = torch.empty((max(nbytes, 4) + 3) // 4, device=dy.device, dtype=torch.float32)
-  check(_lib.lib().iic_conv_wgrad_oihw(_p(col), _p(dy), _p(gcol), 0, _p(ws), ctypes.byref(g1), BF16, _stream()),
-        "iic_conv_wgrad_oihw")
-  check(_lib.lib().iic_stem_col_unpack(_p(gcol), _p(grad_out), int(bool(accumulate)), g.cout, K, _stream()), "iic_stem_col_unpack")
+  nbytes = int(_lib.lib().iic_stem_wgrad_tc_workspace(ctypes.byref(g)))
+  ws = torch.empty(nbytes // 4, device=dy.device, dtype=torch.float32)
+  check(_lib.lib().iic_stem_wgrad_tc(_p(x_nchw), _p(dy), _p(grad_out), int(bool(accumulate)), _p(ws), ctypes.byref(g), _stream()),
+        "iic_stem_wgrad_tc")
   return True
 
 

@@ -170,7 +170,10 @@ typedef struct {
 
 /* weights are repacked from torch's [cout][cin][kh][kw] fp32:
  *   kind 0 (fprop/wgrad layout): [cout][kh][kw][cin]
- *   kind 1 (dgrad layout):       [cin][kh][kw][cout]                                   */
+ *   kind 1 (dgrad layout):       [cin][kh][kw][cout]
+ * dst_dtype IIC_F32 / IIC_BF16 = the storage type of the network; IIC_TF32X3 = the form the 3xTF32 fprop / dgrad take:
+ * fp32, TWO planes of cout*cin*kh*kw elements, [raw w | lo = w - (w truncated to tf32)] (the weights are split once per
+ * step here instead of once per tile in the convolution; the tensor core ignores the 13 low mantissa bits of the raw plane). */
 int iic_pack_weight(const float* w_oihw, void* dst, int dst_dtype, int kind, int cout, int cin, int kh,
                     int kw, void* stream);
 /* Every convolution weight of a trunk repacked in ONE launch (the per-step repacking of ~70 small tensors was
@@ -188,7 +191,8 @@ int iic_unpack_wgrad(const float* dw_packed, float* grad_oihw, int accumulate, i
 
 /* fprop: y[M][cout] = conv(x, w).  dtype IIC_F32 -> SIMT fp32 kernel; IIC_BF16 -> tcgen05 kind::f16;
  * IIC_TF32 / IIC_TF32X3 -> tcgen05 kind::tf32 on fp32 tensors (cin % 32 == 0, cout % 64 == 0).
- * w is the kind-0 packed weight in the storage dtype.  y has the storage dtype. */
+ * w is the kind-0 packed weight in the storage dtype (IIC_TF32X3: the two-plane form of iic_pack_weight).  y has the
+ * storage dtype. */
 int iic_conv_fprop(const void* x, const void* w_packed, void* y, const iic_conv_geom* g, int dtype,
                    void* stream);
 /* fprop with the BatchNorm batch statistics of y fused into the epilogue (IIC_BF16 only; otherwise
@@ -242,12 +246,14 @@ int iic_stem_fprop_stats(const float* x_nchw, const float* w_oihw, void* y, cons
                          float* stat_partial, void* stream);
 int iic_stem_wgrad(const float* x_nchw, const void* dy, float* grad_oihw, int accumulate, void* workspace,
                    long long workspace_bytes, const iic_conv_geom* g, int dtype, void* stream);
-/* Stem wgrad on the tensor cores: iic_stem_im2col writes the patches of the NCHW fp32 input as a [pixels][64] bf16 matrix
- * (columns in OIHW order ci*kh*kw + a*kw + b, zero padded; cin*kh*kw <= 64, stride 1, 'same' padding); the product with
- * dy is then iic_conv_wgrad(_oihw) of a 1x1 convolution with cin = 64, and iic_stem_col_unpack adds the first K columns
- * of its [cout][64] result into the torch-layout gradient [cout][cin][kh][kw]. */
-int iic_stem_im2col(const float* x_nchw, void* col_bf16, const iic_conv_geom* g, void* stream);
-int iic_stem_col_unpack(const float* grad_col, float* grad_oihw, int accumulate, int cout, int K, void* stream);
+/* Stem wgrad on tcgen05 (bf16 dy; cin*kh*kw <= 32, cout = 64, stride 1, 'same' padding): the patches of the NCHW fp32 input
+ * are gathered into shared memory as the K-major operand, dy arrives by TMA as the MN-major operand, one TMEM accumulator per
+ * persistent CTA, per-CTA partials in `workspace` (iic_stem_wgrad_tc_workspace bytes) folded in a fixed order into the
+ * torch-layout gradient [cout][cin][kh][kw] (same contract as iic_stem_wgrad: replaces autograd's conv2d weight gradient of
+ * the first trunk convolution, net5g.py:21; the patches are rounded to bf16). */
+long long iic_stem_wgrad_tc_workspace(const iic_conv_geom* g);
+int iic_stem_wgrad_tc(const float* x_nchw, const void* dy_bf16, float* grad_oihw, int accumulate, void* workspace,
+                      const iic_conv_geom* g, void* stream);
 /* Whole backward of the ClusterNet5g stem, conv3x3(cin 1|2 -> 64, pad 1) -> BatchNorm -> ReLU -> MaxPool(2, 2, pool_pad)
  * (net5g.py:21-26), in two passes over (y, dpool) instead of six over y-sized tensors: the pooled gradient is routed
  * and ReLU-masked on the fly, reduced for the BatchNorm backward, and the BatchNorm input gradient is consumed by the

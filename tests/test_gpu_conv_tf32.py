@@ -49,8 +49,8 @@ def _run(case, mode, x, w, dy, add):
   dt = _modes()[mode]
   g = K.conv_geom(n, h, h, cin, cout, k, k, s, p, d)
   xh, dyh = to_nhwc(x), to_nhwc(dy)
-  y = from_nhwc(K.conv_fprop(xh, K.pack_weight(w, F32, 0), g, dt))
-  wt = K.pack_weight(w, F32, 1)
+  y = from_nhwc(K.conv_fprop(xh, K.pack_weight(w, K.weight_dtype(F32, dt), 0), g, dt))
+  wt = K.pack_weight(w, K.weight_dtype(F32, dt), 1)  # (3xTF32: [raw plane | lo plane])
   dx = from_nhwc(K.conv_dgrad(dyh, wt, g, dt))
   dx2 = from_nhwc(K.conv_dgrad(dyh, wt, g, dt, addend=to_nhwc(add)))
   gw = torch.zeros_like(w)
@@ -119,17 +119,17 @@ def test_tf32x3_recovers_bits_that_tf32_drops():
   w = w.cuda()
   g = K.conv_geom(n, h, h, c, c, 1, 1, 1, 0, 1)
   want = (1.0 + 2.0 ** -14) * (1.0 + 2.0 ** -13)
-  y3 = K.conv_fprop(x, K.pack_weight(w, F32, 0), g, TF32X3)
+  y3 = K.conv_fprop(x, K.pack_weight(w, TF32X3, 0), g, TF32X3)
   y1 = K.conv_fprop(x, K.pack_weight(w, F32, 0), g, TF32)
   assert (y3.double() - want).abs().max().item() < 2e-7
   assert (y1.double() - want).abs().max().item() > 5e-5  # plain tf32 sees 1.0 * 1.0
 
 
-@pytest.mark.unvalidated
+@pytest.mark.parametrize("raw_hi", [0, 1])
 @pytest.mark.parametrize("case", CASES[:5])
-def test_tf32x3_raw_hi_operand(case):
-  """Option tf32x3_raw_hi: the splitter writes only lo and the tensor core truncates the raw fp32 stage itself.  Same
-  tolerance as the explicit split -- if the hardware ROUNDED the low 13 bits instead, hi + lo would double count up to
+def test_tf32x3_raw_hi_operand(case, raw_hi):
+  """Option tf32x3_raw_hi (default 1): the splitter writes only lo and the tensor core truncates the raw fp32 stage
+  itself; 0 = hi written explicitly.  Same tolerance for both -- if the hardware ROUNDED the low 13 bits instead, hi + lo would double count up to
   2^-11 of every operand (5e-4 relative) and this fails."""
   from iic_b200 import kernels as K
   n, h, cin, cout, k, s, p, d = case
@@ -140,7 +140,7 @@ def test_tf32x3_raw_hi_operand(case):
   dy = torch.randn(n, cout, oh, oh, generator=g).cuda()
   add = torch.randn(n, cin, h, h, generator=g).cuda()
   yr, dxr, dwr = _ref(case, x, w, dy)
-  with K.options(tf32x3_raw_hi=1):
+  with K.options(tf32x3_raw_hi=raw_hi):
     y, dx, dx2, gw, gw2 = _run(case, "tf32x3", x, w, dy, add)
   for name, got, want in (("fprop", y, yr), ("dgrad", dx, dxr), ("dgrad+addend", dx2, dxr + add.double().cpu()),
                           ("wgrad", gw, dwr)):

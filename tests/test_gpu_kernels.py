@@ -506,12 +506,19 @@ def test_batched_weight_packing_matches_single_calls():
   from iic_b200._lib import BF16, F32
   g = torch.Generator().manual_seed(42)
   ws = [torch.randn(co, ci, k, k, generator=g).cuda() for co, ci, k in ((64, 64, 3), (128, 64, 1), (128, 64, 3), (512, 256, 3))]
-  for dt in (BF16, F32):
+  from iic_b200._lib import TF32X3
+  for dt in (BF16, F32, TF32X3):
     plan = K.PackPlan(ws, (0, 1), dt)
     out = plan.run()
     for i, w in enumerate(ws):
       for kind in (0, 1):
         assert torch.equal(out[(i, kind)], K.pack_weight(w, dt, kind))
+  # 3xTF32 weights: [raw plane | lo plane], lo = w - (w with the 13 low mantissa bits cleared), exact in fp32
+  w = ws[2]
+  both, raw = K.pack_weight(w, TF32X3, 0), K.pack_weight(w, F32, 0)
+  assert both.shape == (2,) + tuple(raw.shape) and torch.equal(both[0], raw)
+  hi = (raw.view(torch.int32) & -8192).view(torch.float32)
+  assert torch.equal(both[1], raw - hi) and float(both[1].abs().max()) > 0
 
 
 HALO_GEOMS = [
@@ -808,10 +815,10 @@ def test_wgrad_written_in_torch_layout_equals_wgrad_plus_unpack(case, mode):
 
 
 @pytest.mark.unvalidated
-@pytest.mark.parametrize("cin,k,pad,hw,n", [(2, 3, 1, 32, 3), (2, 3, 1, 96, 4), (1, 5, 2, 24, 5), (5, 3, 1, 20, 2)])
+@pytest.mark.parametrize("cin,k,pad,hw,n", [(2, 3, 1, 32, 3), (2, 3, 1, 96, 4), (1, 5, 2, 24, 5), (3, 3, 1, 20, 2), (2, 3, 1, 7, 1)])
 def test_stem_wgrad_on_tensor_cores_matches_the_simt_kernel(cin, k, pad, hw, n):
-  """Stem wgrad as im2col ([pixels][64] bf16 patches) + the tcgen05 1x1 wgrad kernel + column unpack (option
-  STEM_WGRAD_TC) against torch autograd on the same bf16-rounded operands and against the SIMT Gram-product kernel."""
+  """Stem wgrad on tcgen05 (stem_tc.cu: patches gathered into shared memory, dy by TMA; option STEM_WGRAD_TC) against
+  torch autograd on the same bf16-rounded operands and against the SIMT Gram-product kernel."""
   K = _K()
   from iic_b200._lib import BF16
   cout = 64
@@ -820,7 +827,7 @@ def test_stem_wgrad_on_tensor_cores_matches_the_simt_kernel(cin, k, pad, hw, n):
   dy = torch.randn(n, cout, hw, hw, generator=g).cuda().bfloat16().float()
   geo = K.conv_geom(n, hw, hw, cin, cout, k, k, 1, pad, 1)
   wr = torch.zeros(cout, cin, k, k, device="cuda", requires_grad=True)
-  F.conv2d(x.bfloat16().float(), wr, None, 1, pad).backward(dy)  # (the patches are rounded to bf16 by the im2col)
+  F.conv2d(x.bfloat16().float(), wr, None, 1, pad).backward(dy)  # (the patches are rounded to bf16 by the gather)
   dyh = to_nhwc(dy, torch.bfloat16)
   base = torch.randn(cout, cin, k, k, generator=g).cuda()
   a = torch.zeros_like(base)

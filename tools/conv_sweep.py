@@ -48,7 +48,7 @@ for name, h, cin, cout, k, s, p, cnt in LAYERS:
   x = torch.randn(N, h, h, cin, device="cuda").to(TDT)
   w = torch.randn(cout, cin, k, k, device="cuda") * 0.05
   dy = torch.randn(N, g.oh, g.ow, cout, device="cuda").to(TDT)
-  wp, wt = K.pack_weight(w, STORE, 0), K.pack_weight(w, STORE, 1)
+  wp, wt = K.pack_weight(w, K.weight_dtype(STORE, BF16), 0), K.pack_weight(w, K.weight_dtype(STORE, BF16), 1)
   gw = torch.zeros_like(w)
   fl = 2.0 * N * g.oh * g.ow * cout * k * k * cin
   t = {"fprop": timeit(lambda: K.conv_fprop(x, wp, g, BF16)),
