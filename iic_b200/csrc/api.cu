@@ -61,6 +61,10 @@ static Option g_opts[OPT_COUNT] = {
     // shared-memory traffic for the transform warps that bound this mode.  Validated on a B200 in round 2 (precision tests
     // and smoke green; fprop 58.9 -> 43.6 ms, dgrad 61.3 -> 49.8 ms per c4 step, profiles/r02_session_f.md); 0 = write hi too.
     {"tf32x3_raw_hi", "IIC_TF32X3_RAW_HI", 1, 0, false},
+    // wgrad_mt: the bf16 im2col wgrad takes 2 or 3 of its 128-row (tap, cin) tiles per dy k-block (one accumulator buffer
+    // of up to 512 TMEM columns): a third less shared-memory fill per MMA.  Written after the last GPU session: off until
+    // it has run on hardware (tests force it).
+    {"wgrad_mt", "IIC_WGRAD_MT", 0, 0, false},
 };
 
 int option(int id) {

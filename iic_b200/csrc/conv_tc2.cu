@@ -77,9 +77,13 @@ template <int BN, bool RESB = false, int MTP = (RESB ? 2 : 1)> struct Tc2Cfg {
   static constexpr int A_BYTES = MT * TC_BM * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + (RESB ? 0 : B_BYTES);
-  static constexpr int STAGES = (RESB || MT == 2) ? 4 : ((BN >= 256) ? 4 : (BN >= 128 ? 6 : 8));
+  static constexpr int STAGES = (STAGE_BYTES >= 64 * 1024) ? 3 : ((RESB || MT == 2) ? 4 : ((BN >= 256) ? 4 : (BN >= 128 ? 6 : 8)));
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;  // (+ 64 B x N for fused BN statistics)
-  static constexpr int TMEM_COLS = 2 * MT * BN;
+  // two accumulator buffers (the epilogue of a work item overlaps the MMAs of the next) when they fit the 512 TMEM columns;
+  // the multi-tile wgrad work items (MT x BN > 256) run for hundreds of k-blocks and get by with one
+  static constexpr int ACC_BUFS = (2 * MT * BN <= 512) ? 2 : 1;
+  static constexpr int ACC_COLS = ACC_BUFS * MT * BN;
+  static constexpr int TMEM_COLS = ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512));
 };
 
 template <int MODE, int BN, bool RESB = false, int MTP = (RESB ? 2 : 1)>
@@ -89,8 +93,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   constexpr int STAGES = Cfg::STAGES;
   constexpr int MT = Cfg::MT;
   static_assert(!RESB || MODE == M2_FPROP, "resident dense operand: fprop/dgrad only");
-  static_assert(MT == 1 || MODE == M2_FPROP, "two-tile work items: fprop/dgrad only");
-  static_assert(Cfg::TMEM_COLS <= 512 && (!RESB || MT == 2), "TMEM budget / RESB implies two-tile work items");
+  static_assert(MT <= 2 || MODE == M2_WGRAD, "three-tile work items: wgrad only");
+  static_assert(Cfg::ACC_COLS <= 512 && (!RESB || MT == 2), "TMEM budget / RESB implies two-tile work items");
+  constexpr bool TWO_ACC = Cfg::ACC_BUFS == 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t resb = (raw + 1023u) & ~1023u;  // [total_kb][BN x 128 B] resident weights (RESB), else empty
@@ -199,9 +204,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       } else {
+        // A = MT tiles of 128 (tap, cin) rows = 2 MT column blocks of 64 channels; lane b issues block b
         int a_off_w = 0, a_off_h = 0, a_c0 = 0;
         bool a_ok = false;
-        if (lane < 2) {
+        if (lane < 2 * MT) {
           const long long j = m0 + lane * 64;
           a_ok = j < P.Ktot;
           const int tap = (int)(j / P.srcC);
@@ -210,8 +216,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           a_off_h = ta * P.d;
           a_off_w = (tap - ta * P.KW) * P.d;
         }
-        const bool ok0 = m0 < P.Ktot, ok1 = m0 + 64 < P.Ktot;
-        const uint32_t bytes = (uint32_t)((ok0 ? 8192 : 0) + (ok1 ? 8192 : 0) + Cfg::B_BYTES);
+        int nok = 0;
+#pragma unroll
+        for (int b = 0; b < 2 * MT; ++b) nok += (m0 + b * 64 < P.Ktot) ? 1 : 0;
+        const uint32_t bytes = (uint32_t)(nok * 8192 + Cfg::B_BYTES);
         // pixel coordinates of the first row of the k-block, advanced by 64 pixels per k-block
         long long p0 = (long long)kb0 * 64;
         int ox = (int)(p0 % P.rowW);
@@ -225,12 +233,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t sa = base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
           if (lane == 0) mbar_expect_tx(full_bar(s), bytes);
           __syncwarp();
-          if (lane < 2) {
+          if (lane < 2 * MT) {
             if (a_ok)
               tma_load_im2col(sa + lane * 8192, &tmA, full_bar(s), a_c0, ox * P.s + P.lower, oy * P.s + P.lower, img,
                               (uint16_t)a_off_w, (uint16_t)a_off_h);
-          } else if (lane < 2 + BN / 64) {
-            const int b = lane - 2;
+          } else if (lane < 2 * MT + BN / 64) {
+            const int b = lane - 2 * MT;
             tma_load_2d(sb + b * 8192, &tmB, full_bar(s), n0 + b * 64, (int)p0);
           }
           p0 += 64;
@@ -262,8 +270,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int z, n0, kb0, nk;
       long long m0;
       decode(w, z, m0, n0, kb0, nk);
-      const uint32_t as = tile_it & 1u;
-      mbar_wait(tempty_bar(as), ((tile_it >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
+      const uint32_t as = TWO_ACC ? (tile_it & 1u) : 0u;
+      mbar_wait(tempty_bar(as), ((TWO_ACC ? (tile_it >> 1) : tile_it) & 1u) ^ 1u);  // epilogue drained this accumulator
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + as * (MT * BN);
       for (int i = 0; i < nk; ++i) {
@@ -303,7 +311,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int z, n0, kb0, nk;
       long long m0;
       decode(w, z, m0, n0, kb0, nk);
-      const uint32_t as = tile_it & 1u;
+      const uint32_t as = TWO_ACC ? (tile_it & 1u) : 0u;
+      const uint32_t aphase = (TWO_ACC ? (tile_it >> 1) : tile_it) & 1u;
       if constexpr (MODE == M2_FPROP) {
         // this thread's row in each of the MT accumulator tiles (TMEM lane == tile row) and where it is written
         const long long mrow0 = m0 + warp * 32 + lane, mrow1 = mrow0 + TC_BM;
@@ -337,7 +346,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         };
         if (pre) fetch(acur, 0, 0);
-        mbar_wait(tfull_bar(as), (tile_it >> 1) & 1u);
+        mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
 #pragma unroll 1
         for (int j = 0; j < MT * CH; ++j) {
@@ -401,27 +410,30 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       } else {
-        mbar_wait(tfull_bar(as), (tile_it >> 1) & 1u);
+        mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
-        const long long m = m0 + warp * 32 + lane;  // TMEM lane == tile row
-        const uint32_t tmem_acc = tmem_base + as * (MT * BN) + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          if (nk > 0) {
-            tmem_ld32(tmem_acc + (uint32_t)c0, v);
-            tmem_ld_wait();
-          } else {
+        for (int mt = 0; mt < MT; ++mt) {
+          const long long m = m0 + mt * TC_BM + warp * 32 + lane;  // TMEM lane == tile row
+          const uint32_t tmem_acc = tmem_base + as * (MT * BN) + mt * BN + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            if (nk > 0) {
+              tmem_ld32(tmem_acc + (uint32_t)c0, v);
+              tmem_ld_wait();
+            } else {
 #pragma unroll
-            for (int qq = 0; qq < 32; ++qq) v[qq] = 0u;
-          }
-          if (m < P.Ktot) {
-            float* o = P.partial + ((long long)z * P.Ktot + m) * P.N + n0 + c0;
+              for (int qq = 0; qq < 32; ++qq) v[qq] = 0u;
+            }
+            if (m < P.Ktot) {
+              float* o = P.partial + ((long long)z * P.Ktot + m) * P.N + n0 + c0;
 #pragma unroll
-            for (int qq = 0; qq < 8; ++qq)
-              *reinterpret_cast<float4*>(o + qq * 4) =
-                  make_float4(__uint_as_float(v[qq * 4]), __uint_as_float(v[qq * 4 + 1]), __uint_as_float(v[qq * 4 + 2]),
-                              __uint_as_float(v[qq * 4 + 3]));
+              for (int qq = 0; qq < 8; ++qq)
+                *reinterpret_cast<float4*>(o + qq * 4) =
+                    make_float4(__uint_as_float(v[qq * 4]), __uint_as_float(v[qq * 4 + 1]), __uint_as_float(v[qq * 4 + 2]),
+                                __uint_as_float(v[qq * 4 + 3]));
+            }
           }
         }
       }
@@ -1332,12 +1344,24 @@ int tc2_conv_gather_gemm_stats(const __nv_bfloat16* src, int srcH, int srcW, int
   }
 }
 
+// 128-row (tap, cin) tiles per wgrad work item (option wgrad_mt): the dy k-block is loaded once for MT of them, which takes
+// a third off the shared-memory fill per MMA that bounds these launches (xbar -> SM ~ 68 B/clk/SM, profiles/r02_session_f.md).
+// Only exact tilings (no half-empty last tile): 9 x 128 channels = 3 x 384 rows, 9 x 256 = 9 x 256 rows, ...
+static int tc2_wgrad_mt(const iic_conv_geom* g, int bn) {
+  if (option(OPT_WGRAD_MT) == 0) return 1;
+  const int Ktot = g->kh * g->kw * g->cin;
+  if (bn == 128) return Ktot % 384 == 0 ? 3 : (Ktot % 256 == 0 ? 2 : 1);
+  if (bn == 256) return Ktot % 256 == 0 ? 2 : 1;
+  return 1;
+}
+
 static int tc2_wgrad_splits(const iic_conv_geom* g) {
   const long long rows = (long long)g->n * g->oh * g->ow;
   const int total_kb = (int)((rows + 63) / 64);
   const int Ktot = g->kh * g->kw * g->cin;
   const int bn = pick_bn2(g->cout);
-  const long long tiles = (long long)((Ktot + TC_BM - 1) / TC_BM) * (g->cout / (bn ? bn : 64));
+  const int mrows = TC_BM * tc2_wgrad_mt(g, bn ? bn : 64);
+  const long long tiles = (long long)((Ktot + mrows - 1) / mrows) * (g->cout / (bn ? bn : 64));
   // persistent CTAs take work items round-robin: make (tiles x splits) fill a whole number of rounds of
   // one item per SM (never 2.1 rounds), with at least 8 k-blocks per item
   const long long sms = device_sm_count();
@@ -1526,7 +1550,8 @@ int tc2_conv_wgrad_impl(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* 
   P.rowH = g->oh; P.rowW = g->ow; P.KH = g->kh; P.KW = g->kw; P.s = g->stride; P.d = g->dil; P.lower = -g->pad;
   const int upper = g->pad - (g->kh - 1) * g->dil;
   P.srcC = g->cin; P.Ktot = g->kh * g->kw * g->cin; P.N = g->cout;
-  P.mtiles = (P.Ktot + TC_BM - 1) / TC_BM; P.ntiles = g->cout / bn;
+  const int mt = tc2_wgrad_mt(g, bn);
+  P.mtiles = (P.Ktot + mt * TC_BM - 1) / (mt * TC_BM); P.ntiles = g->cout / bn;
   P.splits = tc2_wgrad_splits(g);
   P.total_kb = (int)((P.rows + 63) / 64);
   P.kb_per_split = (P.total_kb + P.splits - 1) / P.splits;
@@ -1547,8 +1572,15 @@ int tc2_conv_wgrad_impl(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* 
     IIC_REQUIRE(r == CUDA_SUCCESS, IIC_ERR_CUDA, "cuTensorMapEncodeTiled(dy) failed (%d)", (int)r);
   }
   switch (bn) {
-    case 256: rc = launch_tc2<M2_WGRAD, 256>(tmA, tmB, P, P.splits, st); break;
-    case 128: rc = launch_tc2<M2_WGRAD, 128>(tmA, tmB, P, P.splits, st); break;
+    case 256:
+      rc = mt == 2 ? launch_tc2_impl<M2_WGRAD, 256, false, 2>(tmA, tmB, P, P.splits, st)
+                   : launch_tc2<M2_WGRAD, 256>(tmA, tmB, P, P.splits, st);
+      break;
+    case 128:
+      rc = mt == 3 ? launch_tc2_impl<M2_WGRAD, 128, false, 3>(tmA, tmB, P, P.splits, st)
+                   : (mt == 2 ? launch_tc2_impl<M2_WGRAD, 128, false, 2>(tmA, tmB, P, P.splits, st)
+                              : launch_tc2<M2_WGRAD, 128>(tmA, tmB, P, P.splits, st));
+      break;
     default: rc = launch_tc2<M2_WGRAD, 64>(tmA, tmB, P, P.splits, st); break;
   }
   if (rc != IIC_OK) return rc;

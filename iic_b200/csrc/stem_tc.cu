@@ -21,12 +21,14 @@
 
 namespace iic {
 
-constexpr int SWT_STAGES = 6;
+constexpr int SWT_STAGES = 8;
 constexpr int SWT_A_BYTES = 128 * 128;  // [128 tap rows][64 pixels] bf16, K-major
 constexpr int SWT_B_BYTES = 64 * 128;   // [64 pixels][64 cout] bf16, MN-major
 constexpr int SWT_STAGE = SWT_A_BYTES + SWT_B_BYTES;
 constexpr int SWT_SMEM = SWT_STAGES * SWT_STAGE + 1024 + 512;
-constexpr int SWT_THREADS = 192;
+constexpr int SWT_GROUPS = 4;                          // builder groups of 128 threads; group g takes the k-blocks i = g (mod 4)
+constexpr int SWT_THREADS = SWT_GROUPS * 128 + 64;    // + MMA issuer warp + TMA producer warp
+constexpr int SWT_MMA_WARP = SWT_GROUPS * 4, SWT_TMA_WARP = SWT_GROUPS * 4 + 1;
 
 struct StemWgTcParams {
   const float* x;
@@ -64,12 +66,13 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, StemWgTcParams P)
     const int ci = t / khw, r = t - ci * khw, a = r / P.kw, b = r - a * P.kw;
     tapinfo[t] = (t < P.K) ? ((ci << 16) | (a << 8) | b) : -1;
   }
-  if (warp == 5 && lane == 0) tma_prefetch_desc(&tmDy);
-  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), 64);
+  if (warp == SWT_TMA_WARP && lane == 0) tma_prefetch_desc(&tmDy);
+  if (warp == SWT_MMA_WARP) tmem_alloc(smem_u32(tmem_slot), 64);
   if (warp < 4) {  // the tap rows >= K (and everything else of the A slots) are zero for the life of the CTA
     uint4* z = reinterpret_cast<uint4*>(base_ptr);
     for (int s = 0; s < SWT_STAGES; ++s)
       for (int i = threadIdx.x; i < SWT_A_BYTES / 16; i += 128) z[s * (SWT_STAGE / 16) + i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();  // (the rows >= K are never written again: this fence is the one that publishes them to the tensor core)
   }
   tc_fence_before();
   __syncthreads();
@@ -81,7 +84,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, StemWgTcParams P)
   if (kb1 > P.kblocks) kb1 = P.kblocks;
   const int nk = kb1 > kb0 ? (int)(kb1 - kb0) : 0;
 
-  if (warp == 5) {
+  if (warp == SWT_TMA_WARP) {
     // =============================== TMA producer: dy ========================================
     for (int i = 0; i < nk; ++i) {
       const int s = i % SWT_STAGES;
@@ -92,7 +95,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, StemWgTcParams P)
       }
       __syncwarp();
     }
-  } else if (warp == 4) {
+  } else if (warp == SWT_MMA_WARP) {
     // =============================== MMA issuer ==============================================
     constexpr uint32_t idesc = make_idesc(64, 0, 1);  // A K-major, B MN-major, M = 128, N = 64
     const uint64_t adesc0 = make_desc(base, 16, 1024);
@@ -119,12 +122,15 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, StemWgTcParams P)
     if (elect_one_sync()) umma_commit(done_bar);
     __syncwarp();
   } else {
-    // =============================== patch builders (warps 0-3) ==============================
-    const int t = threadIdx.x;
+    // =============================== patch builders (4 groups of 4 warps) =====================
+    // The gather is a chain of DRAM-latency loads (x does not stay in L2 beside the streamed dy): one group alone paced
+    // the kernel at ~2400 clocks per k-block (1.85 ms, profiles/r02_session_g.md).  Four groups work on four consecutive
+    // k-blocks at once, each with its next k-block's loads already in flight.
+    const int grp = threadIdx.x >> 7, t = threadIdx.x & 127;
     const int p = t & 63, th = t >> 6;  // pixel of the k-block, tap parity
     const long long HW = (long long)P.H * P.W;
-    // position of this thread's pixel in k-block kb0, advanced by 64 pixels per k-block (no division in the loop)
-    long long q = kb0 * 64 + p;
+    // position of this thread's pixel in the group's first k-block, advanced by SWT_GROUPS * 64 pixels per round
+    long long q = (kb0 + grp) * 64 + p;
     int img = (int)(q / HW);
     int y = (int)((q - (long long)img * HW) / P.W);
     int x0 = (int)(q - (long long)img * HW - (long long)y * P.W);
@@ -141,8 +147,8 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, StemWgTcParams P)
         }
         v[j] = val;
       }
-      q += 64;
-      x0 += 64;
+      q += SWT_GROUPS * 64;
+      x0 += SWT_GROUPS * 64;
       while (x0 >= P.W) {
         x0 -= P.W;
         if (++y == P.H) {
@@ -152,10 +158,10 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, StemWgTcParams P)
       }
     };
     float v[16], vn[16];
-    if (nk > 0) gather(v);
-    for (int i = 0; i < nk; ++i) {
+    if (grp < nk) gather(v);
+    for (int i = grp; i < nk; i += SWT_GROUPS) {
       const int s = i % SWT_STAGES;
-      if (i + 1 < nk) gather(vn);  // the next k-block's loads are in flight while this one is written
+      if (i + SWT_GROUPS < nk) gather(vn);  // the group's next k-block is in flight while this one is written
       mbar_wait(empty_bar(s), ((i / SWT_STAGES) & 1u) ^ 1u);
       uint8_t* a_slot = base_ptr + s * SWT_STAGE;
 #pragma unroll
@@ -194,7 +200,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, StemWgTcParams P)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_acc, 64);
+  if (warp == SWT_MMA_WARP) tmem_dealloc(tmem_acc, 64);
 }
 
 // grad[co][tap] (torch OIHW, flat co * K + tap) (+)= sum over CTAs of partial[cta][tap][co], in CTA order

@@ -136,6 +136,42 @@ def test_tc_conv_exact_small_integers():
   assert torch.equal(gw.cpu(), wr.grad.float())  # fp32 output of exact integer sums
 
 
+@pytest.mark.unvalidated
+@pytest.mark.parametrize("case", [(6, 25, 128, 128, 3, 1, 1), (5, 13, 256, 256, 3, 1, 1), (3, 7, 512, 512, 3, 1, 1),
+                                  (4, 13, 256, 512, 1, 2, 0), (3, 12, 128, 128, 5, 1, 2), (40, 9, 128, 128, 3, 1, 1),
+                                  (3, 25, 64, 128, 3, 2, 1)])
+def test_wgrad_multi_tile_work_items_exact(case):
+  """Option wgrad_mt: 2 or 3 (tap, cin) tiles per dy k-block, single TMEM accumulator buffer.  Exact on small integers
+  (fp32 sums of exactly representable products), with and without accumulation, for 3 x 128-row tiles (N = 128), 2 tiles
+  (N = 256, one and two N tiles), a single 2-tile item (1x1), 5x5 taps, many split-K items, and a shape that stays on the
+  one-tile path."""
+  K = _K()
+  from iic_b200._lib import BF16
+  n, h, cin, cout, k, s, p = case
+  g = torch.Generator().manual_seed(11)
+  oh = (h + 2 * p - k) // s + 1
+  x = torch.randint(-1, 2, (n, cin, h, h), generator=g).float()
+  dy = torch.randint(-1, 2, (n, cout, oh, oh), generator=g).float()
+  wr = torch.zeros(cout, cin, k, k, dtype=torch.float64, requires_grad=True)
+  F.conv2d(x.double(), wr, None, s, p).backward(dy.double())
+  geo = K.conv_geom(n, h, h, cin, cout, k, k, s, p, 1)
+  xh, dyh = to_nhwc(x.cuda(), torch.bfloat16), to_nhwc(dy.cuda(), torch.bfloat16)
+  base = torch.randint(-3, 4, (cout, cin, k, k), generator=g).float().cuda()
+  for fused in (True, False):
+    old = K.WGRAD_FUSED_UNPACK["on"]
+    K.WGRAD_FUSED_UNPACK["on"] = fused
+    try:
+      with K.options(wgrad_mt=1):
+        gw = torch.zeros_like(base)
+        K.conv_wgrad(xh, dyh, geo, BF16, gw, False)
+        acc = base.clone()
+        K.conv_wgrad(xh, dyh, geo, BF16, acc, True)
+    finally:
+      K.WGRAD_FUSED_UNPACK["on"] = old
+    assert torch.equal(gw.cpu(), wr.grad.float()), "max |err| %g" % (gw.cpu() - wr.grad.float()).abs().max().item()
+    assert torch.equal((acc - base).cpu(), wr.grad.float())
+
+
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 @pytest.mark.parametrize("shape", [(5, 13, 13, 64), (2, 25, 25, 128), (3, 7, 7, 512), (64, 3, 3, 256)])
 def test_bn_forward_backward(mode, shape):
@@ -586,7 +622,7 @@ def test_halo_kernels_forced_exact_small_integers(n, h, variant):
 
 def test_runtime_options_roundtrip():
   K = _K()
-  for name in ("conv_halo", "conv_halo_wgrad", "stem_quad", "dgrad_prefetch", "tc2_mt2", "conv_halo_store", "stem_bwd_v2", "bn_bwd_ctas", "conv_halo_stats", "tf32x3_raw_hi"):
+  for name in ("conv_halo", "conv_halo_wgrad", "stem_quad", "dgrad_prefetch", "tc2_mt2", "conv_halo_store", "stem_bwd_v2", "bn_bwd_ctas", "conv_halo_stats", "tf32x3_raw_hi", "wgrad_mt"):
     v = K.get_option(name)
     with K.options(**{name: 0}):
       assert K.get_option(name) == 0
