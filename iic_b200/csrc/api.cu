@@ -65,6 +65,10 @@ static Option g_opts[OPT_COUNT] = {
     // of up to 512 TMEM columns): a third less shared-memory fill per MMA.  Written after the last GPU session: off until
     // it has run on hardware (tests force it).
     {"wgrad_mt", "IIC_WGRAD_MT", 0, 0, false},
+    // halo_addend_tma: the halo dgrad fetches its residual-gradient addend with ONE TMA load into the output staging
+    // buffer and sums in place, instead of 16-byte loads from 32 different lines per warp instruction (the three layer-1
+    // dgrads with an addend ran at ~580 TFLOP/s against 1100 without, profiles/r02_session_f.md).  Off until run on hardware.
+    {"halo_addend_tma", "IIC_HALO_ADDEND_TMA", 0, 0, false},
 };
 
 int option(int id) {

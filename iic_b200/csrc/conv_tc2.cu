@@ -479,6 +479,8 @@ struct HaloParams {
   int img_half;         // images >= img_half belong to view 1
   int addend_prefetch;  // request the addend before waiting for the accumulator (option dgrad_prefetch)
   int tma_store;        // output tile staged in shared memory and written by one TMA store (option conv_halo_store)
+  int addend_tma;       // dgrad: the addend tile is fetched INTO the staging buffer by one TMA load and summed in place
+                        // (option halo_addend_tma; needs tma_store)
 };
 
 // Output path (fprop / dgrad).  With one accumulator row per lane, a warp's 16-byte global stores hit 32 different
@@ -492,7 +494,7 @@ constexpr uint32_t HALO_STAGING_BYTES = HALO_TILE * 128;
 
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmO, HaloParams P) {
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmAdd, HaloParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t resb = (raw + 1023u) & ~1023u;           // [9][64 x 128 B] resident weights
@@ -504,6 +506,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto tfull_bar = [&](int a) { return bars + 8u * (8 + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (10 + a); };
   const uint32_t bres_bar = bars + 8u * 12;
+  const uint32_t add_bar = bars + 8u * 14;  // addend tile landed in the staging buffer (addend_tma)
   uint8_t* bars_ptr = smem_raw + (bars - raw);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_ptr + 8 * 13);
   float* stat = reinterpret_cast<float*>(bars_ptr + 128);  // [8 warps][2 views][2][32]
@@ -521,12 +524,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(tempty_bar(a), 256);
     }
     mbar_init(bres_bar, 1);
+    mbar_init(add_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (P.tma_store) tma_prefetch_desc(&tmO);
+    if (P.addend_tma) tma_prefetch_desc(&tmAdd);
   }
   if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 256);
   tc_fence_before();
@@ -598,9 +603,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // =============================== epilogue (warps 0-7) ======================================
     const int quad = warp & 3, hsel = warp >> 2;
-    const bool has_add = P.addend != nullptr;
-    const bool pre = has_add && P.addend_prefetch != 0;
     const bool ts = P.tma_store != 0;
+    const bool add_tma = ts && P.addend != nullptr && P.addend_tma != 0;
+    const bool has_add = P.addend != nullptr && !add_tma;  // (per-lane global loads of the addend)
+    const bool pre = has_add && P.addend_prefetch != 0;
     uint8_t* staging_ptr = smem_raw + (staging - raw);
     uint32_t it = 0;
     for (int w = blockIdx.x; w < P.total_tiles; w += gridDim.x, ++it) {
@@ -609,7 +615,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int view = img >= P.img_half ? 1 : 0;
       const uint32_t as = it & 1u;
       if (ts) {  // the previous work item's TMA store must have read the staging buffer before it is rewritten
-        if (threadIdx.x == 0) bulk_wait_read0();
+        if (threadIdx.x == 0) {
+          bulk_wait_read0();
+          if (add_tma) {  // the residual-gradient tile of this work item: same box as the store, zero-filled padding
+            mbar_expect_tx(add_bar, (uint32_t)(P.Wp * P.R * 128));
+            tma_load_4d(staging, &tmAdd, add_bar, 0, 0, y0, img);
+          }
+        }
         named_bar_sync(1, 256);
       }
       // this thread's two accumulator rows (TMEM lane, +128 for the second MMA tile) -> output pixels
@@ -640,6 +652,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       mbar_wait(tfull_bar(as), (it >> 1) & 1u);
       tc_fence_after();
+      if (add_tma) mbar_wait(add_bar, it & 1u);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         const bool valid = valid2[mt];
@@ -684,10 +697,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] += ad[e];
             }
-            if (ts)  // staging row m, 16-byte chunk (hsel * 4 + qq) at its SWIZZLE_128B position
-              store8(reinterpret_cast<__nv_bfloat16*>(staging_ptr + m * 128 + (((hsel * 4 + qq) ^ (m & 7)) << 4)), f);
-            else
+            if (ts) {  // staging row m, 16-byte chunk (hsel * 4 + qq) at its SWIZZLE_128B position
+              uint8_t* sp = staging_ptr + m * 128 + (((hsel * 4 + qq) ^ (m & 7)) << 4);
+              if (add_tma && valid) {  // the TMA load put this pixel's addend at the very same position
+                float ad[8];
+                Raw8h rw;
+                rw.v = *reinterpret_cast<const uint4*>(sp);
+                cvt_raw(rw, ad);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += ad[e];
+              }
+              store8(reinterpret_cast<__nv_bfloat16*>(sp), f);
+            } else {
               store8(o + qq * 8, f);
+            }
           }
         }
       }
@@ -1219,12 +1242,16 @@ static HaloPlan halo_wgrad_plan(const iic_conv_geom* g) {
 
 static int launch_halo(const HaloPlan& hp, const __nv_bfloat16* src, int H, int W, int nimg, const Tc2Params& P,
                        const CUtensorMap& tmB, cudaStream_t st) {
-  alignas(64) CUtensorMap tmA, tmO;
+  alignas(64) CUtensorMap tmA, tmO, tmAdd;
+  const bool add_tma = P.addend != nullptr && hp.tma_store && option(OPT_HALO_ADDEND_TMA) != 0;
   {
     int rc = make_halo_map(&tmA, src, H, W, nimg, hp.Wp, hp.R + 2);
     if (rc != IIC_OK) return rc;
     // output map: the load box without the two halo rows; unused (but valid) when the epilogue stores directly
     rc = make_halo_map(&tmO, P.out, H, W, nimg, hp.Wp, hp.R);
+    if (rc != IIC_OK) return rc;
+    // the addend has the geometry of the output (unused copy of the output map when there is none)
+    rc = make_halo_map(&tmAdd, add_tma ? P.addend : P.out, H, W, nimg, hp.Wp, hp.R);
     if (rc != IIC_OK) return rc;
   }
   HaloParams Q = {};
@@ -1238,13 +1265,14 @@ static int launch_halo(const HaloPlan& hp, const __nv_bfloat16* src, int H, int 
   Q.out = P.out; Q.addend = P.addend; Q.stat_partial = P.stat_partial;
   Q.addend_prefetch = P.addend_prefetch;
   Q.tma_store = hp.tma_store;
+  Q.addend_tma = add_tma ? 1 : 0;
   Q.img_half = (P.stat_half < P.rows) ? nimg / 2 : nimg;
   if (option(OPT_HALO_STATS) != 0 && Q.stat_partial != nullptr && Q.addend == nullptr) {
     IIC_CUDA(cudaFuncSetAttribute(conv_halo_fstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hp.smem));
     conv_halo_fstats_kernel<<<tc2_grid(hp.total_tiles), HALO_THREADS, hp.smem, st>>>(tmA, tmB, tmO, Q);
   } else {
     IIC_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hp.smem));
-    conv_halo_kernel<<<tc2_grid(hp.total_tiles), HALO_THREADS, hp.smem, st>>>(tmA, tmB, tmO, Q);
+    conv_halo_kernel<<<tc2_grid(hp.total_tiles), HALO_THREADS, hp.smem, st>>>(tmA, tmB, tmO, tmAdd, Q);
   }
   IIC_LAUNCH_CHECK();
   count_launch();

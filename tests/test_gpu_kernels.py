@@ -565,7 +565,8 @@ HALO_GEOMS = [
 
 
 @pytest.mark.parametrize("n,h", HALO_GEOMS)
-@pytest.mark.parametrize("variant", ["tma-store", "direct-store", "im2col-wgrad"])
+@pytest.mark.parametrize("variant", ["tma-store", "direct-store", "im2col-wgrad",
+                                     pytest.param("tma-addend", marks=pytest.mark.unvalidated)])
 def test_halo_kernels_forced_exact_small_integers(n, h, variant):
   """The halo kernels (3x3 / stride 1 / pad 1 / 64 -> 64: fprop, dgrad, wgrad) forced on every geometry they accept
   (option conv_halo = 2; by default they only run where they pay): EXACT on small-integer operands against CPU fp64,
@@ -599,7 +600,9 @@ def test_halo_kernels_forced_exact_small_integers(n, h, variant):
     torch.cuda.synchronize()
     return y, dx, dx2, gw, st
 
-  with K.options(conv_halo=2, conv_halo_wgrad=halo_wgrad, conv_halo_store=halo_store):
+  # "tma-addend": the dgrad addend arrives by one TMA load in the staging buffer (option halo_addend_tma)
+  with K.options(conv_halo=2, conv_halo_wgrad=halo_wgrad, conv_halo_store=halo_store,
+                 halo_addend_tma=1 if variant == "tma-addend" else 0):
     y, dx, dx2, gw, st = run()
   with K.options(conv_halo=0):
     y0, dx0, dx20, gw0, st0 = run()
@@ -622,7 +625,7 @@ def test_halo_kernels_forced_exact_small_integers(n, h, variant):
 
 def test_runtime_options_roundtrip():
   K = _K()
-  for name in ("conv_halo", "conv_halo_wgrad", "stem_quad", "dgrad_prefetch", "tc2_mt2", "conv_halo_store", "stem_bwd_v2", "bn_bwd_ctas", "conv_halo_stats", "tf32x3_raw_hi", "wgrad_mt"):
+  for name in ("conv_halo", "conv_halo_wgrad", "stem_quad", "dgrad_prefetch", "tc2_mt2", "conv_halo_store", "stem_bwd_v2", "bn_bwd_ctas", "conv_halo_stats", "tf32x3_raw_hi", "wgrad_mt", "halo_addend_tma"):
     v = K.get_option(name)
     with K.options(**{name: 0}):
       assert K.get_option(name) == 0
