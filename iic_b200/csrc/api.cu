@@ -62,9 +62,10 @@ static Option g_opts[OPT_COUNT] = {
     // and smoke green; fprop 58.9 -> 43.6 ms, dgrad 61.3 -> 49.8 ms per c4 step, profiles/r02_session_f.md); 0 = write hi too.
     {"tf32x3_raw_hi", "IIC_TF32X3_RAW_HI", 1, 0, false},
     // wgrad_mt: the bf16 im2col wgrad takes 2 or 3 of its 128-row (tap, cin) tiles per dy k-block (one accumulator buffer
-    // of up to 512 TMEM columns): a third less shared-memory fill per MMA.  Written after the last GPU session: off until
-    // it has run on hardware (tests force it).
-    {"wgrad_mt", "IIC_WGRAD_MT", 0, 0, false},
+    // of up to 512 TMEM columns): a third less shared-memory fill per MMA.  Validated on a B200 in round 2 (exact-integer
+    // tests; wgrad 128->128 708 -> 1126, 256->256 1085 -> 1189, 512->512 897 -> 1014 TFLOP/s live in the c4 step, wgrad of
+    // the step 9.70 -> 8.24 ms, profiles/r02_session_h.md); 0 = one tile per work item.
+    {"wgrad_mt", "IIC_WGRAD_MT", 1, 0, false},
     // halo_addend_tma: the halo dgrad fetches its residual-gradient addend with ONE TMA load into the output staging
     // buffer and sums in place, instead of 16-byte loads from 32 different lines per warp instruction (the three layer-1
     // dgrads with an addend ran at ~580 TFLOP/s against 1100 without, profiles/r02_session_f.md).  Off until run on hardware.

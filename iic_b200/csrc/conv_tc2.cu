@@ -1378,8 +1378,9 @@ int tc2_conv_gather_gemm_stats(const __nv_bfloat16* src, int srcH, int srcW, int
 static int tc2_wgrad_mt(const iic_conv_geom* g, int bn) {
   if (option(OPT_WGRAD_MT) == 0) return 1;
   const int Ktot = g->kh * g->kw * g->cin;
-  if (bn == 128) return Ktot % 384 == 0 ? 3 : (Ktot % 256 == 0 ? 2 : 1);
-  if (bn == 256) return Ktot % 256 == 0 ? 2 : 1;
+  // (at least two work items along M: a single 2-tile item was slower than two 1-tile items, 1x1 256 -> 512: 51 -> 63 us)
+  if (bn == 128) return (Ktot % 384 == 0 && Ktot >= 768) ? 3 : ((Ktot % 256 == 0 && Ktot >= 512) ? 2 : 1);
+  if (bn == 256) return (Ktot % 256 == 0 && Ktot >= 512) ? 2 : 1;
   return 1;
 }
 

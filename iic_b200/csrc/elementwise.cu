@@ -212,25 +212,42 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, long long M,
   mean_invstd[C + c] = invstd;
 }
 
-// conv-epilogue partials [nblk][views][2C] -> per-view scale/shift and mean/invstd in ONE launch: one warp per
-// channel folds both sums of every view (fixed order, fp64) and finalises; running statistics are
-// updated view after view, like the reference's consecutive forward calls.
-__global__ void bn_fold_finalize_kernel(const float* __restrict__ partial, int nblk, int slots, int views, long long M, int C,
-                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                        float momentum, float* running_mean, float* running_var,
-                                        float* __restrict__ scale_shift, float* __restrict__ mean_invstd) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (c >= C) return;
+// conv-epilogue partials [nblk][views][2C] -> per-view scale/shift and mean/invstd in ONE launch.  Block = 32 channels x
+// 8 row groups: thread (cx, by) folds the CTA rows by, by + 8, ... of its channel in fp64 (coalesced across cx, all of a
+// thread's loads independent), the 8 group sums are added in a fixed order, and row group 0 finalises; running statistics
+// are updated view after view, like the reference's consecutive forward calls.  (The first version, one warp per channel
+// with lanes striding over the CTA rows, issued 32-line gathers in a dependent loop: ~16 us per launch, 36 launches a step.)
+__global__ void __launch_bounds__(256)
+bn_fold_finalize_kernel(const float* __restrict__ partial, int nblk, int slots, int views, long long M, int C,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                        float momentum, float* running_mean, float* running_var,
+                        float* __restrict__ scale_shift, float* __restrict__ mean_invstd) {
+  __shared__ double red[2][8][32];
+  const int cx = threadIdx.x & 31, by = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const bool live = c < C;
   const long long stride = (long long)slots * 2 * C;  // a CTA's partial row holds `slots` views
   for (int v = 0; v < views; ++v) {
     double s1 = 0.0, s2 = 0.0;
-    for (int b = lane; b < nblk; b += 32) {
-      s1 += (double)partial[b * stride + (long long)v * 2 * C + c];
-      s2 += (double)partial[b * stride + (long long)v * 2 * C + C + c];
+    if (live) {
+      const float* p = partial + (long long)v * 2 * C + c;
+#pragma unroll 4
+      for (int b = by; b < nblk; b += 8) {
+        s1 += (double)p[b * stride];
+        s2 += (double)p[b * stride + C];
+      }
     }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    if (lane == 0) {
+    red[0][by][cx] = s1;
+    red[1][by][cx] = s2;
+    __syncthreads();
+    if (by == 0 && live) {
+      s1 = red[0][0][cx];
+      s2 = red[1][0][cx];
+#pragma unroll
+      for (int g = 1; g < 8; ++g) {
+        s1 += red[0][g][cx];
+        s2 += red[1][g][cx];
+      }
       const double m = s1 / (double)M;
       double var = s2 / (double)M - m * m;
       if (var < 0.0) var = 0.0;
@@ -248,6 +265,7 @@ __global__ void bn_fold_finalize_kernel(const float* __restrict__ partial, int n
       mi[c] = mean;
       mi[C + c] = invstd;
     }
+    __syncthreads();
   }
 }
 
@@ -909,7 +927,7 @@ extern "C" int iic_bn_stats_from_partials_views(const float* stat_partial, int n
   IIC_REQUIRE(stat_partial && nblk > 0 && views >= 1 && slots >= views && gamma && beta && scale_shift && mean_invstd && M_per_view > 0 &&
                   C > 0,
               IIC_ERR_BAD_ARG, "iic_bn_stats_from_partials_views: bad arguments");
-  bn_fold_finalize_kernel<<<cdiv((long long)C * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+  bn_fold_finalize_kernel<<<cdiv(C, 32), 256, 0, (cudaStream_t)stream>>>(
       stat_partial, nblk, slots, views, M_per_view, C, gamma, beta, eps, momentum, running_mean, running_var,
       scale_shift, mean_invstd);
   IIC_LAUNCH_CHECK();

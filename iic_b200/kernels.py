@@ -484,7 +484,7 @@ def stem_bwd_fused(x_nchw, y, dpool, ss, mi, gamma, dgamma, dbeta, bn_accumulate
 
 
 # host-side switch: stem wgrad as im2col + the tcgen05 1x1 wgrad kernel (bf16 mode; OFF until validated on hardware)
-STEM_WGRAD_TC = {"on": __import__("os").environ.get("IIC_STEM_WGRAD_TC", "0") != "0"}
+STEM_WGRAD_TC = {"on": __import__("os").environ.get("IIC_STEM_WGRAD_TC", "1") != "0"}
 
 
 def stem_wgrad_tc(x_nchw, dy, g, grad_out, accumulate):

@@ -136,7 +136,6 @@ def test_tc_conv_exact_small_integers():
   assert torch.equal(gw.cpu(), wr.grad.float())  # fp32 output of exact integer sums
 
 
-@pytest.mark.unvalidated
 @pytest.mark.parametrize("case", [(6, 25, 128, 128, 3, 1, 1), (5, 13, 256, 256, 3, 1, 1), (3, 7, 512, 512, 3, 1, 1),
                                   (4, 13, 256, 512, 1, 2, 0), (3, 12, 128, 128, 5, 1, 2), (40, 9, 128, 128, 3, 1, 1),
                                   (3, 25, 64, 128, 3, 2, 1)])
@@ -304,10 +303,12 @@ def test_stem(mode, cin, k, pad, hw):
   assert torch.allclose(from_nhwc(y), yr.detach(), **tol)
   yr.backward(dy)
   gw = torch.zeros_like(w)
+  # bf16 mode: the tcgen05 stem wgrad (kernels.STEM_WGRAD_TC) rounds the input patches to bf16 as well (2^-9 per element)
+  wtol = 4e-3 if (mode == "bf16" and K.STEM_WGRAD_TC["on"]) else 1e-3
   K.stem_wgrad(x, to_nhwc(dy, tdt), geo, dt, gw, False)
-  assert torch.allclose(gw, wr.grad, rtol=1e-3, atol=1e-3 * wr.grad.abs().max().item())
+  assert torch.allclose(gw, wr.grad, rtol=1e-3, atol=wtol * wr.grad.abs().max().item())
   K.stem_wgrad(x, to_nhwc(dy, tdt), geo, dt, gw, True)
-  assert torch.allclose(gw, 2 * wr.grad, rtol=1e-3, atol=2e-3 * wr.grad.abs().max().item())
+  assert torch.allclose(gw, 2 * wr.grad, rtol=1e-3, atol=2 * wtol * wr.grad.abs().max().item())
 
 
 @pytest.mark.parametrize("n,F_,S,k", [(37, 512, 5, 10), (64, 512, 5, 70), (33, 4608, 5, 50), (5, 512, 1, 3)])
@@ -853,7 +854,6 @@ def test_wgrad_written_in_torch_layout_equals_wgrad_plus_unpack(case, mode):
   assert torch.equal(outs[False][1], outs[True][1])
 
 
-@pytest.mark.unvalidated
 @pytest.mark.parametrize("cin,k,pad,hw,n", [(2, 3, 1, 32, 3), (2, 3, 1, 96, 4), (1, 5, 2, 24, 5), (3, 3, 1, 20, 2), (2, 3, 1, 7, 1)])
 def test_stem_wgrad_on_tensor_cores_matches_the_simt_kernel(cin, k, pad, hw, n):
   """Stem wgrad on tcgen05 (stem_tc.cu: patches gathered into shared memory, dy by TMA; option STEM_WGRAD_TC) against
