@@ -65,6 +65,8 @@ _SIGS = {
   "iic_conv_wgrad_oihw": (c_int, [_P, _P, _P, c_int, _P, POINTER(ConvGeom), c_int, _P]),
   "iic_stem_fprop": (c_int, [_P, _P, _P, POINTER(ConvGeom), c_int, _P]),
   "iic_stem_wgrad": (c_int, [_P, _P, _P, c_int, _P, c_longlong, POINTER(ConvGeom), c_int, _P]),
+  "iic_stem_fprop_stats_tc_blocks": (c_int, [POINTER(ConvGeom), c_int]),
+  "iic_stem_fprop_stats_tc": (c_int, [_P, _P, _P, POINTER(ConvGeom), c_int, _P, _P]),
   "iic_stem_wgrad_tc_workspace": (c_longlong, [POINTER(ConvGeom)]),
   "iic_stem_wgrad_tc": (c_int, [_P, _P, _P, c_int, _P, POINTER(ConvGeom), _P]),
   "iic_bn_stats": (c_int, [_P, c_int, c_longlong, c_int, _P, _P, c_float, c_float, _P, _P, c_int, _P, _P, _P, _P]),

@@ -448,9 +448,29 @@ def stem_fprop(x_nchw, w, g, dt):
   return y
 
 
+# stem convolution (+ statistics) on tcgen05 in bf16 mode (csrc/stem_tc.cu); written after the last GPU session: off
+STEM_FPROP_TC = {"on": __import__("os").environ.get("IIC_STEM_FPROP_TC", "0") != "0"}
+
+
+def stem_fprop_stats_tc(x_nchw, w, g, views):
+  """-> (y bf16, partial, nblk) or None if the geometry is unsupported (include/iic_b200.h: iic_stem_fprop_stats_tc)."""
+  nblk = int(_lib.lib().iic_stem_fprop_stats_tc_blocks(ctypes.byref(g), views))
+  if nblk <= 0:
+    return None
+  y = torch.empty((g.n, g.oh, g.ow, g.cout), device=x_nchw.device, dtype=torch.bfloat16)
+  partial = torch.empty((nblk, 2, 2, g.cout), device=x_nchw.device, dtype=torch.float32)
+  check(_lib.lib().iic_stem_fprop_stats_tc(_p(x_nchw), _p(w), _p(y), ctypes.byref(g), views, _p(partial), _stream()),
+        "iic_stem_fprop_stats_tc")
+  return y, partial, nblk
+
+
 @_cat("stem_fprop")
 def stem_fprop_stats(x_nchw, w, g, dt, views):
   """Stem conv + fused per-view BN statistics partials.  Returns (y, partial, nblk) or None if unsupported."""
+  if STEM_FPROP_TC["on"] and dt == BF16:
+    r = stem_fprop_stats_tc(x_nchw, w, g, views)
+    if r is not None:
+      return r
   nblk = int(_lib.lib().iic_stem_fprop_stats_blocks(ctypes.byref(g), dt, views))
   if nblk <= 0:
     return None

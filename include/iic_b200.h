@@ -254,6 +254,13 @@ int iic_stem_wgrad(const float* x_nchw, const void* dy, float* grad_oihw, int ac
 long long iic_stem_wgrad_tc_workspace(const iic_conv_geom* g);
 int iic_stem_wgrad_tc(const float* x_nchw, const void* dy_bf16, float* grad_oihw, int accumulate, void* workspace,
                       const iic_conv_geom* g, void* stream);
+/* Stem convolution + BatchNorm statistics partials on tcgen05 (bf16 output; cin*kh*kw <= 32, cout = 64, stride 1, 'same'
+ * padding; two views only if one view is a multiple of 128 pixels): same contract as iic_stem_fprop_stats (net5g.py:21-23,
+ * the first trunk convolution and the batch statistics nn.BatchNorm2d takes of its result), with the input patches and the
+ * weights rounded to bf16.  _blocks() = rows of stat_partial ([blocks][2 views][{sum, sum of squares}][64]), 0 if unsupported. */
+int iic_stem_fprop_stats_tc_blocks(const iic_conv_geom* g, int views);
+int iic_stem_fprop_stats_tc(const float* x_nchw, const float* w_oihw, void* y_bf16, const iic_conv_geom* g, int views,
+                            float* stat_partial, void* stream);
 /* Whole backward of the ClusterNet5g stem, conv3x3(cin 1|2 -> 64, pad 1) -> BatchNorm -> ReLU -> MaxPool(2, 2, pool_pad)
  * (net5g.py:21-26), in two passes over (y, dpool) instead of six over y-sized tensors: the pooled gradient is routed
  * and ReLU-masked on the fly, reduced for the BatchNorm backward, and the BatchNorm input gradient is consumed by the

@@ -884,3 +884,35 @@ def test_stem_wgrad_on_tensor_cores_matches_the_simt_kernel(cin, k, pad, hw, n):
   finally:
     K.STEM_WGRAD_TC["on"] = old
   assert (a - c).abs().max().item() <= 1e-2 * scale  # (the SIMT kernel reads x in fp32)
+
+
+@pytest.mark.unvalidated
+@pytest.mark.parametrize("cin,k,pad,hw,n,views", [(2, 3, 1, 32, 4, 2), (2, 3, 1, 96, 2, 2), (1, 5, 2, 24, 5, 1), (3, 3, 1, 20, 3, 1),
+                                                  (2, 3, 1, 16, 6, 2), (2, 3, 1, 7, 1, 1)])
+def test_stem_fprop_on_tensor_cores(cin, k, pad, hw, n, views):
+  """Stem conv + BN statistics on tcgen05 (stem_tc.cu: patches gathered into shared memory, resident weights, TMA-stored
+  bf16 output) against torch on the same bf16-rounded operands, and its statistics partials against the sums of the
+  fp32 results."""
+  K = _K()
+  g = torch.Generator().manual_seed(21)
+  x = torch.randn(n, cin, hw, hw, generator=g).cuda()
+  w = (torch.randn(64, cin, k, k, generator=g) * 0.3).cuda()
+  geo = K.conv_geom(n, hw, hw, cin, 64, k, k, 1, pad, 1)
+  r = K.stem_fprop_stats_tc(x, w, geo, views)
+  if views == 2 and (n // 2 * hw * hw) % 128 != 0:
+    assert r is None
+    return
+  assert r is not None
+  y, partial, nblk = r
+  yr = F.conv2d(x.bfloat16().double(), w.bfloat16().double(), None, 1, pad)  # exact products of the rounded operands
+  got = from_nhwc(y).double()
+  assert (got - yr).abs().max().item() <= 1e-2 * yr.abs().max().item()  # bf16 rounding of the stored result
+  tot = partial[:nblk].double().sum(0)  # [2 views][{sum, sumsq}][64]
+  nv = n // views
+  for v in range(views):
+    sl = yr[v * nv:(v + 1) * nv]
+    s1, s2 = sl.sum(dim=(0, 2, 3)), (sl * sl).sum(dim=(0, 2, 3))
+    assert (tot[v, 0] - s1).abs().max().item() <= 1e-4 * s2.sqrt().max().item() * (sl[:, 0].numel() ** 0.5)
+    assert torch.allclose(tot[v, 1], s2, rtol=1e-4, atol=0)
+  if views == 1:
+    assert float(tot[1].abs().max()) == 0.0
