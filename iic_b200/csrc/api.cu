@@ -67,9 +67,10 @@ static Option g_opts[OPT_COUNT] = {
     // the step 9.70 -> 8.24 ms, profiles/r02_session_h.md); 0 = one tile per work item.
     {"wgrad_mt", "IIC_WGRAD_MT", 1, 0, false},
     // halo_addend_tma: the halo dgrad fetches its residual-gradient addend with ONE TMA load into the output staging
-    // buffer and sums in place, instead of 16-byte loads from 32 different lines per warp instruction (the three layer-1
-    // dgrads with an addend ran at ~580 TFLOP/s against 1100 without, profiles/r02_session_f.md).  Off until run on hardware.
-    {"halo_addend_tma", "IIC_HALO_ADDEND_TMA", 0, 0, false},
+    // buffer and sums in place, instead of 16-byte loads from 32 different lines per warp instruction.  Validated on a
+    // B200 in round 2 (exact-integer tests; the six layer-1 dgrads of the c4 step 2.12 -> 1.85 ms, profiles/r02_session_i.md);
+    // 0 = per-lane loads (option dgrad_prefetch).
+    {"halo_addend_tma", "IIC_HALO_ADDEND_TMA", 1, 0, false},
 };
 
 int option(int id) {

@@ -566,8 +566,7 @@ HALO_GEOMS = [
 
 
 @pytest.mark.parametrize("n,h", HALO_GEOMS)
-@pytest.mark.parametrize("variant", ["tma-store", "direct-store", "im2col-wgrad",
-                                     pytest.param("tma-addend", marks=pytest.mark.unvalidated)])
+@pytest.mark.parametrize("variant", ["tma-store", "direct-store", "im2col-wgrad", "tma-addend"])
 def test_halo_kernels_forced_exact_small_integers(n, h, variant):
   """The halo kernels (3x3 / stride 1 / pad 1 / 64 -> 64: fprop, dgrad, wgrad) forced on every geometry they accept
   (option conv_halo = 2; by default they only run where they pay): EXACT on small-integer operands against CPU fp64,
