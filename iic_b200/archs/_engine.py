@@ -166,14 +166,15 @@ class _ViewStats(list):
 #                default: its first version is latency bound (7.6 ms against 4.4 ms for the chain at the bench shape,
 #                profiles/r01_bench_v10_variants.md)
 #   bn_bitmask   the ReLU of a residual block's output is kept as a 1-bit mask by the forward apply and read by the bn2
-#                backward instead of the block output (16 -> 12.25 B per element).  Written after the last GPU session
-#                of round 1: OFF until it has run on hardware (its tests carry the `unvalidated` marker)
+#                backward instead of the block output (16 -> 12.25 B per element).  Validated on a B200 in round 2;
+#                on the final build of the round: bn_bwd 8.66 -> 7.81 ms, bn_apply 2.76 -> 3.02 ms, c4 step
+#                40.50 / 40.30 -> 39.63 / 39.29 ms (profiles/r02_session_j.md): ON
 OPTIONS = {
   "bn_merged": os.environ.get("IIC_BN_MERGED", "1") != "0",
   "stem_stats": os.environ.get("IIC_STEM_STATS", "1") != "0",
   "pack_batched": os.environ.get("IIC_PACK_BATCHED", "1") != "0",
   "stem_bwd_fused": os.environ.get("IIC_STEM_BWD_FUSED", "0") != "0",
-  "bn_bitmask": os.environ.get("IIC_BN_BITMASK", "0") != "0",
+  "bn_bitmask": os.environ.get("IIC_BN_BITMASK", "1") != "0",
   # wgrad_stream: weight-gradient convolutions run on a second stream.  A wgrad depends on (x, dy) only and nothing in
   # the backward depends on it, while the critical chain alternates tensor-bound dgrads with HBM-bound BatchNorm passes:
   # with the dgrad enqueued first, the (persistent, one CTA per SM) wgrad starts when the dgrad drains and then shares the

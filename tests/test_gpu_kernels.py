@@ -885,7 +885,6 @@ def test_stem_wgrad_on_tensor_cores_matches_the_simt_kernel(cin, k, pad, hw, n):
   assert (a - c).abs().max().item() <= 1e-2 * scale  # (the SIMT kernel reads x in fp32)
 
 
-@pytest.mark.unvalidated
 @pytest.mark.parametrize("cin,k,pad,hw,n,views", [(2, 3, 1, 32, 4, 2), (2, 3, 1, 96, 2, 2), (1, 5, 2, 24, 5, 1), (3, 3, 1, 20, 3, 1),
                                                   (2, 3, 1, 16, 6, 2), (2, 3, 1, 7, 1, 1)])
 def test_stem_fprop_on_tensor_cores(cin, k, pad, hw, n, views):
