@@ -59,6 +59,7 @@ _SIGS = {
   "iic_bn_stats_from_partials": (c_int, [_P, c_int, c_int, c_int, c_longlong, c_int, _P, _P, c_float, c_float, _P, _P, _P,
                                          _P, _P, _P]),
   "iic_conv_dgrad": (c_int, [_P, _P, _P, _P, POINTER(ConvGeom), c_int, _P]),
+  "iic_conv_dgrad_masked": (c_int, [_P, _P, _P, _P, _P, POINTER(ConvGeom), c_int, _P]),
   "iic_conv_wgrad_workspace": (c_longlong, [POINTER(ConvGeom), c_int]),
   "iic_conv_wgrad": (c_int, [_P, _P, _P, _P, POINTER(ConvGeom), c_int, _P]),
   "iic_conv_wgrad_oihw_workspace": (c_longlong, [POINTER(ConvGeom), c_int]),

@@ -25,6 +25,8 @@ int tc2_conv_gather_gemm_stats(const __nv_bfloat16* src, int srcH, int srcW, int
                                cudaStream_t st);
 int tc2_conv_dgrad_s2(const __nv_bfloat16* dy, const __nv_bfloat16* wpacked_t, const __nv_bfloat16* addend,
                       __nv_bfloat16* dx, const iic_conv_geom* g, cudaStream_t st);
+int tc2_conv_dgrad_masked(const __nv_bfloat16* dy, const __nv_bfloat16* wpacked_t, const __nv_bfloat16* addend,
+                          const unsigned char* addend_mask, __nv_bfloat16* dx, const iic_conv_geom* g, cudaStream_t st);
 int tf32_conv_gather_gemm(const float* src, int srcH, int srcW, int srcC, int rowH, int rowW, int nimg, const iic_conv_geom* g,
                           int transposed, const float* wpacked, int N, const float* addend, float* out, int split,
                           cudaStream_t st);
@@ -97,6 +99,17 @@ extern "C" int iic_conv_dgrad(const void* dy, const void* w_packed_t, const void
                                 (const __nv_bfloat16*)w_packed_t, g->cin, (const __nv_bfloat16*)addend, (__nv_bfloat16*)dx, st);
   set_error("iic_conv_dgrad: bad dtype %d", dtype);
   return IIC_ERR_BAD_ARG;
+}
+
+extern "C" int iic_conv_dgrad_masked(const void* dy, const void* w_packed_t, const void* addend, const unsigned char* addend_mask,
+                                     void* dx, const iic_conv_geom* g, int dtype, void* stream) {
+  int rc = geom_check(g, "iic_conv_dgrad_masked");
+  if (rc != IIC_OK) return rc;
+  IIC_REQUIRE(dy && w_packed_t && addend && addend_mask && dx, IIC_ERR_BAD_ARG, "iic_conv_dgrad_masked: null pointer");
+  IIC_REQUIRE(dtype == IIC_BF16 && g->stride == 1 && g->cin % 64 == 0, IIC_ERR_UNSUPPORTED,
+              "iic_conv_dgrad_masked: bf16, stride 1, cin a multiple of 64");
+  return tc2_conv_dgrad_masked((const __nv_bfloat16*)dy, (const __nv_bfloat16*)w_packed_t, (const __nv_bfloat16*)addend,
+                               addend_mask, (__nv_bfloat16*)dx, g, (cudaStream_t)stream);
 }
 
 extern "C" long long iic_conv_wgrad_workspace(const iic_conv_geom* g, int dtype) {

@@ -42,6 +42,7 @@ struct Tc2Params {
   int mtiles, ntiles, splits, kb_per_split, total_kb;
   __nv_bfloat16* out;
   const __nv_bfloat16* addend;
+  const unsigned char* addend_mask;  // or null: one bit per addend element ([pixel][N / 8] bytes); a clear bit drops the addend
   int addend_prefetch;  // fetch the addend one 32-column chunk ahead of its use (option dgrad_prefetch)
   float* partial;
   // fused BatchNorm statistics (fprop only): per-CTA partial column sums of the fp32 accumulators,
@@ -334,18 +335,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const bool has_add = P.addend != nullptr;
         const bool pre = has_add && P.addend_prefetch != 0;
         uint4 acur[4], anxt[4];
+        uint32_t mcur = 0xffffffffu, mnxt = 0xffffffffu;  // addend mask bits of the 32 columns of the chunk
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) acur[qq] = anxt[qq] = make_uint4(0u, 0u, 0u, 0u);
-        auto fetch = [&](uint4(&dst)[4], int mt, int c0) {
+        auto fetch = [&](uint4(&dst)[4], uint32_t& mdst, int mt, int c0) {
           const long long mr = (MT == 2 && mt == 1) ? mrow1 : mrow0;
           const long long orow = (MT == 2 && mt == 1) ? orow1 : orow0;
           if (mr < P.rows) {
             const uint4* src = reinterpret_cast<const uint4*>(P.addend + orow * P.N + n0 + c0);
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) dst[qq] = src[qq];
+            if (P.addend_mask != nullptr)
+              mdst = *reinterpret_cast<const uint32_t*>(P.addend_mask + ((orow * P.N + n0 + c0) >> 3));
           }
         };
-        if (pre) fetch(acur, 0, 0);
+        if (pre) fetch(acur, mcur, 0, 0);
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
 #pragma unroll 1
@@ -362,7 +366,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
             for (int qq = 0; qq < 32; ++qq) v[qq] = 0u;
           }
-          if (pre && j + 1 < MT * CH) fetch(anxt, (j + 1) / CH, ((j + 1) % CH) * 32);
+          if (pre && j + 1 < MT * CH) fetch(anxt, mnxt, (j + 1) / CH, ((j + 1) % CH) * 32);
           if (nk > 0) tmem_ld_wait();
           if (do_stats) {
             // per-column sums over this warp's 32 rows (rows >= P.rows are exact zeros: TMA zero fill)
@@ -386,7 +390,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
           if (m < P.rows) {
-            if (has_add && !pre) fetch(acur, mt, c0);
+            if (has_add && !pre) fetch(acur, mcur, mt, c0);
             __nv_bfloat16* o = P.out + orow * P.N + n0 + c0;
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) {
@@ -399,7 +403,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 rw.v = acur[qq];
                 cvt_raw(rw, ad);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] += ad[e];
+                for (int e = 0; e < 8; ++e) f[e] += ((mcur >> (qq * 8 + e)) & 1u) ? ad[e] : 0.f;
               }
               store8(o + qq * 8, f);
             }
@@ -407,6 +411,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (pre) {
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) acur[qq] = anxt[qq];
+            mcur = mnxt;
           }
         }
       } else {
@@ -475,6 +480,7 @@ struct HaloParams {
   unsigned char wtap[9];
   __nv_bfloat16* out;
   const __nv_bfloat16* addend;
+  const unsigned char* addend_mask;  // or null: [pixel][8] bytes, one bit per addend element (a clear bit drops it)
   float* stat_partial;  // [cta][view][{sum, sum of squares}][64] or null
   int img_half;         // images >= img_half belong to view 1
   int addend_prefetch;  // request the addend before waiting for the accumulator (option dgrad_prefetch)
@@ -637,10 +643,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // residual-gradient addend (dgrad): both rows' 64 B are requested before the accumulator is complete, so the
       // global-load latency overlaps the MMAs instead of sitting between tcgen05.ld and the stores
       uint4 add2[2][4];
+      uint32_t mw2[2] = {0xffffffffu, 0xffffffffu};  // addend mask bits of this thread's 32 channels of each row
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) add2[mt][qq] = make_uint4(0u, 0u, 0u, 0u);
+      if (P.addend_mask != nullptr) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+          if (valid2[mt]) mw2[mt] = *reinterpret_cast<const uint32_t*>(P.addend_mask + pix2[mt] * 8 + hsel * 4);
+      }
       if (pre) {
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
@@ -695,7 +707,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               rw.v = add2[mt][qq];
               cvt_raw(rw, ad);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] += ad[e];
+              for (int e = 0; e < 8; ++e) f[e] += ((mw2[mt] >> (qq * 8 + e)) & 1u) ? ad[e] : 0.f;
             }
             if (ts) {  // staging row m, 16-byte chunk (hsel * 4 + qq) at its SWIZZLE_128B position
               uint8_t* sp = staging_ptr + m * 128 + (((hsel * 4 + qq) ^ (m & 7)) << 4);
@@ -705,7 +717,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 rw.v = *reinterpret_cast<const uint4*>(sp);
                 cvt_raw(rw, ad);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] += ad[e];
+                for (int e = 0; e < 8; ++e) f[e] += ((mw2[mt] >> (qq * 8 + e)) & 1u) ? ad[e] : 0.f;
               }
               store8(reinterpret_cast<__nv_bfloat16*>(sp), f);
             } else {
@@ -1262,7 +1274,7 @@ static int launch_halo(const HaloPlan& hp, const __nv_bfloat16* src, int H, int 
     Q.shift[t] = (unsigned short)((int)P.offh[t] * hp.Wp + (int)P.offw[t]);
     Q.wtap[t] = P.wtap[t];
   }
-  Q.out = P.out; Q.addend = P.addend; Q.stat_partial = P.stat_partial;
+  Q.out = P.out; Q.addend = P.addend; Q.addend_mask = P.addend_mask; Q.stat_partial = P.stat_partial;
   Q.addend_prefetch = P.addend_prefetch;
   Q.tma_store = hp.tma_store;
   Q.addend_tma = add_tma ? 1 : 0;
@@ -1303,10 +1315,32 @@ int tc2_conv_gather_gemm(const __nv_bfloat16* src, int srcH, int srcW, int srcC,
                                     st);
 }
 
+static int tc2_gather_gemm_impl(const __nv_bfloat16* src, int srcH, int srcW, int srcC, int rowH, int rowW, int nimg,
+                                const iic_conv_geom* g, int transposed, const __nv_bfloat16* wpacked, int N,
+                                const __nv_bfloat16* addend, const unsigned char* addend_mask, __nv_bfloat16* out,
+                                float* stat_partial, int stat_groups, cudaStream_t st);
+
 int tc2_conv_gather_gemm_stats(const __nv_bfloat16* src, int srcH, int srcW, int srcC, int rowH, int rowW, int nimg,
                                const iic_conv_geom* g, int transposed, const __nv_bfloat16* wpacked, int N,
                                const __nv_bfloat16* addend, __nv_bfloat16* out, float* stat_partial, int stat_groups,
                                cudaStream_t st) {
+  return tc2_gather_gemm_impl(src, srcH, srcW, srcC, rowH, rowW, nimg, g, transposed, wpacked, N, addend, nullptr, out,
+                              stat_partial, stat_groups, st);
+}
+
+// stride-1 dgrad whose addend passes only where its mask bit is set: dx = dgrad(dy) + (bit ? addend : 0).  The residual
+// gradient of a BasicBlock is d_out * (out > 0): with the ReLU mask of the block output kept as bits by the forward pass,
+// the BatchNorm backward no longer has to write the masked copy (2 B per element) for this epilogue to read back.
+int tc2_conv_dgrad_masked(const __nv_bfloat16* dy, const __nv_bfloat16* wpacked_t, const __nv_bfloat16* addend,
+                          const unsigned char* addend_mask, __nv_bfloat16* dx, const iic_conv_geom* g, cudaStream_t st) {
+  return tc2_gather_gemm_impl(dy, g->oh, g->ow, g->cout, g->h, g->w, g->n, g, 1, wpacked_t, g->cin, addend, addend_mask, dx,
+                              nullptr, 1, st);
+}
+
+static int tc2_gather_gemm_impl(const __nv_bfloat16* src, int srcH, int srcW, int srcC, int rowH, int rowW, int nimg,
+                                const iic_conv_geom* g, int transposed, const __nv_bfloat16* wpacked, int N,
+                                const __nv_bfloat16* addend, const unsigned char* addend_mask, __nv_bfloat16* out,
+                                float* stat_partial, int stat_groups, cudaStream_t st) {
   int rc = tma_init();
   if (rc != IIC_OK) return rc;
   const int bn = pick_bn2(N);
@@ -1341,7 +1375,7 @@ int tc2_conv_gather_gemm_stats(const __nv_bfloat16* src, int srcH, int srcW, int
   const bool mt2 = !resb && tc2_use_mt2(bn, N, P.rows);
   const int tile_rows = (resb || mt2) ? 2 * TC_BM : TC_BM;
   P.mtiles = (int)((P.rows + tile_rows - 1) / tile_rows);
-  P.out = out; P.addend = addend;
+  P.out = out; P.addend = addend; P.addend_mask = addend_mask;
   P.addend_prefetch = option(OPT_DGRAD_PREFETCH);
   P.stat_partial = stat_partial;
   IIC_REQUIRE(stat_groups == 1 || (stat_groups == 2 && nimg % 2 == 0), IIC_ERR_BAD_ARG, "conv stats: 1 or 2 views");

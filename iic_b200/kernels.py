@@ -408,12 +408,18 @@ def bn_stats_from_partials(partial, nblk, views, view, M, gamma, beta, eps, mome
   return ss, mi
 
 
-def conv_dgrad(dy, wpt, g, dt, addend=None):
+def conv_dgrad(dy, wpt, g, dt, addend=None, addend_mask=None):
+  """addend_mask (uint8 [pixels][cin / 8], bn_apply_views_mask's bits): the addend passes only where its bit is set."""
   _check_packed(wpt, g, dt)
   dx = torch.empty((g.n, g.h, g.w, g.cin), device=dy.device, dtype=_TORCH_DT[dt])
   with _timed("dgrad", g):
-    check(_lib.lib().iic_conv_dgrad(_p(dy), _p(wpt), _p(addend), _p(dx), ctypes.byref(g), dt, _stream()),
-          "iic_conv_dgrad")
+    if addend_mask is not None:
+      assert addend is not None and addend_mask.dtype == torch.uint8 and addend_mask.numel() * 8 == addend.numel()
+      check(_lib.lib().iic_conv_dgrad_masked(_p(dy), _p(wpt), _p(addend), _p(addend_mask), _p(dx), ctypes.byref(g), dt,
+                                             _stream()), "iic_conv_dgrad_masked")
+    else:
+      check(_lib.lib().iic_conv_dgrad(_p(dy), _p(wpt), _p(addend), _p(dx), ctypes.byref(g), dt, _stream()),
+            "iic_conv_dgrad")
   return dx
 
 

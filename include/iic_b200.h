@@ -219,6 +219,12 @@ int iic_bn_stats_from_partials_views(const float* stat_partial, int nblk, int sl
  * w is the kind-1 packed weight. */
 int iic_conv_dgrad(const void* dy, const void* w_packed_t, const void* addend, void* dx,
                    const iic_conv_geom* g, int dtype, void* stream);
+/* Same with an addend that only passes where its mask bit is set (bf16, stride 1, cin % 64 == 0): dx = dgrad(dy) +
+ * (bit ? addend : 0); addend_mask = [pixels][cin / 8] bytes, bit j of byte b = channel 8 b + j (the layout
+ * iic_bn_apply_views_mask writes).  The residual gradient of a BasicBlock, d_out * (out > 0) (residual.py:41-43 under
+ * autograd), is then never materialised. */
+int iic_conv_dgrad_masked(const void* dy, const void* w_packed_t, const void* addend, const unsigned char* addend_mask,
+                          void* dx, const iic_conv_geom* g, int dtype, void* stream);
 /* wgrad: dw_packed fp32 [cout][kh][kw][cin] = sum over pixels.  workspace: fp32, at least
  * iic_conv_wgrad_workspace(g, dtype) bytes (split-K partials; deterministic reduction). */
 long long iic_conv_wgrad_workspace(const iic_conv_geom* g, int dtype);

@@ -302,3 +302,46 @@ def test_bf16_block_with_relu_bitmask(cin, cout, stride, hw, n):
   assert torch.equal(o0, o1) and torch.equal(d0, d1)
   for a, b in zip(g0, g1):
     assert torch.equal(a, b)
+
+
+@pytest.mark.unvalidated
+@pytest.mark.parametrize("halo,mt2,addtma", [(2, 2, 1), (0, 0, 0), (2, 1, 0)])
+@pytest.mark.parametrize("cin,cout,stride,hw,n", [(64, 64, 1, 17, 5), (128, 128, 1, 13, 4), (256, 256, 1, 7, 3), (64, 128, 2, 17, 6),
+                                                  (128, 128, 1, 30, 2)])
+def test_bf16_block_with_masked_addend(cin, cout, stride, hw, n, halo, mt2, addtma):
+  """Engine switch masked_addend: the masked residual gradient is never written; conv1's dgrad epilogue (halo kernel with
+  the TMA-loaded or the per-lane addend, im2col kernel with one or two tiles per work item) or the downsample BatchNorm
+  backward apply the mask bits to d_out.  Bit-identical to the materialised copy."""
+  import torch.nn as nn
+  from iic_b200.archs import _engine as E
+  from iic_b200.archs.cluster.residual import BasicBlock
+  from iic_b200 import kernels as K
+  from iic_b200._lib import BF16
+  ds = None
+  if stride != 1 or cin != cout:
+    ds = nn.Sequential(E.ConvParams(cin, cout, 1, stride, 0), E.BNParams(cout, False))
+  blk = BasicBlock(cin, cout, stride, ds, track_running_stats=False)
+  weights.fill_state_dict(blk, salt=17)
+  blk.cuda()
+  x = torch.relu(weights.normal("madd.x", (2 * n, cin, hw, hw))).permute(0, 2, 3, 1).contiguous().cuda().bfloat16()
+  oh = (hw + 2 - 3) // stride + 1
+  dout = weights.normal("madd.d", (2 * n, oh, oh, cout)).cuda().bfloat16()
+  results = []
+  for flag in (False, True):
+    prev = (E.OPTIONS["bn_bitmask"], E.OPTIONS["masked_addend"])
+    E.OPTIONS["bn_bitmask"], E.OPTIONS["masked_addend"] = True, flag
+    try:
+      with K.options(conv_halo=halo, tc2_mt2=mt2, halo_addend_tma=addtma):
+        ctx = E._Ctx(BF16, True, True, groups=2)
+        out = E.block_forward(ctx, blk, x)
+        sink = E.GradSink()
+        dx = E.block_backward(ctx, sink, ctx.saved[-1], dout)
+        torch.cuda.synchronize()
+      results.append((out, dx, [sink.get(p).clone() for p in blk.parameters()]))
+    finally:
+      E.OPTIONS["bn_bitmask"], E.OPTIONS["masked_addend"] = prev
+  (o0, d0, g0), (o1, d1, g1) = results
+  assert torch.equal(o0, o1)
+  assert torch.equal(d0, d1), "max |diff| %g" % (d0.float() - d1.float()).abs().max().item()
+  for a, b in zip(g0, g1):
+    assert torch.equal(a, b)
