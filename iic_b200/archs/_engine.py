@@ -185,6 +185,11 @@ OPTIONS = {
   # branch; conv1's dgrad epilogue (iic_conv_dgrad_masked) or the downsample BatchNorm backward read d_out and the mask bits.
   # 3.1 GB less written per c4 step.  Written after the last GPU session: off until it has run on hardware.
   "masked_addend": os.environ.get("IIC_MASKED_ADDEND", "0") != "0",
+  # stem_bwd_dy: max-pool routing + ReLU + BatchNorm backward of the 5g stem in two passes over (y, dpool) that write dy for
+  # the (tensor-core) stem wgrad: the routed gradient and the BatchNorm reduce sweep never touch memory (7.5 GB instead of
+  # 13.7 GB at the c4 shape).  The first two passes of stem_bwd_fused, whose SIMT wgrad pass was what made it slow.
+  # Written after the last GPU session: off until it has run on hardware.
+  "stem_bwd_dy": os.environ.get("IIC_STEM_BWD_DY", "0") != "0",
 }
 _WSTREAMS = {}
 
@@ -386,11 +391,19 @@ def stem_backward(ctx, sink, rec, d_out):
                             pool_pad, ctx.dt)
     assert done
     return None
-  if pool_pad is not None:
-    gmask = _bn_relu_maxpool_bwd(ctx, y, ss, d_out, pool_pad)
-    dy, _ = _bn_backward(ctx, sink, bn, gmask, None, y, mi, False)
-  else:
-    dy, _ = _bn_backward(ctx, sink, bn, d_out, None, y, mi, False, mask_ss=ss)
+  dy = None
+  if (pool_pad is not None and OPTIONS["stem_bwd_dy"] and hasattr(ss, "stacked") and hasattr(mi, "stacked")
+      and d_out.is_contiguous() and K.stem_bwd_fused_workspace(g, pool_pad, ss.stacked.shape[0], ctx.dt) > 0):
+    dg, acc1 = sink.buf(bn.weight)
+    db, acc2 = sink.buf(bn.bias)
+    assert acc1 == acc2
+    dy = K.stem_bwd_dy(y, d_out, ss.stacked, mi.stacked, bn.weight.detach(), dg, db, acc1, g, pool_pad, ctx.dt)
+  if dy is None:
+    if pool_pad is not None:
+      gmask = _bn_relu_maxpool_bwd(ctx, y, ss, d_out, pool_pad)
+      dy, _ = _bn_backward(ctx, sink, bn, gmask, None, y, mi, False)
+    else:
+      dy, _ = _bn_backward(ctx, sink, bn, d_out, None, y, mi, False, mask_ss=ss)
   gw, acc = sink.buf(conv.weight)
   K.stem_wgrad(x_nchw, dy, g, ctx.dt, gw, acc)
   return None

@@ -30,6 +30,17 @@ __device__ __forceinline__ void load4(const __nv_bfloat16* p, float (&f)[4]) {
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
 }
 
+__device__ __forceinline__ void store4(float* p, const float (&f)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&f)[4]) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+  uint2 v;
+  v.x = *reinterpret_cast<const uint32_t*>(&a);
+  v.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = v;
+}
+
 struct StemBwdArgs {
   const float* x;     // [n][cin][H][W] network input (fp32, NCHW)
   const void* y;      // [n][H][W][64] stem conv output
@@ -43,6 +54,7 @@ struct StemBwdArgs {
   float* partialA;  // [gridA][128]
   double* sums;     // [views][128]: sum g, sum g*yhat
   float* partialB;  // [gridB][64 * cin * 9]
+  void* dy_out;     // stem_bwd_dy_kernel: [n][H][W][64] gradient of the conv output, storage type
 };
 
 // One pooling window x 4 channels: loads dpool and the window's valid pixels of y, returns the routed and ReLU-masked
@@ -248,6 +260,63 @@ __global__ void __launch_bounds__(256) stem_bwd_wgrad_kernel(StemBwdArgs p) {
   }
 }
 
+// Pass B without the weight gradient (iic_stem_bwd_dy): the gradient of the conv output is WRITTEN (storage type) for the
+// tcgen05 stem wgrad (stem_tc.cu) to read -- the routed gradient g and the BatchNorm reduce sweep over (y, g) still never
+// touch memory: 7.5 GB instead of the chain's 13.7 GB at the c4 shape.  Every pixel belongs to exactly one pooling window
+// (the plan requires the windows to cover the image), so dy is written exactly once.
+template <typename T>
+__global__ void __launch_bounds__(256) stem_bwd_dy_kernel(StemBwdArgs p) {
+  const int Gv = gridDim.x / p.views, v = blockIdx.x / Gv, lb = blockIdx.x % Gv;
+  const int cg = threadIdx.x & 15, wslot = threadIdx.x >> 4;
+  const long long Wv = (long long)(p.n / p.views) * p.oh * p.ow;
+  const T* y = (const T*)p.y;
+  const T* dpool = (const T*)p.dpool;
+  T* dyo = (T*)p.dy_out;
+  const double invM = 1.0 / (double)((long long)(p.n / p.views) * p.H * p.W);  // BatchNorm rows per view
+  float sc[4], sh[4], cA[4], cB[4], cC[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = cg * 4 + j;
+    sc[j] = p.ss[v * 128 + c];
+    sh[j] = p.ss[v * 128 + 64 + c];
+    const float mean = p.mi[v * 128 + c], istd = p.mi[v * 128 + 64 + c];
+    const float m1 = (float)(p.sums[v * 128 + c] * invM), m2 = (float)(p.sums[v * 128 + 64 + c] * invM);
+    const float A = p.gamma[c] * istd;
+    cA[j] = A;
+    cB[j] = -A * m2 * istd;
+    cC[j] = -A * m1 + A * m2 * istd * mean;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 64) {  // d gamma = sum g*yhat, d beta = sum g, over all views
+    const int c = threadIdx.x;
+    double db = 0.0, dg = 0.0;
+    for (int q = 0; q < p.views; ++q) {
+      db += p.sums[q * 128 + c];
+      dg += p.sums[q * 128 + 64 + c];
+    }
+    if (p.dgamma) p.dgamma[c] = p.bn_accumulate ? p.dgamma[c] + (float)dg : (float)dg;
+    if (p.dbeta) p.dbeta[c] = p.bn_accumulate ? p.dbeta[c] + (float)db : (float)db;
+  }
+  for (long long wl = (long long)lb * 16 + wslot; wl < Wv; wl += (long long)Gv * 16) {
+    const long long wi = (long long)v * Wv + wl;
+    const int ox = (int)(wi % p.ow);
+    const long long t = wi / p.ow;
+    const int oy = (int)(t % p.oh);
+    const int img = (int)(t / p.oh);
+    float yv[4][4], g[4][4];
+    bool valid[4];
+    window_grad<T>(y, dpool, img, oy, ox, p.H, p.W, p.oh, p.ow, p.pad, cg, sc, sh, yv, valid, g);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (!valid[q]) continue;
+      const int iy = oy * 2 - p.pad + (q >> 1), ix = ox * 2 - p.pad + (q & 1);
+      float d[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) d[j] = fmaf(cA[j], g[q][j], fmaf(cB[j], yv[q][j], cC[j]));
+      store4(dyo + (((long long)img * p.H + iy) * p.W + ix) * 64 + cg * 4, d);
+    }
+  }
+}
+
 // Second version of pass B (option stem_bwd_v2): the input neighbourhood is fetched cooperatively by the half-warp and
 // broadcast with shuffles (v1 issued 16 * CIN dependent broadcast loads per thread and window and was latency bound).
 template <typename T, int CIN>
@@ -440,6 +509,37 @@ static int stem_bwd_launch(const StemBwdPlan& pl, StemBwdArgs& a, int cin, float
 }  // namespace iic
 
 using namespace iic;
+
+extern "C" int iic_stem_bwd_dy(const void* y, const void* dpool, const float* ss, const float* mi, const float* gamma, float* dgamma,
+                               float* dbeta, int bn_accumulate, void* dy_out, const iic_conv_geom* g, int pool_pad, int views,
+                               int dtype, void* workspace, long long workspace_bytes, void* stream) {
+  const StemBwdPlan pl = stem_bwd_plan(g, pool_pad, views, dtype);
+  IIC_REQUIRE(pl.ok, IIC_ERR_UNSUPPORTED,
+              "iic_stem_bwd_dy: needs conv 3x3/s1/p1 with cin 1 or 2 -> 64, MaxPool(2,2,pad 0|1) covering every pixel, 1-2 views");
+  IIC_REQUIRE(y && dpool && ss && mi && gamma && dy_out && workspace, IIC_ERR_BAD_ARG, "iic_stem_bwd_dy: null pointer");
+  IIC_REQUIRE(workspace_bytes >= pl.bytes, IIC_ERR_BAD_ARG, "iic_stem_bwd_dy: workspace too small (%lld < %lld)", workspace_bytes,
+              pl.bytes);
+  StemBwdArgs a = {};
+  a.y = y; a.dpool = dpool; a.ss = ss; a.mi = mi; a.gamma = gamma;
+  a.dgamma = dgamma; a.dbeta = dbeta; a.bn_accumulate = bn_accumulate; a.dy_out = dy_out;
+  a.n = g->n; a.H = g->h; a.W = g->w; a.pad = pool_pad;
+  a.oh = (g->h + 2 * pool_pad - 2) / 2 + 1; a.ow = (g->w + 2 * pool_pad - 2) / 2 + 1; a.views = views;
+  char* ws = (char*)workspace;
+  a.partialA = (float*)(ws + pl.offA); a.sums = (double*)(ws + pl.offS);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == IIC_F32) stem_bwd_reduce_kernel<float><<<pl.gridA, 256, 0, st>>>(a);
+  else stem_bwd_reduce_kernel<__nv_bfloat16><<<pl.gridA, 256, 0, st>>>(a);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  stem_bwd_fold_kernel<<<cdiv(a.views * 128, 8), 256, 0, st>>>(a.partialA, a.sums, pl.gridA / a.views, a.views);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  if (dtype == IIC_F32) stem_bwd_dy_kernel<float><<<pl.gridA, 256, 0, st>>>(a);
+  else stem_bwd_dy_kernel<__nv_bfloat16><<<pl.gridA, 256, 0, st>>>(a);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
 
 extern "C" long long iic_stem_bwd_fused_workspace(const iic_conv_geom* g, int pool_pad, int views, int dtype) {
   const StemBwdPlan pl = stem_bwd_plan(g, pool_pad, views, dtype);

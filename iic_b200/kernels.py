@@ -492,6 +492,23 @@ def stem_bwd_fused_workspace(g, pool_pad, views, dt):
   return int(_lib.lib().iic_stem_bwd_fused_workspace(ctypes.byref(g), pool_pad, views, dt))
 
 
+@_cat("stem_bwd_dy")
+def stem_bwd_dy(y, dpool, ss, mi, gamma, dgamma, dbeta, bn_accumulate, g, pool_pad, dt):
+  """Max-pool routing + ReLU + BatchNorm backward of the stem in two passes over (y, dpool) -> dy (csrc/stem_bwd.cu:
+  iic_stem_bwd_dy).  ss, mi: [views, 128] stacked per-view BN coefficients.  Returns None if the geometry is unsupported."""
+  views = ss.shape[0]
+  nbytes = stem_bwd_fused_workspace(g, pool_pad, views, dt)
+  if nbytes <= 0:
+    return None
+  assert ss.is_contiguous() and mi.is_contiguous() and ss.shape == mi.shape == (views, 128)
+  assert y.is_contiguous() and dpool.is_contiguous() and iic_dtype(y) == dt == iic_dtype(dpool)
+  ws = torch.empty(nbytes, device=y.device, dtype=torch.uint8)
+  dy = torch.empty_like(y)
+  check(_lib.lib().iic_stem_bwd_dy(_p(y), _p(dpool), _p(ss), _p(mi), _p(gamma), _p(dgamma), _p(dbeta), int(bool(bn_accumulate)),
+                                   _p(dy), ctypes.byref(g), pool_pad, views, dt, _p(ws), nbytes, _stream()), "iic_stem_bwd_dy")
+  return dy
+
+
 @_cat("stem_bwd_fused")
 def stem_bwd_fused(x_nchw, y, dpool, ss, mi, gamma, dgamma, dbeta, bn_accumulate, grad_w, w_accumulate, g, pool_pad, dt):
   """Backward of conv3x3 -> BN -> ReLU -> MaxPool(2,2,pool_pad) of the stem in two passes (csrc/stem_bwd.cu).

@@ -281,6 +281,12 @@ int iic_stem_bwd_fused(const float* x_nchw, const void* y, const void* dpool, co
                        const float* gamma, float* dgamma, float* dbeta, int bn_accumulate, float* dw_oihw,
                        int w_accumulate, const iic_conv_geom* g, int pool_pad, int views, int dtype, void* workspace,
                        long long workspace_bytes, void* stream);
+/* The first two thirds of the same backward: max-pool routing, ReLU and BatchNorm backward in two passes over (y, dpool),
+ * writing dy (gradient of the conv output, storage type) for iic_stem_wgrad / iic_stem_wgrad_tc; the routed gradient and the
+ * BatchNorm reduce sweep never touch memory.  Same geometry conditions and workspace as iic_stem_bwd_fused. */
+int iic_stem_bwd_dy(const void* y, const void* dpool, const float* scale_shift, const float* mean_invstd, const float* gamma,
+                    float* dgamma, float* dbeta, int bn_accumulate, void* dy_out, const iic_conv_geom* g, int pool_pad,
+                    int views, int dtype, void* workspace, long long workspace_bytes, void* stream);
 
 /* ---- BatchNorm2d, train mode (net5g.py:24, residual.py:20,23,56, vgg.py:28-29): statistics
  *      are per forward call over all M = n*h*w rows.

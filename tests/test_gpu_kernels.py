@@ -712,6 +712,55 @@ def test_stem_backward_fused_matches_chain_and_autograd(mode, cin, hw, pool_pad,
     assert torch.allclose(db2.cpu().double(), br.grad, rtol=0, atol=1e-3 * br.grad.abs().max().item())
 
 
+@pytest.mark.unvalidated
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("cin,hw,pool_pad,views,n", [(2, 32, 1, 2, 6), (2, 96, 1, 2, 4), (1, 24, 0, 1, 3), (2, 20, 0, 2, 2),
+                                                     (2, 18, 1, 1, 5)])
+def test_stem_backward_dy_matches_chain(mode, cin, hw, pool_pad, views, n):
+  """iic_stem_bwd_dy (max-pool routing + ReLU + BatchNorm backward in two passes over (y, dpool), dy written) against the
+  two-kernel chain it replaces: dy, dgamma, dbeta, accumulate flag."""
+  K = _K()
+  from iic_b200._lib import BF16, F32
+  dt, tdt = (F32, torch.float32) if mode == "fp32" else (BF16, torch.bfloat16)
+  g = torch.Generator().manual_seed(78)
+  x = torch.randn(n, cin, hw, hw, generator=g).cuda()
+  if views == 2:
+    x[n // 2:] = x[n // 2:] * 1.7 + 0.4
+  w = (torch.randn(64, cin, 3, 3, generator=g) * math.sqrt(2.0 / (cin * 9))).cuda()
+  gamma = (torch.rand(64, generator=g) + 0.5).cuda()
+  beta = (torch.randn(64, generator=g) * 0.2).cuda()
+  geo = K.conv_geom(n, hw, hw, cin, 64, 3, 3, 1, 1, 1)
+  old = K.STEM_FPROP_TC["on"]
+  K.STEM_FPROP_TC["on"] = False
+  try:
+    y = K.stem_fprop(x, w, geo, dt)
+  finally:
+    K.STEM_FPROP_TC["on"] = old
+  nv = n // views
+  ss = torch.empty(views, 128, device="cuda")
+  mi = torch.empty(views, 128, device="cuda")
+  for v in range(views):
+    K.bn_stats(y[v * nv:(v + 1) * nv], gamma, beta, 1e-5, 0.1, None, None, False, ss=ss[v], mi=mi[v])
+  oh = (hw + 2 * pool_pad - 2) // 2 + 1
+  dpool = torch.randn(n, oh, oh, 64, generator=g).cuda().to(tdt)
+  gmask = torch.empty_like(y)
+  for v in range(views):
+    K.bn_relu_maxpool_bwd(y[v * nv:(v + 1) * nv], ss[v], dpool[v * nv:(v + 1) * nv], pool_pad, out=gmask[v * nv:(v + 1) * nv])
+  dg1, db1 = torch.zeros(64).cuda(), torch.zeros(64).cuda()
+  dy1, _ = K.bn_bwd_fused(gmask, None, y, [mi[v] for v in range(views)], gamma, dg1, db1, False, False)
+  dg2, db2 = torch.full((64,), 7.0).cuda(), torch.full((64,), 7.0).cuda()
+  dy2 = K.stem_bwd_dy(y, dpool, ss, mi, gamma, dg2, db2, False, geo, pool_pad, dt)
+  assert dy2 is not None
+  torch.cuda.synchronize()
+  sg, sb, sd = dg1.abs().max().item(), db1.abs().max().item(), dy1.float().abs().max().item()
+  assert (dg2 - dg1).abs().max().item() <= 2e-4 * sg + 1e-5
+  assert (db2 - db1).abs().max().item() <= 2e-4 * sb + 1e-5
+  dtol = 2e-5 if mode == "fp32" else 1e-2  # (bf16: one rounding of dy; the coefficients differ in the last fp32 bits)
+  assert (dy2.float() - dy1.float()).abs().max().item() <= dtol * sd
+  dy3 = K.stem_bwd_dy(y, dpool, ss, mi, gamma, dg2, db2, True, geo, pool_pad, dt)
+  assert (dg2 - 2 * dg1).abs().max().item() <= 4e-4 * sg + 2e-5 and torch.equal(dy3, dy2)
+
+
 def test_stem_backward_fused_reports_unsupported_geometries():
   K = _K()
   from iic_b200._lib import BF16
