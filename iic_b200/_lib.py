@@ -84,8 +84,8 @@ _SIGS = {
   "iic_pack_weights_batched": (c_int, [_P, c_int, c_int, _P]),
   "iic_stem_bwd_fused_workspace": (c_longlong, [POINTER(ConvGeom), c_int, c_int, c_int]),
   "iic_stem_bwd_fused": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, c_int, POINTER(ConvGeom), c_int, c_int, c_int, _P,
-  "iic_stem_bwd_dy": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, _P, POINTER(ConvGeom), c_int, c_int, c_int, _P, c_longlong, _P]),
                                  c_longlong, _P]),
+  "iic_stem_bwd_dy": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, _P, POINTER(ConvGeom), c_int, c_int, c_int, _P, c_longlong, _P]),
   "iic_stem_fprop_stats_blocks": (c_int, [POINTER(ConvGeom), c_int, c_int]),
   "iic_stem_fprop_stats": (c_int, [_P, _P, _P, POINTER(ConvGeom), c_int, c_int, _P, _P]),
   "iic_argmax_rows": (c_int, [_P, c_longlong, c_int, _P, _P]),
