@@ -598,7 +598,7 @@ def run_ours(args):
     from iic_b200.archs import _engine
     variants = {k: kernels.get_option(k) for k in ("conv_halo", "conv_halo_wgrad", "conv_halo_store", "stem_quad",
                                                    "dgrad_prefetch", "tc2_mt2", "conv_halo_stats", "bn_bwd_ctas",
-                                                   "tf32x3_raw_hi", "wgrad_mt", "halo_addend_tma")}
+                                                   "tf32x3_raw_hi", "wgrad_mt", "halo_addend_tma", "dgrad_s2_mt")}
     variants.update({k: int(v) for k, v in _engine.OPTIONS.items()})
     variants.update({"stem_wgrad_tc": int(kernels.STEM_WGRAD_TC["on"]), "wgrad_fused_unpack": int(kernels.WGRAD_FUSED_UNPACK["on"]),
                      "seg_joint_tc": int(kernels.SEG_JOINT_TC["on"]), "seg_corr_tc": int(kernels.SEG_CORR_TC["on"])})

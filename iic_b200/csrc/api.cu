@@ -71,6 +71,10 @@ static Option g_opts[OPT_COUNT] = {
     // B200 in round 2 (exact-integer tests; the six layer-1 dgrads of the c4 step 2.12 -> 1.85 ms, profiles/r02_session_i.md);
     // 0 = per-lane loads (option dgrad_prefetch).
     {"halo_addend_tma", "IIC_HALO_ADDEND_TMA", 1, 0, false},
+    // dgrad_s2_mt: the four parity-class launches of a stride-2 dgrad use the resident-weights (N = 64) / two-tile
+    // (N = 128) variants of the stride-1 path (2 = also at sizes where they would not pay: tests).  Written after the last
+    // GPU session: off until it has run on hardware.
+    {"dgrad_s2_mt", "IIC_DGRAD_S2_MT", 0, 0, false},
 };
 
 int option(int id) {

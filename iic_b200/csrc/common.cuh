@@ -135,7 +135,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 int device_sm_count();
 void count_launch();
 // runtime kernel-variant switches (api.cu); defaults from the environment, iic_set_option overrides
-enum { OPT_CONV_HALO = 0, OPT_CONV_HALO_WGRAD = 1, OPT_STEM_QUAD = 2, OPT_DGRAD_PREFETCH = 3, OPT_TC2_MT2 = 4, OPT_HALO_STORE = 5, OPT_STEM_BWD_V2 = 6, OPT_HALO_STATS = 7, OPT_BN_BWD_CTAS = 8, OPT_TF32X3_RAW_HI = 9, OPT_WGRAD_MT = 10, OPT_HALO_ADDEND_TMA = 11, OPT_COUNT = 12 };
+enum { OPT_CONV_HALO = 0, OPT_CONV_HALO_WGRAD = 1, OPT_STEM_QUAD = 2, OPT_DGRAD_PREFETCH = 3, OPT_TC2_MT2 = 4, OPT_HALO_STORE = 5, OPT_STEM_BWD_V2 = 6, OPT_HALO_STATS = 7, OPT_BN_BWD_CTAS = 8, OPT_TF32X3_RAW_HI = 9, OPT_WGRAD_MT = 10, OPT_HALO_ADDEND_TMA = 11, OPT_DGRAD_S2_MT = 12, OPT_COUNT = 13 };
 int option(int id);
 
 }  // namespace iic

@@ -1510,7 +1510,16 @@ int tc2_conv_dgrad_s2(const __nv_bfloat16* dy, const __nv_bfloat16* wpacked_t, c
         }
       P.scatter = 1; P.outH = g->h; P.outW = g->w; P.py = py; P.px = px;
       P.srcC = g->cout; P.Ktot = P.ntaps * g->cout; P.N = g->cin;
-      P.mtiles = (int)((P.rows + TC_BM - 1) / TC_BM); P.ntiles = g->cin / bn; P.splits = 1; P.total_kb = P.Ktot / 64;
+      P.ntiles = g->cin / bn; P.splits = 1; P.total_kb = P.Ktot / 64;
+      // option dgrad_s2_mt: the parity classes take the resident-weights / two-tile variants of the stride-1 path (N = 64:
+      // the class's whole weight slice stays in shared memory, 24 -> 16 KB of fill per MMA set; N = 128: two tiles per
+      // weight k-block); 2 = whatever the amount of work (tests)
+      const int s2mt = option(OPT_DGRAD_S2_MT);
+      const bool resb = s2mt != 0 && bn == 64 && g->cin == 64 && P.total_kb * (64 * 128) <= 80 * 1024 &&
+                        (s2mt >= 2 || tc2_use_resb(bn, g->cin, P.total_kb, P.rows));
+      const bool mt2 = s2mt != 0 && !resb && tc2_use_mt2(bn, g->cin, P.rows);
+      const int tile_rows = (resb || mt2) ? 2 * TC_BM : TC_BM;
+      P.mtiles = (int)((P.rows + tile_rows - 1) / tile_rows);
       P.out = dx; P.addend = addend;  // (classes without taps keep the pre-filled addend / zero)
       P.addend_prefetch = option(OPT_DGRAD_PREFETCH);
       // base positions per dim must number Hc / Wc: upper = lower + (Hc - H_dy)
@@ -1518,9 +1527,11 @@ int tc2_conv_dgrad_s2(const __nv_bfloat16* dy, const __nv_bfloat16* wpacked_t, c
       IIC_REQUIRE(lo_h >= -128 && up_h <= 127 && lo_w >= -128 && up_w <= 127 && up_h >= -128 && up_w >= -128,
                   IIC_ERR_UNSUPPORTED, "im2col corner range");
       alignas(64) CUtensorMap tmA;
-      rc = make_im2col_map2(&tmA, dy, g->n, g->oh, g->ow, g->cout, lo_w, lo_h, up_w, up_h, 1, TC_BM);
+      rc = make_im2col_map2(&tmA, dy, g->n, g->oh, g->ow, g->cout, lo_w, lo_h, up_w, up_h, 1, tile_rows);
       if (rc != IIC_OK) return rc;
-      switch (bn) {
+      if (resb) rc = launch_tc2_impl<M2_FPROP, 64, true>(tmA, tmB, P, 1, st);
+      else if (mt2) rc = launch_tc2_impl<M2_FPROP, 128, false, 2>(tmA, tmB, P, 1, st);
+      else switch (bn) {
         case 256: rc = launch_tc2<M2_FPROP, 256>(tmA, tmB, P, 1, st); break;
         case 128: rc = launch_tc2<M2_FPROP, 128>(tmA, tmB, P, 1, st); break;
         default: rc = launch_tc2<M2_FPROP, 64>(tmA, tmB, P, 1, st); break;

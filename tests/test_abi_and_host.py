@@ -90,12 +90,12 @@ def test_default_kernel_variants_are_the_validated_set():
   import sys
   code = ("import json, iic_b200.kernels as K, iic_b200.archs._engine as E;"
           "print(json.dumps([{n: K.get_option(n) for n in ('conv_halo','conv_halo_wgrad','conv_halo_store','tc2_mt2',"
-          "'dgrad_prefetch','stem_quad','stem_bwd_v2','conv_halo_stats','bn_bwd_ctas','tf32x3_raw_hi','wgrad_mt','halo_addend_tma')}, E.OPTIONS]))")
+          "'dgrad_prefetch','stem_quad','stem_bwd_v2','conv_halo_stats','bn_bwd_ctas','tf32x3_raw_hi','wgrad_mt','halo_addend_tma','dgrad_s2_mt')}, E.OPTIONS]))")
   env = {k: v for k, v in os.environ.items() if not k.startswith("IIC_")}
   out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, check=True).stdout
   import json
   lib_opts, host_opts = json.loads(out.strip().splitlines()[-1])
   assert lib_opts == {"conv_halo": 1, "conv_halo_wgrad": 1, "conv_halo_store": 1, "tc2_mt2": 1, "dgrad_prefetch": 1,
-                      "stem_quad": 2, "stem_bwd_v2": 0, "conv_halo_stats": 1, "bn_bwd_ctas": 2, "tf32x3_raw_hi": 1, "wgrad_mt": 1, "halo_addend_tma": 1}
+                      "stem_quad": 2, "stem_bwd_v2": 0, "conv_halo_stats": 1, "bn_bwd_ctas": 2, "tf32x3_raw_hi": 1, "wgrad_mt": 1, "halo_addend_tma": 1, "dgrad_s2_mt": 0}
   assert host_opts == {"bn_merged": True, "stem_stats": True, "pack_batched": True, "stem_bwd_fused": False, "bn_bitmask": True,
                        "wgrad_stream": False, "masked_addend": False, "stem_bwd_dy": False}

@@ -625,7 +625,7 @@ def test_halo_kernels_forced_exact_small_integers(n, h, variant):
 
 def test_runtime_options_roundtrip():
   K = _K()
-  for name in ("conv_halo", "conv_halo_wgrad", "stem_quad", "dgrad_prefetch", "tc2_mt2", "conv_halo_store", "stem_bwd_v2", "bn_bwd_ctas", "conv_halo_stats", "tf32x3_raw_hi", "wgrad_mt", "halo_addend_tma"):
+  for name in ("conv_halo", "conv_halo_wgrad", "stem_quad", "dgrad_prefetch", "tc2_mt2", "conv_halo_store", "stem_bwd_v2", "bn_bwd_ctas", "conv_halo_stats", "tf32x3_raw_hi", "wgrad_mt", "halo_addend_tma", "dgrad_s2_mt"):
     v = K.get_option(name)
     with K.options(**{name: 0}):
       assert K.get_option(name) == 0
@@ -963,3 +963,34 @@ def test_stem_fprop_on_tensor_cores(cin, k, pad, hw, n, views):
     assert torch.allclose(tot[v, 1], s2, rtol=1e-4, atol=0)
   if views == 1:
     assert float(tot[1].abs().max()) == 0.0
+
+
+@pytest.mark.unvalidated
+@pytest.mark.parametrize("n,h,cin,cout,k,p", [(4, 25, 64, 128, 3, 1), (3, 49, 64, 128, 3, 1), (3, 25, 128, 256, 3, 1), (2, 24, 64, 128, 5, 2),
+                                              (3, 25, 64, 128, 1, 0), (2, 13, 256, 512, 3, 1)])
+def test_stride2_dgrad_resident_and_two_tile_variants_exact(n, h, cin, cout, k, p):
+  """Option dgrad_s2_mt = 2: every parity class of a stride-2 dgrad through the resident-weights (cin 64) or two-tile
+  (cin 128, with tc2_mt2 = 2) kernels, scattering epilogue with and without addend: exact on small integers and
+  bit-identical to the one-tile launches."""
+  K = _K()
+  from iic_b200._lib import BF16
+  g = torch.Generator().manual_seed(300 + h + cin)
+  w = torch.randint(-1, 2, (cout, cin, k, k), generator=g).float()
+  geo = K.conv_geom(n, h, h, cin, cout, k, k, 2, p, 1)
+  dy = torch.randint(-1, 2, (n, cout, geo.oh, geo.ow), generator=g).float()
+  add = torch.randint(-2, 3, (n, cin, h, h), generator=g).float()
+  xr = torch.zeros(n, cin, h, h, dtype=torch.float64, requires_grad=True)
+  F.conv2d(xr, w.double(), None, 2, p).backward(dy.double())
+  assert xr.grad.abs().max() <= 250
+  dyh, addh = to_nhwc(dy.cuda(), torch.bfloat16), to_nhwc(add.cuda(), torch.bfloat16)
+  wp1 = K.pack_weight(w.cuda(), BF16, 1)
+  outs = []
+  for mode in (0, 2):
+    with K.options(dgrad_s2_mt=mode, tc2_mt2=2 if mode else 1):
+      dx = K.conv_dgrad(dyh, wp1, geo, BF16)
+      dx2 = K.conv_dgrad(dyh, wp1, geo, BF16, addend=addh)
+      torch.cuda.synchronize()
+    outs.append((dx, dx2))
+  for dx, dx2 in outs:
+    assert torch.equal(from_nhwc(dx).cpu(), xr.grad.float())
+    assert torch.equal(from_nhwc(dx2).cpu(), (xr.grad + add.double()).float())
