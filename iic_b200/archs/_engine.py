@@ -183,8 +183,9 @@ OPTIONS = {
   "wgrad_stream": os.environ.get("IIC_WGRAD_STREAM", "0") != "0",
   # masked_addend (needs bn_bitmask): the bn2 backward of a residual block does not write d_out * (out > 0) for the residual
   # branch; conv1's dgrad epilogue (iic_conv_dgrad_masked) or the downsample BatchNorm backward read d_out and the mask bits.
-  # 3.1 GB less written per c4 step.  Written after the last GPU session: off until it has run on hardware.
-  "masked_addend": os.environ.get("IIC_MASKED_ADDEND", "0") != "0",
+  # 3.1 GB less written per c4 step.  Validated on a B200 in round 2 (bit-identical block backward in 45 kernel / option
+  # combinations, step / precision / net suites and smoke green with it; bn_bwd 7.95 -> 7.50 ms, profiles/r02_session_k.md).
+  "masked_addend": os.environ.get("IIC_MASKED_ADDEND", "1") != "0",
   # stem_bwd_dy: max-pool routing + ReLU + BatchNorm backward of the 5g stem in two passes over (y, dpool) that write dy for
   # the (tensor-core) stem wgrad: the routed gradient and the BatchNorm reduce sweep never touch memory (7.5 GB instead of
   # 13.7 GB at the c4 shape).  The first two passes of stem_bwd_fused, whose SIMT wgrad pass was what made it slow.

@@ -98,4 +98,4 @@ def test_default_kernel_variants_are_the_validated_set():
   assert lib_opts == {"conv_halo": 1, "conv_halo_wgrad": 1, "conv_halo_store": 1, "tc2_mt2": 1, "dgrad_prefetch": 1,
                       "stem_quad": 2, "stem_bwd_v2": 0, "conv_halo_stats": 1, "bn_bwd_ctas": 2, "tf32x3_raw_hi": 1, "wgrad_mt": 1, "halo_addend_tma": 1, "dgrad_s2_mt": 0}
   assert host_opts == {"bn_merged": True, "stem_stats": True, "pack_batched": True, "stem_bwd_fused": False, "bn_bitmask": True,
-                       "wgrad_stream": False, "masked_addend": False, "stem_bwd_dy": False}
+                       "wgrad_stream": False, "masked_addend": True, "stem_bwd_dy": False}

@@ -304,7 +304,6 @@ def test_bf16_block_with_relu_bitmask(cin, cout, stride, hw, n):
     assert torch.equal(a, b)
 
 
-@pytest.mark.unvalidated
 @pytest.mark.parametrize("halo,mt2,addtma", [(2, 2, 1), (0, 0, 0), (2, 1, 0)])
 @pytest.mark.parametrize("cin,cout,stride,hw,n", [(64, 64, 1, 17, 5), (128, 128, 1, 13, 4), (256, 256, 1, 7, 3), (64, 128, 2, 17, 6),
                                                   (128, 128, 1, 30, 2)])
