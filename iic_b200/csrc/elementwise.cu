@@ -335,12 +335,21 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const T* __restric
   const int cg = C >> 3;
   const long long total = (long long)n * oh * ow * cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % cg);
-    long long p = i / cg;
-    const int ox = (int)(p % ow);
-    p /= ow;
-    const int oy = (int)(p % oh);
-    const int ni = (int)(p / oh);
+    int c8, ox, oy, ni;
+    if (total <= 0xffffffffll) {  // (the usual case: 32-bit divisions; the 64-bit ones cost more than the memory traffic)
+      unsigned u = (unsigned)i;
+      c8 = (int)(u % (unsigned)cg); u /= (unsigned)cg;
+      ox = (int)(u % (unsigned)ow); u /= (unsigned)ow;
+      oy = (int)(u % (unsigned)oh);
+      ni = (int)(u / (unsigned)oh);
+    } else {
+      c8 = (int)(i % cg);
+      long long p = i / cg;
+      ox = (int)(p % ow);
+      p /= ow;
+      oy = (int)(p % oh);
+      ni = (int)(p / oh);
+    }
     float sc[8], sh[8], m[8];
     load8(ss + c8 * 8, sc);
     load8(ss + C + c8 * 8, sh);
@@ -371,12 +380,21 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_bwd_kernel(const T* __res
   const int cg = C >> 3;
   const long long total = (long long)n * oh * ow * cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % cg);
-    long long p = i / cg;
-    const int ox = (int)(p % ow);
-    p /= ow;
-    const int oy = (int)(p % oh);
-    const int ni = (int)(p / oh);
+    int c8, ox, oy, ni;
+    if (total <= 0xffffffffll) {  // (the usual case: 32-bit divisions; the 64-bit ones cost more than the memory traffic)
+      unsigned u = (unsigned)i;
+      c8 = (int)(u % (unsigned)cg); u /= (unsigned)cg;
+      ox = (int)(u % (unsigned)ow); u /= (unsigned)ow;
+      oy = (int)(u % (unsigned)oh);
+      ni = (int)(u / (unsigned)oh);
+    } else {
+      c8 = (int)(i % cg);
+      long long p = i / cg;
+      ox = (int)(p % ow);
+      p /= ow;
+      oy = (int)(p % oh);
+      ni = (int)(p / oh);
+    }
     float sc[8], sh[8], m[8], dp[8];
     int arg[8];
     load8(ss + c8 * 8, sc);
@@ -832,9 +850,19 @@ template <typename T>
 __global__ void grey_sobel_kernel(const T* __restrict__ in, float* __restrict__ out, int n, int h, int w) {
   const long long total = (long long)n * h * w, plane = (long long)h * w;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % w);
-    const int y = (int)((i / w) % h);
-    const long long ni = i / plane;
+    int x, y;
+    long long ni;
+    if (total <= 0xffffffffll) {  // 32-bit divisions
+      const unsigned u = (unsigned)i, row = u / (unsigned)w;
+      x = (int)(u - row * (unsigned)w);
+      const unsigned im = row / (unsigned)h;
+      y = (int)(row - im * (unsigned)h);
+      ni = im;
+    } else {
+      x = (int)(i % w);
+      y = (int)((i / w) % h);
+      ni = i / plane;
+    }
     const T* r = in + ni * 3 * plane;
     float v[3][3];
 #pragma unroll

@@ -115,10 +115,18 @@ __global__ void __launch_bounds__(256) stem_bwd_reduce_kernel(StemBwdArgs p) {
   }
   for (long long wl = (long long)lb * 16 + wslot; wl < Wv; wl += (long long)Gv * 16) {
     const long long wi = (long long)v * Wv + wl;
-    const int ox = (int)(wi % p.ow);
-    const long long t = wi / p.ow;
-    const int oy = (int)(t % p.oh);
-    const int img = (int)(t / p.oh);
+    int ox, oy, img;
+    if ((long long)p.views * Wv <= 0xffffffffll) {  // 32-bit divisions (the 64-bit ones cost more than the memory traffic)
+      const unsigned u = (unsigned)wi, t = u / (unsigned)p.ow;
+      ox = (int)(u - t * (unsigned)p.ow);
+      img = (int)(t / (unsigned)p.oh);
+      oy = (int)(t - (unsigned)img * (unsigned)p.oh);
+    } else {
+      ox = (int)(wi % p.ow);
+      const long long t = wi / p.ow;
+      oy = (int)(t % p.oh);
+      img = (int)(t / p.oh);
+    }
     float yv[4][4], g[4][4];
     bool valid[4];
     window_grad<T>(y, dpool, img, oy, ox, p.H, p.W, p.oh, p.ow, p.pad, cg, sc, sh, yv, valid, g);
@@ -198,10 +206,18 @@ __global__ void __launch_bounds__(256) stem_bwd_wgrad_kernel(StemBwdArgs p) {
     for (int k = 0; k < K; ++k) acc[j][k] = 0.f;
   for (long long wl = (long long)lb * 16 + wslot; wl < Wv; wl += (long long)Gv * 16) {
     const long long wi = (long long)v * Wv + wl;
-    const int ox = (int)(wi % p.ow);
-    const long long t = wi / p.ow;
-    const int oy = (int)(t % p.oh);
-    const int img = (int)(t / p.oh);
+    int ox, oy, img;
+    if ((long long)p.views * Wv <= 0xffffffffll) {  // 32-bit divisions (the 64-bit ones cost more than the memory traffic)
+      const unsigned u = (unsigned)wi, t = u / (unsigned)p.ow;
+      ox = (int)(u - t * (unsigned)p.ow);
+      img = (int)(t / (unsigned)p.oh);
+      oy = (int)(t - (unsigned)img * (unsigned)p.oh);
+    } else {
+      ox = (int)(wi % p.ow);
+      const long long t = wi / p.ow;
+      oy = (int)(t % p.oh);
+      img = (int)(t / p.oh);
+    }
     float yv[4][4], g[4][4], dy[4][4];
     bool valid[4];
     window_grad<T>(y, dpool, img, oy, ox, p.H, p.W, p.oh, p.ow, p.pad, cg, sc, sh, yv, valid, g);
@@ -298,10 +314,18 @@ __global__ void __launch_bounds__(256) stem_bwd_dy_kernel(StemBwdArgs p) {
   }
   for (long long wl = (long long)lb * 16 + wslot; wl < Wv; wl += (long long)Gv * 16) {
     const long long wi = (long long)v * Wv + wl;
-    const int ox = (int)(wi % p.ow);
-    const long long t = wi / p.ow;
-    const int oy = (int)(t % p.oh);
-    const int img = (int)(t / p.oh);
+    int ox, oy, img;
+    if ((long long)p.views * Wv <= 0xffffffffll) {  // 32-bit divisions (the 64-bit ones cost more than the memory traffic)
+      const unsigned u = (unsigned)wi, t = u / (unsigned)p.ow;
+      ox = (int)(u - t * (unsigned)p.ow);
+      img = (int)(t / (unsigned)p.oh);
+      oy = (int)(t - (unsigned)img * (unsigned)p.oh);
+    } else {
+      ox = (int)(wi % p.ow);
+      const long long t = wi / p.ow;
+      oy = (int)(t % p.oh);
+      img = (int)(t / p.oh);
+    }
     float yv[4][4], g[4][4];
     bool valid[4];
     window_grad<T>(y, dpool, img, oy, ox, p.H, p.W, p.oh, p.ow, p.pad, cg, sc, sh, yv, valid, g);

@@ -712,7 +712,6 @@ def test_stem_backward_fused_matches_chain_and_autograd(mode, cin, hw, pool_pad,
     assert torch.allclose(db2.cpu().double(), br.grad, rtol=0, atol=1e-3 * br.grad.abs().max().item())
 
 
-@pytest.mark.unvalidated
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 @pytest.mark.parametrize("cin,hw,pool_pad,views,n", [(2, 32, 1, 2, 6), (2, 96, 1, 2, 4), (1, 24, 0, 1, 3), (2, 20, 0, 2, 2),
                                                      (2, 18, 1, 1, 5)])
@@ -965,7 +964,6 @@ def test_stem_fprop_on_tensor_cores(cin, k, pad, hw, n, views):
     assert float(tot[1].abs().max()) == 0.0
 
 
-@pytest.mark.unvalidated
 @pytest.mark.parametrize("n,h,cin,cout,k,p", [(4, 25, 64, 128, 3, 1), (3, 49, 64, 128, 3, 1), (3, 25, 128, 256, 3, 1), (2, 24, 64, 128, 5, 2),
                                               (3, 25, 64, 128, 1, 0), (2, 13, 256, 512, 3, 1)])
 def test_stride2_dgrad_resident_and_two_tile_variants_exact(n, h, cin, cout, k, p):
