@@ -134,10 +134,18 @@ __global__ void __launch_bounds__(256, 2) stem_fprop64q_kernel(const float* __re
   for (int c = 0; c < 16; ++c) s1[c] = s2[c] = 0.f;
   for (long long ql = (long long)lb * 64 + qslot; ql < Qv; ql += (long long)Gv * 64) {
     const long long q = (long long)v * Qv + ql;
-    const int ox0 = (int)(q % qpr) * 4;
-    const long long t = q / qpr;
-    const int oy = (int)(t % g.oh);
-    const int n = (int)(t / g.oh);
+    int ox0, oy, n;
+    if ((long long)views * Qv <= 0xffffffffll) {  // 32-bit divisions
+      const unsigned u = (unsigned)q, t = u / (unsigned)qpr;
+      ox0 = (int)(u - t * (unsigned)qpr) * 4;
+      n = (int)(t / (unsigned)g.oh);
+      oy = (int)(t - (unsigned)n * (unsigned)g.oh);
+    } else {
+      ox0 = (int)(q % qpr) * 4;
+      const long long t = q / qpr;
+      oy = (int)(t % g.oh);
+      n = (int)(t / g.oh);
+    }
     float acc[4][16];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
