@@ -486,6 +486,9 @@ def verify(args, world, rank, dev):
   if c["kind"] != "cluster":
     return {"parity_ok": None, "why": "verify covers the clustering workloads"}
   B = min(pairs_for(args, world), 48)
+  import copy
+  args = copy.copy(args)
+  args.graph = False  # (a graphed step runs warm-up optimiser steps before its capture: the check compares ONE eager step)
   job = Job(args, args.precision, dev)
   batches = [_verify_batch(args, B, 5000 + r, dev) for r in range(world)]
   _condition_for_verify(job.net, args, batches[0][0])
