@@ -126,6 +126,52 @@ __global__ void colsum_kernel(const float* __restrict__ a, float* __restrict__ o
 
 using namespace iic;
 
+// Split-K for the skinny head GEMMs (N = S*k = 50..350 columns, K = 512..4608): with one 64x64 tile per 64 rows the
+// ClusterNet6c logits (1400 x 4608 x 50) ran on 22 CTAs.  Partials in a per-device scratch, folded in split order.
+static float* heads_scratch(size_t bytes) {
+  static float* buf[64] = {nullptr};
+  static size_t cap[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (cap[dev] < bytes) {
+    if (buf[dev]) cudaFree(buf[dev]);
+    buf[dev] = nullptr;
+    cap[dev] = 0;
+    if (cudaMalloc(&buf[dev], bytes) != cudaSuccess) return nullptr;
+    cap[dev] = bytes;
+  }
+  return buf[dev];
+}
+static int heads_splits(int M, int N, int K) {
+  const long long tiles = (long long)cdiv(M, ST_BM) * cdiv(N, ST_BN);
+  const int sms = device_sm_count();
+  if (tiles >= sms || K < 512) return 1;
+  long long s = (2ll * sms) / tiles;
+  if (s > K / 128) s = K / 128;
+  if (s > 32) s = 32;
+  return (int)(s < 1 ? 1 : s);
+}
+template <class AL, class BL, bool AK, bool BKC>
+static int heads_gemm(AL A, BL B, float* out, long long ldc, int M, int N, int K, cudaStream_t st) {
+  const int splits = heads_splits(M, N, K);
+  if (splits == 1 || ldc != N) {
+    StoreOut<float> St{out, nullptr, ldc};
+    return launch_simt<AL, BL, StoreOut<float>, AK, BKC>(A, B, St, M, N, K, 1, st);
+  }
+  float* ws = heads_scratch((size_t)splits * M * N * sizeof(float));
+  IIC_REQUIRE(ws != nullptr, IIC_ERR_CUDA, "heads: scratch allocation failed");
+  StorePartial Sp{ws};
+  int rc = launch_simt<AL, BL, StorePartial, AK, BKC>(A, B, Sp, M, N, K, splits, st);
+  if (rc != IIC_OK) return rc;
+  const long long count = (long long)M * N;
+  long long blocks = cdiv(count, 256);
+  if (blocks > 1024) blocks = 1024;
+  splitk_reduce_kernel<<<(int)blocks, 256, 0, st>>>(ws, out, count, splits, 0);
+  IIC_LAUNCH_CHECK();
+  count_launch();
+  return IIC_OK;
+}
+
 extern "C" int iic_heads_fwd(const float* feat, const float* w, const float* b, float* logits_ws, float* z, int n,
                              int F, int S, int k, void* stream) {
   IIC_REQUIRE(feat && w && b && logits_ws && z && n > 0 && F > 0 && S > 0 && k > 0, IIC_ERR_BAD_ARG,
@@ -134,8 +180,7 @@ extern "C" int iic_heads_fwd(const float* feat, const float* w, const float* b, 
   const int N = S * k;
   DenseLoad<float> A{feat, (long long)F, 1, n, F};
   DenseLoad<float> B{w, (long long)F, 1, N, F};
-  StoreOut<float> St{logits_ws, nullptr, (long long)N};
-  int rc = launch_simt<DenseLoad<float>, DenseLoad<float>, StoreOut<float>, true, true>(A, B, St, n, N, F, 1, st);
+  int rc = heads_gemm<DenseLoad<float>, DenseLoad<float>, true, true>(A, B, logits_ws, (long long)N, n, N, F, st);
   if (rc != IIC_OK) return rc;
   add_bias_kernel<<<cdiv((long long)n * N, 256), 256, 0, st>>>(logits_ws, b, n, N);
   IIC_LAUNCH_CHECK();
@@ -161,8 +206,7 @@ extern "C" int iic_heads_bwd(const float* feat, const float* w, const float* z, 
   {  // dw[N][F] = dlogits^T [N][n] x feat [n][F]
     DenseLoad<float> A{dlogits_ws, 1, (long long)N, N, n};  // A(i=col, k=row)
     DenseLoad<float> B{feat, 1, (long long)F, F, n};        // B(i=f, k=row)
-    StoreOut<float> St{dw, nullptr, (long long)F};
-    int rc = launch_simt<DenseLoad<float>, DenseLoad<float>, StoreOut<float>, false, false>(A, B, St, N, F, n, 1, st);
+    int rc = heads_gemm<DenseLoad<float>, DenseLoad<float>, false, false>(A, B, dw, (long long)F, N, F, n, st);
     if (rc != IIC_OK) return rc;
   }
   if (dfeat != nullptr) {  // dfeat[n][F] = dlogits [n][N] x w [N][F]

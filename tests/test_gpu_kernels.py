@@ -311,7 +311,8 @@ def test_stem(mode, cin, k, pad, hw):
   assert torch.allclose(gw, 2 * wr.grad, rtol=1e-3, atol=2 * wtol * wr.grad.abs().max().item())
 
 
-@pytest.mark.parametrize("n,F_,S,k", [(37, 512, 5, 10), (64, 512, 5, 70), (33, 4608, 5, 50), (5, 512, 1, 3)])
+@pytest.mark.parametrize("n,F_,S,k", [(37, 512, 5, 10), (64, 512, 5, 70), (33, 4608, 5, 50), (5, 512, 1, 3),
+                                      (700, 4608, 5, 10), (1408, 512, 5, 10)])  # (the last two: split-K logits / dw GEMMs)
 def test_heads(n, F_, S, k):
   K = _K()
   g = torch.Generator().manual_seed(6)
