@@ -34,9 +34,11 @@ struct StemWgTcParams {
   const float* x;
   int n, cin, H, W, kh, kw, pad, K;
   long long total_px, kblocks, kb_per_cta;
-  float* partial;  // [gridDim.x][32][64]
+  float* partial;  // [gridDim.x][KMAX][64]
 };
 
+// KMAX = 32 | 64: taps handled per pixel (two per builder thread and iteration); the accumulator rows 0 .. KMAX-1 are read back
+template <int KMAX>
 __global__ void __launch_bounds__(SWT_THREADS, 1)
 stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, StemWgTcParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -49,7 +51,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, StemWgTcParams P)
   auto empty_bar = [&](int s) { return bars + 8u * (2 * SWT_STAGES + s); };   // MMAs of the stage retired
   const uint32_t done_bar = bars + 8u * (3 * SWT_STAGES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base_ptr + SWT_STAGES * SWT_STAGE + (3 * SWT_STAGES + 1) * 8);
-  int* tapinfo = reinterpret_cast<int*>(base_ptr + SWT_STAGES * SWT_STAGE + 256);  // [32] packed (ci << 16 | a << 8 | b)
+  int* tapinfo = reinterpret_cast<int*>(base_ptr + SWT_STAGES * SWT_STAGE + 256);  // [KMAX] packed (ci << 16 | a << 8 | b)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -61,7 +63,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, StemWgTcParams P)
     mbar_init(done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x < 32) {
+  if (threadIdx.x < KMAX) {
     const int t = threadIdx.x, khw = P.kh * P.kw;
     const int ci = t / khw, r = t - ci * khw, a = r / P.kw, b = r - a * P.kw;
     tapinfo[t] = (t < P.K) ? ((ci << 16) | (a << 8) | b) : -1;
@@ -134,10 +136,11 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, StemWgTcParams P)
     int img = (int)(q / HW);
     int y = (int)((q - (long long)img * HW) / P.W);
     int x0 = (int)(q - (long long)img * HW - (long long)y * P.W);
-    auto gather = [&](float (&v)[16]) {
+    constexpr int NT = KMAX / 2;  // taps per builder thread
+    auto gather = [&](float (&v)[NT]) {
       const bool live = q < P.total_px;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < NT; ++j) {
         const int info = tapinfo[2 * j + th];
         float val = 0.f;
         if (live && info >= 0) {
@@ -157,7 +160,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, StemWgTcParams P)
         }
       }
     };
-    float v[16], vn[16];
+    float v[NT], vn[NT];
     if (grp < nk) gather(v);
     for (int i = grp; i < nk; i += SWT_GROUPS) {
       const int s = i % SWT_STAGES;
@@ -165,7 +168,7 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, StemWgTcParams P)
       mbar_wait(empty_bar(s), ((i / SWT_STAGES) & 1u) ^ 1u);
       uint8_t* a_slot = base_ptr + s * SWT_STAGE;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < NT; ++j) {
         const int tap = 2 * j + th;
         if (tap < P.K)
           *reinterpret_cast<__nv_bfloat16*>(a_slot + tap * 128 + ((((uint32_t)p >> 3) ^ ((uint32_t)tap & 7u)) << 4) + (p & 7) * 2) =
@@ -174,18 +177,19 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, StemWgTcParams P)
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
       mbar_arrive(built_bar(s));
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = vn[j];
+      for (int j = 0; j < NT; ++j) v[j] = vn[j];
     }
-    if (warp == 0) {
-      // =============================== epilogue: lanes 0..31 of the accumulator = taps ========
-      float* dst = P.partial + ((long long)blockIdx.x * 32 + lane) * 64;
+    if (warp < KMAX / 32) {
+      // =============================== epilogue: lanes 0 .. KMAX-1 of the accumulator = taps ==
+      // (warp w of the CTA may read TMEM lanes 32 (w % 4) .. +31: warps 0 and 1 of builder group 0)
+      float* dst = P.partial + ((long long)blockIdx.x * KMAX + warp * 32 + lane) * 64;
       if (nk > 0) {
         mbar_wait(done_bar, 0);
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t r[32];
-          tmem_ld32(tmem_acc + (uint32_t)(c * 32), r);
+          tmem_ld32(tmem_acc + (uint32_t)(c * 32) + ((uint32_t)(warp * 32) << 16), r);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
@@ -205,13 +209,13 @@ stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, StemWgTcParams P)
 
 // grad[co][tap] (torch OIHW, flat co * K + tap) (+)= sum over CTAs of partial[cta][tap][co], in CTA order
 __global__ void stem_wgrad_tc_fold_kernel(const float* __restrict__ partial, float* __restrict__ grad, int K, int cout, int nblk,
-                                          int accumulate) {
+                                          int accumulate, int kmax) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // tap * 64 + co
   if (i >= K * 64) return;
   const int tap = i >> 6, co = i & 63;
   if (co >= cout) return;
   float t = 0.f;
-  for (int b = 0; b < nblk; ++b) t += partial[(long long)b * 2048 + i];
+  for (int b = 0; b < nblk; ++b) t += partial[(long long)b * kmax * 64 + i];
   float* g = grad + (long long)co * K + tap;
   *g = accumulate ? *g + t : t;
 }
@@ -244,16 +248,16 @@ using namespace iic;
 
 extern "C" long long iic_stem_wgrad_tc_workspace(const iic_conv_geom* g) {
   if (g == nullptr) return 0;
-  return (long long)swt_grid(g) * 32 * 64 * (long long)sizeof(float);
+  return (long long)swt_grid(g) * 64 * 64 * (long long)sizeof(float);
 }
 
 extern "C" int iic_stem_wgrad_tc(const float* x_nchw, const void* dy_bf16, float* grad_oihw, int accumulate, void* workspace,
                                  const iic_conv_geom* g, void* stream) {
   IIC_REQUIRE(x_nchw && dy_bf16 && grad_oihw && workspace && g, IIC_ERR_BAD_ARG, "iic_stem_wgrad_tc: null pointer");
   const int K = g->cin * g->kh * g->kw;
-  IIC_REQUIRE(K >= 1 && K <= 32 && g->cout == 64 && g->stride == 1 && g->dil == 1 && g->oh == g->h && g->ow == g->w &&
+  IIC_REQUIRE(K >= 1 && K <= 64 && g->cout == 64 && g->stride == 1 && g->dil == 1 && g->oh == g->h && g->ow == g->w &&
                   g->kh <= 255 && g->kw <= 255,
-              IIC_ERR_UNSUPPORTED, "iic_stem_wgrad_tc: needs cin*kh*kw <= 32, cout = 64, stride 1, dilation 1, 'same' padding");
+              IIC_ERR_UNSUPPORTED, "iic_stem_wgrad_tc: needs cin*kh*kw <= 64, cout = 64, stride 1, dilation 1, 'same' padding");
   const long long total_px = (long long)g->n * g->h * g->w;
   IIC_REQUIRE(total_px + 64 < (1ll << 31), IIC_ERR_UNSUPPORTED, "iic_stem_wgrad_tc: more than 2^31 pixels");
   int rc = swt_init();
@@ -280,13 +284,16 @@ extern "C" int iic_stem_wgrad_tc(const float* x_nchw, const void* dy_bf16, float
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr = false;
   if (!attr) {
-    IIC_CUDA(cudaFuncSetAttribute(stem_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SWT_SMEM));
+    IIC_CUDA(cudaFuncSetAttribute(stem_wgrad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWT_SMEM));
+    IIC_CUDA(cudaFuncSetAttribute(stem_wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWT_SMEM));
     attr = true;
   }
-  stem_wgrad_tc_kernel<<<grid, SWT_THREADS, SWT_SMEM, st>>>(tm, P);
+  const int kmax = K <= 32 ? 32 : 64;
+  if (kmax == 32) stem_wgrad_tc_kernel<32><<<grid, SWT_THREADS, SWT_SMEM, st>>>(tm, P);
+  else stem_wgrad_tc_kernel<64><<<grid, SWT_THREADS, SWT_SMEM, st>>>(tm, P);
   IIC_LAUNCH_CHECK();
   count_launch();
-  stem_wgrad_tc_fold_kernel<<<cdiv(K * 64, 256), 256, 0, st>>>((const float*)workspace, grad_oihw, K, g->cout, grid, accumulate);
+  stem_wgrad_tc_fold_kernel<<<cdiv(K * 64, 256), 256, 0, st>>>((const float*)workspace, grad_oihw, K, g->cout, grid, accumulate, kmax);
   IIC_LAUNCH_CHECK();
   count_launch();
   return IIC_OK;

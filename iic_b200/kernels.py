@@ -533,7 +533,7 @@ STEM_WGRAD_TC = {"on": __import__("os").environ.get("IIC_STEM_WGRAD_TC", "1") !=
 def stem_wgrad_tc(x_nchw, dy, g, grad_out, accumulate):
   """bf16 tcgen05 stem wgrad (include/iic_b200.h: iic_stem_wgrad_tc); returns False if the geometry is unsupported."""
   K = g.cin * g.kh * g.kw
-  if not (K <= 32 and g.cout == 64 and g.stride == 1 and g.dil == 1 and g.oh == g.h and g.ow == g.w and dy.dtype == torch.bfloat16):
+  if not (K <= 64 and g.cout == 64 and g.stride == 1 and g.dil == 1 and g.oh == g.h and g.ow == g.w and dy.dtype == torch.bfloat16):
     return False
   nbytes = int(_lib.lib().iic_stem_wgrad_tc_workspace(ctypes.byref(g)))
   ws = torch.empty(nbytes // 4, device=dy.device, dtype=torch.float32)

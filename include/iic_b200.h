@@ -252,7 +252,7 @@ int iic_stem_fprop_stats(const float* x_nchw, const float* w_oihw, void* y, cons
                          float* stat_partial, void* stream);
 int iic_stem_wgrad(const float* x_nchw, const void* dy, float* grad_oihw, int accumulate, void* workspace,
                    long long workspace_bytes, const iic_conv_geom* g, int dtype, void* stream);
-/* Stem wgrad on tcgen05 (bf16 dy; cin*kh*kw <= 32, cout = 64, stride 1, 'same' padding): the patches of the NCHW fp32 input
+/* Stem wgrad on tcgen05 (bf16 dy; cin*kh*kw <= 64, cout = 64, stride 1, 'same' padding): the patches of the NCHW fp32 input
  * are gathered into shared memory as the K-major operand, dy arrives by TMA as the MN-major operand, one TMEM accumulator per
  * persistent CTA, per-CTA partials in `workspace` (iic_stem_wgrad_tc_workspace bytes) folded in a fixed order into the
  * torch-layout gradient [cout][cin][kh][kw] (same contract as iic_stem_wgrad: replaces autograd's conv2d weight gradient of

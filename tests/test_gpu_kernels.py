@@ -902,7 +902,8 @@ def test_wgrad_written_in_torch_layout_equals_wgrad_plus_unpack(case, mode):
   assert torch.equal(outs[False][1], outs[True][1])
 
 
-@pytest.mark.parametrize("cin,k,pad,hw,n", [(2, 3, 1, 32, 3), (2, 3, 1, 96, 4), (1, 5, 2, 24, 5), (3, 3, 1, 20, 2), (2, 3, 1, 7, 1)])
+@pytest.mark.parametrize("cin,k,pad,hw,n", [(2, 3, 1, 32, 3), (2, 3, 1, 96, 4), (1, 5, 2, 24, 5), (3, 3, 1, 20, 2), (2, 3, 1, 7, 1),
+                                            (5, 3, 1, 20, 2), (4, 3, 1, 128, 2), (2, 5, 2, 24, 3)])  # (the last three: 33..64 taps)
 def test_stem_wgrad_on_tensor_cores_matches_the_simt_kernel(cin, k, pad, hw, n):
   """Stem wgrad on tcgen05 (stem_tc.cu: patches gathered into shared memory, dy by TMA; option STEM_WGRAD_TC) against
   torch autograd on the same bf16-rounded operands and against the SIMT Gram-product kernel."""
