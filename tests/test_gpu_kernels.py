@@ -326,9 +326,11 @@ def test_heads(n, F_, S, k):
   assert torch.allclose(z, zr.detach(), rtol=1e-4, atol=1e-6)
   zr.backward(dz)
   dw, db, dfeat = K.heads_bwd(feat, w, z, dz, S, k, True)
-  assert torch.allclose(dw, wr.grad, rtol=1e-3, atol=1e-5)
-  assert torch.allclose(db, br.grad, rtol=1e-3, atol=1e-5)
-  assert torch.allclose(dfeat, fr.grad, rtol=1e-3, atol=1e-5)
+  # (fp32 sums of n terms in a different order than torch: absolute tolerance ~ 1e-6 of the largest entry per 100 rows)
+  atol = lambda t: max(1e-5, 2e-6 * t.abs().max().item() * max(1.0, n / 100.0))  # noqa: E731
+  assert torch.allclose(dw, wr.grad, rtol=1e-3, atol=atol(wr.grad))
+  assert torch.allclose(db, br.grad, rtol=1e-3, atol=atol(br.grad))
+  assert torch.allclose(dfeat, fr.grad, rtol=1e-3, atol=atol(fr.grad))
 
 
 def test_sobel_matches_oracle():
