@@ -530,13 +530,14 @@ def stem_bwd_fused(x_nchw, y, dpool, ss, mi, gamma, dgamma, dbeta, bn_accumulate
 STEM_WGRAD_TC = {"on": __import__("os").environ.get("IIC_STEM_WGRAD_TC", "1") != "0"}
 
 
-STEM_WGRAD_TC64 = {"on": __import__("os").environ.get("IIC_STEM_WGRAD_TC64", "0") != "0"}
+STEM_WGRAD_TC64 = {"on": __import__("os").environ.get("IIC_STEM_WGRAD_TC64", "1") != "0"}
 
 
 def stem_wgrad_tc(x_nchw, dy, g, grad_out, accumulate):
   """bf16 tcgen05 stem wgrad (include/iic_b200.h: iic_stem_wgrad_tc); returns False if the geometry is unsupported."""
   K = g.cin * g.kh * g.kw
-  # (33..64 taps -- SegmentationNet10a -- were written after the last GPU session of the round: behind STEM_WGRAD_TC64)
+  # (33..64 taps -- SegmentationNet10a: validated in the last GPU call of round 2, profiles/r02_session_u.md; its effect on the
+  # c5 step was not measured any more: IIC_STEM_WGRAD_TC64=0 returns those stems to the SIMT kernel)
   kmax = 64 if STEM_WGRAD_TC64["on"] else 32
   if not (K <= kmax and g.cout == 64 and g.stride == 1 and g.dil == 1 and g.oh == g.h and g.ow == g.w and dy.dtype == torch.bfloat16):
     return False

@@ -904,20 +904,14 @@ def test_wgrad_written_in_torch_layout_equals_wgrad_plus_unpack(case, mode):
   assert torch.equal(outs[False][1], outs[True][1])
 
 
-_U = pytest.mark.unvalidated  # 33..64 taps: written after the last GPU session of round 2
-
-
 @pytest.mark.parametrize("cin,k,pad,hw,n", [(2, 3, 1, 32, 3), (2, 3, 1, 96, 4), (1, 5, 2, 24, 5), (3, 3, 1, 20, 2), (2, 3, 1, 7, 1),
-                                            pytest.param(5, 3, 1, 20, 2, marks=_U), pytest.param(4, 3, 1, 128, 2, marks=_U),
-                                            pytest.param(2, 5, 2, 24, 3, marks=_U)])
+                                            (5, 3, 1, 20, 2), (4, 3, 1, 128, 2), (2, 5, 2, 24, 3)])  # (the last three: 33..64 taps)
 def test_stem_wgrad_on_tensor_cores_matches_the_simt_kernel(cin, k, pad, hw, n):
   """Stem wgrad on tcgen05 (stem_tc.cu: patches gathered into shared memory, dy by TMA; option STEM_WGRAD_TC) against
   torch autograd on the same bf16-rounded operands and against the SIMT Gram-product kernel."""
   K = _K()
   from iic_b200._lib import BF16
   cout = 64
-  if cin * k * k > 32:
-    K.STEM_WGRAD_TC64["on"] = True  # (stays on for the rest of an IIC_RUN_UNVALIDATED session: that is what it is for)
   g = torch.Generator().manual_seed(9)
   x = torch.randn(n, cin, hw, hw, generator=g).cuda()
   dy = torch.randn(n, cout, hw, hw, generator=g).cuda().bfloat16().float()
