@@ -5,7 +5,8 @@ ClusterNet5gTwoHead + IID_loss (k=10 head B, 5 sub-heads) on synthetic 96x96 bat
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path, default workload c4
     python bench.py --config {c2,c3,c4,c4-strong,c5}         # the other BASELINE.json configurations
     python bench.py --impl reference ...                     # the reference algorithm on the host CPUs
-    torchrun ... bench.py --gpus N --verify                  # + N-rank result == one-device sharded emulation
+    torchrun ... bench.py --gpus N                           # N > 1 also checks N-rank result == one-device sharded
+                                                             # emulation (parity_ok; --no-verify to skip, --verify at N = 1)
 
 A step = one pass of the reference's per-batch loop (cluster_sobel_twohead.py:286-355 / segmentation_twohead.py:
 262-361): zero_grad, (grey+)sobel x2, net(x), net(x_tf), IID loss over the sub-heads, backward, gradient all-reduce
