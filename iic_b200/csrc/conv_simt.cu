@@ -134,10 +134,11 @@ static float* heads_scratch(size_t bytes) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   if (cap[dev] < bytes) {
-    if (buf[dev]) cudaFree(buf[dev]);
-    buf[dev] = nullptr;
-    cap[dev] = 0;
-    if (cudaMalloc(&buf[dev], bytes) != cudaSuccess) return nullptr;
+    // grown, never freed: a captured CUDA graph (iic_b200/graph.py) may hold the old pointer, and a later eager call with a
+    // larger batch (an evaluation pass between graphed training steps) must not pull it from under the replays
+    float* nb = nullptr;
+    if (cudaMalloc(&nb, bytes) != cudaSuccess) return nullptr;
+    buf[dev] = nb;
     cap[dev] = bytes;
   }
   return buf[dev];
