@@ -99,3 +99,23 @@ def test_default_kernel_variants_are_the_validated_set():
                       "stem_quad": 2, "stem_bwd_v2": 0, "conv_halo_stats": 1, "bn_bwd_ctas": 2, "tf32x3_raw_hi": 1, "wgrad_mt": 1, "halo_addend_tma": 1, "dgrad_s2_mt": 0}
   assert host_opts == {"bn_merged": True, "stem_stats": True, "pack_batched": True, "stem_bwd_fused": False, "bn_bitmask": True,
                        "wgrad_stream": False, "masked_addend": True, "stem_bwd_dy": False}
+
+
+def test_weight_packing_contract_of_the_precision_modes():
+  """Host side of the packed-weight contract (include/iic_b200.h: iic_pack_weight): 3xTF32 convolutions take their
+  weights pre-split as [raw plane | lo plane]; every other mode packs in the storage dtype; the conv wrappers refuse a
+  buffer packed for another mode before any pointer reaches the library."""
+  from iic_b200 import kernels as K
+  from iic_b200._lib import BF16, F32, TF32, TF32X3
+  assert K.weight_dtype(F32, TF32X3) == TF32X3 and K.weight_dtype(F32, TF32) == F32
+  assert K.weight_dtype(BF16, BF16) == BF16 and K.weight_dtype(F32, F32) == F32
+  w = torch.zeros(128, 64, 3, 3)
+  assert K._packed_shape(w, F32, 0) == (128, 3, 3, 64) and K._packed_shape(w, BF16, 1) == (64, 3, 3, 128)
+  assert K._packed_shape(w, TF32X3, 0) == (2, 128, 3, 3, 64) and K._packed_shape(w, TF32X3, 1) == (2, 64, 3, 3, 128)
+  g = K.conv_geom(1, 8, 8, 64, 128, 3, 3, 1, 1, 1)
+  K._check_packed(torch.empty(K._packed_shape(w, TF32X3, 0)), g, TF32X3)
+  K._check_packed(torch.empty(K._packed_shape(w, F32, 0)), g, TF32)
+  with pytest.raises(AssertionError, match="pack_weight"):
+    K._check_packed(torch.empty(K._packed_shape(w, F32, 0)), g, TF32X3)
+  with pytest.raises(AssertionError, match="pack_weight"):
+    K._check_packed(torch.empty(K._packed_shape(w, TF32X3, 0)), g, BF16)
